@@ -1,0 +1,106 @@
+"""Pin the CPU oracle (oracle/) against fixtures produced by the unmodified reference modules
+(tools/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import lightglue as olg
+from oracle import matchers as om
+from oracle import superpoint as osp
+from conftest import lg_pair_from_source, match_f1
+
+SP_CONFS = {
+    "api": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4},
+    "max1024": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.005, "remove_borders": 4},
+    "nocap": {"nms_radius": 4, "max_keypoints": -1, "keypoint_threshold": 0.005, "remove_borders": 4},
+    "max2048": {"nms_radius": 3, "max_keypoints": 2048, "keypoint_threshold": 0.005, "remove_borders": 4},
+}
+
+
+@pytest.mark.parametrize("case,confs", [("sp_real", ["api", "max1024", "nocap"]), ("sp_synth", ["max1024", "max2048"])])
+def test_superpoint_oracle_matches_reference(golden, case, confs):
+    g = golden(case)
+    w = oracle.load_weights("superpoint_v1.pt")
+    images = torch.from_numpy(g["images"])
+    for c in confs:
+        for b in range(images.shape[0]):
+            out = osp.forward(w, images[b:b + 1], SP_CONFS[c])
+            # keypoint set + order bit-exact, scores/descriptors to 1e-5 (same machine class: ~0)
+            assert np.array_equal(out["keypoints"][0].numpy().astype(np.int16), g[f"{c}/{b}/keypoints"]), (case, c, b)
+            np.testing.assert_allclose(out["scores"][0].numpy(), g[f"{c}/{b}/scores"], atol=1e-5)
+            np.testing.assert_allclose(out["descriptors"][0].numpy(), g[f"{c}/{b}/descriptors"], atol=1e-4)
+
+
+def test_superpoint_oracle_dense_maps(golden):
+    g = golden("sp_real")
+    w = oracle.load_weights("superpoint_v1.pt")
+    out = osp.forward(w, torch.from_numpy(g["images"]), SP_CONFS["api"], return_dense=True)
+    for b in range(2):
+        np.testing.assert_allclose(out["dense_scores"][b].numpy(), g[f"dense/{b}/scores"], atol=2e-6)
+        assert np.array_equal(out["nms_scores"][b].numpy() > 0, g[f"dense/{b}/nms3"] > 0)
+        np.testing.assert_allclose(out["dense_descriptors"][b, :, ::4, ::4].numpy(), g[f"dense/{b}/desc_sub"], atol=1e-5)
+
+
+def test_superpoint_oracle_rejects_bad_max_keypoints():
+    w = oracle.load_weights("superpoint_v1.pt")
+    with pytest.raises(ValueError):
+        osp.forward(w, torch.zeros(1, 1, 16, 16), {"max_keypoints": 0})
+
+
+MODES = {
+    "full": dict(depth_confidence=-1, width_confidence=-1, pruning_min_kpts=-1),
+    "cuda": dict(depth_confidence=0.95, width_confidence=0.99, pruning_min_kpts=1536),
+    "cpu": dict(depth_confidence=0.95, width_confidence=0.99, pruning_min_kpts=-1),
+}
+
+
+@pytest.mark.parametrize("case", ["lg_real", "lg_synth"])
+@pytest.mark.parametrize("mode", ["full", "cuda", "cpu"])
+def test_lightglue_oracle_matches_reference(golden, case, mode):
+    g = golden(case)
+    w = oracle.load_weights("superpoint_lightglue.pt")
+    for p, src in enumerate(g["sources"]):
+        k0, d0, k1, d1 = lg_pair_from_source(golden, src)
+        out = olg.forward(w, torch.from_numpy(k0)[None], torch.from_numpy(d0).t().contiguous()[None],
+                          torch.from_numpy(k1)[None], torch.from_numpy(d1).t().contiguous()[None], MODES[mode])
+        pre = f"{mode}/{p}/"
+        assert out["stop"] == int(g[pre + "stop"])
+        assert np.array_equal(out["matches0"][0].numpy(), g[pre + "matches0"]), (case, mode, p, match_f1(out["matches0"][0].numpy(), g[pre + "matches0"]))
+        assert np.array_equal(out["matches1"][0].numpy(), g[pre + "matches1"])
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[pre + "matching_scores0"], atol=1e-4)
+        assert np.array_equal(out["prune0"][0].numpy().astype(np.int32), g[pre + "prune0"])
+        assert np.array_equal(out["prune1"][0].numpy().astype(np.int32), g[pre + "prune1"])
+
+
+def _matcher_inputs(golden, p):
+    g = golden("matchers")
+    if p == 0:
+        s = golden("sp_real")
+        return s["api/0/descriptors"], s["api/1/descriptors"]
+    return g[f"in/{p}/descriptors0"], g[f"in/{p}/descriptors1"]
+
+
+@pytest.mark.parametrize("p", [0, 1])
+def test_matchers_oracle_matches_reference(golden, p):
+    g = golden("matchers")
+    d0, d1 = (torch.from_numpy(x)[None] for x in _matcher_inputs(golden, p))
+    cases = {
+        "nn": om.nearest_neighbor(d0, d1),
+        "nn_ratio": om.nearest_neighbor(d0, d1, ratio_threshold=0.9, distance_threshold=0.9),
+        "nn_nomutual": om.nearest_neighbor(d0, d1, do_mutual_check=False),
+        "dsm": om.dual_softmax(d0, d1, match_threshold=0.01, inv_temperature=20),
+    }
+    for tag, out in cases.items():
+        assert np.array_equal(out["matches0"][0].numpy(), g[f"{tag}/{p}/matches0"]), tag
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{tag}/{p}/matching_scores0"], atol=1e-6)
+    assert cases["dsm"]["matching_scores0"].dtype == torch.float64
+
+
+def test_matchers_oracle_empty_inputs():
+    e = torch.zeros(1, 128, 0)
+    d = torch.randn(1, 128, 5)
+    for fn in (om.nearest_neighbor, om.dual_softmax):
+        out = fn(e, d)
+        assert out["matches0"].shape == (1, 128) or out["matches0"].shape == (1, 128)  # reference quirk: shape[:2]
+        assert (out["matches0"] == -1).all()

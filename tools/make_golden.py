@@ -1,0 +1,193 @@
+"""Mint golden vectors by running the UNMODIFIED reference modules (build container only).
+
+    cd /tmp && python /root/repo/tools/make_golden.py
+
+Writes tests/golden/*.npz.  Imports /root/reference through tools/ref_import.py (SURVEY.md 8(c)
+recipe); runs single-threaded-deterministic CPU fp32.  The reference's own tests hold no golden
+vectors, so these fixtures are what pins the oracle and the CUDA path.
+"""
+import importlib.util
+import sys
+from pathlib import Path
+
+import cv2
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+import ref_import as R  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("synth", ROOT / "image-matching-webui_b200/utils/synth.py")
+synth = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(synth)
+
+OUT = ROOT / "tests" / "golden"
+torch.set_grad_enabled(False)
+
+SP_CONFS = {
+    # ImageMatchingAPI defaults written over superpoint_max (api/core.py:36-38,80-97): test_one path
+    "api": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4},
+    # hloc/configs/extractors.py:31-37 with the API's 1024 cap (BASELINE config 2)
+    "max1024": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.005, "remove_borders": 4},
+    # no cap: row-major keypoint order
+    "nocap": {"nms_radius": 4, "max_keypoints": -1, "keypoint_threshold": 0.005, "remove_borders": 4},
+    "max2048": {"nms_radius": 3, "max_keypoints": 2048, "keypoint_threshold": 0.005, "remove_borders": 4},
+}
+
+
+def preprocess_like_extract(rgb):
+    """hloc/extract_features.py:106-170 with the superpoint_max preprocessing conf
+    (grayscale, resize_max 1600, force_resize 640x480, dfactor 8), executed with the same cv2 /
+    torchvision calls the reference makes."""
+    import torchvision.transforms.functional as TF
+    gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)
+    image = gray.astype(np.float32, copy=False)
+    size = image.shape[:2][::-1]
+    scale = 1600 / max(size)
+    if scale < 1.0:
+        size_new = tuple(int(round(x * scale)) for x in size)
+        image = cv2.resize(image, size_new, interpolation=cv2.INTER_AREA)
+    h, w = image.shape[:2]
+    interp = cv2.INTER_AREA if not (w < 640 or h < 480) else cv2.INTER_LINEAR
+    image = cv2.resize(image, (640, 480), interpolation=interp)
+    image = torch.from_numpy(image[None] / 255.0).float()
+    size_new = tuple(int(x // 8 * 8) for x in image.shape[-2:])
+    image = TF.resize(image, size=size_new, antialias=True)
+    return image[None], np.array(size)
+
+
+def run_sp(net, image, conf):
+    out = net({"image": image}, conf)
+    return out
+
+
+def sp_case(name, images, confs, dense_for=()):
+    """images: fp32 [B,1,H,W]"""
+    sp_mod = R.superpoint_module()
+    net = R.make_superpoint({"nms_radius": 4, "max_keypoints": -1, "keypoint_threshold": 0.005})
+    blob = {"images_u8": None, "images": images.numpy()}
+    for cname, conf in confs.items():
+        for b in range(images.shape[0]):
+            out = net({"image": images[b:b + 1]}, conf)
+            blob[f"{cname}/{b}/keypoints"] = out["keypoints"][0].numpy().astype(np.int16)
+            blob[f"{cname}/{b}/scores"] = out["scores"][0].numpy()
+            blob[f"{cname}/{b}/descriptors"] = out["descriptors"][0].numpy()
+    # dense intermediates (conf-independent up to NMS radius): score map before NMS
+    for b in dense_for:
+        x = images[b:b + 1]
+        r = net.relu
+        h = r(net.conv1a(x)); h = r(net.conv1b(h)); h = net.pool(h)
+        h = r(net.conv2a(h)); h = r(net.conv2b(h)); h = net.pool(h)
+        h = r(net.conv3a(h)); h = r(net.conv3b(h)); h = net.pool(h)
+        h = r(net.conv4a(h)); h = r(net.conv4b(h))
+        logits = net.convPb(r(net.convPa(h)))
+        s = torch.nn.functional.softmax(logits, 1)[:, :-1]
+        bb, _, hh, ww = s.shape
+        s = s.permute(0, 2, 3, 1).reshape(bb, hh, ww, 8, 8).permute(0, 1, 3, 2, 4).reshape(bb, hh * 8, ww * 8)
+        blob[f"dense/{b}/scores"] = s[0].numpy()
+        blob[f"dense/{b}/nms3"] = sp_mod.simple_nms(s, 3)[0].numpy()
+        d = torch.nn.functional.normalize(net.convDb(r(net.convDa(h))), p=2, dim=1)
+        blob[f"dense/{b}/desc_sub"] = d[0, :, ::4, ::4].numpy()
+        blob[f"dense/{b}/feat_sub"] = h[0, :, ::4, ::4].numpy()
+    del blob["images_u8"]
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+    print("wrote", name, {k: v.shape for k, v in list(blob.items())[:6]})
+    return blob
+
+
+LG_MODES = {
+    # oracle A: full depth, no pruning (deterministic compute graph)
+    "full": dict(depth_confidence=-1, width_confidence=-1, prune_th=-1),
+    # oracle B: what the reference does on CUDA+flash for <=1536 kpts: early stop only
+    "cuda": dict(depth_confidence=0.95, width_confidence=0.99, prune_th=1536),
+    # oracle C: reference CPU defaults: early stop + prune at every layer
+    "cpu": dict(depth_confidence=0.95, width_confidence=0.99, prune_th=-1),
+}
+
+
+def lg_case(name, pairs, sources):
+    """pairs: list of (kpts0 [N,2], desc0 [256,N], kpts1, desc1) numpy; sources: "file:conf:i:j" each."""
+    lgm = R.lightglue_module()
+    blob = {}
+    for mname, mode in LG_MODES.items():
+        lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = mode["prune_th"]
+        net = R.make_lightglue(filter_threshold=0.2, depth_confidence=mode["depth_confidence"],
+                               width_confidence=mode["width_confidence"])
+        for p, (k0, d0, k1, d1) in enumerate(pairs):
+            data = {
+                "image0": {"keypoints": torch.from_numpy(k0).float()[None],
+                           "descriptors": torch.from_numpy(d0).t().contiguous()[None]},
+                "image1": {"keypoints": torch.from_numpy(k1).float()[None],
+                           "descriptors": torch.from_numpy(d1).t().contiguous()[None]},
+            }
+            out = net(data)
+            pre = f"{mname}/{p}/"
+            blob[pre + "matches0"] = out["matches0"][0].numpy().astype(np.int32)
+            blob[pre + "matches1"] = out["matches1"][0].numpy().astype(np.int32)
+            blob[pre + "matching_scores0"] = out["matching_scores0"][0].numpy()
+            blob[pre + "matching_scores1"] = out["matching_scores1"][0].numpy()
+            blob[pre + "stop"] = np.int32(out["stop"])
+            blob[pre + "prune0"] = out["prune0"][0].numpy().astype(np.int32)
+            blob[pre + "prune1"] = out["prune1"][0].numpy().astype(np.int32)
+            print(name, mname, p, "stop", out["stop"], "matches", int((out["matches0"] > -1).sum()))
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = -1
+    # inputs are the reference SuperPoint outputs already stored in sp_*.npz: record where
+    blob["sources"] = np.array(sources)
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
+def matcher_case(name, pairs):
+    nn_mod, ds_mod = R.hloc_matchers()
+    blob = {}
+    nn = nn_mod.NearestNeighbor({"do_mutual_check": True})
+    nn_ratio = nn_mod.NearestNeighbor({"do_mutual_check": True, "ratio_threshold": 0.9, "distance_threshold": 0.9})
+    nn_nomut = nn_mod.NearestNeighbor({"do_mutual_check": False})
+    ds = ds_mod.DualSoftMax({"match_threshold": 0.01, "inv_temperature": 20})
+    for p, (d0, d1) in enumerate(pairs):
+        data = {"descriptors0": torch.from_numpy(d0)[None], "descriptors1": torch.from_numpy(d1)[None]}
+        for tag, model in (("nn", nn), ("nn_ratio", nn_ratio), ("nn_nomutual", nn_nomut), ("dsm", ds)):
+            out = model(data)
+            blob[f"{tag}/{p}/matches0"] = out["matches0"][0].numpy().astype(np.int32)
+            blob[f"{tag}/{p}/matching_scores0"] = out["matching_scores0"][0].numpy()
+            print(name, tag, p, int((out["matches0"] > -1).sum()), out["matching_scores0"].dtype)
+        if p > 0:  # pair 0 = sp_real api descriptors, already stored there
+            blob[f"in/{p}/descriptors0"] = d0
+            blob[f"in/{p}/descriptors1"] = d1
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    (OUT / "data").mkdir(exist_ok=True)
+    # ---- real pair (tests/data of the reference; BASELINE config 1) -------------------------------
+    names = ["02928139_3448003521.jpg", "17295357_9106075285.jpg"]
+    imgs = []
+    for n in names:
+        bgr = cv2.imread(str(R.REF / "tests/data" / n))
+        rgb = np.ascontiguousarray(bgr[:, :, ::-1])
+        x, orig = preprocess_like_extract(rgb)
+        imgs.append(x)
+        # keep a small decoded copy of the fixture image for the a1 (pre-processing) parity test
+        np.savez_compressed(OUT / "data" / (Path(n).stem + ".npz"), rgb=rgb)
+    real = torch.cat(imgs, 0)
+    rb = sp_case("sp_real", real, {k: SP_CONFS[k] for k in ("api", "max1024", "nocap")}, dense_for=(0, 1))
+    # ---- synthetic pairs (BASELINE config 2 stream, seeds 0..1) -----------------------------------
+    a, b = synth.make_pair_batch([0, 1])
+    syn_u8 = np.stack([a[0], b[0], a[1], b[1]])
+    syn = torch.from_numpy(syn_u8.astype(np.float32) / 255.0)[:, None]
+    sb = sp_case("sp_synth", syn, {k: SP_CONFS[k] for k in ("max1024", "max2048")})
+
+    def pair(blob, conf, i, j):
+        return (blob[f"{conf}/{i}/keypoints"].astype(np.float32), blob[f"{conf}/{i}/descriptors"],
+                blob[f"{conf}/{j}/keypoints"].astype(np.float32), blob[f"{conf}/{j}/descriptors"])
+
+    lg_case("lg_real", [pair(rb, "api", 0, 1), pair(rb, "nocap", 0, 1)], ["sp_real:api:0:1", "sp_real:nocap:0:1"])
+    lg_case("lg_synth", [pair(sb, "max1024", 0, 1), pair(sb, "max1024", 2, 3), pair(sb, "max2048", 0, 1)],
+            ["sp_synth:max1024:0:1", "sp_synth:max1024:2:3", "sp_synth:max2048:0:1"])
+    d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
+    matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
+
+
+if __name__ == "__main__":
+    main()

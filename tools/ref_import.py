@@ -1,0 +1,78 @@
+"""Import the UNMODIFIED reference modules from /root/reference (this container only).
+
+Test/fixture infrastructure: used by tools/make_golden.py and tools/fetch_weights.py to
+mint golden vectors and convert weights.  Nothing here travels to the GPU box and
+nothing in the product path imports it.  Recipe follows SURVEY.md section 8(c).
+"""
+import importlib.util
+import os
+import sys
+import types
+from pathlib import Path
+
+REF = Path(os.environ.get("IMW_REFERENCE", "/root/reference"))
+TP = REF / "imcui" / "third_party"
+SP_WEIGHTS = TP / "SE2LoFTR/third_party/SuperGluePretrainedNetwork/models/weights/superpoint_v1.pth"
+SG_WEIGHTS = TP / "SE2LoFTR/third_party/SuperGluePretrainedNetwork/models/weights"
+LG_GIM_CKPT = TP / "gim/weights/gim_lightglue_100h.ckpt"
+
+
+def available() -> bool:
+    return (REF / "imcui").is_dir()
+
+
+def _load_file(name, path):
+    if name in sys.modules:  # one module object per process (class attributes are patched by tools)
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, str(path))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def superpoint_module():
+    """third_party/SuperGluePretrainedNetwork/models/superpoint.py (the one hloc uses)."""
+    return _load_file("_ref_superpoint", TP / "SuperGluePretrainedNetwork/models/superpoint.py")
+
+
+def superglue_module():
+    return _load_file("_ref_superglue", TP / "SuperGluePretrainedNetwork/models/superglue.py")
+
+
+def lightglue_module():
+    """third_party/LightGlue/lightglue/lightglue.py loaded by file (package __init__ needs kornia)."""
+    return _load_file("_ref_lightglue", TP / "LightGlue/lightglue/lightglue.py")
+
+
+def make_superpoint(conf):
+    import contextlib, io
+    sp = superpoint_module()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = sp.SuperPoint({**conf, "weights_path": str(SP_WEIGHTS)})
+    return net.eval()
+
+
+def lightglue_state_dict():
+    import torch
+    ck = torch.load(str(LG_GIM_CKPT), map_location="cpu", weights_only=False)
+    sd = ck["state_dict"]
+    return {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+
+
+def make_lightglue(**conf):
+    lg = lightglue_module()
+    net = lg.LightGlue(features=None, input_dim=256, weights=None, **conf)
+    missing, unexpected = net.load_state_dict(lightglue_state_dict(), strict=False)
+    assert not unexpected, unexpected
+    assert all("confidence_thresholds" in m for m in missing), missing
+    return net.eval()
+
+
+def hloc_matchers():
+    """imcui.hloc.matchers.{nearest_neighbor,dual_softmax} import as-is (run from a scratch cwd:
+    importing imcui.hloc writes log.txt)."""
+    if str(REF) not in sys.path:
+        sys.path.insert(0, str(REF))
+    from imcui.hloc.matchers import nearest_neighbor, dual_softmax
+    return nearest_neighbor, dual_softmax

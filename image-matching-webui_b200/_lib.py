@@ -1,0 +1,119 @@
+"""ctypes binding of libimw_b200.so (include/imw_b200.h).  Fails loudly when the library is missing:
+there is no CPU or PyTorch fallback in the product path."""
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libimw_b200.so"
+IMW_LG_MAX_LAYERS = 16
+fp = C.POINTER(C.c_float)
+
+
+class SPWeights(C.Structure):
+    _fields_ = [("w", C.c_void_p * 12), ("b", C.c_void_p * 12)]
+
+
+class SPConf(C.Structure):
+    _fields_ = [("nms_radius", C.c_int), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int),
+                ("remove_borders", C.c_int)]
+
+
+class LGBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("qkv_w", "qkv_b", "out_w", "out_b", "ffn0_w", "ffn0_b", "ln_g", "ln_b", "ffn3_w", "ffn3_b")]
+
+
+class LGLayer(C.Structure):
+    _fields_ = [("self_blk", LGBlock), ("cross_blk", LGBlock)]
+
+
+class LGWeights(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("input_dim", C.c_int), ("posenc_wr", C.c_void_p),
+                ("token_w", C.c_void_p), ("token_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+                ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS)]
+
+
+class LGConf(C.Structure):
+    _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
+                ("pruning_min_kpts", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  The B200 engine has no CPU/PyTorch fallback.")
+        L = C.CDLL(str(LIB_PATH))
+        L.imw_last_error.restype = C.c_char_p
+        L.imw_version.restype = C.c_int
+        for name in ("imw_superpoint_workspace_bytes", "imw_lightglue_workspace_bytes", "imw_matcher_workspace_bytes"):
+            getattr(L, name).restype = C.c_size_t
+        L.imw_superpoint_workspace_bytes.argtypes = [C.c_int] * 3
+        L.imw_lightglue_workspace_bytes.argtypes = [C.c_int] * 2
+        L.imw_matcher_workspace_bytes.argtypes = [C.c_int] * 2
+        vp = C.c_void_p
+        L.imw_superpoint_forward.restype = C.c_int
+        L.imw_superpoint_forward.argtypes = [C.POINTER(SPWeights), C.POINTER(SPConf), C.c_int, C.c_int, C.c_int, vp,
+                                             C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+        L.imw_lightglue_forward.restype = C.c_int
+        L.imw_lightglue_forward.argtypes = [C.POINTER(LGWeights), C.POINTER(LGConf), C.c_int, C.c_int, vp, vp, vp, vp,
+                                            vp, vp, vp, vp, C.c_size_t, vp]
+        L.imw_nearest_neighbor.restype = C.c_int
+        L.imw_nearest_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp,
+                                           vp, C.c_size_t, vp]
+        L.imw_dual_softmax.restype = C.c_int
+        L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, vp, vp, vp,
+                                       C.c_size_t, vp]
+        _lib = L
+    return _lib
+
+
+class ImwError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().imw_last_error().decode()
+        if rc == -1:  # IMW_ERR_ARG: the reference raises ValueError for bad conf values
+            raise ValueError(msg)
+        raise ImwError(f"imw error {rc}: {msg}")
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; the B200 engine only runs on CUDA devices "
+                           "(no CPU fallback)")
+
+
+class WorkspaceCache:
+    """One growing scratch tensor per (device, tag): no allocation in the steady state."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, device, nbytes, tag="ws"):
+        key = (str(device), tag)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
+
+
+workspaces = WorkspaceCache()

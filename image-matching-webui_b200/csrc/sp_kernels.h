@@ -1,0 +1,22 @@
+// Internal launchers for the SuperPoint stages (not part of the C ABI; see include/imw_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+int sp_conv3x3(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
+               int relu, int pool, cudaStream_t st);
+int sp_conv3x3_c1(const float* img, const float* w, const float* bias, float* out, int B, int H, int W, cudaStream_t st);
+
+// logits [B][h][w][65] (NHWC) -> dense scores [B][8h][8w]
+int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st);
+// dense [B][H][W] -> nms [B][H][W] (scores kept at surviving maxima, 0 elsewhere)
+int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cudaStream_t st);
+// nms -> keypoints/scores per image (row-major order, or descending score when more than max_kpts pass)
+// keys: scratch [B][key_cap] u64.  kpts [B][cap][2] float (x,y), scores [B][cap], counts [B].
+int sp_select(const float* nms, unsigned long long* keys, int key_cap, float* kpts, float* scores, int* counts,
+              int B, int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st);
+size_t sp_select_key_cap(int H, int W);
+// in-place L2 normalisation of rows of 256 ([cells][256])
+int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st);
+// bilinear sample of dense descriptors [B][h][w][256] at kpts, then L2 norm -> desc [B][cap][256]
+int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts, float* desc, int B, int h, int w,
+                   int cap, int C, cudaStream_t st);

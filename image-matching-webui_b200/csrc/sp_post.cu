@@ -1,0 +1,349 @@
+// SuperPoint detector / descriptor post-processing (HBM-bound integer/compare work).
+// Follows third_party/SuperGluePretrainedNetwork/models/superpoint.py:
+//   :167-170 softmax-65 + drop dustbin + 8x8 depth-to-space      -> sp_softmax_d2s
+//   :47-62   simple_nms (3 rounds, exact float equality)         -> sp_nms
+//   :174-191 threshold, row-major nonzero, border, top-k         -> sp_select
+//   :196     channel L2 norm of the dense descriptor map         -> sp_l2norm_rows
+//   :80-92   bilinear sampling (align_corners=True) + L2 norm    -> sp_sample_desc
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "sp_kernels.h"
+
+namespace {
+
+// ---- softmax over 65 channels + depth-to-space -----------------------------------------------
+// one warp per 8x8 cell; lane l owns channels l, l+32 (and lane 0 the dustbin, channel 64).
+__global__ void __launch_bounds__(256) softmax_d2s_kernel(const float* __restrict__ logits, float* __restrict__ dense,
+                                                          int B, int h, int w) {
+  const long long cell = (long long)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const long long ncell = (long long)B * h * w;
+  if (cell >= ncell) return;
+  const float* p = logits + cell * 65;
+  float a = p[lane], b = p[lane + 32];
+  float d = (lane == 0) ? p[64] : -CUDART_INF_F;
+  float m = warp_max(fmaxf(fmaxf(a, b), d));
+  float ea = expf(a - m), eb = expf(b - m);
+  float ed = (lane == 0) ? expf(d - m) : 0.f;
+  float s = warp_sum(ea + eb + ed);
+  const int bi = (int)(cell / ((long long)h * w));
+  const int rem = (int)(cell % ((long long)h * w));
+  const int cy = rem / w, cx = rem % w;
+  const int W = w * 8;
+  float* o = dense + ((long long)bi * h * 8 + cy * 8) * W + cx * 8;
+  // channel c -> pixel (8cy + c/8, 8cx + c%8)
+  o[(lane / 8) * W + (lane % 8)] = __fdiv_rn(ea, s);
+  o[(lane / 8 + 4) * W + (lane % 8)] = __fdiv_rn(eb, s);
+}
+
+// ---- simple_nms ---------------------------------------------------------------------------------
+// CTA = 32x32 output pixels + halo of 5r (three max-pools and two dilations of radius r chained).
+constexpr int NMS_T = 32;
+
+__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dense, float* __restrict__ out, int H, int W,
+                                                  int r) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  const int halo = 5 * r, R = NMS_T + 2 * halo, RR = R * R;
+  float* S = reinterpret_cast<float*>(nms_smem);  // scores (-inf outside the image)
+  float* A = S + RR;                              // row-pooled temp
+  float* SS = A + RR;                             // suppressed scores
+  unsigned char* mask = reinterpret_cast<unsigned char*>(SS + RR);
+  unsigned char* supp = mask + RR;
+  unsigned char* tmpb = supp + RR;
+
+  const int tiles_x = (W + NMS_T - 1) / NMS_T;
+  const int x0 = (blockIdx.x % tiles_x) * NMS_T - halo, y0 = (blockIdx.x / tiles_x) * NMS_T - halo;
+  const float* img = dense + (long long)blockIdx.z * H * W;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < RR; i += 256) {
+    int yy = i / R, xx = i % R, gy = y0 + yy, gx = x0 + xx;
+    S[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(long long)gy * W + gx] : -CUDART_INF_F;
+  }
+  __syncthreads();
+  // max_mask = scores == max_pool(scores)
+  for (int i = tid; i < RR; i += 256) {
+    int yy = i / R, xx = i % R;
+    float m = -CUDART_INF_F;
+    for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, S[yy * R + d]);
+    A[i] = m;
+  }
+  __syncthreads();
+  for (int i = tid; i < RR; i += 256) {
+    int yy = i / R, xx = i % R;
+    float m = -CUDART_INF_F;
+    for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
+    mask[i] = (S[i] == m) && (S[i] != -CUDART_INF_F);
+  }
+  __syncthreads();
+  for (int it = 0; it < 2; it++) {
+    // supp = max_pool(max_mask) > 0
+    for (int i = tid; i < RR; i += 256) {
+      int yy = i / R, xx = i % R;
+      unsigned char m = 0;
+      for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m |= mask[yy * R + d];
+      tmpb[i] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < RR; i += 256) {
+      int yy = i / R, xx = i % R;
+      unsigned char m = 0;
+      for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m |= tmpb[d * R + xx];
+      supp[i] = m;
+      // supp_scores = where(supp, 0, scores); stays -inf outside the image (max_pool2d padding)
+      SS[i] = (S[i] == -CUDART_INF_F) ? -CUDART_INF_F : (m ? 0.f : S[i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < RR; i += 256) {
+      int yy = i / R, xx = i % R;
+      float m = -CUDART_INF_F;
+      for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, SS[yy * R + d]);
+      A[i] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < RR; i += 256) {
+      int yy = i / R, xx = i % R;
+      float m = -CUDART_INF_F;
+      for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
+      bool new_max = (SS[i] == m) && (SS[i] != -CUDART_INF_F);
+      if (new_max && !supp[i]) mask[i] = 1;
+    }
+    __syncthreads();
+  }
+  float* o = out + (long long)blockIdx.z * H * W;
+  for (int i = tid; i < NMS_T * NMS_T; i += 256) {
+    int yy = i / NMS_T, xx = i % NMS_T;
+    int gy = y0 + halo + yy, gx = x0 + halo + xx;
+    if (gy < H && gx < W) {
+      int si = (yy + halo) * R + xx + halo;
+      o[(long long)gy * W + gx] = mask[si] ? S[si] : 0.f;
+    }
+  }
+}
+
+// ---- threshold / border / ordered compaction / top-k -------------------------------------------
+// key = score bits (positive float => order-preserving) << 32 | (~pixel index): sorting keys in
+// descending order yields descending score with ascending row-major index on ties.
+__device__ __forceinline__ unsigned long long make_key(float s, unsigned idx) {
+  return ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* a, int n_pad, int tid, int nthreads) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n_pad; i += nthreads) {
+        int l = i ^ j;
+        if (l > i) {
+          unsigned long long x = a[i], y = a[l];
+          bool desc = ((i & k) == 0);
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_SMEM_KEYS = 16384;  // 128 KB of shared memory for the in-CTA sort
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __restrict__ nms, unsigned long long* __restrict__ keys_all,
+                                                             int key_cap, float* __restrict__ kpts, float* __restrict__ scores,
+                                                             int* __restrict__ counts, int H, int W, float thr, int border,
+                                                             int max_kpts, int cap) {
+  extern __shared__ __align__(16) unsigned long long s_keys[];
+  __shared__ int s_scan[SEL_THREADS / 32];
+  __shared__ int s_total;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* img = nms + (long long)b * H * W;
+  unsigned long long* keys = keys_all + (long long)b * key_cap;
+  const int npix = H * W;
+  const int lane = tid % 32, wid = tid / 32;
+  // each warp scans a contiguous range of pixels 32 at a time (coalesced); row-major order is kept
+  // through ballot ranks inside a step and a running offset across steps.
+  const int per_warp = ((npix + (SEL_THREADS / 32) - 1) / (SEL_THREADS / 32) + 31) / 32 * 32;
+  const int p0 = wid * per_warp, p1 = min(p0 + per_warp, npix);
+
+  auto pass = [&](int p, float v) -> bool {
+    int y = p / W, x = p % W;
+    return (v > thr) && (y >= border) && (y < H - border) && (x >= border) && (x < W - border);
+  };
+  int cnt = 0;
+  for (int p = p0 + lane; p < p0 + per_warp; p += 32) {
+    bool ok = (p < p1) && pass(p, img[p]);
+    cnt += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  if (lane == 0) s_scan[wid] = cnt;
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_scan[lane];
+    int winc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_scan[lane] = winc - v;
+    if (lane == 31) s_total = winc;
+  }
+  __syncthreads();
+  int off = s_scan[wid];
+  const int n = s_total;
+  for (int p = p0 + lane; p < p0 + per_warp; p += 32) {
+    float v = (p < p1) ? img[p] : 0.f;
+    bool ok = (p < p1) && pass(p, v);
+    unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (ok) keys[off + __popc(bal & ((1u << lane) - 1u))] = make_key(v, (unsigned)p);
+    off += __popc(bal);
+  }
+  __syncthreads();  // global writes by this CTA are visible to this CTA after the barrier
+
+  int n_out;
+  unsigned long long* src = keys;
+  if (max_kpts >= 0 && n > max_kpts) {
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    if (n_pad <= SEL_SMEM_KEYS) {
+      for (int i = tid; i < n_pad; i += SEL_THREADS) s_keys[i] = (i < n) ? keys[i] : 0ull;
+      __syncthreads();
+      bitonic_sort_desc(s_keys, n_pad, tid, SEL_THREADS);
+      src = s_keys;
+    } else {
+      for (int i = n + tid; i < n_pad && i < key_cap; i += SEL_THREADS) keys[i] = 0ull;
+      __syncthreads();
+      // key_cap is sized to the next power of two of H*W, so n_pad <= key_cap always holds
+      bitonic_sort_desc(keys, n_pad, tid, SEL_THREADS);
+    }
+    n_out = max_kpts;
+  } else {
+    n_out = n;
+  }
+  if (tid == 0) {
+    counts[b] = min(n_out, cap);      // keypoints written
+    counts[gridDim.x + b] = n_out;    // keypoints the reference would return (overflow check)
+  }
+  n_out = min(n_out, cap);
+  for (int i = tid; i < n_out; i += SEL_THREADS) {
+    unsigned long long k = src[i];
+    unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    float s = __uint_as_float((unsigned)(k >> 32));
+    kpts[((long long)b * cap + i) * 2 + 0] = (float)(idx % W);
+    kpts[((long long)b * cap + i) * 2 + 1] = (float)(idx / W);
+    scores[(long long)b * cap + i] = s;
+  }
+}
+
+// ---- L2 normalisation of rows -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x, long long rows, int C) {
+  long long row = (long long)blockIdx.x * 8 + threadIdx.x / 32;
+  if (row >= rows) return;
+  int lane = threadIdx.x % 32;
+  float* p = x + row * C;
+  float ss = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(p + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  float d = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(p + c);
+    v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+    *reinterpret_cast<float4*>(p + c) = v;
+  }
+}
+
+// ---- descriptor sampling ---------------------------------------------------------------------------
+// warp per keypoint; C = 256 -> 8 channels per lane.
+__global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restrict__ dd, const float* __restrict__ kpts,
+                                                          const int* __restrict__ counts, float* __restrict__ desc, int h,
+                                                          int w, int cap, int C) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (i >= counts[b]) return;
+  const float kx = kpts[((long long)b * cap + i) * 2], ky = kpts[((long long)b * cap + i) * 2 + 1];
+  const float s = 8.f;
+  // superpoint.py:83-86: (k - s/2 + 0.5) / (w*s - s/2 - 0.5) * 2 - 1, then grid_sample unnormalise
+  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(kx, s / 2), 0.5f), (w * s - s / 2 - 0.5f)), 2.f), 1.f);
+  float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(ky, s / 2), 0.5f), (h * s - s / 2 - 0.5f)), 2.f), 1.f);
+  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1));
+  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
+  float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  float w_nw = wx0 * wy0, w_ne = wx1 * wy0, w_sw = wx0 * wy1, w_se = wx1 * wy1;
+  const float* base = dd + (long long)b * h * w * C;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.f;
+  auto add = [&](int yy, int xx, float wt) {
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const float* p = base + ((long long)yy * w + xx) * C + lane * 8;
+      float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+      acc[0] += a.x * wt; acc[1] += a.y * wt; acc[2] += a.z * wt; acc[3] += a.w * wt;
+      acc[4] += c.x * wt; acc[5] += c.y * wt; acc[6] += c.z * wt; acc[7] += c.w * wt;
+    }
+  };
+  add(y0, x0, w_nw); add(y0, x1, w_ne); add(y1, x0, w_sw); add(y1, x1, w_se);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) ss += acc[k] * acc[k];
+  ss = warp_sum(ss);
+  float d = fmaxf(sqrtf(ss), 1e-12f);
+  float* o = desc + ((long long)b * cap + i) * C + lane * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(__fdiv_rn(acc[0], d), __fdiv_rn(acc[1], d), __fdiv_rn(acc[2], d), __fdiv_rn(acc[3], d));
+  *reinterpret_cast<float4*>(o + 4) = make_float4(__fdiv_rn(acc[4], d), __fdiv_rn(acc[5], d), __fdiv_rn(acc[6], d), __fdiv_rn(acc[7], d));
+}
+
+}  // namespace
+
+int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st) {
+  long long ncell = (long long)B * h * w;
+  softmax_d2s_kernel<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(logits, dense, B, h, w);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cudaStream_t st) {
+  IMW_REQUIRE(radius >= 0 && radius <= 8, "sp_nms: nms_radius must be in [0,8] (got %d)", radius);
+  int R = NMS_T + 10 * radius;
+  size_t smem = (size_t)R * R * (3 * sizeof(float) + 3);
+  IMW_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(W, NMS_T) * ceil_div(H, NMS_T), 1, B);
+  nms_kernel<<<grid, 256, smem, st>>>(dense, nms, H, W, radius);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+size_t sp_select_key_cap(int H, int W) {
+  size_t n = 1;
+  while (n < (size_t)H * W) n <<= 1;
+  return n;
+}
+
+int sp_select(const float* nms, unsigned long long* keys, int key_cap, float* kpts, float* scores, int* counts, int B,
+              int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st) {
+  size_t smem = (size_t)SEL_SMEM_KEYS * sizeof(unsigned long long);
+  IMW_CHECK_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_kernel<<<B, SEL_THREADS, smem, st>>>(nms, keys, key_cap, kpts, scores, counts, H, W, threshold, border, max_kpts, cap);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st) {
+  IMW_REQUIRE(C % 4 == 0, "sp_l2norm_rows: C %% 4");
+  l2norm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, C);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts, float* desc, int B, int h, int w, int cap,
+                   int C, cudaStream_t st) {
+  IMW_REQUIRE(C == 256, "sp_sample_desc: descriptor_dim must be 256");
+  dim3 grid(ceil_div(cap, 8), B);
+  sample_desc_kernel<<<grid, 256, 0, st>>>(dense_desc, kpts, counts, desc, h, w, cap, C);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}

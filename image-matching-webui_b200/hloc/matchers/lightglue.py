@@ -1,0 +1,83 @@
+"""LightGlue matcher plugin -- drop-in for imcui/hloc/matchers/lightglue.py:14-75.
+Same default_conf / required_inputs / output dict; the forward pass runs in libimw_b200.so
+(imw_lightglue_forward) instead of third_party/LightGlue/lightglue/lightglue.py."""
+from pathlib import Path
+
+import torch
+
+from .. import MODEL_REPO_ID, logger
+from ..utils.base_model import BaseModel
+from ... import ops
+
+
+class LightGlue(BaseModel):
+    default_conf = {
+        "match_threshold": 0.2,
+        "filter_threshold": 0.2,
+        "width_confidence": 0.99,  # for point pruning
+        "depth_confidence": 0.95,  # for early stopping,
+        "features": "superpoint",
+        "model_name": "superpoint_lightglue.pth",
+        "flash": True,  # reference: selects the CUDA pruning threshold 1536 (flash) vs 1024
+        "mp": False,
+        "add_scale_ori": False,
+        "n_layers": 9,
+    }
+    required_inputs = ["image0", "keypoints0", "scores0", "descriptors0", "image1", "keypoints1", "scores1",
+                       "descriptors1"]
+
+    def _init(self, conf):
+        logger.info("Loading lightglue model, {}".format(conf["model_name"]))
+        if conf["features"] != "superpoint":
+            raise ValueError(f"Unsupported features: {conf['features']} (B200 engine build: superpoint)")
+        model_path = self._download_model(
+            repo_id=MODEL_REPO_ID, filename="{}/{}".format(Path(__file__).stem, self.conf["model_name"]))
+        sd = torch.load(str(model_path), map_location="cpu")
+        conf["filter_threshold"] = conf["match_threshold"]  # hloc/matchers/lightglue.py:50
+        self.conf["filter_threshold"] = conf["match_threshold"]
+        for k, v in ops.lg_pack_weights(sd, conf["n_layers"]).items():
+            self.register_buffer(k.replace(".", "__"), v, persistent=False)
+        logger.info("Load lightglue model done.")
+
+    def _bufs(self):
+        return {k.replace("__", "."): v for k, v in self.named_buffers()}
+
+    def _kernel_conf(self):
+        c = self.conf
+        pth = c.get("pruning_min_kpts")
+        if pth is None:  # lightglue.py:339-344,663-667 on a CUDA device
+            pth = 1536 if c["flash"] else 1024
+        return {"depth_confidence": c["depth_confidence"], "width_confidence": c["width_confidence"],
+                "filter_threshold": c["filter_threshold"], "pruning_min_kpts": pth}
+
+    def _forward(self, data):
+        k0, k1 = data["keypoints0"], data["keypoints1"]
+        d0, d1 = data["descriptors0"].permute(0, 2, 1), data["descriptors1"].permute(0, 2, 1)  # [1,N,D]
+        assert k0.shape[0] == 1 and k1.shape[0] == 1, "one pair per call (reference semantics are B=1)"
+        assert d0.shape[-1] == 256 and d1.shape[-1] == 256  # lightglue.py:510-511
+        m, n = k0.shape[1], k1.shape[1]
+        dev = k0.device
+        cap = max(4, (max(m, n) + 3) // 4 * 4)
+        kp = torch.zeros(2, cap, 2, device=dev)
+        ds = torch.zeros(2, cap, 256, device=dev)
+        kp[0, :m], kp[1, :n] = k0[0].float(), k1[0].float()
+        ds[0, :m], ds[1, :n] = d0[0].float(), d1[0].float()
+        counts = torch.tensor([m, n], dtype=torch.int32, device=dev)
+        out = ops.lightglue_forward(self._bufs(), self.conf["n_layers"], kp, ds, counts, self._kernel_conf())
+        m0, m1 = out["matches"][0, :m].long()[None], out["matches"][1, :n].long()[None]
+        ms0, ms1 = out["scores"][0, :m][None], out["scores"][1, :n][None]
+        valid = m0[0] > -1
+        mi0 = torch.where(valid)[0]
+        do_prune = self.conf["width_confidence"] > 0
+        prune0, prune1 = out["prune"][0, :m][None], out["prune"][1, :n][None]
+        if not do_prune:
+            prune0, prune1 = prune0.float(), prune1.float()  # reference: ones_like(mscores) * n_layers
+        else:
+            prune0, prune1 = prune0.long(), prune1.long()
+        return {
+            "matches0": m0, "matches1": m1, "matching_scores0": ms0, "matching_scores1": ms1,
+            "stop": int(out["stop"][0]),
+            "matches": [torch.stack([mi0, m0[0][valid]], -1)],
+            "scores": [ms0[0][valid]],
+            "prune0": prune0, "prune1": prune1,
+        }

@@ -1,0 +1,36 @@
+"""Mutual nearest-neighbour matcher -- drop-in for imcui/hloc/matchers/nearest_neighbor.py:27-66."""
+import torch
+
+from ..utils.base_model import BaseModel
+from ... import ops
+
+
+def _pack_pair(d0, d1):
+    """[1,D,N],[1,D,M] channel-first (reference layout) -> token-major slots [2,cap,D] + counts."""
+    n, m, dim = d0.shape[-1], d1.shape[-1], d0.shape[1]
+    cap = max(4, (max(n, m) + 3) // 4 * 4)
+    ds = torch.zeros(2, cap, dim, device=d0.device)
+    ds[0, :n], ds[1, :m] = d0[0].t().float(), d1[0].t().float()
+    return ds, torch.tensor([n, m], dtype=torch.int32, device=d0.device), n, m
+
+
+class NearestNeighbor(BaseModel):
+    default_conf = {
+        "ratio_threshold": None,
+        "distance_threshold": None,
+        "do_mutual_check": True,
+    }
+    required_inputs = ["descriptors0", "descriptors1"]
+
+    def _init(self, conf):
+        pass
+
+    def _forward(self, data):
+        d0, d1 = data["descriptors0"], data["descriptors1"]
+        if d0.size(-1) == 0 or d1.size(-1) == 0:  # nearest_neighbor.py:39-48
+            matches0 = torch.full(d0.shape[:2], -1, device=d0.device)
+            return {"matches0": matches0, "matching_scores0": torch.zeros_like(matches0)}
+        ds, counts, n, m = _pack_pair(d0, d1)
+        m0, s0 = ops.nearest_neighbor(ds, counts, self.conf["ratio_threshold"], self.conf["distance_threshold"],
+                                      self.conf["do_mutual_check"])
+        return {"matches0": m0[:, :n].long(), "matching_scores0": s0[:, :n]}

@@ -1,0 +1,177 @@
+"""Thin torch-tensor front-ends of the C ABI (include/imw_b200.h): allocate outputs + workspace with
+torch (plumbing), pass raw pointers and the current CUDA stream to the library."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+# ---------------------------------------------------------------------------------------------------
+# SuperPoint
+# ---------------------------------------------------------------------------------------------------
+SP_LAYERS = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
+             "convDa", "convDb"]
+
+
+def sp_pack_weights(state_dict):
+    """Re-lay the reference's Conv2d parameters ([Cout,Cin,kh,kw]) for the kernels:
+    3x3 -> [ky*3+kx][Cin][Cout]; 1x1 -> [Cout][Cin].  Returns {name: tensor} (CPU fp32)."""
+    out = {}
+    for name in SP_LAYERS:
+        w = state_dict[name + ".weight"].float()
+        if w.shape[-1] == 3:
+            w = w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0])
+        else:
+            w = w.reshape(w.shape[0], w.shape[1])
+        out[name + "_w"] = w.contiguous()
+        out[name + "_b"] = state_dict[name + ".bias"].float().contiguous()
+    return out
+
+
+def sp_weights_struct(bufs):
+    s = L.SPWeights()
+    for i, name in enumerate(SP_LAYERS):
+        s.w[i] = bufs[name + "_w"].data_ptr()
+        s.b[i] = bufs[name + "_b"].data_ptr()
+    return s
+
+
+def superpoint_forward(bufs, image, conf, cap, out=None, want_dense=False):
+    """image [B,1,H,W] fp32 CUDA.  Returns dict of batch buffers: keypoints [B,cap,2], scores [B,cap],
+    descriptors [B,cap,256], counts [2,B] int32 (written, total)."""
+    L.require_cuda(image, "superpoint_forward(image)")
+    assert image.dim() == 4 and image.shape[1] == 1 and image.dtype == torch.float32
+    image = image.contiguous()
+    B, _, H, W = image.shape
+    dev = image.device
+    if out is None:
+        out = {
+            "keypoints": torch.empty(B, cap, 2, device=dev),
+            "scores": torch.empty(B, cap, device=dev),
+            "descriptors": torch.empty(B, cap, 256, device=dev),
+            "counts": torch.empty(2, B, dtype=torch.int32, device=dev),
+        }
+    dense = torch.empty(B, H, W, device=dev) if want_dense else None
+    lib = L.lib()
+    nbytes = lib.imw_superpoint_workspace_bytes(B, H, W)
+    ws = L.workspaces.get(dev, nbytes, "sp")
+    c = L.SPConf(int(conf["nms_radius"]), float(conf["keypoint_threshold"]), int(conf["max_keypoints"]),
+                 int(conf["remove_borders"]))
+    wstruct = sp_weights_struct(bufs)
+    with torch.cuda.device(dev):
+        rc = lib.imw_superpoint_forward(C.byref(wstruct), C.byref(c), B, H, W, L.ptr(image), cap, L.ptr(out["keypoints"]),
+                                        L.ptr(out["scores"]), L.ptr(out["descriptors"]), L.ptr(out["counts"]), L.ptr(dense),
+                                        L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    if want_dense:
+        out["dense_scores"] = dense
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# LightGlue
+# ---------------------------------------------------------------------------------------------------
+def lg_pack_weights(sd, n_layers=9, heads=4):
+    """Flat reference state dict -> kernel layout (CPU fp32 tensors).
+    Wqkv rows are permuted from [head][dim][q,k,v] (lightglue.py:166) to [q|k|v][head][dim];
+    cross to_qk / to_v are stacked to one [512,256] projection."""
+    out = {"posenc_wr": sd["posenc.Wr.weight"].float().contiguous()}
+    d = sd["transformers.0.self_attn.out_proj.weight"].shape[0]
+    hd = d // heads
+    for i in range(n_layers):
+        p = f"transformers.{i}.self_attn."
+        w = sd[p + "Wqkv.weight"].float().view(heads, hd, 3, d).permute(2, 0, 1, 3).reshape(3 * d, d)
+        b = sd[p + "Wqkv.bias"].float().view(heads, hd, 3).permute(2, 0, 1).reshape(3 * d)
+        out[f"l{i}.self.qkv_w"], out[f"l{i}.self.qkv_b"] = w.contiguous(), b.contiguous()
+        out[f"l{i}.self.out_w"], out[f"l{i}.self.out_b"] = sd[p + "out_proj.weight"].float(), sd[p + "out_proj.bias"].float()
+        c = f"transformers.{i}.cross_attn."
+        out[f"l{i}.cross.qkv_w"] = torch.cat([sd[c + "to_qk.weight"], sd[c + "to_v.weight"]], 0).float().contiguous()
+        out[f"l{i}.cross.qkv_b"] = torch.cat([sd[c + "to_qk.bias"], sd[c + "to_v.bias"]], 0).float().contiguous()
+        out[f"l{i}.cross.out_w"], out[f"l{i}.cross.out_b"] = sd[c + "to_out.weight"].float(), sd[c + "to_out.bias"].float()
+        for blk, pre in (("self", p), ("cross", c)):
+            out[f"l{i}.{blk}.ffn0_w"], out[f"l{i}.{blk}.ffn0_b"] = sd[pre + "ffn.0.weight"].float(), sd[pre + "ffn.0.bias"].float()
+            out[f"l{i}.{blk}.ln_g"], out[f"l{i}.{blk}.ln_b"] = sd[pre + "ffn.1.weight"].float(), sd[pre + "ffn.1.bias"].float()
+            out[f"l{i}.{blk}.ffn3_w"], out[f"l{i}.{blk}.ffn3_b"] = sd[pre + "ffn.3.weight"].float(), sd[pre + "ffn.3.bias"].float()
+    out["token_w"] = torch.stack([sd[f"token_confidence.{i}.token.0.weight"].float().reshape(d) for i in range(n_layers - 1)])
+    out["token_b"] = torch.stack([sd[f"token_confidence.{i}.token.0.bias"].float().reshape(()) for i in range(n_layers - 1)])
+    out["final_w"] = torch.stack([sd[f"log_assignment.{i}.final_proj.weight"].float() for i in range(n_layers)])
+    out["final_b"] = torch.stack([sd[f"log_assignment.{i}.final_proj.bias"].float() for i in range(n_layers)])
+    out["match_w"] = torch.stack([sd[f"log_assignment.{i}.matchability.weight"].float().reshape(d) for i in range(n_layers)])
+    out["match_b"] = torch.stack([sd[f"log_assignment.{i}.matchability.bias"].float().reshape(()) for i in range(n_layers)])
+    return {k: v.contiguous() for k, v in out.items()}
+
+
+def lg_weights_struct(bufs, n_layers=9):
+    s = L.LGWeights()
+    s.n_layers, s.input_dim = n_layers, 256
+    s.posenc_wr = bufs["posenc_wr"].data_ptr()
+    for k in ("token_w", "token_b", "final_w", "final_b", "match_w", "match_b"):
+        setattr(s, k, bufs[k].data_ptr())
+    for i in range(n_layers):
+        for blk, dst in (("self", s.layers[i].self_blk), ("cross", s.layers[i].cross_blk)):
+            for f in ("qkv_w", "qkv_b", "out_w", "out_b", "ffn0_w", "ffn0_b", "ln_g", "ln_b", "ffn3_w", "ffn3_b"):
+                setattr(dst, f, bufs[f"l{i}.{blk}.{f}"].data_ptr())
+    return s
+
+
+def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=None):
+    """keypoints [2P,cap,2], descriptors [2P,cap,256], counts [2P] int32 (all CUDA, contiguous).
+    Returns dict: matches [2P,cap] int32, scores [2P,cap], stop [P] int32, prune [2P,cap] int32."""
+    L.require_cuda(keypoints, "lightglue_forward(keypoints)")
+    S, cap, _ = keypoints.shape
+    assert S % 2 == 0 and descriptors.shape == (S, cap, 256) and counts.numel() == S and counts.dtype == torch.int32
+    assert keypoints.is_contiguous() and descriptors.is_contiguous() and counts.is_contiguous()
+    P, dev = S // 2, keypoints.device
+    if out is None:
+        out = {
+            "matches": torch.empty(S, cap, dtype=torch.int32, device=dev),
+            "scores": torch.empty(S, cap, device=dev),
+            "stop": torch.empty(P, dtype=torch.int32, device=dev),
+            "prune": torch.empty(S, cap, dtype=torch.int32, device=dev),
+        }
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_lightglue_workspace_bytes(P, cap), "lg")
+    c = L.LGConf(float(conf["depth_confidence"]), float(conf["width_confidence"]), float(conf["filter_threshold"]),
+                 int(conf["pruning_min_kpts"]))
+    wstruct = lg_weights_struct(bufs, n_layers)
+    with torch.cuda.device(dev):
+        rc = lib.imw_lightglue_forward(C.byref(wstruct), C.byref(c), P, cap, L.ptr(keypoints), L.ptr(descriptors), L.ptr(counts),
+                                       L.ptr(out["matches"]), L.ptr(out["scores"]), L.ptr(out["stop"]), L.ptr(out["prune"]),
+                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# hloc first-party matchers
+# ---------------------------------------------------------------------------------------------------
+def _matcher_common(descriptors, counts):
+    L.require_cuda(descriptors, "matcher(descriptors)")
+    S, cap, dim = descriptors.shape
+    assert S % 2 == 0 and counts.numel() == S and counts.dtype == torch.int32 and descriptors.is_contiguous()
+    dev = descriptors.device
+    m0 = torch.empty(S // 2, cap, dtype=torch.int32, device=dev)
+    s0 = torch.empty(S // 2, cap, device=dev)
+    ws = L.workspaces.get(dev, L.lib().imw_matcher_workspace_bytes(S // 2, cap), "mt")
+    return S // 2, cap, dim, dev, m0, s0, ws
+
+
+def nearest_neighbor(descriptors, counts, ratio_threshold=None, distance_threshold=None, do_mutual_check=True):
+    """descriptors [2P,cap,dim] token-major, counts [2P].  -> matches0 [P,cap] int32, scores0 [P,cap]."""
+    P, cap, dim, dev, m0, s0, ws = _matcher_common(descriptors, counts)
+    with torch.cuda.device(dev):
+        rc = L.lib().imw_nearest_neighbor(P, cap, dim, L.ptr(descriptors), L.ptr(counts), float(ratio_threshold or 0.0),
+                                          float(distance_threshold or 0.0), int(bool(do_mutual_check)), L.ptr(m0), L.ptr(s0),
+                                          L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    return m0, s0
+
+
+def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0):
+    P, cap, dim, dev, m0, s0, ws = _matcher_common(descriptors, counts)
+    with torch.cuda.device(dev):
+        rc = L.lib().imw_dual_softmax(P, cap, dim, L.ptr(descriptors), L.ptr(counts), float(match_threshold),
+                                      float(inv_temperature), L.ptr(m0), L.ptr(s0), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    return m0, s0

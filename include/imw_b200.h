@@ -1,0 +1,127 @@
+/* imw_b200 -- C ABI of the B200-native image-pair matching hot path.
+ *
+ * Drop-in boundary for the reference's plugin layer (imcui/hloc/utils/base_model.py:9-55): every
+ * entry point below replaces the forward pass of one BaseModel plugin.  The reference is pure
+ * Python + PyTorch, so the reference-side binding is a ctypes stub inside the plugin's
+ * `_forward`; signatures carry only raw device pointers, sizes and a
+ * cudaStream_t -- no torch types.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated; fp32 / int32; no allocation, no host
+ *     synchronisation and no implicit stream inside any call (ui/api callers own memory + stream);
+ *   - `*_workspace_bytes` returns the scratch size the matching call needs;
+ *   - return value: 0 = ok, <0 = error (imw_last_error() holds the message); the Python shim turns
+ *     errors into the exceptions the reference raises (ValueError / AssertionError);
+ *   - empty inputs are not errors (counts may be 0), as in the reference.
+ */
+#ifndef IMW_B200_H
+#define IMW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* imw_stream_t; /* == cudaStream_t */
+
+const char* imw_last_error(void);
+int imw_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SuperPoint extractor.
+ * Replaces: hloc/extractors/superpoint.py:56-57 (SuperPoint._forward) ->
+ *           third_party/SuperGluePretrainedNetwork/models/superpoint.py:145-206.
+ * Weights: conv kernels re-laid out by the host to [ky*3+kx][Cin][Cout] (1x1: [Cout][Cin]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w[12]; /* conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db */
+  const float* b[12];
+} imw_sp_weights;
+
+typedef struct {
+  int nms_radius;           /* conf["nms_radius"]        (re-read every call, superpoint.py:145-150) */
+  float keypoint_threshold; /* conf["keypoint_threshold"] */
+  int max_keypoints;        /* conf["max_keypoints"]; -1 = no cap; 0 or < -1 -> error (superpoint.py:139-141) */
+  int remove_borders;       /* conf["remove_borders"] */
+} imw_sp_conf;
+
+size_t imw_superpoint_workspace_bytes(int batch, int height, int width);
+
+/* image [B][1][H][W] in [0,1] (H,W multiples of 8).
+ * keypoints [B][cap][2] (x,y) pixel coords, scores [B][cap], descriptors [B][cap][256] (token-major;
+ * the plugin exposes the [256,N] view the reference returns), counts [2][B] = {written[B], total[B]}:
+ * total > written means `cap` was too small for max_keypoints = -1 (call again with a larger cap).
+ * Optional debug outputs (may be NULL): dense_scores [B][H][W] (before NMS). */
+int imw_superpoint_forward(const imw_sp_weights* weights, const imw_sp_conf* conf, int batch, int height, int width,
+                           const float* image, int cap, float* keypoints, float* scores, float* descriptors,
+                           int* counts, float* dense_scores, void* workspace, size_t workspace_bytes,
+                           imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LightGlue matcher.
+ * Replaces: hloc/matchers/lightglue.py:54-75 (LightGlue._forward) ->
+ *           third_party/LightGlue/lightglue/lightglue.py:488-634, for a batch of independent pairs
+ *           (each pair keeps the reference's B=1 semantics: own early exit, own pruning).
+ * ---------------------------------------------------------------------------------------------- */
+#define IMW_LG_MAX_LAYERS 16
+
+typedef struct {
+  /* self block: qkv_w [768][256] rows permuted to [q|k|v][head][dim]; cross block: [to_qk; to_v] [512][256] */
+  const float *qkv_w, *qkv_b, *out_w, *out_b;
+  const float *ffn0_w, *ffn0_b, *ln_g, *ln_b, *ffn3_w, *ffn3_b;
+} imw_lg_block;
+
+typedef struct {
+  imw_lg_block self_blk, cross_blk;
+} imw_lg_layer;
+
+typedef struct {
+  int n_layers;
+  int input_dim;              /* 256 (Identity input_proj) */
+  const float* posenc_wr;     /* [32][2] */
+  const float *token_w, *token_b; /* [L-1][256], [L-1]   token_confidence */
+  const float *final_w, *final_b; /* [L][256][256], [L][256] log_assignment.final_proj */
+  const float *match_w, *match_b; /* [L][256], [L]       log_assignment.matchability */
+  imw_lg_layer layers[IMW_LG_MAX_LAYERS];
+} imw_lg_weights;
+
+typedef struct {
+  float depth_confidence; /* <= 0 disables early stopping (conf -1) */
+  float width_confidence; /* <= 0 disables point pruning */
+  float filter_threshold; /* hloc: = match_threshold (hloc/matchers/lightglue.py:50) */
+  int pruning_min_kpts;   /* lightglue.py:339-344: 1536 = CUDA+flash, 1024 = CUDA, -1 = CPU semantics */
+} imw_lg_conf;
+
+size_t imw_lightglue_workspace_bytes(int n_pairs, int cap);
+
+/* Slot s = 2*pair + side.  keypoints [2P][cap][2], descriptors [2P][cap][256], counts [2P].
+ * Outputs: matches [2P][cap] (matches0 in even slots, matches1 in odd; -1 = unmatched),
+ * matching_scores [2P][cap], stop [P], prune [2P][cap]. */
+int imw_lightglue_forward(const imw_lg_weights* weights, const imw_lg_conf* conf, int n_pairs, int cap,
+                          const float* keypoints, const float* descriptors, const int* counts, int* matches,
+                          float* matching_scores, int* stop, int* prune, void* workspace, size_t workspace_bytes,
+                          imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mutual nearest neighbour.   Replaces hloc/matchers/nearest_neighbor.py:38-66.
+ * Dual-softmax.               Replaces hloc/matchers/dual_softmax.py:50-71.
+ * descriptors [2P][cap][dim] token-major (dim % 4 == 0, dim <= 256), counts [2P].
+ * matches0 [P][cap] (int32, -1 = none), scores0 [P][cap].
+ * ---------------------------------------------------------------------------------------------- */
+size_t imw_matcher_workspace_bytes(int n_pairs, int cap);
+
+int imw_nearest_neighbor(int n_pairs, int cap, int dim, const float* descriptors, const int* counts,
+                         float ratio_threshold /* <=0: none */, float distance_threshold /* <=0: none */,
+                         int do_mutual_check, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
+                         imw_stream_t stream);
+
+int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, const int* counts, float match_threshold,
+                     float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
+                     imw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMW_B200_H */

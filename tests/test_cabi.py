@@ -1,0 +1,62 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/imw_b200.h
+declares; the plugin registry resolves like the reference's dynamic_load; host-side weight re-layout."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from imcui_b200 import _lib
+    header = (ROOT / "include" / "imw_b200.h").read_text()
+    names = set(re.findall(r"\b(imw_[a-z0-9_]+)\s*\(", header))
+    assert {"imw_superpoint_forward", "imw_lightglue_forward", "imw_nearest_neighbor", "imw_dual_softmax"} <= names
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in imw_b200.h but not exported"
+    assert _lib.lib().imw_version() >= 100
+
+
+def test_struct_sizes_match_header():
+    from imcui_b200 import _lib
+    assert ctypes.sizeof(_lib.SPWeights) == 24 * 8
+    assert ctypes.sizeof(_lib.LGBlock) == 10 * 8
+    assert ctypes.sizeof(_lib.LGWeights) == 8 + 7 * 8 + 16 * 20 * 8
+    assert ctypes.sizeof(_lib.LGConf) == 16 and ctypes.sizeof(_lib.SPConf) == 16
+
+
+def test_dynamic_load_registry():
+    from imcui_b200.hloc import extractors, matchers
+    from imcui_b200.hloc.utils.base_model import BaseModel, dynamic_load
+    for root, name in ((extractors, "superpoint"), (matchers, "lightglue"), (matchers, "nearest_neighbor"), (matchers, "dual_softmax")):
+        cls = dynamic_load(root, name)
+        assert issubclass(cls, BaseModel) and isinstance(cls.default_conf, dict)
+    m = dynamic_load(matchers, "nearest_neighbor")({})
+    with pytest.raises(AssertionError):
+        m({"descriptors0": torch.zeros(1, 4, 0)})
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing elsewhere."""
+    from imcui_b200.hloc import matchers
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    m = dynamic_load(matchers, "nearest_neighbor")({})
+    with pytest.raises(RuntimeError):
+        m({"descriptors0": torch.randn(1, 8, 3), "descriptors1": torch.randn(1, 8, 4)})
+
+
+def test_qkv_permutation_is_a_relabelling():
+    from imcui_b200 import ops
+    import oracle
+    sd = oracle.load_weights("superpoint_lightglue.pt")
+    packed = ops.lg_pack_weights(sd)
+    w = sd["transformers.0.self_attn.Wqkv.weight"]
+    x = torch.randn(5, 256)
+    ref = (x @ w.t()).unflatten(-1, (4, 64, 3))          # lightglue.py:166
+    mine = (x @ packed["l0.self.qkv_w"].t()).view(5, 3, 4, 64)
+    for which in range(3):
+        assert torch.allclose(ref[..., which], mine[:, which], atol=1e-5)

@@ -1,0 +1,225 @@
+"""GPU parity: the CUDA path, called through the plugin classes -> ctypes -> C ABI, against the golden
+vectors minted from the reference and against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import lg_pair_from_source, match_f1
+
+pytestmark = pytest.mark.gpu
+
+SP_CONFS = {
+    "api": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4},
+    "max1024": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.005, "remove_borders": 4},
+    "nocap": {"nms_radius": 4, "max_keypoints": -1, "keypoint_threshold": 0.005, "remove_borders": 4},
+    "max2048": {"nms_radius": 3, "max_keypoints": 2048, "keypoint_threshold": 0.005, "remove_borders": 4},
+}
+DESC_TOL = 1e-3   # north_star: descriptor/score tensors within 1e-3 fp32
+SCORE_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _load(root, name, conf, dev):
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    return dynamic_load(root, name)(conf).eval().to(dev)
+
+
+@pytest.mark.parametrize("case,confs", [("sp_real", ["api", "max1024", "nocap"]), ("sp_synth", ["max1024", "max2048"])])
+def test_superpoint_matches_reference(golden, dev, case, confs):
+    from imcui_b200.hloc import extractors
+    g = golden(case)
+    images = torch.from_numpy(g["images"]).to(dev)
+    model = _load(extractors, "superpoint", {}, dev)
+    for c in confs:
+        model.conf.update(SP_CONFS[c])  # mutable conf, as the UI/API do
+        for b in range(images.shape[0]):
+            out = model({"image": images[b:b + 1]})
+            k = out["keypoints"][0].cpu().numpy().astype(np.int16)
+            gk = g[f"{c}/{b}/keypoints"]
+            same = k.shape == gk.shape and np.array_equal(k, gk)
+            if not same:
+                a, bb = {tuple(x) for x in k.tolist()}, {tuple(x) for x in gk.tolist()}
+                raise AssertionError(f"{case}/{c}/{b}: keypoints differ: lost {len(bb - a)} gained {len(a - bb)} of {len(bb)}; "
+                                     f"same set, different order: {a == bb}")
+            np.testing.assert_allclose(out["scores"][0].cpu().numpy(), g[f"{c}/{b}/scores"], atol=SCORE_TOL)
+            d = out["descriptors"][0].cpu().numpy()
+            assert d.shape == g[f"{c}/{b}/descriptors"].shape
+            np.testing.assert_allclose(d, g[f"{c}/{b}/descriptors"], atol=DESC_TOL)
+
+
+def test_superpoint_dense_scores(golden, dev):
+    from imcui_b200 import ops
+    from imcui_b200.hloc import extractors
+    g = golden("sp_real")
+    model = _load(extractors, "superpoint", SP_CONFS["api"], dev)
+    out = ops.superpoint_forward(model._bufs(), torch.from_numpy(g["images"]).to(dev), model.conf, 1024, want_dense=True)
+    for b in range(2):
+        np.testing.assert_allclose(out["dense_scores"][b].cpu().numpy(), g[f"dense/{b}/scores"], atol=1e-5)
+
+
+def test_superpoint_batch_equals_single(golden, dev):
+    """Batched call == per-image calls (the reference loops over the batch in Python)."""
+    from imcui_b200.hloc import extractors
+    g = golden("sp_synth")
+    images = torch.from_numpy(g["images"]).to(dev)
+    model = _load(extractors, "superpoint", SP_CONFS["max1024"], dev)
+    outb = model({"image": images})
+    for b in range(images.shape[0]):
+        o = model({"image": images[b:b + 1]})
+        assert torch.equal(o["keypoints"][0], outb["keypoints"][b])
+        assert torch.equal(o["descriptors"][0], outb["descriptors"][b])
+
+
+def test_superpoint_bad_conf(dev):
+    from imcui_b200.hloc import extractors
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    with pytest.raises(ValueError):
+        dynamic_load(extractors, "superpoint")({"max_keypoints": 0})
+    model = _load(extractors, "superpoint", {}, dev)
+    with pytest.raises(AssertionError):
+        model({})
+    model.conf["max_keypoints"] = -5
+    with pytest.raises(ValueError):
+        model({"image": torch.zeros(1, 1, 64, 64, device=dev)})
+
+
+def test_superpoint_blank_image(dev):
+    """No keypoints is not an error."""
+    from imcui_b200.hloc import extractors
+    model = _load(extractors, "superpoint", {"max_keypoints": 128, "keypoint_threshold": 0.9}, dev)
+    out = model({"image": torch.zeros(1, 1, 64, 96, device=dev)})
+    assert out["keypoints"][0].shape == (0, 2) and out["descriptors"][0].shape == (256, 0)
+
+
+LG_MODES = {
+    "full": dict(depth_confidence=-1, width_confidence=-1, pruning_min_kpts=-1),
+    "cuda": dict(depth_confidence=0.95, width_confidence=0.99, pruning_min_kpts=1536),
+    "cpu": dict(depth_confidence=0.95, width_confidence=0.99, pruning_min_kpts=-1),
+}
+
+
+def _lg_inputs(k0, d0, k1, d1, dev):
+    t = lambda a: torch.from_numpy(a).to(dev)
+    return {"image0": torch.empty(1, 1, 480, 640, device=dev), "image1": torch.empty(1, 1, 480, 640, device=dev),
+            "keypoints0": t(k0)[None], "keypoints1": t(k1)[None],
+            "scores0": torch.ones(1, len(k0), device=dev), "scores1": torch.ones(1, len(k1), device=dev),
+            "descriptors0": t(d0)[None], "descriptors1": t(d1)[None]}
+
+
+@pytest.mark.parametrize("case", ["lg_real", "lg_synth"])
+@pytest.mark.parametrize("mode", ["full", "cuda", "cpu"])
+def test_lightglue_matches_reference(golden, dev, case, mode):
+    from imcui_b200.hloc import matchers
+    g = golden(case)
+    model = _load(matchers, "lightglue", {"match_threshold": 0.2, **LG_MODES[mode]}, dev)
+    for p, src in enumerate(g["sources"]):
+        k0, d0, k1, d1 = lg_pair_from_source(golden, src)
+        out = model(_lg_inputs(k0, d0, k1, d1, dev))
+        pre = f"{mode}/{p}/"
+        m0 = out["matches0"][0].cpu().numpy()
+        f1 = match_f1(m0, g[pre + "matches0"])
+        assert out["stop"] == int(g[pre + "stop"]), (case, mode, p, out["stop"], int(g[pre + "stop"]), f1)
+        assert np.array_equal(m0, g[pre + "matches0"]), (case, mode, p, "F1", f1)
+        assert np.array_equal(out["matches1"][0].cpu().numpy(), g[pre + "matches1"])
+        np.testing.assert_allclose(out["matching_scores0"][0].cpu().numpy(), g[pre + "matching_scores0"], atol=SCORE_TOL)
+        np.testing.assert_allclose(out["matching_scores1"][0].cpu().numpy(), g[pre + "matching_scores1"], atol=SCORE_TOL)
+        assert np.array_equal(out["prune0"][0].cpu().numpy().astype(np.int32), g[pre + "prune0"])
+        assert np.array_equal(out["prune1"][0].cpu().numpy().astype(np.int32), g[pre + "prune1"])
+        assert out["matches0"].dtype == torch.int64 and out["matches"][0].shape[1] == 2
+
+
+def test_lightglue_empty_and_tiny(dev):
+    from imcui_b200.hloc import matchers
+    model = _load(matchers, "lightglue", {}, dev)
+    k = np.zeros((0, 2), np.float32); d = np.zeros((256, 0), np.float32)
+    k1 = np.random.RandomState(0).rand(7, 2).astype(np.float32) * 100
+    d1 = np.random.RandomState(1).randn(256, 7).astype(np.float32)
+    out = model(_lg_inputs(k, d, k1, d1, dev))
+    assert out["matches0"].shape == (1, 0) and (out["matches1"] == -1).all() and out["stop"] == 1
+
+
+def test_lightglue_batched_pairs_independent(golden, dev):
+    """A batch of pairs == the same pairs run one by one (per-pair early exit, ragged counts)."""
+    from imcui_b200 import ops
+    from imcui_b200.hloc import matchers
+    g = golden("lg_synth")
+    model = _load(matchers, "lightglue", {"match_threshold": 0.2, **LG_MODES["cuda"]}, dev)
+    pairs = [lg_pair_from_source(golden, s) for s in g["sources"][:2]] + [lg_pair_from_source(golden, golden("lg_real")["sources"][0])]
+    cap = 1024
+    kp = torch.zeros(6, cap, 2, device=dev); ds = torch.zeros(6, cap, 256, device=dev)
+    counts = torch.zeros(6, dtype=torch.int32, device=dev)
+    for p, (k0, d0, k1, d1) in enumerate(pairs):
+        for s, (k, d) in enumerate(((k0, d0), (k1, d1))):
+            kp[2 * p + s, :len(k)] = torch.from_numpy(k).to(dev)
+            ds[2 * p + s, :len(k)] = torch.from_numpy(d).t().to(dev)
+            counts[2 * p + s] = len(k)
+    out = ops.lightglue_forward(model._bufs(), 9, kp, ds, counts, model._kernel_conf())
+    golds = [("lg_synth", 0), ("lg_synth", 1), ("lg_real", 0)]
+    for p, (case, q) in enumerate(golds):
+        gg = golden(case)
+        n0 = len(pairs[p][0])
+        assert int(out["stop"][p]) == int(gg[f"cuda/{q}/stop"])
+        assert np.array_equal(out["matches"][2 * p, :n0].cpu().numpy(), gg[f"cuda/{q}/matches0"])
+
+
+def _matcher_inputs(golden, p):
+    g = golden("matchers")
+    if p == 0:
+        s = golden("sp_real")
+        return s["api/0/descriptors"], s["api/1/descriptors"]
+    return g[f"in/{p}/descriptors0"], g[f"in/{p}/descriptors1"]
+
+
+@pytest.mark.parametrize("p", [0, 1])
+def test_matchers_match_reference(golden, dev, p):
+    from imcui_b200.hloc import matchers
+    g = golden("matchers")
+    d0, d1 = (torch.from_numpy(x).to(dev)[None] for x in _matcher_inputs(golden, p))
+    data = {"descriptors0": d0, "descriptors1": d1}
+    cases = {
+        "nn": _load(matchers, "nearest_neighbor", {"do_mutual_check": True}, dev),
+        "nn_ratio": _load(matchers, "nearest_neighbor", {"do_mutual_check": True, "ratio_threshold": 0.9, "distance_threshold": 0.9}, dev),
+        "nn_nomutual": _load(matchers, "nearest_neighbor", {"do_mutual_check": False}, dev),
+        "dsm": _load(matchers, "dual_softmax", {"match_threshold": 0.01, "inv_temperature": 20}, dev),
+    }
+    for tag, model in cases.items():
+        out = model(data)
+        m = out["matches0"][0].cpu().numpy()
+        assert np.array_equal(m, g[f"{tag}/{p}/matches0"]), (tag, match_f1(m, g[f"{tag}/{p}/matches0"]))
+        np.testing.assert_allclose(out["matching_scores0"][0].cpu().numpy(), g[f"{tag}/{p}/matching_scores0"], atol=1e-4)
+    assert cases["dsm"](data)["matching_scores0"].dtype == torch.float64
+
+
+def test_matchers_empty(dev):
+    from imcui_b200.hloc import matchers
+    for name in ("nearest_neighbor", "dual_softmax"):
+        model = _load(matchers, name, {}, dev)
+        out = model({"descriptors0": torch.zeros(1, 128, 0, device=dev), "descriptors1": torch.randn(1, 128, 5, device=dev)})
+        assert (out["matches0"] == -1).all()
+
+
+def test_dual_softmax_large_property(dev):
+    """BASELINE config 5 size (4096 x 4096 x 128): planted permutation is recovered and the result equals
+    the oracle formula evaluated with torch on the GPU for a random subset of rows."""
+    import importlib.util
+    from pathlib import Path
+    from imcui_b200 import ops
+    spec = importlib.util.spec_from_file_location("synth", Path(__file__).parent.parent / "image-matching-webui_b200/utils/synth.py")
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    d0, d1 = synth.make_descriptor_pair(7, n=4096, dim=128)
+    ds = torch.stack([torch.from_numpy(d0).t(), torch.from_numpy(d1).t()]).contiguous().to(dev)
+    counts = torch.tensor([4096, 4096], dtype=torch.int32, device=dev)
+    m0, s0 = ops.dual_softmax(ds, counts, 0.01, 20.0)
+    a, b = ds[0], ds[1]
+    sim = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t() * 20
+    P = sim.softmax(0) * sim.softmax(1)
+    mask = (P == P.max(1, keepdim=True).values) & (P == P.max(0, keepdim=True).values) & (P > 0.01)
+    ref = torch.where(mask.any(1), mask.float().argmax(1), torch.full((4096,), -1, device=dev))
+    agree = (ref == m0[0].long()).float().mean().item()
+    assert agree > 0.999, agree
+    assert (m0[0] > -1).sum() > 1500

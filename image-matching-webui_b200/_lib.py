@@ -37,7 +37,7 @@ class LGWeights(C.Structure):
 
 class LGConf(C.Structure):
     _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
-                ("pruning_min_kpts", C.c_int)]
+                ("pruning_min_kpts", C.c_int), ("use_tensor_cores", C.c_int)]
 
 
 _lib = None
@@ -53,6 +53,7 @@ def lib():
         L = C.CDLL(str(LIB_PATH))
         L.imw_last_error.restype = C.c_char_p
         L.imw_version.restype = C.c_int
+        L.imw_launch_count.restype = C.c_ulonglong
         for name in ("imw_superpoint_workspace_bytes", "imw_lightglue_workspace_bytes", "imw_matcher_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         L.imw_superpoint_workspace_bytes.argtypes = [C.c_int] * 3
@@ -71,6 +72,9 @@ def lib():
         L.imw_dual_softmax.restype = C.c_int
         L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, vp, vp, vp,
                                        C.c_size_t, vp]
+        for name in ("imw_debug_gemm_tf32", "imw_debug_gemm_fp32"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 

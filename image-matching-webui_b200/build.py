@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcuda"])
+    subprocess.check_call([NVCC, "-arch=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)])
     return LIB
 
 

@@ -16,6 +16,8 @@ void imw_set_error(const char* fmt, ...) {
 }
 extern "C" const char* imw_last_error(void) { return g_err; }
 extern "C" int imw_version(void) { return 100; }
+unsigned long long g_imw_launches = 0;
+extern "C" unsigned long long imw_launch_count(void) { return g_imw_launches; }
 
 // =====================================================================================================
 // SuperPoint
@@ -110,6 +112,12 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
   RUN(sp_sample_desc(b.dd, keypoints, counts, descriptors, B, h, w, cap, 256, st));
 #undef RUN
   return IMW_OK;
+}
+
+// single 3x3 conv layer (NHWC fp32, weights [9][Cin][Cout]); used by bench.py to time the dominant kernel alone
+extern "C" int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
+                                 int Cout, int relu, int pool, cudaStream_t st) {
+  return sp_conv3x3(in, w, bias, out, B, H, W, Cin, Cout, relu, pool, st);
 }
 
 // =====================================================================================================

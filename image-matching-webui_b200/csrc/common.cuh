@@ -22,7 +22,13 @@ void imw_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define IMW_CHECK_LAUNCH() IMW_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+extern unsigned long long g_imw_launches;
+#define IMW_CHECK_LAUNCH()               \
+  do {                                   \
+    ++g_imw_launches;                    \
+    IMW_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
 
 #define IMW_REQUIRE(cond, ...)                                                            \
   do {                                                                                    \

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "simreduce.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
@@ -507,6 +508,23 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   const long long sXM = (long long)cap * 512, sD = (long long)cap * D;
   const dim3 rows8(ceil_div(cap, 8), S);
 
+  const bool use_tc = conf->use_tensor_cores != 0;
+  IMW_REQUIRE(!use_tc || cap % 128 == 0, "imw_lightglue_forward: use_tensor_cores needs cap %% 128 == 0 (got %d)", cap);
+  // Y = X W^T (+ functor epilogue) over all slots: tcgen05 TF32 tiles or the exact-fp32 CUDA-core kernel
+  auto linear = [&](const float* A, int lda, const float* Wt, long long w_rows, int N, int K, auto epi, const int* skip,
+                    const int* wsel) -> int {
+    if (use_tc) {
+      TcGemmArgs t{};
+      t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.counts; t.skip = skip; t.skip_shift = 1;
+      t.wsel_minus1 = wsel; t.wsel_shift = 1; t.wsel_rows = N;
+      return launch_tc_gemm<128>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
+    }
+    GemmArgs g{};
+    g.A = A; g.strideA = (long long)cap * lda; g.lda = lda; g.W = Wt; g.strideW = 0; g.ldw = K; g.M = cap; g.N = N; g.K = K;
+    g.Mdyn = b.counts; g.skip = skip; g.skip_shift = 1; g.wsel_minus1 = wsel; g.wsel_shift = 1; g.strideWsel = (long long)N * K;
+    IMW_CHECK_CUDA(launch_gemm(g, S, epi, st));
+    return IMW_OK;
+  };
   auto gemm = [&](const float* A, long long sA, int lda, const float* Wt, int N, int K) {
     GemmArgs g{};
     g.A = A; g.strideA = sA; g.lda = lda; g.W = Wt; g.strideW = 0; g.ldw = K; g.M = cap; g.N = N; g.K = K;
@@ -515,10 +533,10 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   };
   auto ffn = [&](const imw_lg_block& blk) -> int {
     float* xm = b.xm[cur];
-    IMW_CHECK_CUDA(launch_gemm(gemm(xm, sXM, 512, blk.ffn0_w, 512, 512), S, EpiStore{b.h, 512, sXM, blk.ffn0_b, 0}, st));
+    if (int e = linear(xm, 512, blk.ffn0_w, 512, 512, 512, EpiStore{b.h, 512, sXM, blk.ffn0_b, 0}, b.done, nullptr)) return e;
     ln_gelu_kernel<<<rows8, 256, 0, st>>>(b.h, b.counts, b.done, blk.ln_g, blk.ln_b, cap);
     IMW_CHECK_LAUNCH();
-    IMW_CHECK_CUDA(launch_gemm(gemm(b.h, sXM, 512, blk.ffn3_w, D, 512), S, EpiStore{xm, 512, sXM, blk.ffn3_b, 1}, st));
+    if (int e = linear(b.h, 512, blk.ffn3_w, D, D, 512, EpiStore{xm, 512, sXM, blk.ffn3_b, 1}, b.done, nullptr)) return e;
     return IMW_OK;
   };
 
@@ -527,18 +545,16 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     float* xm = b.xm[cur];
     float* enc = b.enc[cur];
     // ---- self attention (lightglue.py:159-172)
-    IMW_CHECK_CUDA(launch_gemm(gemm(xm, sXM, 512, ly.self_blk.qkv_w, 3 * D, D), S,
-                               EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap}, st));
+    if (int e = linear(xm, 512, ly.self_blk.qkv_w, 3 * D, 3 * D, D, EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap}, b.done, nullptr)) return e;
     attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(b.q, b.k, b.v, b.ctx, b.counts, b.done, cap, 0.125f, 0);
     IMW_CHECK_LAUNCH();
-    IMW_CHECK_CUDA(launch_gemm(gemm(b.ctx, sD, D, ly.self_blk.out_w, D, D), S, EpiStore{xm + D, 512, sXM, ly.self_blk.out_b, 0}, st));
+    if (int e = linear(b.ctx, D, ly.self_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.self_blk.out_b, 0}, b.done, nullptr)) return e;
     if (int e = ffn(ly.self_blk)) return e;
     // ---- cross attention (lightglue.py:199-230)
-    IMW_CHECK_CUDA(launch_gemm(gemm(xm, sXM, 512, ly.cross_blk.qkv_w, 2 * D, D), S,
-                               EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f}, st));
+    if (int e = linear(xm, 512, ly.cross_blk.qkv_w, 2 * D, 2 * D, D, EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f}, b.done, nullptr)) return e;
     attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(b.q, b.q, b.v, b.ctx, b.counts, b.done, cap, 1.0f, 1);
     IMW_CHECK_LAUNCH();
-    IMW_CHECK_CUDA(launch_gemm(gemm(b.ctx, sD, D, ly.cross_blk.out_w, D, D), S, EpiStore{xm + D, 512, sXM, ly.cross_blk.out_b, 0}, st));
+    if (int e = linear(b.ctx, D, ly.cross_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.cross_blk.out_b, 0}, b.done, nullptr)) return e;
     if (int e = ffn(ly.cross_blk)) return e;
     if (i == L - 1) break;
     // ---- early stop / pruning (lightglue.py:549-571)
@@ -562,6 +578,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   // ---- assignment with the weights of the layer each pair stopped at (lightglue.py:595-597)
   {
     float* xm = b.xm[cur];
+    // the assignment (mutual arg-max on near-equal scores) stays on the exact-fp32 path
     GemmArgs g = gemm(xm, sXM, 512, W->final_w, D, D);
     g.skip = b.empty; g.wsel_minus1 = stop; g.wsel_shift = 1; g.strideWsel = (long long)D * D;
     IMW_CHECK_CUDA(launch_gemm(g, S, EpiFinalProj{b.md, cap, W->final_b, stop}, st));

@@ -1,0 +1,135 @@
+// tcgen05 TF32 GEMM   C[M,N] = A[M,K] * W[N,K]^T   (fp32 operands read as TF32, fp32 accumulate in TMEM).
+//
+//   warp 0      TMA producer: A tile [128 x 32 f32] and W tile [BN x 32 f32] per k-block, SWIZZLE_128B,
+//               through a STAGES-deep full/empty mbarrier ring
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=8 per instruction)
+//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one TMEM lane = one output row per
+//               thread), apply the same functor epilogues as the CUDA-core GEMM, store
+//
+// One output tile per CTA; two CTAs are co-resident per SM (smem <= 100 KB, <= 256 TMEM columns each)
+// so one CTA's epilogue overlaps the other's main loop.  Rows are [slots][cap] with cap % 128 == 0:
+// a tile never straddles two slots, finished pairs / rows beyond the slot's count are skipped on the
+// device.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+struct TcGemmArgs {
+  int K;                 // % 32 == 0
+  int N;                 // % BN == 0
+  int tiles_per_slot;    // cap / 128
+  const int* counts;     // [slots] valid rows (nullable: all rows valid)
+  const int* skip;       // optional skip[z >> skip_shift]
+  int skip_shift;
+  const int* wsel_minus1;  // optional per-pair weight slab selection: W rows offset (wsel-1) * wsel_rows
+  int wsel_shift;
+  int wsel_rows;
+};
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+
+template <int BN>
+constexpr size_t tc_gemm_smem_bytes() {
+  return (size_t)TC_STAGES * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi) {
+  const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
+  const int z = m_tile / g.tiles_per_slot;
+  const int row_in_slot0 = (m_tile % g.tiles_per_slot) * TC_BM;
+  if (g.skip && g.skip[z >> g.skip_shift]) return;
+  const int nrows = g.counts ? g.counts[z] : (g.tiles_per_slot * TC_BM);
+  if (row_in_slot0 >= nrows) return;
+
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tmem_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+    for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int KB = g.K / TC_BK;
+  const int w_row0 = n0 + (g.wsel_minus1 ? (g.wsel_minus1[z >> g.wsel_shift] - 1) * g.wsel_rows : 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        tc::mbar_wait(empty + s, ph ^ 1);
+        tc::mbar_expect_tx(full + s, STAGE);
+        tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
+        tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmW, full + s, kb * TC_BK, w_row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        tc::mbar_wait(full + s, ph);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; k++) {
+          // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
+          uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
+          tc::mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+        }
+        tc::mma_commit(empty + s);  // smem stage free once these MMAs have read it
+      }
+      tc::mma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    const int q = warp % 4;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+    const int row = row_in_slot0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      if (row < nrows) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) epi(z, row, n0 + c0 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), 4);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32.
+template <int BN, class Epi>
+static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, const float* W, long long w_rows, TcGemmArgs g,
+                                 Epi epi, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, TC_BK, TC_BM)) return e;
+  if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)w_rows, (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
+  constexpr size_t smem = tc_gemm_smem_bytes<BN>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_tf32_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(g.N / BN, (unsigned)(rows_total / TC_BM));
+  tc_gemm_tf32_kernel<BN, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}

@@ -22,6 +22,9 @@ class LightGlue(BaseModel):
         "mp": False,
         "add_scale_ori": False,
         "n_layers": 9,
+        # B200 engine switch (not in the reference): linear layers on tcgen05 with TF32 operands
+        # (TF32 linears keep the match set identical); False = exact-fp32 CUDA cores
+        "tensor_cores": True,
     }
     required_inputs = ["image0", "keypoints0", "scores0", "descriptors0", "image1", "keypoints1", "scores1",
                        "descriptors1"]
@@ -48,7 +51,8 @@ class LightGlue(BaseModel):
         if pth is None:  # lightglue.py:339-344,663-667 on a CUDA device
             pth = 1536 if c["flash"] else 1024
         return {"depth_confidence": c["depth_confidence"], "width_confidence": c["width_confidence"],
-                "filter_threshold": c["filter_threshold"], "pruning_min_kpts": pth}
+                "filter_threshold": c["filter_threshold"], "pruning_min_kpts": pth,
+                "use_tensor_cores": c["tensor_cores"]}
 
     def _forward(self, data):
         k0, k1 = data["keypoints0"], data["keypoints1"]
@@ -57,7 +61,7 @@ class LightGlue(BaseModel):
         assert d0.shape[-1] == 256 and d1.shape[-1] == 256  # lightglue.py:510-511
         m, n = k0.shape[1], k1.shape[1]
         dev = k0.device
-        cap = max(4, (max(m, n) + 3) // 4 * 4)
+        cap = max(128, (max(m, n) + 127) // 128 * 128)  # 128-row tiles of the tcgen05 path
         kp = torch.zeros(2, cap, 2, device=dev)
         ds = torch.zeros(2, cap, 256, device=dev)
         kp[0, :m], kp[1, :n] = k0[0].float(), k1[0].float()

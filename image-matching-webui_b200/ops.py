@@ -133,7 +133,7 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
     lib = L.lib()
     ws = L.workspaces.get(dev, lib.imw_lightglue_workspace_bytes(P, cap), "lg")
     c = L.LGConf(float(conf["depth_confidence"]), float(conf["width_confidence"]), float(conf["filter_threshold"]),
-                 int(conf["pruning_min_kpts"]))
+                 int(conf["pruning_min_kpts"]), int(bool(conf.get("use_tensor_cores", True)) and cap % 128 == 0))
     wstruct = lg_weights_struct(bufs, n_layers)
     with torch.cuda.device(dev):
         rc = lib.imw_lightglue_forward(C.byref(wstruct), C.byref(c), P, cap, L.ptr(keypoints), L.ptr(descriptors), L.ptr(counts),
@@ -175,3 +175,15 @@ def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0)
                                       float(inv_temperature), L.ptr(m0), L.ptr(s0), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc)
     return m0, s0
+
+
+def debug_gemm(A, W, bias, tensor_cores=True):
+    """out = A @ W.T + bias through the tcgen05 (TF32) or CUDA-core (fp32) GEMM (unit-test hook)."""
+    L.require_cuda(A, "debug_gemm(A)")
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device=A.device)
+    fn = L.lib().imw_debug_gemm_tf32 if tensor_cores else L.lib().imw_debug_gemm_fp32
+    with torch.cuda.device(A.device):
+        L.check(fn(L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K, L.stream_ptr(A.device)))
+    return out

@@ -28,6 +28,8 @@ typedef struct CUstream_st* imw_stream_t; /* == cudaStream_t */
 
 const char* imw_last_error(void);
 int imw_version(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+unsigned long long imw_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * SuperPoint extractor.
@@ -92,6 +94,8 @@ typedef struct {
   float width_confidence; /* <= 0 disables point pruning */
   float filter_threshold; /* hloc: = match_threshold (hloc/matchers/lightglue.py:50) */
   int pruning_min_kpts;   /* lightglue.py:339-344: 1536 = CUDA+flash, 1024 = CUDA, -1 = CPU semantics */
+  int use_tensor_cores;   /* 1: linear layers on tcgen05 (TF32 operands, fp32 accumulate; needs cap % 128 == 0),
+                             0: exact-fp32 CUDA-core path */
 } imw_lg_conf;
 
 size_t imw_lightglue_workspace_bytes(int n_pairs, int cap);
@@ -120,6 +124,17 @@ int imw_nearest_neighbor(int n_pairs, int cap, int dim, const float* descriptors
 int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, const int* counts, float match_threshold,
                      float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
                      imw_stream_t stream);
+
+/* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 (TF32) and CUDA-core (fp32) paths. */
+int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
+                        imw_stream_t stream);
+int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
+                        imw_stream_t stream);
+
+/* One 3x3 conv layer of the SuperPoint stack (NHWC fp32 in/out, weights [9][Cin][Cout], optional ReLU and fused
+ * 2x2 max-pool): bench.py times the dominant kernel alone through this hook. */
+int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,
+                      int cin, int cout, int relu, int pool, imw_stream_t stream);
 
 #ifdef __cplusplus
 }

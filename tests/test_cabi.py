@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.SPWeights) == 24 * 8
     assert ctypes.sizeof(_lib.LGBlock) == 10 * 8
     assert ctypes.sizeof(_lib.LGWeights) == 8 + 7 * 8 + 16 * 20 * 8
-    assert ctypes.sizeof(_lib.LGConf) == 16 and ctypes.sizeof(_lib.SPConf) == 16
+    assert ctypes.sizeof(_lib.LGConf) == 20 and ctypes.sizeof(_lib.SPConf) == 16
 
 
 def test_dynamic_load_registry():

@@ -12,12 +12,12 @@ fp = C.POINTER(C.c_float)
 
 
 class SPWeights(C.Structure):
-    _fields_ = [("w", C.c_void_p * 12), ("b", C.c_void_p * 12)]
+    _fields_ = [("w", C.c_void_p * 12), ("b", C.c_void_p * 12), ("wp", C.c_void_p * 12)]
 
 
 class SPConf(C.Structure):
     _fields_ = [("nms_radius", C.c_int), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int),
-                ("remove_borders", C.c_int)]
+                ("remove_borders", C.c_int), ("use_tensor_cores", C.c_int)]
 
 
 class LGBlock(C.Structure):
@@ -72,9 +72,14 @@ def lib():
         L.imw_dual_softmax.restype = C.c_int
         L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, vp, vp, vp,
                                        C.c_size_t, vp]
-        for name in ("imw_debug_gemm_tf32", "imw_debug_gemm_fp32"):
-            getattr(L, name).restype = C.c_int
-            getattr(L, name).argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.imw_debug_gemm_tf32.restype = C.c_int
+        L.imw_debug_gemm_tf32.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.imw_debug_gemm_fp32.restype = C.c_int
+        L.imw_debug_gemm_fp32.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.imw_debug_conv3x3.restype = C.c_int
+        L.imw_debug_conv3x3.argtypes = [vp] * 4 + [C.c_int] * 7 + [vp]
+        L.imw_debug_conv3x3_tc.restype = C.c_int
+        L.imw_debug_conv3x3_tc.argtypes = [vp] * 4 + [C.c_int] * 7 + [vp, C.c_size_t, vp]
         _lib = L
     return _lib
 

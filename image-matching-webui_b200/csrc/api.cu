@@ -34,14 +34,15 @@ struct SPBuffers {
 size_t sp_carve(Workspace& ws, SPBuffers& b, int B, int H, int W) {
   const size_t sb = (size_t)(B < SP_SUB ? B : SP_SUB);
   const size_t h = H / 8, w = W / 8;
-  b.a1 = ws.take<float>(sb * H * W * 64);
-  b.a2 = ws.take<float>(sb * (H / 2) * (W / 2) * 64);
-  b.a3 = ws.take<float>(sb * (H / 2) * (W / 2) * 64);
-  b.a4 = ws.take<float>(sb * (H / 4) * (W / 4) * 64);
-  b.a5 = ws.take<float>(sb * (H / 4) * (W / 4) * 128);
-  b.a6 = ws.take<float>(sb * h * w * 128);
-  b.a7 = ws.take<float>(sb * h * w * 128);
-  b.a8 = ws.take<float>(sb * h * w * 128);
+  // x3/2: the same buffers hold either fp32 or three bf16 planes (6 bytes per element)
+  b.a1 = ws.take<float>(sb * H * W * 64 * 3 / 2);
+  b.a2 = ws.take<float>(sb * (H / 2) * (W / 2) * 64 * 3 / 2);
+  b.a3 = ws.take<float>(sb * (H / 2) * (W / 2) * 64 * 3 / 2);
+  b.a4 = ws.take<float>(sb * (H / 4) * (W / 4) * 64 * 3 / 2);
+  b.a5 = ws.take<float>(sb * (H / 4) * (W / 4) * 128 * 3 / 2);
+  b.a6 = ws.take<float>(sb * h * w * 128 * 3 / 2);
+  b.a7 = ws.take<float>(sb * h * w * 128 * 3 / 2);
+  b.a8 = ws.take<float>(sb * h * w * 128 * 3 / 2);
   b.pa = ws.take<float>(sb * h * w * 256);
   b.logits = ws.take<float>(sb * h * w * 65 + 64);
   b.da = ws.take<float>(sb * h * w * 256);
@@ -74,29 +75,48 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
   sp_carve(ws, b, B, H, W);
   if (ws.overflow) { imw_set_error("imw_superpoint_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return IMW_ERR_WORKSPACE; }
   const int h = H / 8, w = W / 8;
+  const bool use_tc = conf->use_tensor_cores != 0;
+  if (use_tc) {
+    IMW_REQUIRE(W % 128 == 0, "imw_superpoint_forward: the tensor-core path needs W %% 128 == 0 (got %d)", W);
+    for (int l : {1, 2, 3, 4, 5, 6, 7, 8, 10}) IMW_REQUIRE(wt->wp[l] != nullptr, "imw_superpoint_forward: bf16-plane weights missing for layer %d", l);
+  }
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
   for (int b0 = 0; b0 < B; b0 += SP_SUB) {
     const int nb = (B - b0 < SP_SUB) ? (B - b0) : SP_SUB;
     const float* img = image + (size_t)b0 * H * W;
-    RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], b.a1, nb, H, W, st));
-    RUN(sp_conv3x3(b.a1, wt->w[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, st));
-    RUN(sp_conv3x3(b.a2, wt->w[2], wt->b[2], b.a3, nb, H / 2, W / 2, 64, 64, 1, 0, st));
-    RUN(sp_conv3x3(b.a3, wt->w[3], wt->b[3], b.a4, nb, H / 2, W / 2, 64, 64, 1, 1, st));
-    RUN(sp_conv3x3(b.a4, wt->w[4], wt->b[4], b.a5, nb, H / 4, W / 4, 64, 128, 1, 0, st));
-    RUN(sp_conv3x3(b.a5, wt->w[5], wt->b[5], b.a6, nb, H / 4, W / 4, 128, 128, 1, 1, st));
-    RUN(sp_conv3x3(b.a6, wt->w[6], wt->b[6], b.a7, nb, h, w, 128, 128, 1, 0, st));
-    RUN(sp_conv3x3(b.a7, wt->w[7], wt->b[7], b.a8, nb, h, w, 128, 128, 1, 0, st));
-    // detector head (superpoint.py:165-170)
-    RUN(sp_conv3x3(b.a8, wt->w[8], wt->b[8], b.pa, nb, h, w, 128, 256, 1, 0, st));
+    if (use_tc) {
+      // encoder + both 3x3 head convs on tcgen05, activations carried as three bf16 planes
+      RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], nullptr, b.a1, nb, H, W, st));
+      RUN(tc_conv3x3(b.a1, wt->wp[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, 0, st));
+      RUN(tc_conv3x3(b.a2, wt->wp[2], wt->b[2], b.a3, nb, H / 2, W / 2, 64, 64, 1, 0, 0, st));
+      RUN(tc_conv3x3(b.a3, wt->wp[3], wt->b[3], b.a4, nb, H / 2, W / 2, 64, 64, 1, 1, 0, st));
+      RUN(tc_conv3x3(b.a4, wt->wp[4], wt->b[4], b.a5, nb, H / 4, W / 4, 64, 128, 1, 0, 0, st));
+      RUN(tc_conv3x3(b.a5, wt->wp[5], wt->b[5], b.a6, nb, H / 4, W / 4, 128, 128, 1, 1, 0, st));
+      RUN(tc_conv3x3(b.a6, wt->wp[6], wt->b[6], b.a7, nb, h, w, 128, 128, 1, 0, 0, st));
+      RUN(tc_conv3x3(b.a7, wt->wp[7], wt->b[7], b.a8, nb, h, w, 128, 128, 1, 0, 0, st));
+      RUN(tc_conv3x3(b.a8, wt->wp[8], wt->b[8], b.pa, nb, h, w, 128, 256, 1, 0, 1, st));
+      RUN(tc_conv3x3(b.a8, wt->wp[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, 1, st));
+    } else {
+      RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], b.a1, nullptr, nb, H, W, st));
+      RUN(sp_conv3x3(b.a1, wt->w[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, st));
+      RUN(sp_conv3x3(b.a2, wt->w[2], wt->b[2], b.a3, nb, H / 2, W / 2, 64, 64, 1, 0, st));
+      RUN(sp_conv3x3(b.a3, wt->w[3], wt->b[3], b.a4, nb, H / 2, W / 2, 64, 64, 1, 1, st));
+      RUN(sp_conv3x3(b.a4, wt->w[4], wt->b[4], b.a5, nb, H / 4, W / 4, 64, 128, 1, 0, st));
+      RUN(sp_conv3x3(b.a5, wt->w[5], wt->b[5], b.a6, nb, H / 4, W / 4, 128, 128, 1, 1, st));
+      RUN(sp_conv3x3(b.a6, wt->w[6], wt->b[6], b.a7, nb, h, w, 128, 128, 1, 0, st));
+      RUN(sp_conv3x3(b.a7, wt->w[7], wt->b[7], b.a8, nb, h, w, 128, 128, 1, 0, st));
+      RUN(sp_conv3x3(b.a8, wt->w[8], wt->b[8], b.pa, nb, h, w, 128, 256, 1, 0, st));   // detector head (superpoint.py:165)
+      RUN(sp_conv3x3(b.a8, wt->w[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, st)); // descriptor head (superpoint.py:194)
+    }
+    // detector head 1x1 + softmax + depth-to-space (superpoint.py:166-170)
     {
       GemmArgs g{};
       g.A = b.pa; g.lda = 256; g.W = wt->w[9]; g.ldw = 256; g.M = nb * h * w; g.N = 65; g.K = 256;
       IMW_CHECK_CUDA(launch_gemm(g, 1, EpiBias{b.logits, 0, 65, wt->b[9], 0}, st));
     }
     RUN(sp_softmax_d2s(b.logits, b.dense + (size_t)b0 * H * W, nb, h, w, st));
-    // descriptor head (superpoint.py:194-196)
-    RUN(sp_conv3x3(b.a8, wt->w[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, st));
+    // descriptor head 1x1 + channel L2 norm (superpoint.py:195-196)
     {
       float* dd = b.dd + (size_t)b0 * h * w * 256;
       GemmArgs g{};

@@ -508,7 +508,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   const long long sXM = (long long)cap * 512, sD = (long long)cap * D;
   const dim3 rows8(ceil_div(cap, 8), S);
 
-  const bool use_tc = conf->use_tensor_cores != 0;
+  const int use_tc = conf->use_tensor_cores;
   IMW_REQUIRE(!use_tc || cap % 128 == 0, "imw_lightglue_forward: use_tensor_cores needs cap %% 128 == 0 (got %d)", cap);
   // Y = X W^T (+ functor epilogue) over all slots: tcgen05 TF32 tiles or the exact-fp32 CUDA-core kernel
   auto linear = [&](const float* A, int lda, const float* Wt, long long w_rows, int N, int K, auto epi, const int* skip,
@@ -517,7 +517,8 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
       TcGemmArgs t{};
       t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.counts; t.skip = skip; t.skip_shift = 1;
       t.wsel_minus1 = wsel; t.wsel_shift = 1; t.wsel_rows = N;
-      return launch_tc_gemm<128>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
+      if (use_tc == 2) return launch_tc_gemm<128, 1>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
+      return launch_tc_gemm<128, 3>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
     }
     GemmArgs g{};
     g.A = A; g.strideA = (long long)cap * lda; g.lda = lda; g.W = Wt; g.strideW = 0; g.ldw = K; g.M = cap; g.N = N; g.K = K;

@@ -4,7 +4,9 @@
 
 int sp_conv3x3(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
                int relu, int pool, cudaStream_t st);
-int sp_conv3x3_c1(const float* img, const float* w, const float* bias, float* out, int B, int H, int W, cudaStream_t st);
+// out (fp32 NHWC) or, when out_planes != NULL, three bf16 planes [3][B][H][W][64]
+int sp_conv3x3_c1(const float* img, const float* w, const float* bias, float* out, void* out_planes, int B, int H, int W,
+                  cudaStream_t st);
 
 // logits [B][h][w][65] (NHWC) -> dense scores [B][8h][8w]
 int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st);
@@ -20,3 +22,9 @@ int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st);
 // bilinear sample of dense descriptors [B][h][w][256] at kpts, then L2 norm -> desc [B][cap][256]
 int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts, float* desc, int B, int h, int w,
                    int cap, int C, cudaStream_t st);
+
+// tcgen05 split-precision conv (tc_conv.cu): activations / weights as three bf16 planes
+int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,
+               int Cout, int relu, int pool, int out_fp32, cudaStream_t st);
+int tc_split_planes(const float* in, void* out_planes, size_t n, cudaStream_t st);
+int tc_merge_planes(const void* in_planes, float* out, size_t n, cudaStream_t st);

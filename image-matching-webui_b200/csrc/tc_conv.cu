@@ -1,0 +1,288 @@
+// tcgen05 implicit-GEMM 3x3 convolution with fp32-equivalent precision (bf16 x 3 split operands).
+//
+// Why split precision: SuperPoint's detector branch feeds exact-equality NMS, a hard threshold and a top-k
+// cut; single TF32/BF16 operands flip 1.5 % / 8.7 % of the keypoints.  Every fp32
+// value is carried as three bf16 planes x = x1 + x2 + x3 (8 + 8 + 8 mantissa bits, exact to 2^-24 relative)
+// and the product is assembled from the six leading partial products
+//     a1b1 + a1b2 + a2b1 + a1b3 + a2b2 + a3b1        (dropped terms <= 2^-24 |a||b|)
+// accumulated in fp32 in TMEM: six kind::f16 (bf16) MMAs per k-step = 1/6 of the bf16 tensor peak.
+//
+// GEMM view: M = 128 output pixels (8 rows x 16 cols of one image), N = Cout tile (64 / 128), K = 9 taps x Cin.
+// The nine taps are nine shifted TMA box loads of the NHWC activation planes (4-D tensor map, out-of-bounds
+// coordinates zero-filled = the conv's zero padding), 64 channels = one 128-byte swizzled row per pixel.
+//   warp 0: TMA producer (3 activation planes + 3 weight planes per (tap, 64-channel chunk) stage)
+//   warp 1: TMEM alloc + tcgen05.mma issue (24 MMAs per stage)
+//   warps 2-5: epilogue: tcgen05.ld, bias, ReLU, optional fused 2x2 max-pool (lane shuffles: the 2x2
+//              window lives in one warp), re-split into bf16 planes (or fp32) and store NHWC.
+#include <cuda_bf16.h>
+
+#include "../../include/imw_b200.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int CV_TH = 8, CV_TW = 16;          // pixel tile (rows x cols) = 128 = MMA M
+constexpr int CV_CK = 64;                     // channels per stage (128 B of bf16)
+constexpr int CV_A_BYTES = 128 * 128;         // one activation plane tile
+constexpr int CV_THREADS = 192;
+
+struct ConvArgs {
+  int H, W, Cin, Cout, B;
+  int relu, pool, out_fp32;
+  const float* bias;
+  __nv_bfloat16* out_planes;  // [3][B][Ho][Wo][Cout]
+  float* out_f32;             // [B][Ho][Wo][Cout]
+};
+
+template <int BN>
+constexpr int conv_stage_bytes() { return 3 * CV_A_BYTES + 3 * BN * 128; }
+template <int BN>
+constexpr int conv_stages() { return BN == 64 ? 3 : 2; }
+template <int BN>
+constexpr size_t conv_smem_bytes() { return (size_t)conv_stages<BN>() * conv_stage_bytes<BN>() + 1024 + 256; }
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(x);
+  float r = x - __bfloat162float(a);
+  b = __float2bfloat16_rn(r);
+  c = __float2bfloat16_rn(r - __bfloat162float(b));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g) {
+  constexpr int STAGES = conv_stages<BN>(), STAGE = conv_stage_bytes<BN>(), B_BYTES = BN * 128;
+  extern __shared__ uint8_t cv_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int tiles_x = g.W / CV_TW, tiles_y = (g.H + CV_TH - 1) / CV_TH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y; t /= tiles_y;
+  const int b = t;
+  const int n0 = blockIdx.y * BN;
+  const int x0 = tx * CV_TW, y0 = ty * CV_TH;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+    for (int s = 0; s < STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int chunks = g.Cin / CV_CK, steps = 9 * chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < steps; it++) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int tap = it / chunks, ck = it % chunks, dy = tap / 3 - 1, dx = tap % 3 - 1;
+        tc::mbar_wait(empty + s, ph ^ 1);
+        tc::mbar_expect_tx(full + s, STAGE);
+        uint8_t* st = smem + s * STAGE;
+#pragma unroll
+        for (int p = 0; p < 3; p++)  // activation planes: tensor dims (C, W, H, plane*B + b)
+          tc::tma_load_4d(st + p * CV_A_BYTES, &tmA, full + s, ck * CV_CK, x0 + dx, y0 + dy, p * g.B + b);
+#pragma unroll
+        for (int p = 0; p < 3; p++)  // weight planes: rows (plane*9 + tap)*Cout + n, cols Cin
+          tc::tma_load_2d(st + 3 * CV_A_BYTES + p * B_BYTES, &tmW, full + s, ck * CV_CK, (p * 9 + tap) * g.Cout + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
+      for (int it = 0; it < steps; it++) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        tc::mbar_wait(full + s, ph);
+        tc::fence_after_sync();
+        const uint32_t a0 = tc::smem_u32(smem + s * STAGE), b0 = a0 + 3 * CV_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < CV_CK / 16; k++) {
+          uint64_t ad[3], bd[3];
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            ad[p] = tc::make_smem_desc_sw128(a0 + p * CV_A_BYTES + k * 32);
+            bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
+          }
+          // largest terms last does not matter for fp32 accumulation in TMEM; keep a fixed order
+          tc::mma_f16(tmem_base, ad[0], bd[0], idesc, (it | k) ? 1u : 0u);
+          tc::mma_f16(tmem_base, ad[0], bd[1], idesc, 1u);
+          tc::mma_f16(tmem_base, ad[1], bd[0], idesc, 1u);
+          tc::mma_f16(tmem_base, ad[0], bd[2], idesc, 1u);
+          tc::mma_f16(tmem_base, ad[1], bd[1], idesc, 1u);
+          tc::mma_f16(tmem_base, ad[2], bd[0], idesc, 1u);
+        }
+        tc::mma_commit(empty + s);
+      }
+      tc::mma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp % 4;
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+    const int m = q * 32 + lane;              // pixel index in the tile: row m/16, col m%16
+    const int py = y0 + m / CV_TW, px = x0 + m % CV_TW;
+    const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
+    const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 16) == 0) : true;
+    const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
+    const bool in_img = (py < g.H) && (px < g.W);
+    const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
+    const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float x = v[j] + g.bias[n0 + c0 + j];
+        if (g.relu) x = fmaxf(x, 0.f);
+        if (g.pool) {  // 2x2 window = lanes {l, l^1, l^16}: all inside this warp (2 image rows x 16 cols)
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+        }
+        v[j] = x;
+      }
+      if (writer && in_img) {
+        if (g.out_fp32) {
+          float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
+          uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
+          uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
+          uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            o0[j] = reinterpret_cast<const uint4*>(p0)[j];
+            o1[j] = reinterpret_cast<const uint4*>(p1)[j];
+            o2[j] = reinterpret_cast<const uint4*>(p2)[j];
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// fp32 NHWC -> three bf16 planes (and back): interop with the CUDA-core path and the unit tests
+__global__ void split_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __nv_bfloat16 a, b, c;
+  split3(in[i], a, b, c);
+  out[i] = a; out[n + i] = b; out[2 * n + i] = c;
+}
+__global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (__bfloat162float(in[i]) + __bfloat162float(in[n + i])) + __bfloat162float(in[2 * n + i]);
+}
+
+int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C) {
+  PFN_encodeTiled fn = tc_get_encode_fn();
+  if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B3};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {CV_CK, CV_TW, CV_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { imw_set_error("cuTensorMapEncodeTiled(act) failed: %d", (int)r); return IMW_ERR_CUDA; }
+  return IMW_OK;
+}
+int make_map_wgt(CUtensorMap* map, const void* base, int rows, int Cin, int BN) {
+  PFN_encodeTiled fn = tc_get_encode_fn();
+  if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+  cuuint32_t box[2] = {CV_CK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { imw_set_error("cuTensorMapEncodeTiled(wgt) failed: %d", (int)r); return IMW_ERR_CUDA; }
+  return IMW_OK;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+  constexpr size_t smem = conv_smem_bytes<BN>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(g.B * ceil_div(g.H, CV_TH) * (g.W / CV_TW)), g.Cout / BN);
+  tc_conv3x3_kernel<BN><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, g);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+}  // namespace
+
+// in_planes [3][B][H][W][Cin] bf16, w_planes [3][9][Cout][Cin] bf16, bias [Cout] fp32.
+// out: planes [3][B][Ho][Wo][Cout] bf16 or fp32 [B][Ho][Wo][Cout].
+int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,
+               int Cout, int relu, int pool, int out_fp32, cudaStream_t st) {
+  IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0 && W % CV_TW == 0, "tc_conv3x3: Cin %% 64, Cout %% 64, W %% 16 (got %d,%d,%d)", Cin, Cout, W);
+  IMW_REQUIRE(!pool || (H % 2 == 0), "tc_conv3x3: pooled conv needs even H");
+  CUtensorMap tmA, tmW;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, BN)) return e;
+  ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+  return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
+}
+
+int tc_split_planes(const float* in, void* out_planes, size_t n, cudaStream_t st) {
+  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat16*)out_planes, n);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+int tc_merge_planes(const void* in_planes, float* out, size_t n, cudaStream_t st) {
+  merge_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)in_planes, out, n);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+__global__ void transpose_taps_kernel(const float* __restrict__ in, float* __restrict__ out, int Cin, int Cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = 9 * Cin * Cout;
+  if (i >= n) return;
+  int co = i % Cout, ci = (i / Cout) % Cin, t = i / (Cout * Cin);
+  out[((size_t)t * Cout + co) * Cin + ci] = in[i];
+}
+
+// unit-test hook: fp32 NHWC in/out, weights fp32 [9][Cin][Cout] (the CUDA-core layout); splits on the fly.
+extern "C" int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout, const float* bias, float* out, int B, int H,
+                                    int W, int Cin, int Cout, int relu, int pool, void* scratch, size_t scratch_bytes,
+                                    cudaStream_t st) {
+  const size_t n_in = (size_t)B * H * W * Cin, n_w = (size_t)9 * Cout * Cin;
+  Workspace ws(scratch, scratch_bytes);
+  __nv_bfloat16* in_p = ws.take<__nv_bfloat16>(3 * n_in);
+  float* w_t = ws.take<float>(n_w);
+  __nv_bfloat16* w_p = ws.take<__nv_bfloat16>(3 * n_w);
+  if (ws.overflow) { imw_set_error("imw_debug_conv3x3_tc: scratch too small (%zu needed)", ws.off); return IMW_ERR_WORKSPACE; }
+  if (int e = tc_split_planes(in, in_p, n_in, st)) return e;
+  transpose_taps_kernel<<<(unsigned)((n_w + 255) / 256), 256, 0, st>>>(w_tap_cin_cout, w_t, Cin, Cout);  // -> [tap][Cout][Cin]
+  IMW_CHECK_LAUNCH();
+  if (int e = tc_split_planes(w_t, w_p, n_w, st)) return e;
+  return tc_conv3x3(in_p, w_p, bias, out, B, H, W, Cin, Cout, relu, pool, 1, st);
+}

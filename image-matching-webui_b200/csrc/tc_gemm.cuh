@@ -1,4 +1,12 @@
-// tcgen05 TF32 GEMM   C[M,N] = A[M,K] * W[N,K]^T   (fp32 operands read as TF32, fp32 accumulate in TMEM).
+// tcgen05 TF32 GEMM   C[M,N] = A[M,K] * W[N,K]^T   (fp32 accumulate in TMEM).
+//
+// SPLIT = 1: operands read as single TF32 (10-bit mantissa): fast mode.
+// SPLIT = 3: 3xTF32 split precision = fp32-equivalent products: after TMA lands the fp32 tiles, the four
+//            epilogue warps rewrite them in shared memory as x_hi (low 13 mantissa bits cleared, exactly
+//            TF32-representable) and x_lo = x - x_hi in a twin tile (same swizzled offsets), and the MMA warp
+//            issues  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (dropped lo*lo term and the TF32 rounding of the lo
+//            parts are <= 2^-21 relative).  This is the default: LightGlue scores stay within the 1e-3 parity
+//            tolerance, which single TF32 does not (measured 1.4e-2 on the golden pairs).
 //
 //   warp 0      TMA producer: A tile [128 x 32 f32] and W tile [BN x 32 f32] per k-block, SWIZZLE_128B,
 //               through a STAGES-deep full/empty mbarrier ring
@@ -28,12 +36,12 @@ struct TcGemmArgs {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
 
-template <int BN>
+template <int BN, int SPLIT>
 constexpr size_t tc_gemm_smem_bytes() {
-  return (size_t)TC_STAGES * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return (size_t)TC_STAGES * (SPLIT == 3 ? 2 : 1) * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
 
-template <int BN, class Epi>
+template <int BN, int SPLIT, class Epi>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi) {
   const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
@@ -45,17 +53,20 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
 
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  // stage layout: [A | W] (TMA destination, becomes hi in place) and for SPLIT == 3 [A_lo | W_lo] behind it
+  constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, TILE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE = (SPLIT == 3 ? 2 : 1) * TILE_BYTES;
   uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
   uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;
+  uint64_t* ready = empty + TC_STAGES;   // SPLIT == 3: hi/lo tiles written by the splitter warps
+  uint64_t* tmem_full = ready + TC_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
-    for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 128); }
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
         tc::mbar_wait(empty + s, ph ^ 1);
-        tc::mbar_expect_tx(full + s, STAGE);
+        tc::mbar_expect_tx(full + s, TILE_BYTES);
         tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
         tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmW, full + s, kb * TC_BK, w_row0);
       }
@@ -82,7 +93,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        tc::mbar_wait(full + s, ph);
+        tc::mbar_wait(SPLIT == 3 ? ready + s : full + s, ph);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
@@ -90,6 +101,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
           // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
           uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
           tc::mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          if (SPLIT == 3) {
+            uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
+            tc::mma_tf32(tmem_base, ad, bdl, idesc, 1u);
+            tc::mma_tf32(tmem_base, adl, bd, idesc, 1u);
+          }
         }
         tc::mma_commit(empty + s);  // smem stage free once these MMAs have read it
       }
@@ -97,6 +113,29 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
     }
   } else {
     const int q = warp % 4;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    if (SPLIT == 3) {
+      // splitter: x -> (x_hi in place, x_lo in the twin tile); elementwise, so the TMA swizzle is irrelevant
+      const int t = threadIdx.x - 64;  // 0..127
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        tc::mbar_wait(full + s, ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
+        uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
+#pragma unroll 4
+        for (int i = t; i < TILE_BYTES / 16; i += 128) {
+          uint4 v = hi[i], h, l;
+          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        tc::mbar_arrive(ready + s);
+      }
+    }
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
     const int row = row_in_slot0 + q * 32 + lane;
@@ -116,20 +155,20 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
 }
 
 // A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32.
-template <int BN, class Epi>
+template <int BN, int SPLIT, class Epi>
 static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, const float* W, long long w_rows, TcGemmArgs g,
                                  Epi epi, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, TC_BK, TC_BM)) return e;
   if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)w_rows, (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
-  constexpr size_t smem = tc_gemm_smem_bytes<BN>();
+  constexpr size_t smem = tc_gemm_smem_bytes<BN, SPLIT>();
   static bool attr_set = false;
   if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_tf32_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_tf32_kernel<BN, SPLIT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid(g.N / BN, (unsigned)(rows_total / TC_BM));
-  tc_gemm_tf32_kernel<BN, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi);
+  tc_gemm_tf32_kernel<BN, SPLIT, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -36,11 +36,12 @@ int tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64
 
 // out[M][N] = A[M][K] W[N][K]^T + bias  on the tcgen05 path (unit test hook; M % 128 == 0, N % 128 == 0, K % 32 == 0)
 extern "C" int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
-                                   cudaStream_t st) {
+                                   int split, cudaStream_t st) {
   IMW_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 32 == 0, "imw_debug_gemm_tf32: M%%128, N%%128, K%%32");
   TcGemmArgs g{};
   g.K = K; g.N = N; g.tiles_per_slot = M / 128;
-  return launch_tc_gemm<128>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
+  if (split == 3) return launch_tc_gemm<128, 3>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
+  return launch_tc_gemm<128, 1>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
 }
 
 // same product on the CUDA-core path (reference for the unit test)

@@ -11,7 +11,7 @@ from .hloc import WEIGHTS_DIR
 
 SP_CONF_DEFAULT = {"nms_radius": 3, "keypoint_threshold": 0.005, "max_keypoints": 1024, "remove_borders": 4}
 LG_CONF_DEFAULT = {"depth_confidence": 0.95, "width_confidence": 0.99, "filter_threshold": 0.2, "pruning_min_kpts": 1536,
-                   "use_tensor_cores": True}
+                   "use_tensor_cores": 1}
 
 
 class PairEngine:

@@ -16,6 +16,9 @@ class SuperPoint(BaseModel):
         "max_keypoints": -1,
         "remove_borders": 4,
         "fix_sampling": False,
+        # B200 engine switch (not in the reference): encoder convs on tcgen05 with bf16 x 3 split operands
+        # (fp32-equivalent products, needs W % 128 == 0); False = fp32 CUDA-core convs
+        "tensor_cores": True,
     }
     required_inputs = ["image"]
     detection_noise = 2.0

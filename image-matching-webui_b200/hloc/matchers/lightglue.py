@@ -22,8 +22,9 @@ class LightGlue(BaseModel):
         "mp": False,
         "add_scale_ori": False,
         "n_layers": 9,
-        # B200 engine switch (not in the reference): linear layers on tcgen05 with TF32 operands
-        # (TF32 linears keep the match set identical); False = exact-fp32 CUDA cores
+        # B200 engine switch (not in the reference): linear layers on tcgen05.
+        # True / "3xtf32": split-precision TF32 (fp32-equivalent, parity-grade); "tf32": single TF32 (fast mode,
+        # match-F1 >= 0.99 but scores only within ~1.5e-2); False: fp32 CUDA cores
         "tensor_cores": True,
     }
     required_inputs = ["image0", "keypoints0", "scores0", "descriptors0", "image1", "keypoints1", "scores1",
@@ -52,7 +53,7 @@ class LightGlue(BaseModel):
             pth = 1536 if c["flash"] else 1024
         return {"depth_confidence": c["depth_confidence"], "width_confidence": c["width_confidence"],
                 "filter_threshold": c["filter_threshold"], "pruning_min_kpts": pth,
-                "use_tensor_cores": c["tensor_cores"]}
+                "use_tensor_cores": {False: 0, True: 1, "3xtf32": 1, "tf32": 2}[c["tensor_cores"]]}
 
     def _forward(self, data):
         k0, k1 = data["keypoints0"], data["keypoints1"]

@@ -26,7 +26,22 @@ def sp_pack_weights(state_dict):
             w = w.reshape(w.shape[0], w.shape[1])
         out[name + "_w"] = w.contiguous()
         out[name + "_b"] = state_dict[name + ".bias"].float().contiguous()
+        if name in SP_TC_LAYERS:  # [3 planes][tap][Cout][Cin] bf16, w = p0 + p1 + p2 (tcgen05 split-precision path)
+            wt = state_dict[name + ".weight"].float().permute(2, 3, 0, 1).reshape(9, w.shape[2], w.shape[1]).contiguous()
+            out[name + "_wp"] = split_bf16_planes(wt)
     return out
+
+
+SP_TC_LAYERS = ["conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convDa"]
+
+
+def split_bf16_planes(x):
+    """fp32 -> [3, ...] bf16 with x == p0 + p1 + p2 to 2^-24 relative (round-to-nearest at each step)."""
+    p0 = x.bfloat16()
+    r = x - p0.float()
+    p1 = r.bfloat16()
+    p2 = (r - p1.float()).bfloat16()
+    return torch.stack([p0, p1, p2]).contiguous()
 
 
 def sp_weights_struct(bufs):
@@ -34,6 +49,7 @@ def sp_weights_struct(bufs):
     for i, name in enumerate(SP_LAYERS):
         s.w[i] = bufs[name + "_w"].data_ptr()
         s.b[i] = bufs[name + "_b"].data_ptr()
+        s.wp[i] = bufs[name + "_wp"].data_ptr() if (name + "_wp") in bufs else None
     return s
 
 
@@ -56,8 +72,9 @@ def superpoint_forward(bufs, image, conf, cap, out=None, want_dense=False):
     lib = L.lib()
     nbytes = lib.imw_superpoint_workspace_bytes(B, H, W)
     ws = L.workspaces.get(dev, nbytes, "sp")
+    use_tc = bool(conf.get("tensor_cores", True)) and W % 128 == 0
     c = L.SPConf(int(conf["nms_radius"]), float(conf["keypoint_threshold"]), int(conf["max_keypoints"]),
-                 int(conf["remove_borders"]))
+                 int(conf["remove_borders"]), int(use_tc))
     wstruct = sp_weights_struct(bufs)
     with torch.cuda.device(dev):
         rc = lib.imw_superpoint_forward(C.byref(wstruct), C.byref(c), B, H, W, L.ptr(image), cap, L.ptr(out["keypoints"]),
@@ -133,7 +150,7 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
     lib = L.lib()
     ws = L.workspaces.get(dev, lib.imw_lightglue_workspace_bytes(P, cap), "lg")
     c = L.LGConf(float(conf["depth_confidence"]), float(conf["width_confidence"]), float(conf["filter_threshold"]),
-                 int(conf["pruning_min_kpts"]), int(bool(conf.get("use_tensor_cores", True)) and cap % 128 == 0))
+                 int(conf["pruning_min_kpts"]), int(conf.get("use_tensor_cores", 1)) if cap % 128 == 0 else 0)
     wstruct = lg_weights_struct(bufs, n_layers)
     with torch.cuda.device(dev):
         rc = lib.imw_lightglue_forward(C.byref(wstruct), C.byref(c), P, cap, L.ptr(keypoints), L.ptr(descriptors), L.ptr(counts),
@@ -177,13 +194,33 @@ def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0)
     return m0, s0
 
 
-def debug_gemm(A, W, bias, tensor_cores=True):
-    """out = A @ W.T + bias through the tcgen05 (TF32) or CUDA-core (fp32) GEMM (unit-test hook)."""
+def debug_gemm(A, W, bias, mode="3xtf32"):
+    """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32") or the CUDA-core GEMM ("fp32")."""
     L.require_cuda(A, "debug_gemm(A)")
     M, K = A.shape
     N = W.shape[0]
     out = torch.empty(M, N, device=A.device)
-    fn = L.lib().imw_debug_gemm_tf32 if tensor_cores else L.lib().imw_debug_gemm_fp32
+    args = (L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K)
     with torch.cuda.device(A.device):
-        L.check(fn(L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K, L.stream_ptr(A.device)))
+        if mode == "fp32":
+            L.check(L.lib().imw_debug_gemm_fp32(*args, L.stream_ptr(A.device)))
+        else:
+            L.check(L.lib().imw_debug_gemm_tf32(*args, 3 if mode == "3xtf32" else 1, L.stream_ptr(A.device)))
+    return out
+
+
+def debug_conv3x3(x, w, bias, relu=True, pool=False, tensor_cores=True):
+    """One 3x3 conv layer, NHWC fp32 in/out; w [9][Cin][Cout] fp32.  tensor_cores: tcgen05 bf16x3 path."""
+    L.require_cuda(x, "debug_conv3x3(x)")
+    B, H, W_, Cin = x.shape
+    Cout = w.shape[2]
+    out = torch.empty(B, H // 2 if pool else H, W_ // 2 if pool else W_, Cout, device=x.device)
+    with torch.cuda.device(x.device):
+        if tensor_cores:
+            scratch = torch.empty(int(6 * x.numel() + 10 * w.numel() + 4096), dtype=torch.uint8, device=x.device)
+            L.check(L.lib().imw_debug_conv3x3_tc(L.ptr(x.contiguous()), L.ptr(w.contiguous()), L.ptr(bias), L.ptr(out), B, H, W_, Cin, Cout,
+                                                 int(relu), int(pool), L.ptr(scratch), scratch.numel(), L.stream_ptr(x.device)))
+        else:
+            L.check(L.lib().imw_debug_conv3x3(L.ptr(x.contiguous()), L.ptr(w.contiguous()), L.ptr(bias), L.ptr(out), B, H, W_, Cin, Cout,
+                                              int(relu), int(pool), L.stream_ptr(x.device)))
     return out

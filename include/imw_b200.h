@@ -40,6 +40,9 @@ unsigned long long imw_launch_count(void);
 typedef struct {
   const float* w[12]; /* conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db */
   const float* b[12];
+  /* optional: 3x3 kernels of conv1b..conv4b, convPa, convDa as three bf16 planes [3][9][Cout][Cin]
+     (w = p0 + p1 + p2) for the tcgen05 split-precision path; NULL entries -> CUDA-core path only */
+  const void* wp[12];
 } imw_sp_weights;
 
 typedef struct {
@@ -47,6 +50,7 @@ typedef struct {
   float keypoint_threshold; /* conf["keypoint_threshold"] */
   int max_keypoints;        /* conf["max_keypoints"]; -1 = no cap; 0 or < -1 -> error (superpoint.py:139-141) */
   int remove_borders;       /* conf["remove_borders"] */
+  int use_tensor_cores;     /* 1: encoder convs on tcgen05 (bf16 x 3 split operands = fp32-equivalent), 0: fp32 CUDA cores */
 } imw_sp_conf;
 
 size_t imw_superpoint_workspace_bytes(int batch, int height, int width);
@@ -94,8 +98,8 @@ typedef struct {
   float width_confidence; /* <= 0 disables point pruning */
   float filter_threshold; /* hloc: = match_threshold (hloc/matchers/lightglue.py:50) */
   int pruning_min_kpts;   /* lightglue.py:339-344: 1536 = CUDA+flash, 1024 = CUDA, -1 = CPU semantics */
-  int use_tensor_cores;   /* 1: linear layers on tcgen05 (TF32 operands, fp32 accumulate; needs cap % 128 == 0),
-                             0: exact-fp32 CUDA-core path */
+  int use_tensor_cores;   /* linear layers: 1 = tcgen05 3xTF32 split precision (fp32-equivalent, default),
+                             2 = tcgen05 single TF32 (fast mode), 0 = fp32 CUDA cores; 1/2 need cap % 128 == 0 */
 } imw_lg_conf;
 
 size_t imw_lightglue_workspace_bytes(int n_pairs, int cap);
@@ -125,14 +129,18 @@ int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, co
                      float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
                      imw_stream_t stream);
 
-/* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 (TF32) and CUDA-core (fp32) paths. */
-int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
+/* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 path (split = 1: single TF32,
+ * split = 3: 3xTF32 fp32-equivalent) and on the CUDA-core fp32 path. */
+int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K, int split,
                         imw_stream_t stream);
 int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
                         imw_stream_t stream);
 
 /* One 3x3 conv layer of the SuperPoint stack (NHWC fp32 in/out, weights [9][Cin][Cout], optional ReLU and fused
  * 2x2 max-pool): bench.py times the dominant kernel alone through this hook. */
+int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout, const float* bias, float* out, int batch, int height,
+                         int width, int cin, int cout, int relu, int pool, void* scratch, size_t scratch_bytes,
+                         imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,
                       int cin, int cout, int relu, int pool, imw_stream_t stream);
 

@@ -23,10 +23,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     from imcui_b200 import _lib
-    assert ctypes.sizeof(_lib.SPWeights) == 24 * 8
+    assert ctypes.sizeof(_lib.SPWeights) == 36 * 8
     assert ctypes.sizeof(_lib.LGBlock) == 10 * 8
     assert ctypes.sizeof(_lib.LGWeights) == 8 + 7 * 8 + 16 * 20 * 8
-    assert ctypes.sizeof(_lib.LGConf) == 20 and ctypes.sizeof(_lib.SPConf) == 16
+    assert ctypes.sizeof(_lib.LGConf) == 20 and ctypes.sizeof(_lib.SPConf) == 20
 
 
 def test_dynamic_load_registry():

@@ -6,6 +6,10 @@
 // and the product is assembled from the six leading partial products
 //     a1b1 + a1b2 + a2b1 + a1b3 + a2b2 + a3b1        (dropped terms <= 2^-24 |a||b|)
 // accumulated in fp32 in TMEM: six kind::f16 (bf16) MMAs per k-step = 1/6 of the bf16 tensor peak.
+// The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+// accumulating MMAs (measured: ~1e-5 relative after 216 MMAs into one accumulator).  The accumulation is therefore
+// spread over FOUR TMEM accumulators -- the leading a1*b1 term per kernel row dy (12-24 MMAs each) and one for all
+// cross terms (2^-8 of the magnitude, so its truncation error is negligible) -- summed in fp32 in the epilogue.
 //
 // GEMM view: M = 128 output pixels (8 rows x 16 cols of one image), N = Cout tile (64 / 128), K = 9 taps x Cin.
 // The nine taps are nine shifted TMA box loads of the NHWC activation planes (4-D tensor map, out-of-bounds
@@ -76,7 +80,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 4 * BN);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -115,13 +119,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ad[p] = tc::make_smem_desc_sw128(a0 + p * CV_A_BYTES + k * 32);
             bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
           }
-          // largest terms last does not matter for fp32 accumulation in TMEM; keep a fixed order
-          tc::mma_f16(tmem_base, ad[0], bd[0], idesc, (it | k) ? 1u : 0u);
-          tc::mma_f16(tmem_base, ad[0], bd[1], idesc, 1u);
-          tc::mma_f16(tmem_base, ad[1], bd[0], idesc, 1u);
-          tc::mma_f16(tmem_base, ad[0], bd[2], idesc, 1u);
-          tc::mma_f16(tmem_base, ad[1], bd[1], idesc, 1u);
-          tc::mma_f16(tmem_base, ad[2], bd[0], idesc, 1u);
+          const int tap = it / chunks, ck = it % chunks;
+          const uint32_t d_main = tmem_base + (tap / 3) * BN, d_cross = tmem_base + 3 * BN;
+          tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % 3) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
+          tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
+          tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
+          tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
+          tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
+          tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
         }
         tc::mma_commit(empty + s);
       }
@@ -141,8 +146,18 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      float v[32], t[32];
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+      tc::tmem_ld32(lane_base, v);
+      tc::tmem_ld32(lane_base + BN, t);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += t[j];
+      tc::tmem_ld32(lane_base + 2 * BN, t);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += t[j];
+      tc::tmem_ld32(lane_base + 3 * BN, t);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += t[j];
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         float x = v[j] + g.bias[n0 + c0 + j];
@@ -177,7 +192,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 4 * BN);
 }
 
 // fp32 NHWC -> three bf16 planes (and back): interop with the CUDA-core path and the unit tests

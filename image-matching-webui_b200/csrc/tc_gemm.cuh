@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  // SPLIT == 3: two accumulators (hi*hi and the cross terms): the tensor core truncates when it adds into the
+  // fp32 accumulator; keeping the 2^-11-sized cross terms apart makes their truncation error negligible
+  constexpr int ACC_COLS = (SPLIT == 3 ? 2 : 1) * BN;
+  if (warp == 1) tc::tmem_alloc(tmem_slot, ACC_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -103,8 +106,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
           tc::mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
           if (SPLIT == 3) {
             uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
-            tc::mma_tf32(tmem_base, ad, bdl, idesc, 1u);
-            tc::mma_tf32(tmem_base, adl, bd, idesc, 1u);
+            tc::mma_tf32(tmem_base + BN, ad, bdl, idesc, (kb | k) ? 1u : 0u);
+            tc::mma_tf32(tmem_base + BN, adl, bd, idesc, 1u);
           }
         }
         tc::mma_commit(empty + s);  // smem stage free once these MMAs have read it
@@ -143,6 +146,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      if (SPLIT == 3) {
+        float t[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + BN + c0, t);
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] += t[j];
+      }
       if (row < nrows) {
 #pragma unroll
         for (int j = 0; j < 8; j++) epi(z, row, n0 + c0 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), 4);
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, ACC_COLS);
 }
 
 // A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32.

@@ -115,4 +115,10 @@ struct EpiBias {
         o[j] = x;
       }
   }
+  // tcgen05 epilogue form: one element per lane, lanes along consecutive columns of one row
+  __device__ void elem(int z, int row, int col, float v) const {
+    float x = v + (bias ? bias[col] : 0.f);
+    if (relu) x = fmaxf(x, 0.f);
+    out[(long long)z * strideOut + (long long)row * ldo + col] = x;
+  }
 };

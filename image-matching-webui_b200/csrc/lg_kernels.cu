@@ -67,6 +67,18 @@ struct EpiQKVRotary {
     }
     *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
   }
+  // tcgen05 epilogue form (lanes along columns; the rotary partner of dim d is the neighbouring lane d^1)
+  __device__ void elem(int z, int row, int col, float a) const {
+    float r = a + bias[col];
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    float partner = __shfl_xor_sync(0xffffffffu, r, 1);
+    if (which < 2) {
+      const float* e = enc + ((long long)z * cap + row) * 64;
+      float cs = e[d / 2], sn = e[32 + d / 2];
+      r = (d & 1) ? __fadd_rn(__fmul_rn(r, cs), __fmul_rn(partner, sn)) : __fadd_rn(__fmul_rn(r, cs), __fmul_rn(-partner, sn));
+    }
+    (which == 0 ? q : which == 1 ? k : v)[(((long long)z * HEADS + head) * cap + row) * HD + d] = r;
+  }
 };
 
 // Cross-attention projection: columns [qk | v] x [head][dim]; qk scaled by dim_head^-0.25
@@ -80,6 +92,12 @@ struct EpiCrossQKV {
     if (which == 0) { r[0] *= qk_scale; r[1] *= qk_scale; r[2] *= qk_scale; r[3] *= qk_scale; }
     *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
   }
+  __device__ void elem(int z, int row, int col, float a) const {
+    float r = a + bias[col];
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which == 0) r *= qk_scale;
+    (which == 0 ? qk : v)[(((long long)z * HEADS + head) * cap + row) * HD + d] = r;
+  }
 };
 
 // out[z][row][col] (+)= acc + bias  -- plain / residual variants, N % 4 == 0
@@ -91,6 +109,12 @@ struct EpiStore {
     if (residual) { float4 x = *o; r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; }
     *o = r;
   }
+  __device__ void elem(int z, int row, int col, float a) const {
+    float* o = out + z * strideOut + (long long)row * ldo + col;
+    float r = a + bias[col];
+    if (residual) r += *o;
+    *o = r;
+  }
 };
 
 // final_proj of the layer the pair stopped at; output divided by d^0.25 = 4 (lightglue.py:288-290)
@@ -100,6 +124,9 @@ struct EpiFinalProj {
     const float* b = bias_all + (stop[z >> 1] - 1) * D;
     float4 r = make_float4((a.x + b[col]) * 0.25f, (a.y + b[col + 1]) * 0.25f, (a.z + b[col + 2]) * 0.25f, (a.w + b[col + 3]) * 0.25f);
     *reinterpret_cast<float4*>(out + ((long long)z * cap + row) * D + col) = r;
+  }
+  __device__ void elem(int z, int row, int col, float a) const {
+    out[((long long)z * cap + row) * D + col] = (a + bias_all[(stop[z >> 1] - 1) * D + col]) * 0.25f;
   }
 };
 

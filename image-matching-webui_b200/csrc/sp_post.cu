@@ -55,68 +55,67 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dens
   const int tiles_x = (W + NMS_T - 1) / NMS_T;
   const int x0 = (blockIdx.x % tiles_x) * NMS_T - halo, y0 = (blockIdx.x / tiles_x) * NMS_T - halo;
   const float* img = dense + (long long)blockIdx.z * H * W;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x % 32, wrp = threadIdx.x / 32;
+  // rows are distributed over the 8 warps, columns over the lanes: no integer division in the inner loops
+#define NMS_FOR_EACH(yy, xx) for (int yy = wrp; yy < R; yy += 8) for (int xx = lane; xx < R; xx += 32)
 
-  for (int i = tid; i < RR; i += 256) {
-    int yy = i / R, xx = i % R, gy = y0 + yy, gx = x0 + xx;
-    S[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(long long)gy * W + gx] : -CUDART_INF_F;
+  NMS_FOR_EACH(yy, xx) {
+    int gy = y0 + yy, gx = x0 + xx;
+    S[yy * R + xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(long long)gy * W + gx] : -CUDART_INF_F;
   }
   __syncthreads();
-  // max_mask = scores == max_pool(scores)
-  for (int i = tid; i < RR; i += 256) {
-    int yy = i / R, xx = i % R;
+  // max_mask = scores == max_pool(scores)   (separable: rows then columns)
+  NMS_FOR_EACH(yy, xx) {
     float m = -CUDART_INF_F;
     for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, S[yy * R + d]);
-    A[i] = m;
+    A[yy * R + xx] = m;
   }
   __syncthreads();
-  for (int i = tid; i < RR; i += 256) {
-    int yy = i / R, xx = i % R;
+  NMS_FOR_EACH(yy, xx) {
     float m = -CUDART_INF_F;
     for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
-    mask[i] = (S[i] == m) && (S[i] != -CUDART_INF_F);
+    float s = S[yy * R + xx];
+    mask[yy * R + xx] = (s == m) && (s != -CUDART_INF_F);
   }
   __syncthreads();
   for (int it = 0; it < 2; it++) {
     // supp = max_pool(max_mask) > 0
-    for (int i = tid; i < RR; i += 256) {
-      int yy = i / R, xx = i % R;
+    NMS_FOR_EACH(yy, xx) {
       unsigned char m = 0;
       for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m |= mask[yy * R + d];
-      tmpb[i] = m;
+      tmpb[yy * R + xx] = m;
     }
     __syncthreads();
-    for (int i = tid; i < RR; i += 256) {
-      int yy = i / R, xx = i % R;
+    NMS_FOR_EACH(yy, xx) {
       unsigned char m = 0;
       for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m |= tmpb[d * R + xx];
-      supp[i] = m;
+      supp[yy * R + xx] = m;
       // supp_scores = where(supp, 0, scores); stays -inf outside the image (max_pool2d padding)
-      SS[i] = (S[i] == -CUDART_INF_F) ? -CUDART_INF_F : (m ? 0.f : S[i]);
+      float s = S[yy * R + xx];
+      SS[yy * R + xx] = (s == -CUDART_INF_F) ? -CUDART_INF_F : (m ? 0.f : s);
     }
     __syncthreads();
-    for (int i = tid; i < RR; i += 256) {
-      int yy = i / R, xx = i % R;
+    NMS_FOR_EACH(yy, xx) {
       float m = -CUDART_INF_F;
       for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, SS[yy * R + d]);
-      A[i] = m;
+      A[yy * R + xx] = m;
     }
     __syncthreads();
-    for (int i = tid; i < RR; i += 256) {
-      int yy = i / R, xx = i % R;
+    NMS_FOR_EACH(yy, xx) {
       float m = -CUDART_INF_F;
       for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
-      bool new_max = (SS[i] == m) && (SS[i] != -CUDART_INF_F);
-      if (new_max && !supp[i]) mask[i] = 1;
+      float s = SS[yy * R + xx];
+      bool new_max = (s == m) && (s != -CUDART_INF_F);
+      if (new_max && !supp[yy * R + xx]) mask[yy * R + xx] = 1;
     }
     __syncthreads();
   }
+#undef NMS_FOR_EACH
   float* o = out + (long long)blockIdx.z * H * W;
-  for (int i = tid; i < NMS_T * NMS_T; i += 256) {
-    int yy = i / NMS_T, xx = i % NMS_T;
-    int gy = y0 + halo + yy, gx = x0 + halo + xx;
+  for (int yy = wrp; yy < NMS_T; yy += 8) {
+    int gy = y0 + halo + yy, gx = x0 + halo + lane;
     if (gy < H && gx < W) {
-      int si = (yy + halo) * R + xx + halo;
+      int si = (yy + halo) * R + lane + halo;
       o[(long long)gy * W + gx] = mask[si] ? S[si] : 0.f;
     }
   }

@@ -38,7 +38,8 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
 
 template <int BN, int SPLIT>
 constexpr size_t tc_gemm_smem_bytes() {
-  return (size_t)TC_STAGES * (SPLIT == 3 ? 2 : 1) * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return (size_t)TC_STAGES * (SPLIT == 3 ? 2 : 1) * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+         4 * 32 * 33 * sizeof(float) /*epilogue transpose tiles*/;
 }
 
 template <int BN, int SPLIT, class Epi>
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
   uint64_t* ready = empty + TC_STAGES;   // SPLIT == 3: hi/lo tiles written by the splitter warps
   uint64_t* tmem_full = ready + TC_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* epi_tiles = (float*)(smem + TC_STAGES * STAGE + 256);  // [4 warps][32][33]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -141,7 +143,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
     }
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
-    const int row = row_in_slot0 + q * 32 + lane;
+    // TMEM gives one output ROW per thread; global memory wants one row per warp instruction.  Transpose each
+    // 32x32 block through a padded smem tile so that lanes run along the columns: every load/store of the
+    // functor epilogue is one fully coalesced 128-byte line (the per-thread-row version was 5x slower on the
+    // residual epilogue: 32 dependent, uncoalesced round trips per thread).
+    float* T = epi_tiles + (warp - 2) * 32 * 33;
+    const int row_base = row_in_slot0 + q * 32;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
@@ -152,10 +159,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += t[j];
       }
-      if (row < nrows) {
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; j++) epi(z, row, n0 + c0 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), 4);
-      }
+      for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int rmax = min(32, nrows - row_base);  // warp-uniform
+#pragma unroll 4
+      for (int r = 0; r < rmax; r++) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane]);
     }
   }
   tc::fence_before_sync();

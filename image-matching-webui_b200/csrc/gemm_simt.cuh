@@ -121,4 +121,5 @@ struct EpiBias {
     if (relu) x = fmaxf(x, 0.f);
     out[(long long)z * strideOut + (long long)row * ldo + col] = x;
   }
+  __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };

@@ -11,6 +11,7 @@
 #include "gemm_simt.cuh"
 #include "simreduce.cuh"
 #include "tc_gemm.cuh"
+#include "tc_attn.cuh"
 
 namespace {
 
@@ -50,8 +51,15 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ k
 // ---- GEMM epilogues ---------------------------------------------------------------------------------
 // Self-attention projection: columns [q | k | v] x [head][dim]; rotary on q,k (lightglue.py:58-65,
 // 165-169).  Output buffers [slots][HEADS][cap][HD].
+// hi/lo split used by the tcgen05 attention operands: hi = 13 low mantissa bits cleared, lo = x - hi
+__device__ __forceinline__ void split_hi_lo(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
 struct EpiQKVRotary {
   float *q, *k, *v; const float* bias; const float* enc; int cap;
+  long long plane;   // tcgen05 attention layout: elements per hi/lo plane (0 = CUDA-core layout, no planes)
   __device__ void operator()(int z, int row, int col, float4 a, int) const {
     float r[4] = {a.x + bias[col], a.y + bias[col + 1], a.z + bias[col + 2], a.w + bias[col + 3]};
     int which = col / D, c = col % D, head = c / HD, d = c % HD;
@@ -77,7 +85,26 @@ struct EpiQKVRotary {
       float cs = e[d / 2], sn = e[32 + d / 2];
       r = (d & 1) ? __fadd_rn(__fmul_rn(r, cs), __fmul_rn(partner, sn)) : __fadd_rn(__fmul_rn(r, cs), __fmul_rn(-partner, sn));
     }
-    (which == 0 ? q : which == 1 ? k : v)[(((long long)z * HEADS + head) * cap + row) * HD + d] = r;
+    float* dst = (which == 0 ? q : which == 1 ? k : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    else dst[off] = r;
+  }
+  // tcgen05 attention wants V transposed ([head][d][token], tokens contiguous): taken straight from the
+  // thread-per-row TMEM layout (lanes = consecutive tokens -> coalesced), before the epilogue transpose.
+  __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
+    if (!plane || col0 < 2 * D) return false;
+    const int c = col0 - 2 * D, head = c / HD, d0 = c % HD;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float hi, lo;
+        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
+        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
+        v[off] = hi; v[plane + off] = lo;
+      }
+    }
+    return true;
   }
 };
 
@@ -85,6 +112,7 @@ struct EpiQKVRotary {
 // (lightglue.py:216: each side multiplied by scale**0.5).
 struct EpiCrossQKV {
   float *qk, *v; const float* bias; int cap; float qk_scale;
+  long long plane;
   __device__ void operator()(int z, int row, int col, float4 a, int) const {
     float r[4] = {a.x + bias[col], a.y + bias[col + 1], a.z + bias[col + 2], a.w + bias[col + 3]};
     int which = col / D, c = col % D, head = c / HD, d = c % HD;
@@ -96,7 +124,24 @@ struct EpiCrossQKV {
     float r = a + bias[col];
     int which = col / D, c = col % D, head = c / HD, d = c % HD;
     if (which == 0) r *= qk_scale;
-    (which == 0 ? qk : v)[(((long long)z * HEADS + head) * cap + row) * HD + d] = r;
+    float* dst = (which == 0 ? qk : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    else dst[off] = r;
+  }
+  __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
+    if (!plane || col0 < D) return false;
+    const int c = col0 - D, head = c / HD, d0 = c % HD;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float hi, lo;
+        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
+        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
+        v[off] = hi; v[plane + off] = lo;
+      }
+    }
+    return true;
   }
 };
 
@@ -115,6 +160,7 @@ struct EpiStore {
     if (residual) r += *o;
     *o = r;
   }
+  __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
 
 // final_proj of the layer the pair stopped at; output divided by d^0.25 = 4 (lightglue.py:288-290)
@@ -128,6 +174,7 @@ struct EpiFinalProj {
   __device__ void elem(int z, int row, int col, float a) const {
     out[((long long)z * cap + row) * D + col] = (a + bias_all[(stop[z >> 1] - 1) * D + col]) * 0.25f;
   }
+  __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
 
 // ---- LayerNorm(512) + exact GELU, in place (lightglue.py:152-157) -------------------------------
@@ -483,7 +530,8 @@ struct LGBuffers {
 static size_t lg_carve(Workspace& ws, LGBuffers& b, int P, int cap) {
   const size_t S = 2 * (size_t)P, T = S * cap;
   for (int i = 0; i < 2; i++) { b.xm[i] = ws.take<float>(T * 512); b.enc[i] = ws.take<float>(T * 64); b.ind[i] = ws.take<int>(T); }
-  b.q = ws.take<float>(T * D); b.k = ws.take<float>(T * D); b.v = ws.take<float>(T * D);
+  // x2: hi/lo planes for the tcgen05 attention operands (the CUDA-core path uses the first plane only)
+  b.q = ws.take<float>(2 * T * D); b.k = ws.take<float>(2 * T * D); b.v = ws.take<float>(2 * T * D);
   b.ctx = ws.take<float>(T * D); b.h = ws.take<float>(T * 512);
   b.conf = ws.take<float>(T); b.mscore = ws.take<float>(T); b.md = ws.take<float>(T * D); b.zl = ws.take<float>(T);
   b.rmax = ws.take<float>(T); b.rlse = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
@@ -553,6 +601,18 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     IMW_CHECK_CUDA(launch_gemm(g, S, epi, st));
     return IMW_OK;
   };
+  // attention: tcgen05 flash attention on hi/lo planes (tensor-core modes) or the fp32 CUDA-core kernel
+  const long long plane = use_tc ? (long long)S * cap * D : 0;
+  if (use_tc) IMW_CHECK_CUDA(cudaMemsetAsync(b.v, 0, sizeof(float) * 2 * plane, st));  // V^T tail columns must be finite
+  auto attention = [&](const float* q, const float* k, const float* v, float scale, int cross) -> int {
+    if (use_tc) {
+      TcAttnArgs a{b.ctx, b.counts, b.done, cap, S, scale, cross, (long long)S * HEADS * cap, (long long)S * HEADS * HD};
+      return launch_tc_attn(q, k, v, a, st);
+    }
+    attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(q, k, v, b.ctx, b.counts, b.done, cap, scale, cross);
+    IMW_CHECK_LAUNCH();
+    return IMW_OK;
+  };
   auto gemm = [&](const float* A, long long sA, int lda, const float* Wt, int N, int K) {
     GemmArgs g{};
     g.A = A; g.strideA = sA; g.lda = lda; g.W = Wt; g.strideW = 0; g.ldw = K; g.M = cap; g.N = N; g.K = K;
@@ -573,15 +633,13 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     float* xm = b.xm[cur];
     float* enc = b.enc[cur];
     // ---- self attention (lightglue.py:159-172)
-    if (int e = linear(xm, 512, ly.self_blk.qkv_w, 3 * D, 3 * D, D, EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap}, b.done, nullptr)) return e;
-    attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(b.q, b.k, b.v, b.ctx, b.counts, b.done, cap, 0.125f, 0);
-    IMW_CHECK_LAUNCH();
+    if (int e = linear(xm, 512, ly.self_blk.qkv_w, 3 * D, 3 * D, D, EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap, plane}, b.done, nullptr)) return e;
+    if (int e = attention(b.q, b.k, b.v, 0.125f, 0)) return e;
     if (int e = linear(b.ctx, D, ly.self_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.self_blk.out_b, 0}, b.done, nullptr)) return e;
     if (int e = ffn(ly.self_blk)) return e;
     // ---- cross attention (lightglue.py:199-230)
-    if (int e = linear(xm, 512, ly.cross_blk.qkv_w, 2 * D, 2 * D, D, EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f}, b.done, nullptr)) return e;
-    attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(b.q, b.q, b.v, b.ctx, b.counts, b.done, cap, 1.0f, 1);
-    IMW_CHECK_LAUNCH();
+    if (int e = linear(xm, 512, ly.cross_blk.qkv_w, 2 * D, 2 * D, D, EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f, plane}, b.done, nullptr)) return e;
+    if (int e = attention(b.q, b.q, b.v, 1.0f, 1)) return e;
     if (int e = linear(b.ctx, D, ly.cross_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.cross_blk.out_b, 0}, b.done, nullptr)) return e;
     if (int e = ffn(ly.cross_blk)) return e;
     if (i == L - 1) break;
@@ -622,4 +680,47 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     IMW_CHECK_LAUNCH();
   }
   return IMW_OK;
+}
+
+// =====================================================================================================
+// unit-test hook: attention on standard-layout q/k/v [slots][4][cap][64] through the CUDA-core kernel
+// (use_tc = 0) or the tcgen05 kernel (use_tc = 1: operands are split to hi/lo planes and V transposed here).
+namespace {
+__global__ void attn_prep_planes_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                        float* __restrict__ qp, float* __restrict__ kp, float* __restrict__ vtp, long long n,
+                                        int cap) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float hi, lo;
+  split_hi_lo(q[i], hi, lo); qp[i] = hi; qp[n + i] = lo;
+  split_hi_lo(k[i], hi, lo); kp[i] = hi; kp[n + i] = lo;
+  const int d = (int)(i % HD);
+  const long long row = (i / HD) % cap, zh = i / ((long long)HD * cap);
+  split_hi_lo(v[i], hi, lo);
+  const long long o = (zh * HD + d) * cap + row;
+  vtp[o] = hi; vtp[n + o] = lo;
+}
+}  // namespace
+
+extern "C" int imw_debug_attention(const float* q, const float* k, const float* v, const int* counts, int slots, int cap,
+                                   float scale, int cross, int use_tc, float* ctx, void* scratch, size_t scratch_bytes,
+                                   cudaStream_t st) {
+  IMW_REQUIRE(slots % 2 == 0 && cap % 128 == 0, "imw_debug_attention: slots even, cap %% 128");
+  Workspace ws(scratch, scratch_bytes);
+  const long long n = (long long)slots * HEADS * cap * HD;
+  int* skip = ws.take<int>(slots / 2);
+  float* qp = ws.take<float>(2 * n); float* kp = ws.take<float>(2 * n); float* vtp = ws.take<float>(2 * n);
+  if (ws.overflow) { imw_set_error("imw_debug_attention: scratch too small (%zu needed)", ws.off); return IMW_ERR_WORKSPACE; }
+  IMW_CHECK_CUDA(cudaMemsetAsync(skip, 0, sizeof(int) * (slots / 2), st));
+  if (!use_tc) {
+    const size_t at_smem = (size_t)4 * 64 * ATP * sizeof(float);
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem));
+    attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, slots), 256, at_smem, st>>>(q, k, v, ctx, counts, skip, cap, scale, cross);
+    IMW_CHECK_LAUNCH();
+    return IMW_OK;
+  }
+  attn_prep_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, k, v, qp, kp, vtp, n, cap);
+  IMW_CHECK_LAUNCH();
+  TcAttnArgs a{ctx, counts, skip, cap, slots, scale, cross, (long long)slots * HEADS * cap, (long long)slots * HEADS * HD};
+  return launch_tc_attn(qp, kp, vtp, a, st);
 }

@@ -1,0 +1,256 @@
+// tcgen05 flash attention for LightGlue (head dim 64, fp32-equivalent via 3xTF32 split operands).
+//
+//   ctx[z][row][h*64 + d] = softmax_j(scale * <q_row, k_j>) v_j      self: k,v of slot z; cross: of slot z^1
+//
+// Operands arrive pre-split from the projection epilogues as hi/lo planes (hi = 13 low mantissa bits cleared,
+// lo = x - hi): q, k  [plane][slot][head][cap][64],  v transposed  [plane][slot][head][64][cap]  (kv contiguous,
+// so that V^T is a plain K-major B operand).  Per CTA: one (slot, head, 128-row q tile).
+//   warp 0     TMA producer: Q once, then K_j / V_j tiles of 64 keys (single-buffered; K_{j+1} is fetched while
+//              softmax_j and P_j V_j run, V_{j+1} while S_{j+1} and softmax_{j+1} run)
+//   warp 1     MMA issuer: S_j = Q K_j^T into one of two TMEM buffers (main hi*hi and cross-term accumulators),
+//              O_j = P_j V_j into a fresh TMEM tile (never rescaled in place)
+//   warps 2-5  one q row per thread: tcgen05.ld S_j, mask, running max / sum, P_j = exp(S_j - m) written to shared
+//              memory as hi/lo K-major SWIZZLE_128B tiles for the second MMA, and the running output
+//              acc = (acc + O_{j-1}) * exp(m_{j-1} - m_j) kept in registers.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+struct TcAttnArgs {
+  float* ctx;            // [slots][cap][256]
+  const int* counts;     // [slots]
+  const int* skip;       // [pairs]
+  int cap, slots;
+  float scale;
+  int cross;
+  long long plane_rows_qk;  // slots*4*cap : row offset of the lo plane in the q/k tensor maps
+  long long plane_rows_vt;  // slots*4*64
+};
+
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 192;
+constexpr int TA_Q_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 k-subtiles x [128 x 32 f32]  = 64 KB
+constexpr int TA_K_BYTES = 2 * 2 * TA_BKV * 128;    // hi/lo x 2 subtiles x [64 x 32]        = 32 KB
+constexpr int TA_V_BYTES = 2 * 2 * 64 * 128;        // hi/lo x 2 kv-subtiles x [64 d x 32 kv] = 32 KB
+constexpr int TA_P_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 kv-subtiles x [128 x 32]     = 64 KB
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256;
+
+// TMEM columns: S buffers 2 x (main 64 + cross 64) = 256, O main 64 + cross 64 -> 384 (allocate 512)
+constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
+
+__global__ void __launch_bounds__(TA_THREADS, 1)
+tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, TcAttnArgs g) {
+  const int z = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * TA_BQ;
+  if (g.skip[z >> 1]) return;
+  const int nq = g.counts[z], zk = g.cross ? (z ^ 1) : z, nk = g.counts[zk];
+  if (q0 >= nq) return;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (nk == 0) {  // empty key set -> zeros (lightglue.py:113-114)
+    for (int i = threadIdx.x; i < TA_BQ * 16; i += TA_THREADS) {
+      int r = q0 + i / 16, c = (i % 16) * 4;
+      if (r < nq) *reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + r) * 256 + head * 64 + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  extern __shared__ uint8_t ta_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)ta_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                 // [plane][sub][128 rows][128 B]
+  uint8_t* sK = sQ + TA_Q_BYTES;      // [plane][sub][64 rows][128 B]
+  uint8_t* sV = sK + TA_K_BYTES;      // [plane][sub][64 d rows][128 B]
+  uint8_t* sP = sV + TA_V_BYTES;      // [plane][sub][128 rows][128 B]
+  uint64_t* bars = (uint64_t*)(sP + TA_P_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+           *s_full = bars + 5 /*[2]*/, *p_full = bars + 7, *o_full = bars + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
+    tc::mbar_init(q_full, 1); tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
+    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, 128);
+    tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TA_TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = (nk + TA_BKV - 1) / TA_BKV;
+  const int q_row = (z * 4 + head) * g.cap + q0;          // row in the [slots*4*cap][64] q/k tensors
+  const int k_row0 = (zk * 4 + head) * g.cap;
+  const int v_row = (zk * 4 + head) * 64;                 // row in the [slots*4*64][cap] v^T tensor
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(q_full, TA_Q_BYTES);
+      for (int p = 0; p < 2; p++)
+        for (int sub = 0; sub < 2; sub++)
+          tc::tma_load_2d(sQ + (p * 2 + sub) * TA_BQ * 128, &tmQ, q_full, sub * 32, (int)(p * g.plane_rows_qk) + q_row);
+      for (int j = 0; j < T; j++) {
+        if (j > 0) tc::mbar_wait(k_empty, (j - 1) & 1);
+        tc::mbar_expect_tx(k_full, TA_K_BYTES);
+        for (int p = 0; p < 2; p++)
+          for (int sub = 0; sub < 2; sub++)
+            tc::tma_load_2d(sK + (p * 2 + sub) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + j * TA_BKV);
+        if (j > 0) tc::mbar_wait(v_empty, (j - 1) & 1);
+        tc::mbar_expect_tx(v_full, TA_V_BYTES);
+        for (int p = 0; p < 2; p++)
+          for (int sub = 0; sub < 2; sub++)
+            tc::tma_load_2d(sV + (p * 2 + sub) * 64 * 128, &tmV, v_full, j * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
+      const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+      auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi
+        tc::mbar_wait(k_full, j & 1);
+        tc::fence_after_sync();
+        const uint32_t d_main = tmem_base + TA_S_COL + (j & 1) * 128, d_cross = d_main + 64;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          const int sub = ks / 4, ko = (ks % 4) * 32;
+          uint64_t qh = tc::make_smem_desc_sw128(aQ + (0 * 2 + sub) * TA_BQ * 128 + ko), ql = tc::make_smem_desc_sw128(aQ + (1 * 2 + sub) * TA_BQ * 128 + ko);
+          uint64_t kh = tc::make_smem_desc_sw128(aK + (0 * 2 + sub) * TA_BKV * 128 + ko), kl = tc::make_smem_desc_sw128(aK + (1 * 2 + sub) * TA_BKV * 128 + ko);
+          tc::mma_tf32(d_main, qh, kh, idesc, ks ? 1u : 0u);
+          tc::mma_tf32(d_cross, qh, kl, idesc, ks ? 1u : 0u);
+          tc::mma_tf32(d_cross, ql, kh, idesc, 1u);
+        }
+        tc::mma_commit(k_empty);
+        tc::mma_commit(s_full + (j & 1));
+      };
+      tc::mbar_wait(q_full, 0);
+      issue_S(0);
+      for (int j = 0; j < T; j++) {
+        if (j + 1 < T) issue_S(j + 1);
+        tc::mbar_wait(v_full, j & 1);
+        tc::mbar_wait(p_full, j & 1);
+        tc::fence_after_sync();
+        const uint32_t d_main = tmem_base + TA_O_COL, d_cross = d_main + 64;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {  // O_j = P_j V_j, K = 64 keys
+          const int sub = ks / 4, ko = (ks % 4) * 32;
+          uint64_t ph = tc::make_smem_desc_sw128(aP + (0 * 2 + sub) * TA_BQ * 128 + ko), pl = tc::make_smem_desc_sw128(aP + (1 * 2 + sub) * TA_BQ * 128 + ko);
+          uint64_t vh = tc::make_smem_desc_sw128(aV + (0 * 2 + sub) * 64 * 128 + ko), vl = tc::make_smem_desc_sw128(aV + (1 * 2 + sub) * 64 * 128 + ko);
+          tc::mma_tf32(d_main, ph, vh, idesc, ks ? 1u : 0u);
+          tc::mma_tf32(d_cross, ph, vl, idesc, ks ? 1u : 0u);
+          tc::mma_tf32(d_cross, pl, vh, idesc, 1u);
+        }
+        tc::mma_commit(v_empty);
+        tc::mma_commit(o_full);
+      }
+    }
+  } else {
+    const int q = warp % 4, r = q * 32 + lane;           // TMEM lane = q row inside the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY, l = 0.f, acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; c++) acc[c] = 0.f;
+    for (int j = 0; j < T; j++) {
+      tc::mbar_wait(s_full + (j & 1), (j >> 1) & 1);
+      tc::fence_after_sync();
+      float s[64];
+      {
+        float t[32];
+        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128;
+        tc::tmem_ld32(a, *reinterpret_cast<float(*)[32]>(&s[0]));
+        tc::tmem_ld32(a + 32, *reinterpret_cast<float(*)[32]>(&s[32]));
+        tc::tmem_ld32(a + 64, t);
+#pragma unroll
+        for (int c = 0; c < 32; c++) s[c] += t[c];
+        tc::tmem_ld32(a + 96, t);
+#pragma unroll
+        for (int c = 0; c < 32; c++) s[32 + c] += t[c];
+      }
+      const int kv0 = j * TA_BKV;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c++) {
+        s[c] = (kv0 + c < nk) ? s[c] * g.scale : -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      const float m_new = fmaxf(m, mx);          // finite: at least one key of this tile is valid
+      const float alpha = __expf(m - m_new);     // 0 on the first tile (m = -inf)
+      float ps = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
+      l = l * alpha + ps;
+      m = m_new;
+      if (j > 0) {  // fold in O_{j-1} (computed relative to m_{j-1}), then move the reference to m_j
+        tc::mbar_wait(o_full, (j - 1) & 1);
+        tc::fence_after_sync();
+        float t[32];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+          tc::tmem_ld32(lane_addr + TA_O_COL + h * 32, t);  // h 0,1: main cols 0..63; h 2,3: cross
+#pragma unroll
+          for (int c = 0; c < 32; c++) acc[(h & 1) * 32 + c] += t[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 64; c++) acc[c] *= alpha;
+      // P_j -> shared memory, hi/lo planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk c of
+      // row r lives at chunk c ^ (r & 7)); the previous P V MMA has completed (o_full above)
+      tc::fence_before_sync();
+#pragma unroll
+      for (int sub = 0; sub < 2; sub++) {
+        uint8_t* ph = sP + (0 * 2 + sub) * TA_BQ * 128 + r * 128;
+        uint8_t* pl = sP + (1 * 2 + sub) * TA_BQ * 128 + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+          uint4 h4, l4;
+          const float* v = &s[sub * 32 + ch * 4];
+          h4.x = __float_as_uint(v[0]) & 0xFFFFE000u; h4.y = __float_as_uint(v[1]) & 0xFFFFE000u;
+          h4.z = __float_as_uint(v[2]) & 0xFFFFE000u; h4.w = __float_as_uint(v[3]) & 0xFFFFE000u;
+          l4.x = __float_as_uint(v[0] - __uint_as_float(h4.x)); l4.y = __float_as_uint(v[1] - __uint_as_float(h4.y));
+          l4.z = __float_as_uint(v[2] - __uint_as_float(h4.z)); l4.w = __float_as_uint(v[3] - __uint_as_float(h4.w));
+          const int pos = (ch ^ (r & 7)) * 16;
+          *reinterpret_cast<uint4*>(ph + pos) = h4;
+          *reinterpret_cast<uint4*>(pl + pos) = l4;
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(p_full);
+    }
+    // last tile's O, normalise, store
+    tc::mbar_wait(o_full, (T - 1) & 1);
+    tc::fence_after_sync();
+    {
+      float t[32];
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        tc::tmem_ld32(lane_addr + TA_O_COL + h * 32, t);
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc[(h & 1) * 32 + c] += t[c];
+      }
+    }
+    const int row = q0 + r;
+    if (row < nq) {
+      const float inv = 1.f / l;
+      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64);
+#pragma unroll
+      for (int c = 0; c < 16; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TA_TMEM_COLS);
+}
+
+// q_planes / k_planes: [2][slots*4*cap][64] fp32, vt_planes: [2][slots*4*64][cap] fp32
+static inline int launch_tc_attn(const float* q_planes, const float* k_planes, const float* vt_planes, TcAttnArgs g, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV;
+  const long long rows_qk = 2 * g.plane_rows_qk, rows_vt = 2 * g.plane_rows_vt;
+  if (int e = tc_make_map_2d_f32(&tmQ, q_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BQ)) return e;
+  if (int e = tc_make_map_2d_f32(&tmK, k_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BKV)) return e;
+  if (int e = tc_make_map_2d_f32(&tmV, vt_planes, (uint64_t)rows_vt, (uint64_t)g.cap, (uint64_t)g.cap, 32, 64)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(g.cap / TA_BQ, 4, g.slots);
+  tc_attn_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(tmQ, tmK, tmV, g);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}

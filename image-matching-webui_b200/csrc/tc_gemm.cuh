@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += t[j];
       }
+      // functors may consume a 32-column chunk in the native thread-per-row layout (V^T for the attention kernel)
+      if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];

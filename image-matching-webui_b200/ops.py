@@ -224,3 +224,16 @@ def debug_conv3x3(x, w, bias, relu=True, pool=False, tensor_cores=True):
             L.check(L.lib().imw_debug_conv3x3(L.ptr(x.contiguous()), L.ptr(w.contiguous()), L.ptr(bias), L.ptr(out), B, H, W_, Cin, Cout,
                                               int(relu), int(pool), L.stream_ptr(x.device)))
     return out
+
+
+def debug_attention(q, k, v, counts, scale, cross=False, tensor_cores=True):
+    """q,k,v [slots,4,cap,64] fp32 -> ctx [slots,cap,256]; counts [slots] int32 (unit-test hook)."""
+    L.require_cuda(q, "debug_attention(q)")
+    S, Hh, cap, hd = q.shape
+    ctx = torch.zeros(S, cap, 256, device=q.device)
+    scratch = torch.empty(int(q.numel() * 4 * 6 + 8192), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        L.check(L.lib().imw_debug_attention(L.ptr(q.contiguous()), L.ptr(k.contiguous()), L.ptr(v.contiguous()), L.ptr(counts), S, cap,
+                                            float(scale), int(cross), int(tensor_cores), L.ptr(ctx), L.ptr(scratch), scratch.numel(),
+                                            L.stream_ptr(q.device)))
+    return ctx

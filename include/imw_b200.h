@@ -138,6 +138,9 @@ int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float
 
 /* One 3x3 conv layer of the SuperPoint stack (NHWC fp32 in/out, weights [9][Cin][Cout], optional ReLU and fused
  * 2x2 max-pool): bench.py times the dominant kernel alone through this hook. */
+/* Attention on q/k/v [slots][4 heads][cap][64] -> ctx [slots][cap][256]; use_tc: tcgen05 3xTF32 kernel vs fp32 CUDA cores */
+int imw_debug_attention(const float* q, const float* k, const float* v, const int* counts, int slots, int cap, float scale,
+                        int cross, int use_tc, float* ctx, void* scratch, size_t scratch_bytes, imw_stream_t stream);
 int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout, const float* bias, float* out, int batch, int height,
                          int width, int cin, int cout, int relu, int pool, void* scratch, size_t scratch_bytes,
                          imw_stream_t stream);

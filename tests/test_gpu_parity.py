@@ -201,6 +201,28 @@ def test_tcgen05_conv_unit(dev):
     assert float((out.permute(0, 3, 1, 2) - ref.float()).abs().max()) < 1e-5
 
 
+def test_tcgen05_attention_unit(dev):
+    """tcgen05 3xTF32 flash attention == fp32 CUDA-core attention == torch SDPA (fp64), ragged key/query counts,
+    self and cross pairing."""
+    from imcui_b200 import ops
+    torch.manual_seed(2)
+    S, cap = 4, 256
+    q, k, v = (torch.randn(S, 4, cap, 64, device=dev) for _ in range(3))
+    counts = torch.tensor([256, 200, 131, 64], dtype=torch.int32, device=dev)
+    for cross in (False, True):
+        simt = ops.debug_attention(q, k, v, counts, 0.125, cross, tensor_cores=False)
+        tcg = ops.debug_attention(q, k, v, counts, 0.125, cross, tensor_cores=True)
+        torch.cuda.synchronize()
+        for z in range(S):
+            zk = z ^ 1 if cross else z
+            nq, nk = int(counts[z]), int(counts[zk])
+            ref = torch.nn.functional.scaled_dot_product_attention(q[z, :, :nq].double(), k[zk, :, :nk].double(), v[zk, :, :nk].double())
+            ref = ref.transpose(0, 1).reshape(nq, 256).float()
+            e_simt = float((simt[z, :nq] - ref).abs().max()); e_tc = float((tcg[z, :nq] - ref).abs().max())
+            print(f"[attn] cross={cross} slot {z} ({nq}x{nk}): fp32 {e_simt:.2e} tcgen05 {e_tc:.2e}")
+            assert e_simt < 1e-5 and e_tc < 2e-5, (cross, z, e_simt, e_tc)
+
+
 def test_lightglue_empty_and_tiny(dev):
     from imcui_b200.hloc import matchers
     model = _load(matchers, "lightglue", {}, dev)

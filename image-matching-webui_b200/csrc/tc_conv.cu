@@ -195,6 +195,166 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tc::tmem_dealloc(tmem_base, 4 * BN);
 }
 
+// ---- Cin = Cout = 64 specialisation (conv1b / conv2a / conv2b: 60 % of SuperPoint's FLOPs) ------------------
+// The generic kernel re-fetches the activation tile for each of the nine taps and is L2->SM bandwidth bound at
+// N = 64 (648 KB per CTA).  Here the pixel tile is 16 rows x 8 cols and, per plane, three copies of the halo
+// patch are loaded ONCE, pre-shifted by dx = -1,0,+1 (box 64ch x 8 cols x 18 rows = 18 KB each).  Tap (dy,dx)
+// is then the plain K-major SWIZZLE_128B operand starting dy*8 rows = dy*1024 B into copy dx: whole 1024-byte
+// swizzle atoms, no descriptor tricks.  Activation traffic drops 432 KB -> 162 KB per CTA; weights stream
+// through a 2-stage ring (24 KB per tap).
+constexpr int C64_TH = 16, C64_TW = 8;
+constexpr int C64_COPY = 18 * 8 * 128;            // one (plane, dx) halo copy: 18 rows x 8 px x 128 B
+constexpr int C64_A_BYTES = 9 * C64_COPY;         // 3 planes x 3 dx
+constexpr int C64_B_STAGE = 3 * 64 * 128;         // 3 weight planes of one tap
+constexpr int C64_B_STAGES = 2;
+constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256;
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g) {
+  constexpr int BN = 64;
+  extern __shared__ uint8_t cv_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // [dx][plane][18*8 rows][128 B]
+  uint8_t* sB = smem + C64_A_BYTES;         // [stage][plane][64 rows][128 B]
+  uint64_t* a_full = (uint64_t*)(sB + C64_B_STAGES * C64_B_STAGE);  // [3] one per dx
+  uint64_t* b_full = a_full + 3;            // [stages]
+  uint64_t* b_empty = b_full + C64_B_STAGES;
+  uint64_t* tmem_full = b_empty + C64_B_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int tiles_x = g.W / C64_TW, tiles_y = (g.H + C64_TH - 1) / C64_TH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y; t /= tiles_y;
+  const int b = t;
+  const int x0 = tx * C64_TW, y0 = ty * C64_TH;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+    for (int i = 0; i < 3; i++) tc::mbar_init(a_full + i, 1);
+    for (int s = 0; s < C64_B_STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 4 * BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // taps are visited dx-major so that the MMAs of column dx can start as soon as its three copies landed
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < 9; it++) {
+        const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
+        if (dyi == 0) {
+          tc::mbar_expect_tx(a_full + dxi, 3 * C64_COPY);
+#pragma unroll
+          for (int p = 0; p < 3; p++)
+            tc::tma_load_4d(sA + (dxi * 3 + p) * C64_COPY, &tmA, a_full + dxi, 0, x0 + dxi - 1, y0 - 1, p * g.B + b);
+        }
+        const int s = it % C64_B_STAGES, ph = (it / C64_B_STAGES) & 1;
+        tc::mbar_wait(b_empty + s, ph ^ 1);
+        tc::mbar_expect_tx(b_full + s, C64_B_STAGE);
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+          tc::tma_load_2d(sB + s * C64_B_STAGE + p * 64 * 128, &tmW, b_full + s, 0, (p * 9 + tap) * g.Cout);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
+      for (int it = 0; it < 9; it++) {
+        const int dxi = it / 3, dyi = it % 3;
+        const int s = it % C64_B_STAGES, ph = (it / C64_B_STAGES) & 1;
+        if (dyi == 0) tc::mbar_wait(a_full + dxi, 0);
+        tc::mbar_wait(b_full + s, ph);
+        tc::fence_after_sync();
+        const uint32_t a0 = tc::smem_u32(sA + dxi * 3 * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
+        const uint32_t d_main = tmem_base + dyi * BN, d_cross = tmem_base + 3 * BN;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint64_t ad[3], bd[3];
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
+            bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
+          }
+          tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
+          tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
+          tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
+          tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
+          tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
+          tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+        }
+        tc::mma_commit(b_empty + s);
+      }
+      tc::mma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp % 4;
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+    const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
+    const int py = y0 + m / C64_TW, px = x0 + m % C64_TW;
+    const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
+    const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
+    const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
+    const bool in_img = (py < g.H) && (px < g.W);
+    const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
+    const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32], tt[32];
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+      tc::tmem_ld32(lane_base, v);
+      tc::tmem_ld32(lane_base + BN, tt);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += tt[j];
+      tc::tmem_ld32(lane_base + 2 * BN, tt);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += tt[j];
+      tc::tmem_ld32(lane_base + 3 * BN, tt);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += tt[j];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float x = v[j] + g.bias[c0 + j];
+        if (g.relu) x = fmaxf(x, 0.f);
+        if (g.pool) {  // 2x2 window = lanes {l, l^1, l^8}: 4 image rows x 8 cols per warp
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+        }
+        v[j] = x;
+      }
+      if (writer && in_img) {
+        if (g.out_fp32) {
+          float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
+          uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
+          uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
+          uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            o0[j] = reinterpret_cast<const uint4*>(p0)[j];
+            o1[j] = reinterpret_cast<const uint4*>(p1)[j];
+            o2[j] = reinterpret_cast<const uint4*>(p2)[j];
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 4 * BN);
+}
+
 // fp32 NHWC -> three bf16 planes (and back): interop with the CUDA-core path and the unit tests
 __global__ void split_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,12 +369,12 @@ __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ in, float*
   out[i] = (__bfloat162float(in[i]) + __bfloat162float(in[n + i])) + __bfloat162float(in[2 * n + i]);
 }
 
-int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C) {
+int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C, int box_w = CV_TW, int box_h = CV_TH) {
   PFN_encodeTiled fn = tc_get_encode_fn();
   if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B3};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {CV_CK, CV_TW, CV_TH, 1};
+  cuuint32_t box[4] = {CV_CK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -260,6 +420,20 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
   IMW_REQUIRE(!pool || (H % 2 == 0), "tc_conv3x3: pooled conv needs even H");
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
+  if (Cin == 64 && Cout == 64 && W % C64_TW == 0) {  // halo-copy specialisation
+    if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, C64_TW, C64_TH + 2)) return e;
+    if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, 64)) return e;
+    ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+    static bool attr_set = false;
+    if (!attr_set) {
+      IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)(B * ceil_div(H, C64_TH) * (W / C64_TW)), 1);
+    tc_conv3x3_c64_kernel<<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g);
+    IMW_CHECK_LAUNCH();
+    return IMW_OK;
+  }
   if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin)) return e;
   if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, BN)) return e;
   ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};

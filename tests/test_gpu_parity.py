@@ -183,7 +183,8 @@ def test_tcgen05_conv_unit(dev):
     fused ReLU / 2x2 max-pool, partial tiles (H % 8 != 0) and both Cout tile widths."""
     from imcui_b200 import ops
     torch.manual_seed(1)
-    for (B, H, W, Cin, Cout, pool) in ((1, 16, 32, 64, 64, False), (2, 48, 64, 64, 64, True), (1, 24, 32, 64, 128, False),
+    for (B, H, W, Cin, Cout, pool) in ((1, 16, 32, 64, 64, False), (2, 48, 64, 64, 64, True), (1, 24, 48, 64, 64, True),
+                                       (1, 40, 16, 64, 64, False), (1, 24, 32, 64, 128, False),
                                        (2, 32, 48, 128, 128, True), (1, 60, 80, 128, 256, False)):
         x = torch.rand(B, H, W, Cin, device=dev)
         w = torch.randn(9, Cin, Cout, device=dev) / (9 * Cin) ** 0.5

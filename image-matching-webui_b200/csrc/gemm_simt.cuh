@@ -116,7 +116,8 @@ struct EpiBias {
       }
   }
   // tcgen05 epilogue form: one element per lane, lanes along consecutive columns of one row
-  __device__ void elem(int z, int row, int col, float v) const {
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void elem(int z, int row, int col, float v, float2) const {
     float x = v + (bias ? bias[col] : 0.f);
     if (relu) x = fmaxf(x, 0.f);
     out[(long long)z * strideOut + (long long)row * ldo + col] = x;

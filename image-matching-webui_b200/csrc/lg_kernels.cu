@@ -76,13 +76,17 @@ struct EpiQKVRotary {
     *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
   }
   // tcgen05 epilogue form (lanes along columns; the rotary partner of dim d is the neighbouring lane d^1)
-  __device__ void elem(int z, int row, int col, float a) const {
+  __device__ float2 prefetch(int z, int row, int col) const {  // (cos, sin) of this lane's rotary frequency
+    if (col >= 2 * D) return make_float2(0.f, 0.f);
+    const float* e = enc + ((long long)z * cap + row) * 64 + (col % HD) / 2;
+    return make_float2(e[0], e[32]);
+  }
+  __device__ void elem(int z, int row, int col, float a, float2 cs_sn) const {
     float r = a + bias[col];
     int which = col / D, c = col % D, head = c / HD, d = c % HD;
     float partner = __shfl_xor_sync(0xffffffffu, r, 1);
     if (which < 2) {
-      const float* e = enc + ((long long)z * cap + row) * 64;
-      float cs = e[d / 2], sn = e[32 + d / 2];
+      const float cs = cs_sn.x, sn = cs_sn.y;
       r = (d & 1) ? __fadd_rn(__fmul_rn(r, cs), __fmul_rn(partner, sn)) : __fadd_rn(__fmul_rn(r, cs), __fmul_rn(-partner, sn));
     }
     float* dst = (which == 0 ? q : which == 1 ? k : v);
@@ -120,7 +124,8 @@ struct EpiCrossQKV {
     if (which == 0) { r[0] *= qk_scale; r[1] *= qk_scale; r[2] *= qk_scale; r[3] *= qk_scale; }
     *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
   }
-  __device__ void elem(int z, int row, int col, float a) const {
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void elem(int z, int row, int col, float a, float2) const {
     float r = a + bias[col];
     int which = col / D, c = col % D, head = c / HD, d = c % HD;
     if (which == 0) r *= qk_scale;
@@ -154,11 +159,11 @@ struct EpiStore {
     if (residual) { float4 x = *o; r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; }
     *o = r;
   }
-  __device__ void elem(int z, int row, int col, float a) const {
-    float* o = out + z * strideOut + (long long)row * ldo + col;
-    float r = a + bias[col];
-    if (residual) r += *o;
-    *o = r;
+  __device__ float2 prefetch(int z, int row, int col) const {
+    return make_float2(residual ? out[z * strideOut + (long long)row * ldo + col] : 0.f, 0.f);
+  }
+  __device__ void elem(int z, int row, int col, float a, float2 res) const {
+    out[z * strideOut + (long long)row * ldo + col] = (a + bias[col]) + res.x;
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
@@ -171,7 +176,8 @@ struct EpiFinalProj {
     float4 r = make_float4((a.x + b[col]) * 0.25f, (a.y + b[col + 1]) * 0.25f, (a.z + b[col + 2]) * 0.25f, (a.w + b[col + 3]) * 0.25f);
     *reinterpret_cast<float4*>(out + ((long long)z * cap + row) * D + col) = r;
   }
-  __device__ void elem(int z, int row, int col, float a) const {
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void elem(int z, int row, int col, float a, float2) const {
     out[((long long)z * cap + row) * D + col] = (a + bias_all[(stop[z >> 1] - 1) * D + col]) * 0.25f;
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }

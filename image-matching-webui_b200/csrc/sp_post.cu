@@ -41,8 +41,11 @@ __global__ void __launch_bounds__(256) softmax_d2s_kernel(const float* __restric
 // CTA = 32x32 output pixels + halo of 5r (three max-pools and two dilations of radius r chained).
 constexpr int NMS_T = 32;
 
+// RAD > 0: compile-time radius (fully unrolled 2r+1-tap windows); RAD = 0: run-time radius `r_dyn`
+template <int RAD>
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dense, float* __restrict__ out, int H, int W,
-                                                  int r) {
+                                                  int r_dyn) {
+  const int r = RAD > 0 ? RAD : r_dyn;
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int halo = 5 * r, R = NMS_T + 2 * halo, RR = R * R;
   float* S = reinterpret_cast<float*>(nms_smem);  // scores (-inf outside the image)
@@ -66,14 +69,20 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dens
   __syncthreads();
   // max_mask = scores == max_pool(scores)   (separable: rows then columns)
   NMS_FOR_EACH(yy, xx) {
+    // windows that would leave the staged region are skipped: those cells lie in the halo margin that the
+    // 5r budget already writes off, and fixed-size windows unroll completely for a compile-time radius
+    if (xx < r || xx >= R - r) continue;
     float m = -CUDART_INF_F;
-    for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, S[yy * R + d]);
+#pragma unroll
+    for (int d = -r; d <= r; d++) m = fmaxf(m, S[yy * R + xx + d]);
     A[yy * R + xx] = m;
   }
   __syncthreads();
   NMS_FOR_EACH(yy, xx) {
+    if (yy < r || yy >= R - r) { mask[yy * R + xx] = 0; continue; }
     float m = -CUDART_INF_F;
-    for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
+#pragma unroll
+    for (int d = -r; d <= r; d++) m = fmaxf(m, A[(yy + d) * R + xx]);
     float s = S[yy * R + xx];
     mask[yy * R + xx] = (s == m) && (s != -CUDART_INF_F);
   }
@@ -81,14 +90,19 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dens
   for (int it = 0; it < 2; it++) {
     // supp = max_pool(max_mask) > 0
     NMS_FOR_EACH(yy, xx) {
+      if (xx < r || xx >= R - r) { tmpb[yy * R + xx] = 0; continue; }
       unsigned char m = 0;
-      for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m |= mask[yy * R + d];
+#pragma unroll
+      for (int d = -r; d <= r; d++) m |= mask[yy * R + xx + d];
       tmpb[yy * R + xx] = m;
     }
     __syncthreads();
     NMS_FOR_EACH(yy, xx) {
       unsigned char m = 0;
-      for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m |= tmpb[d * R + xx];
+      if (yy >= r && yy < R - r) {
+#pragma unroll
+        for (int d = -r; d <= r; d++) m |= tmpb[(yy + d) * R + xx];
+      }
       supp[yy * R + xx] = m;
       // supp_scores = where(supp, 0, scores); stays -inf outside the image (max_pool2d padding)
       float s = S[yy * R + xx];
@@ -96,14 +110,18 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ dens
     }
     __syncthreads();
     NMS_FOR_EACH(yy, xx) {
+      if (xx < r || xx >= R - r) continue;
       float m = -CUDART_INF_F;
-      for (int d = max(xx - r, 0); d <= min(xx + r, R - 1); d++) m = fmaxf(m, SS[yy * R + d]);
+#pragma unroll
+      for (int d = -r; d <= r; d++) m = fmaxf(m, SS[yy * R + xx + d]);
       A[yy * R + xx] = m;
     }
     __syncthreads();
     NMS_FOR_EACH(yy, xx) {
+      if (yy < r || yy >= R - r) continue;
       float m = -CUDART_INF_F;
-      for (int d = max(yy - r, 0); d <= min(yy + r, R - 1); d++) m = fmaxf(m, A[d * R + xx]);
+#pragma unroll
+      for (int d = -r; d <= r; d++) m = fmaxf(m, A[(yy + d) * R + xx]);
       float s = SS[yy * R + xx];
       bool new_max = (s == m) && (s != -CUDART_INF_F);
       if (new_max && !supp[yy * R + xx]) mask[yy * R + xx] = 1;
@@ -309,9 +327,16 @@ int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cuda
   IMW_REQUIRE(radius >= 0 && radius <= 8, "sp_nms: nms_radius must be in [0,8] (got %d)", radius);
   int R = NMS_T + 10 * radius;
   size_t smem = (size_t)R * R * (3 * sizeof(float) + 3);
-  IMW_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(W, NMS_T) * ceil_div(H, NMS_T), 1, B);
-  nms_kernel<<<grid, 256, smem, st>>>(dense, nms, H, W, radius);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, st>>>(dense, nms, H, W, radius);
+    return cudaSuccess;
+  };
+  if (radius == 3) IMW_CHECK_CUDA(launch(nms_kernel<3>));
+  else if (radius == 4) IMW_CHECK_CUDA(launch(nms_kernel<4>));
+  else IMW_CHECK_CUDA(launch(nms_kernel<0>));
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

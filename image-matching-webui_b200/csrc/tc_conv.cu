@@ -209,35 +209,35 @@ constexpr int C64_B_STAGE = 3 * 64 * 128;         // 3 weight planes of one tap
 constexpr int C64_B_STAGES = 2;
 constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256;
 
+// Persistent: one CTA per SM walks the tile list.  The three dx-copy slots, the weight ring and two TMEM
+// accumulator sets (2 x 4 x 64 = 512 columns) are all recycled through mbarriers, so the next tile's loads and
+// MMAs run while the epilogue warps drain the previous tile.
 __global__ void __launch_bounds__(CV_THREADS, 1)
-tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g) {
+tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles) {
   constexpr int BN = 64;
   extern __shared__ uint8_t cv_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                       // [dx][plane][18*8 rows][128 B]
   uint8_t* sB = smem + C64_A_BYTES;         // [stage][plane][64 rows][128 B]
-  uint64_t* a_full = (uint64_t*)(sB + C64_B_STAGES * C64_B_STAGE);  // [3] one per dx
-  uint64_t* b_full = a_full + 3;            // [stages]
+  uint64_t* a_full = (uint64_t*)(sB + C64_B_STAGES * C64_B_STAGE);  // [3] one per dx slot
+  uint64_t* a_empty = a_full + 3;
+  uint64_t* b_full = a_empty + 3;           // [stages]
   uint64_t* b_empty = b_full + C64_B_STAGES;
-  uint64_t* tmem_full = b_empty + C64_B_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = b_empty + C64_B_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int tiles_x = g.W / C64_TW, tiles_y = (g.H + C64_TH - 1) / C64_TH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y; t /= tiles_y;
-  const int b = t;
-  const int x0 = tx * C64_TW, y0 = ty * C64_TH;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
-    for (int i = 0; i < 3; i++) tc::mbar_init(a_full + i, 1);
+    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
     for (int s = 0; s < C64_B_STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
-    tc::mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 4 * BN);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -246,105 +246,129 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   // taps are visited dx-major so that the MMAs of column dx can start as soon as its three copies landed
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < 9; it++) {
-        const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
-        if (dyi == 0) {
-          tc::mbar_expect_tx(a_full + dxi, 3 * C64_COPY);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const int x0 = tx * C64_TW, y0 = ty * C64_TH;
+        for (int it = 0; it < 9; it++) {
+          const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
+          if (dyi == 0) {
+            tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);
+            tc::mbar_expect_tx(a_full + dxi, 3 * C64_COPY);
+#pragma unroll
+            for (int p = 0; p < 3; p++)
+              tc::tma_load_4d(sA + (dxi * 3 + p) * C64_COPY, &tmA, a_full + dxi, 0, x0 + dxi - 1, y0 - 1, p * g.B + b);
+          }
+          const int c = i * 9 + it, s = c % C64_B_STAGES, ph = (c / C64_B_STAGES) & 1;
+          tc::mbar_wait(b_empty + s, ph ^ 1);
+          tc::mbar_expect_tx(b_full + s, C64_B_STAGE);
 #pragma unroll
           for (int p = 0; p < 3; p++)
-            tc::tma_load_4d(sA + (dxi * 3 + p) * C64_COPY, &tmA, a_full + dxi, 0, x0 + dxi - 1, y0 - 1, p * g.B + b);
+            tc::tma_load_2d(sB + s * C64_B_STAGE + p * 64 * 128, &tmW, b_full + s, 0, (p * 9 + tap) * g.Cout);
         }
-        const int s = it % C64_B_STAGES, ph = (it / C64_B_STAGES) & 1;
-        tc::mbar_wait(b_empty + s, ph ^ 1);
-        tc::mbar_expect_tx(b_full + s, C64_B_STAGE);
-#pragma unroll
-        for (int p = 0; p < 3; p++)
-          tc::tma_load_2d(sB + s * C64_B_STAGE + p * 64 * 128, &tmW, b_full + s, 0, (p * 9 + tap) * g.Cout);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
-      for (int it = 0; it < 9; it++) {
-        const int dxi = it / 3, dyi = it % 3;
-        const int s = it % C64_B_STAGES, ph = (it / C64_B_STAGES) & 1;
-        if (dyi == 0) tc::mbar_wait(a_full + dxi, 0);
-        tc::mbar_wait(b_full + s, ph);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
+        const int acc = i & 1;
+        tc::mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator set
         tc::fence_after_sync();
-        const uint32_t a0 = tc::smem_u32(sA + dxi * 3 * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
-        const uint32_t d_main = tmem_base + dyi * BN, d_cross = tmem_base + 3 * BN;
+        const uint32_t d_base = tmem_base + acc * 256;
+        for (int it = 0; it < 9; it++) {
+          const int dxi = it / 3, dyi = it % 3;
+          const int c = i * 9 + it, s = c % C64_B_STAGES, ph = (c / C64_B_STAGES) & 1;
+          if (dyi == 0) tc::mbar_wait(a_full + dxi, i & 1);
+          tc::mbar_wait(b_full + s, ph);
+          tc::fence_after_sync();
+          const uint32_t a0 = tc::smem_u32(sA + dxi * 3 * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
+          const uint32_t d_main = d_base + dyi * BN, d_cross = d_base + 3 * BN;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          uint64_t ad[3], bd[3];
+          for (int k = 0; k < 4; k++) {
+            uint64_t ad[3], bd[3];
 #pragma unroll
-          for (int p = 0; p < 3; p++) {
-            ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
-            bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
+            for (int p = 0; p < 3; p++) {
+              ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
+              bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
+            }
+            tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
+            tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
+            tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
+            tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
+            tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
+            tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
           }
-          tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
-          tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
-          tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
-          tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
-          tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
-          tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+          tc::mma_commit(b_empty + s);
+          if (dyi == 2) tc::mma_commit(a_empty + dxi);  // the three taps of this dx slot are done
         }
-        tc::mma_commit(b_empty + s);
+        tc::mma_commit(tmem_full + acc);
       }
-      tc::mma_commit(tmem_full);
     }
   } else {
     const int q = warp % 4;
-    tc::mbar_wait(tmem_full, 0);
-    tc::fence_after_sync();
     const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
-    const int py = y0 + m / C64_TW, px = x0 + m % C64_TW;
     const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
     const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
-    const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
-    const bool in_img = (py < g.H) && (px < g.W);
     const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
-    const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int x0 = tx * C64_TW, y0 = ty * C64_TH;
+      const int acc = i & 1;
+      tc::mbar_wait(tmem_full + acc, (i >> 1) & 1);
+      tc::fence_after_sync();
+      const int py = y0 + m / C64_TW, px = x0 + m % C64_TW;
+      const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
+      const bool in_img = (py < g.H) && (px < g.W);
+      const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32], tt[32];
-      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-      tc::tmem_ld32(lane_base, v);
-      tc::tmem_ld32(lane_base + BN, tt);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32], tt[32];
+        const uint32_t lane_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + c0;
+        tc::tmem_ld32(lane_base, v);
+        tc::tmem_ld32(lane_base + BN, tt);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += tt[j];
-      tc::tmem_ld32(lane_base + 2 * BN, tt);
+        for (int j = 0; j < 32; j++) v[j] += tt[j];
+        tc::tmem_ld32(lane_base + 2 * BN, tt);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += tt[j];
-      tc::tmem_ld32(lane_base + 3 * BN, tt);
+        for (int j = 0; j < 32; j++) v[j] += tt[j];
+        tc::tmem_ld32(lane_base + 3 * BN, tt);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += tt[j];
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        float x = v[j] + g.bias[c0 + j];
-        if (g.relu) x = fmaxf(x, 0.f);
-        if (g.pool) {  // 2x2 window = lanes {l, l^1, l^8}: 4 image rows x 8 cols per warp
-          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+        for (int j = 0; j < 32; j++) v[j] += tt[j];
+        if (c0 + 32 >= BN) {  // last TMEM read of this accumulator set: hand it back to the MMA warp
+          tc::fence_before_sync();
+          tc::mbar_arrive(tmem_empty + acc);
         }
-        v[j] = x;
-      }
-      if (writer && in_img) {
-        if (g.out_fp32) {
-          float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
 #pragma unroll
-          for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
+        for (int j = 0; j < 32; j++) {
+          float x = v[j] + g.bias[c0 + j];
+          if (g.relu) x = fmaxf(x, 0.f);
+          if (g.pool) {  // 2x2 window = lanes {l, l^1, l^8}: 4 image rows x 8 cols per warp
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+          }
+          v[j] = x;
+        }
+        if (writer && in_img) {
+          if (g.out_fp32) {
+            float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
 #pragma unroll
-          for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
-          uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
-          uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
-          uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
+            for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            o0[j] = reinterpret_cast<const uint4*>(p0)[j];
-            o1[j] = reinterpret_cast<const uint4*>(p1)[j];
-            o2[j] = reinterpret_cast<const uint4*>(p2)[j];
+            for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
+            uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
+            uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
+            uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              o0[j] = reinterpret_cast<const uint4*>(p0)[j];
+              o1[j] = reinterpret_cast<const uint4*>(p1)[j];
+              o2[j] = reinterpret_cast<const uint4*>(p2)[j];
+            }
           }
         }
       }
@@ -352,7 +376,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 4 * BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // fp32 NHWC -> three bf16 planes (and back): interop with the CUDA-core path and the unit tests
@@ -429,8 +453,15 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
       IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
       attr_set = true;
     }
-    dim3 grid((unsigned)(B * ceil_div(H, C64_TH) * (W / C64_TW)), 1);
-    tc_conv3x3_c64_kernel<<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g);
+    const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      IMW_CHECK_CUDA(cudaGetDevice(&dev));
+      IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    dim3 grid((unsigned)(total < num_sms ? total : num_sms), 1);
+    tc_conv3x3_c64_kernel<<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   }

@@ -166,8 +166,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
       for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
       __syncwarp();
       const int rmax = min(32, nrows - row_base);  // warp-uniform
-#pragma unroll 4
-      for (int r = 0; r < rmax; r++) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane]);
+      // all global reads of the epilogue (residual / rotary table) are issued before the first dependent use:
+      // 32 independent loads in flight per lane instead of one round trip per row
+      float2 pre[32];
+#pragma unroll
+      for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 32; r++)
+        if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
     }
   }
   tc::fence_before_sync();

@@ -100,7 +100,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = tc::elect_one();
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
       const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
       auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi
@@ -112,12 +113,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int sub = ks / 4, ko = (ks % 4) * 32;
           uint64_t qh = tc::make_smem_desc_sw128(aQ + (0 * 2 + sub) * TA_BQ * 128 + ko), ql = tc::make_smem_desc_sw128(aQ + (1 * 2 + sub) * TA_BQ * 128 + ko);
           uint64_t kh = tc::make_smem_desc_sw128(aK + (0 * 2 + sub) * TA_BKV * 128 + ko), kl = tc::make_smem_desc_sw128(aK + (1 * 2 + sub) * TA_BKV * 128 + ko);
-          tc::mma_tf32(d_main, qh, kh, idesc, ks ? 1u : 0u);
-          tc::mma_tf32(d_cross, qh, kl, idesc, ks ? 1u : 0u);
-          tc::mma_tf32(d_cross, ql, kh, idesc, 1u);
+          if (leader) {
+            tc::mma_tf32(d_main, qh, kh, idesc, ks ? 1u : 0u);
+            tc::mma_tf32(d_cross, qh, kl, idesc, ks ? 1u : 0u);
+            tc::mma_tf32(d_cross, ql, kh, idesc, 1u);
+          }
         }
-        tc::mma_commit(k_empty);
-        tc::mma_commit(s_full + (j & 1));
+        if (leader) {
+          tc::mma_commit(k_empty);
+          tc::mma_commit(s_full + (j & 1));
+        }
+        __syncwarp();
       };
       tc::mbar_wait(q_full, 0);
       issue_S(0);
@@ -132,12 +138,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int sub = ks / 4, ko = (ks % 4) * 32;
           uint64_t ph = tc::make_smem_desc_sw128(aP + (0 * 2 + sub) * TA_BQ * 128 + ko), pl = tc::make_smem_desc_sw128(aP + (1 * 2 + sub) * TA_BQ * 128 + ko);
           uint64_t vh = tc::make_smem_desc_sw128(aV + (0 * 2 + sub) * 64 * 128 + ko), vl = tc::make_smem_desc_sw128(aV + (1 * 2 + sub) * 64 * 128 + ko);
-          tc::mma_tf32(d_main, ph, vh, idesc, ks ? 1u : 0u);
-          tc::mma_tf32(d_cross, ph, vl, idesc, ks ? 1u : 0u);
-          tc::mma_tf32(d_cross, pl, vh, idesc, 1u);
+          if (leader) {
+            tc::mma_tf32(d_main, ph, vh, idesc, ks ? 1u : 0u);
+            tc::mma_tf32(d_cross, ph, vl, idesc, ks ? 1u : 0u);
+            tc::mma_tf32(d_cross, pl, vh, idesc, 1u);
+          }
         }
-        tc::mma_commit(v_empty);
-        tc::mma_commit(o_full);
+        if (leader) {
+          tc::mma_commit(v_empty);
+          tc::mma_commit(o_full);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -104,7 +104,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = tc::elect_one();
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
       for (int it = 0; it < steps; it++) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
@@ -121,16 +122,20 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const int tap = it / chunks, ck = it % chunks;
           const uint32_t d_main = tmem_base + (tap / 3) * BN, d_cross = tmem_base + 3 * BN;
-          tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % 3) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
-          tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
-          tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
-          tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
-          tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
-          tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+          if (leader) {
+            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % 3) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
+            tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
+            tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
+            tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
+            tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
+            tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+          }
         }
-        tc::mma_commit(empty + s);
+        if (leader) tc::mma_commit(empty + s);
+        __syncwarp();
       }
-      tc::mma_commit(tmem_full);
+      if (leader) tc::mma_commit(tmem_full);
+      __syncwarp();
     }
   } else {
     const int q = warp % 4;
@@ -269,7 +274,8 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = tc::elect_one();
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
       int i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
@@ -293,17 +299,23 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
               bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
             }
-            tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
-            tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
-            tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
-            tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
-            tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
-            tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+            if (leader) {
+              tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
+              tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
+              tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
+              tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
+              tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
+              tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+            }
           }
-          tc::mma_commit(b_empty + s);
-          if (dyi == 2) tc::mma_commit(a_empty + dxi);  // the three taps of this dx slot are done
+          if (leader) {
+            tc::mma_commit(b_empty + s);
+            if (dyi == 2) tc::mma_commit(a_empty + dxi);  // the three taps of this dx slot are done
+          }
+          __syncwarp();
         }
-        tc::mma_commit(tmem_full + acc);
+        if (leader) tc::mma_commit(tmem_full + acc);
+        __syncwarp();
       }
     }
   } else {

@@ -34,7 +34,7 @@ struct TcGemmArgs {
   int wsel_rows;
 };
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 320;
 
 template <int BN, int SPLIT>
 constexpr size_t tc_gemm_smem_bytes() {
@@ -42,26 +42,26 @@ constexpr size_t tc_gemm_smem_bytes() {
          4 * 32 * 33 * sizeof(float) /*epilogue transpose tiles*/;
 }
 
+// Persistent: one CTA per SM walks the (m-tile, n-tile) list (n fastest, so the CTAs that share an A tile run
+// together and hit L2).  Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 hi/lo splitters (SPLIT == 3),
+// 6-9 epilogue.  The smem ring runs across tile boundaries and two TMEM accumulator sets alternate, so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int SPLIT, class Epi>
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi) {
-  const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
-  const int z = m_tile / g.tiles_per_slot;
-  const int row_in_slot0 = (m_tile % g.tiles_per_slot) * TC_BM;
-  if (g.skip && g.skip[z >> g.skip_shift]) return;
-  const int nrows = g.counts ? g.counts[z] : (g.tiles_per_slot * TC_BM);
-  if (row_in_slot0 >= nrows) return;
-
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi,
+                                                                    int m_tiles) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   // stage layout: [A | W] (TMA destination, becomes hi in place) and for SPLIT == 3 [A_lo | W_lo] behind it
   constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, TILE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGE = (SPLIT == 3 ? 2 : 1) * TILE_BYTES;
+  constexpr int ACC_COLS = (SPLIT == 3 ? 2 : 1) * BN;   // SPLIT == 3: hi*hi and cross-term accumulators (see header)
   uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* ready = empty + TC_STAGES;   // SPLIT == 3: hi/lo tiles written by the splitter warps
-  uint64_t* tmem_full = ready + TC_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = ready + TC_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   float* epi_tiles = (float*)(smem + TC_STAGES * STAGE + 256);  // [4 warps][32][33]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -69,35 +69,54 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
     for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 128); }
-    tc::mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
     tc::fence_barrier_init();
   }
-  // SPLIT == 3: two accumulators (hi*hi and the cross terms): the tensor core truncates when it adds into the
-  // fp32 accumulator; keeping the 2^-11-sized cross terms apart makes their truncation error negligible
-  constexpr int ACC_COLS = (SPLIT == 3 ? 2 : 1) * BN;
-  if (warp == 1) tc::tmem_alloc(tmem_slot, ACC_COLS);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int KB = g.K / TC_BK;
-  const int w_row0 = n0 + (g.wsel_minus1 ? (g.wsel_minus1[z >> g.wsel_shift] - 1) * g.wsel_rows : 0);
+  const int KB = g.K / TC_BK, n_tiles = g.N / BN, total = m_tiles * n_tiles;
+
+  // every role walks the same tile sequence and skips the same tiles (finished pairs, rows beyond the count)
+  auto tile_info = [&](int tile, int& m_tile, int& n0, int& z, int& row0, int& nrows) -> bool {
+    m_tile = tile / n_tiles; n0 = (tile % n_tiles) * BN;
+    z = m_tile / g.tiles_per_slot; row0 = (m_tile % g.tiles_per_slot) * TC_BM;
+    if (g.skip && g.skip[z >> g.skip_shift]) return false;
+    nrows = g.counts ? g.counts[z] : (g.tiles_per_slot * TC_BM);
+    return row0 < nrows;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        tc::mbar_wait(empty + s, ph ^ 1);
-        tc::mbar_expect_tx(full + s, TILE_BYTES);
-        tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
-        tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmW, full + s, kb * TC_BK, w_row0);
+      int c = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int m_tile, n0, z, row0, nrows;
+        if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+        const int w_row0 = n0 + (g.wsel_minus1 ? (g.wsel_minus1[z >> g.wsel_shift] - 1) * g.wsel_rows : 0);
+        for (int kb = 0; kb < KB; kb++, c++) {
+          const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+          tc::mbar_wait(empty + s, ph ^ 1);
+          tc::mbar_expect_tx(full + s, TILE_BYTES);
+          tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
+          tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmW, full + s, kb * TC_BK, w_row0);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
-      for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
+    int c = 0, i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int m_tile, n0, z, row0, nrows;
+      if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+      const int acc = i & 1;
+      tc::mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator set
+      tc::fence_after_sync();
+      const uint32_t d_main = tmem_base + acc * ACC_COLS, d_cross = d_main + BN;
+      for (int kb = 0; kb < KB; kb++, c++) {
+        const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
         tc::mbar_wait(SPLIT == 3 ? ready + s : full + s, ph);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
@@ -105,80 +124,101 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_tf32_kernel(const __grid_c
         for (int k = 0; k < TC_BK / 8; k++) {
           // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
           uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
-          tc::mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
-          if (SPLIT == 3) {
-            uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
-            tc::mma_tf32(tmem_base + BN, ad, bdl, idesc, (kb | k) ? 1u : 0u);
-            tc::mma_tf32(tmem_base + BN, adl, bd, idesc, 1u);
+          uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
+          if (leader) {
+            tc::mma_tf32(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            if (SPLIT == 3) {
+              tc::mma_tf32(d_cross, ad, bdl, idesc, (kb | k) ? 1u : 0u);
+              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);
+            }
           }
         }
-        tc::mma_commit(empty + s);  // smem stage free once these MMAs have read it
+        if (leader) tc::mma_commit(empty + s);  // smem stage free once these MMAs have read it
+        __syncwarp();
       }
-      tc::mma_commit(tmem_full);    // accumulator complete
+      if (leader) tc::mma_commit(tmem_full + acc);  // accumulator complete
+      __syncwarp();
+      i++;
     }
-  } else {
-    const int q = warp % 4;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+  } else if (warp < 6) {
     if (SPLIT == 3) {
       // splitter: x -> (x_hi in place, x_lo in the twin tile); elementwise, so the TMA swizzle is irrelevant
       const int t = threadIdx.x - 64;  // 0..127
-      for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        tc::mbar_wait(full + s, ph);
-        uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
-        uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
-#pragma unroll 4
-        for (int i = t; i < TILE_BYTES / 16; i += 128) {
-          uint4 v = hi[i], h, l;
-          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[i] = h;
-          lo[i] = l;
+      int c = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int m_tile, n0, z, row0, nrows;
+        if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+        for (int kb = 0; kb < KB; kb++, c++) {
+          const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+          tc::mbar_wait(full + s, ph);
+          uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
+          uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
+#pragma unroll 8
+          for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
+            uint4 v = hi[idx], h, l;
+            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            hi[idx] = h;
+            lo[idx] = l;
+          }
+          tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          tc::mbar_arrive(ready + s);
         }
-        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        tc::mbar_arrive(ready + s);
       }
     }
-    tc::mbar_wait(tmem_full, 0);
-    tc::fence_after_sync();
+  } else {
+    const int q = warp % 4;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
     // TMEM gives one output ROW per thread; global memory wants one row per warp instruction.  Transpose each
     // 32x32 block through a padded smem tile so that lanes run along the columns: every load/store of the
-    // functor epilogue is one fully coalesced 128-byte line (the per-thread-row version was 5x slower on the
-    // residual epilogue: 32 dependent, uncoalesced round trips per thread).
-    float* T = epi_tiles + (warp - 2) * 32 * 33;
-    const int row_base = row_in_slot0 + q * 32;
+    // functor epilogue is one fully coalesced 128-byte line.
+    float* T = epi_tiles + (warp - 6) * 32 * 33;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int m_tile, n0, z, row0, nrows;
+      if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+      const int acc = i & 1;
+      tc::mbar_wait(tmem_full + acc, (i >> 1) & 1);
+      tc::fence_after_sync();
+      const int row_base = row0 + q * 32;
+      const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      if (SPLIT == 3) {
-        float t[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + BN + c0, t);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(lane_addr + c0, v);
+        if (SPLIT == 3) {
+          float t[32];
+          tc::tmem_ld32(lane_addr + BN + c0, t);
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += t[j];
+          for (int j = 0; j < 32; j++) v[j] += t[j];
+        }
+        if (c0 + 32 >= BN) {  // last TMEM read of this accumulator set: hand it back to the MMA warp
+          tc::fence_before_sync();
+          tc::mbar_arrive(tmem_empty + acc);
+        }
+        // functors may consume a 32-column chunk in the native thread-per-row layout (V^T for the attention kernel)
+        if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int rmax = min(32, nrows - row_base);  // warp-uniform
+        // all global reads of the epilogue (residual / rotary table) are issued before the first dependent use
+        float2 pre[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+          if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
       }
-      // functors may consume a 32-column chunk in the native thread-per-row layout (V^T for the attention kernel)
-      if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
-      __syncwarp();
-      const int rmax = min(32, nrows - row_base);  // warp-uniform
-      // all global reads of the epilogue (residual / rotary table) are issued before the first dependent use:
-      // 32 independent loads in flight per lane instead of one round trip per row
-      float2 pre[32];
-#pragma unroll
-      for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < 32; r++)
-        if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
+      i++;
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, ACC_COLS);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
 // A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32.
@@ -190,12 +230,17 @@ static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, 
   if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)w_rows, (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
   constexpr size_t smem = tc_gemm_smem_bytes<BN, SPLIT>();
   static bool attr_set = false;
+  static int num_sms = 0;
   if (!attr_set) {
     IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_tf32_kernel<BN, SPLIT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IMW_CHECK_CUDA(cudaGetDevice(&dev));
+    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
-  dim3 grid(g.N / BN, (unsigned)(rows_total / TC_BM));
-  tc_gemm_tf32_kernel<BN, SPLIT, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi);
+  const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
+  dim3 grid((unsigned)(total < num_sms ? total : num_sms));
+  tc_gemm_tf32_kernel<BN, SPLIT, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

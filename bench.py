@@ -180,23 +180,27 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(dev):
-    """CUDA-event timing of the dominant kernel (SuperPoint conv1b: 3x3, 64->64 @480x640, fused ReLU+pool)
-    launched alone on the stream bench uses, 8 images per launch."""
-    from imcui_b200 import _lib as L
-    import ctypes as C
+def time_dominant_kernel(dev, tensor_cores=True):
+    """CUDA-event timing of the dominant kernel -- SuperPoint conv1b (3x3, 64->64 @480x640, fused ReLU + 2x2 max-pool),
+    8 images per launch as in the engine -- launched alone on the stream the bench uses.  Tensor-core path:
+    tc_conv3x3_c64_kernel on pre-split bf16 planes; otherwise the fp32 CUDA-core kernel."""
+    from imcui_b200 import _lib as L, ops
     lib = L.lib()
-    if not hasattr(lib, "imw_debug_conv3x3"):
-        return None
     nb = 8
     x = torch.rand(nb, H, W, 64, device=dev)
-    w = torch.randn(9, 64, 64, device=dev) * 0.05
+    w = torch.randn(9, 64, 64, device=dev) * 0.05   # [tap][Cin][Cout]
     b = torch.zeros(64, device=dev)
-    y = torch.empty(nb, H // 2, W // 2, 64, device=dev)
-    lib.imw_debug_conv3x3.restype = C.c_int
-    lib.imw_debug_conv3x3.argtypes = [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]
     st = L.stream_ptr(dev)
-    run = lambda: L.check(lib.imw_debug_conv3x3(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), nb, H, W, 64, 64, 1, 1, st))
+    if tensor_cores:
+        xp = ops.split_bf16_planes(x)
+        wp = ops.split_bf16_planes(w.permute(0, 2, 1).contiguous())  # [3][tap][Cout][Cin]
+        y = torch.empty(3, nb, H // 2, W // 2, 64, dtype=torch.bfloat16, device=dev)
+        run = lambda: L.check(lib.imw_debug_conv3x3_tc_planes(L.ptr(xp), L.ptr(wp), L.ptr(b), L.ptr(y), nb, H, W, 64, 64, 1, 1, st))
+        name = "tc_conv3x3_c64_kernel (SuperPoint conv1b 64->64 @480x640, tcgen05 bf16x3 split = fp32-equivalent)"
+    else:
+        y = torch.empty(nb, H // 2, W // 2, 64, device=dev)
+        run = lambda: L.check(lib.imw_debug_conv3x3(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), nb, H, W, 64, 64, 1, 1, st))
+        name = "conv3x3_nhwc_kernel (SuperPoint conv1b 64->64 @480x640, fp32 CUDA cores)"
     for _ in range(3):
         run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -208,7 +212,7 @@ def time_dominant_kernel(dev):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"ms": ms, "gflop": CONV1B_GFLOP_PER_IMAGE * nb, "images": nb}
+    return {"ms": ms, "gflop": CONV1B_GFLOP_PER_IMAGE * nb, "images": nb, "name": name}
 
 
 def main():
@@ -309,11 +313,17 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
     roof = None
-    k = time_dominant_kernel(dev)
+    k = time_dominant_kernel(dev, tensor_cores=not (args.fp32 or args.sp_simt))
     if k:
-        ach = k["gflop"] / k["ms"]  # GFLOP/ms == TFLOP/s
-        roof = {"kernel": "conv3x3_nhwc_kernel (SuperPoint conv1b 64->64 @480x640, fp32 CUDA cores)", "bound": "tensor",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        ach = k["gflop"] / k["ms"]  # GFLOP/ms == TFLOP/s (algorithmic fp32 FLOPs: 2*9*Cin*Cout per output pixel)
+        traffic = None
+        try:  # per-launch DRAM bytes of this kernel from the committed ncu --set full capture
+            traffic = json.loads((ROOT / "profiles" / "r1_conv1b_ncu.json").read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"kernel": k["name"], "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "note": "split precision issues 6 bf16 MMAs per fp32-equivalent product: tensor-pipe FLOP/s = 6 x achieved",
                 "peak_source": "measured bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback 1.59 PFLOP/s",
                 "launch_ms": k["ms"], "algorithmic_gflop_per_launch": k["gflop"]}
 

@@ -78,6 +78,8 @@ def lib():
         L.imw_debug_gemm_fp32.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.imw_debug_conv3x3.restype = C.c_int
         L.imw_debug_conv3x3.argtypes = [vp] * 4 + [C.c_int] * 7 + [vp]
+        L.imw_debug_conv3x3_tc_planes.restype = C.c_int
+        L.imw_debug_conv3x3_tc_planes.argtypes = [vp] * 4 + [C.c_int] * 7 + [vp]
         L.imw_debug_attention.restype = C.c_int
         L.imw_debug_attention.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]
         L.imw_debug_conv3x3_tc.restype = C.c_int

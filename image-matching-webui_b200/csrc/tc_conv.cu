@@ -518,3 +518,9 @@ extern "C" int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout
   if (int e = tc_split_planes(w_t, w_p, n_w, st)) return e;
   return tc_conv3x3(in_p, w_p, bias, out, B, H, W, Cin, Cout, relu, pool, 1, st);
 }
+
+// bench hook: the tcgen05 conv alone on pre-split operands (planes in, planes out)
+extern "C" int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, const float* bias, void* out_planes, int B,
+                                           int H, int W, int Cin, int Cout, int relu, int pool, cudaStream_t st) {
+  return tc_conv3x3(in_planes, w_planes, bias, out_planes, B, H, W, Cin, Cout, relu, pool, 0, st);
+}

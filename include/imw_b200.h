@@ -144,6 +144,9 @@ int imw_debug_attention(const float* q, const float* k, const float* v, const in
 int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout, const float* bias, float* out, int batch, int height,
                          int width, int cin, int cout, int relu, int pool, void* scratch, size_t scratch_bytes,
                          imw_stream_t stream);
+/* the tcgen05 conv alone on pre-split operands: in [3][B][H][W][Cin] bf16, w [3][9][Cout][Cin] bf16, out planes */
+int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, const float* bias, void* out_planes, int batch,
+                                int height, int width, int cin, int cout, int relu, int pool, imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,
                       int cin, int cout, int relu, int pool, imw_stream_t stream);
 

@@ -35,6 +35,23 @@ class LGWeights(C.Structure):
                 ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS)]
 
 
+IMW_SG_MAX_LAYERS = 32
+
+
+class SGLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_w", "qkv_b", "merge_w", "merge_b", "mlp0_w", "mlp0_b", "mlp1_w", "mlp1_b")] + \
+               [("is_cross", C.c_int), ("pad_", C.c_int)]
+
+
+class SGWeights(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("bin_score", C.c_float), ("kenc_w", C.c_void_p * 5), ("kenc_b", C.c_void_p * 5),
+                ("final_w", C.c_void_p), ("final_b", C.c_void_p), ("layers", SGLayer * IMW_SG_MAX_LAYERS)]
+
+
+class SGConf(C.Structure):
+    _fields_ = [("sinkhorn_iterations", C.c_int), ("match_threshold", C.c_float), ("use_tensor_cores", C.c_int)]
+
+
 class LGConf(C.Structure):
     _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
                 ("pruning_min_kpts", C.c_int), ("use_tensor_cores", C.c_int)]
@@ -54,11 +71,13 @@ def lib():
         L.imw_last_error.restype = C.c_char_p
         L.imw_version.restype = C.c_int
         L.imw_launch_count.restype = C.c_ulonglong
-        for name in ("imw_superpoint_workspace_bytes", "imw_lightglue_workspace_bytes", "imw_matcher_workspace_bytes"):
+        for name in ("imw_superpoint_workspace_bytes", "imw_lightglue_workspace_bytes", "imw_matcher_workspace_bytes",
+                     "imw_superglue_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         L.imw_superpoint_workspace_bytes.argtypes = [C.c_int] * 3
         L.imw_lightglue_workspace_bytes.argtypes = [C.c_int] * 2
         L.imw_matcher_workspace_bytes.argtypes = [C.c_int] * 2
+        L.imw_superglue_workspace_bytes.argtypes = [C.c_int] * 2
         vp = C.c_void_p
         L.imw_superpoint_forward.restype = C.c_int
         L.imw_superpoint_forward.argtypes = [C.POINTER(SPWeights), C.POINTER(SPConf), C.c_int, C.c_int, C.c_int, vp,
@@ -66,6 +85,9 @@ def lib():
         L.imw_lightglue_forward.restype = C.c_int
         L.imw_lightglue_forward.argtypes = [C.POINTER(LGWeights), C.POINTER(LGConf), C.c_int, C.c_int, vp, vp, vp, vp,
                                             vp, vp, vp, vp, C.c_size_t, vp]
+        L.imw_superglue_forward.restype = C.c_int
+        L.imw_superglue_forward.argtypes = [C.POINTER(SGWeights), C.POINTER(SGConf), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                            vp, C.c_size_t, vp]
         L.imw_nearest_neighbor.restype = C.c_int
         L.imw_nearest_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp,
                                            vp, C.c_size_t, vp]

@@ -37,7 +37,7 @@ constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1
 // TMEM columns: S buffers 2 x (main 64 + cross 64) = 256, O main 64 + cross 64 -> 384 (allocate 512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
 
-__global__ void __launch_bounds__(TA_THREADS, 1)
+static __global__ void __launch_bounds__(TA_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, TcAttnArgs g) {
   const int z = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * TA_BQ;

@@ -32,6 +32,8 @@ struct TcGemmArgs {
   const int* wsel_minus1;  // optional per-pair weight slab selection: W rows offset (wsel-1) * wsel_rows
   int wsel_shift;
   int wsel_rows;
+  int pair_product;      // 1: "W" is the OTHER slot of the pair in the same row space as A (rows (z^1)*cap + n0) and
+                         //    only even slots produce output: C[pair] = X_0 X_1^T (score matrices)
 };
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 320;
@@ -84,7 +86,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
     m_tile = tile / n_tiles; n0 = (tile % n_tiles) * BN;
     z = m_tile / g.tiles_per_slot; row0 = (m_tile % g.tiles_per_slot) * TC_BM;
     if (g.skip && g.skip[z >> g.skip_shift]) return false;
+    if (g.pair_product && (z & 1)) return false;
     nrows = g.counts ? g.counts[z] : (g.tiles_per_slot * TC_BM);
+    if (g.pair_product && g.counts && n0 >= g.counts[z ^ 1]) return false;
     return row0 < nrows;
   };
 
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         int m_tile, n0, z, row0, nrows;
         if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
-        const int w_row0 = n0 + (g.wsel_minus1 ? (g.wsel_minus1[z >> g.wsel_shift] - 1) * g.wsel_rows : 0);
+        const int w_row0 = g.pair_product ? (z ^ 1) * g.tiles_per_slot * TC_BM + n0
+                                          : n0 + (g.wsel_minus1 ? (g.wsel_minus1[z >> g.wsel_shift] - 1) * g.wsel_rows : 0);
         for (int kb = 0; kb < KB; kb++, c++) {
           const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
           tc::mbar_wait(empty + s, ph ^ 1);

@@ -1,0 +1,150 @@
+// Functor epilogues of the token GEMMs shared by the LightGlue and SuperGlue matchers (CUDA-core operator()
+// form: 4 columns per call; tcgen05 form: elem()/prefetch()/rowwise(), see tc_gemm.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace {
+constexpr int D = 256, HEADS = 4, HD = 64, NF = 32;
+
+// ---- GEMM epilogues ---------------------------------------------------------------------------------
+// Self-attention projection: columns [q | k | v] x [head][dim]; rotary on q,k (lightglue.py:58-65,
+// 165-169).  Output buffers [slots][HEADS][cap][HD].
+// hi/lo split used by the tcgen05 attention operands: hi = 13 low mantissa bits cleared, lo = x - hi
+__device__ __forceinline__ void split_hi_lo(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+struct EpiQKVRotary {
+  float *q, *k, *v; const float* bias; const float* enc; int cap;
+  long long plane;   // tcgen05 attention layout: elements per hi/lo plane (0 = CUDA-core layout, no planes)
+  __device__ void operator()(int z, int row, int col, float4 a, int) const {
+    float r[4] = {a.x + bias[col], a.y + bias[col + 1], a.z + bias[col + 2], a.w + bias[col + 3]};
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    float* dst = (which == 0 ? q : which == 1 ? k : v) + (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (which < 2 && enc) {
+      const float* e = enc + ((long long)z * cap + row) * 64;
+      float c0 = e[d / 2], c1 = e[d / 2 + 1], s0 = e[32 + d / 2], s1 = e[32 + d / 2 + 1];
+      float o0 = __fadd_rn(__fmul_rn(r[0], c0), __fmul_rn(-r[1], s0));
+      float o1 = __fadd_rn(__fmul_rn(r[1], c0), __fmul_rn(r[0], s0));
+      float o2 = __fadd_rn(__fmul_rn(r[2], c1), __fmul_rn(-r[3], s1));
+      float o3 = __fadd_rn(__fmul_rn(r[3], c1), __fmul_rn(r[2], s1));
+      r[0] = o0; r[1] = o1; r[2] = o2; r[3] = o3;
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  // tcgen05 epilogue form (lanes along columns; the rotary partner of dim d is the neighbouring lane d^1)
+  __device__ float2 prefetch(int z, int row, int col) const {  // (cos, sin) of this lane's rotary frequency
+    if (col >= 2 * D || !enc) return make_float2(1.f, 0.f);
+    const float* e = enc + ((long long)z * cap + row) * 64 + (col % HD) / 2;
+    return make_float2(e[0], e[32]);
+  }
+  __device__ void elem(int z, int row, int col, float a, float2 cs_sn) const {
+    float r = a + bias[col];
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    float partner = __shfl_xor_sync(0xffffffffu, r, 1);
+    if (which < 2) {
+      const float cs = cs_sn.x, sn = cs_sn.y;
+      r = (d & 1) ? __fadd_rn(__fmul_rn(r, cs), __fmul_rn(partner, sn)) : __fadd_rn(__fmul_rn(r, cs), __fmul_rn(-partner, sn));
+    }
+    float* dst = (which == 0 ? q : which == 1 ? k : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    else dst[off] = r;
+  }
+  // tcgen05 attention wants V transposed ([head][d][token], tokens contiguous): taken straight from the
+  // thread-per-row TMEM layout (lanes = consecutive tokens -> coalesced), before the epilogue transpose.
+  __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
+    if (!plane || col0 < 2 * D) return false;
+    const int c = col0 - 2 * D, head = c / HD, d0 = c % HD;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float hi, lo;
+        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
+        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
+        v[off] = hi; v[plane + off] = lo;
+      }
+    }
+    return true;
+  }
+};
+
+// Cross-attention projection: columns [qk | v] x [head][dim]; qk scaled by dim_head^-0.25
+// (lightglue.py:216: each side multiplied by scale**0.5).
+struct EpiCrossQKV {
+  float *qk, *v; const float* bias; int cap; float qk_scale;
+  long long plane;
+  __device__ void operator()(int z, int row, int col, float4 a, int) const {
+    float r[4] = {a.x + bias[col], a.y + bias[col + 1], a.z + bias[col + 2], a.w + bias[col + 3]};
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    float* dst = (which == 0 ? qk : v) + (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (which == 0) { r[0] *= qk_scale; r[1] *= qk_scale; r[2] *= qk_scale; r[3] *= qk_scale; }
+    *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void elem(int z, int row, int col, float a, float2) const {
+    float r = a + bias[col];
+    int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which == 0) r *= qk_scale;
+    float* dst = (which == 0 ? qk : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    else dst[off] = r;
+  }
+  __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
+    if (!plane || col0 < D) return false;
+    const int c = col0 - D, head = c / HD, d0 = c % HD;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float hi, lo;
+        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
+        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
+        v[off] = hi; v[plane + off] = lo;
+      }
+    }
+    return true;
+  }
+};
+
+// out[z][row][col] (+)= acc + bias  -- plain / residual variants, N % 4 == 0
+struct EpiStore {
+  float* out; int ldo; long long strideOut; const float* bias; int residual;
+  int relu = 0;        // SuperGlue MLP: ReLU after the (BatchNorm-folded) first layer
+  float scale = 1.f;   // applied to acc before the bias (SuperGlue score matrix: 1/sqrt(256))
+  __device__ void operator()(int z, int row, int col, float4 a, int) const {
+    float4* o = reinterpret_cast<float4*>(out + z * strideOut + (long long)row * ldo + col);
+    float4 r = make_float4(a.x * scale + (bias ? bias[col] : 0.f), a.y * scale + (bias ? bias[col + 1] : 0.f),
+                           a.z * scale + (bias ? bias[col + 2] : 0.f), a.w * scale + (bias ? bias[col + 3] : 0.f));
+    if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+    if (residual) { float4 x = *o; r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; }
+    *o = r;
+  }
+  __device__ float2 prefetch(int z, int row, int col) const {
+    return make_float2(residual ? out[z * strideOut + (long long)row * ldo + col] : 0.f, 0.f);
+  }
+  __device__ void elem(int z, int row, int col, float a, float2 res) const {
+    float r = a * scale + (bias ? bias[col] : 0.f);
+    if (relu) r = fmaxf(r, 0.f);
+    out[z * strideOut + (long long)row * ldo + col] = r + res.x;
+  }
+  __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
+};
+
+// final_proj of the layer the pair stopped at; output divided by d^0.25 = 4 (lightglue.py:288-290)
+struct EpiFinalProj {
+  float* out; int cap; const float* bias_all; const int* stop;
+  __device__ void operator()(int z, int row, int col, float4 a, int) const {
+    const float* b = bias_all + (stop[z >> 1] - 1) * D;
+    float4 r = make_float4((a.x + b[col]) * 0.25f, (a.y + b[col + 1]) * 0.25f, (a.z + b[col + 2]) * 0.25f, (a.w + b[col + 3]) * 0.25f);
+    *reinterpret_cast<float4*>(out + ((long long)z * cap + row) * D + col) = r;
+  }
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void elem(int z, int row, int col, float a, float2) const {
+    out[((long long)z * cap + row) * D + col] = (a + bias_all[(stop[z >> 1] - 1) * D + col]) * 0.25f;
+  }
+  __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
+};
+
+}  // namespace

@@ -2,6 +2,15 @@
 _PRE = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "force_resize": False}
 
 confs = {
+    "superglue": {
+        "output": "matches-superglue",
+        "model": {"name": "superglue", "weights": "outdoor", "sinkhorn_iterations": 50, "match_threshold": 0.2},
+        "preprocessing": dict(_PRE),
+    },
+    "superglue-fast": {
+        "output": "matches-superglue-it5",
+        "model": {"name": "superglue", "weights": "outdoor", "sinkhorn_iterations": 5, "match_threshold": 0.2},
+    },
     "superpoint-lightglue": {
         "output": "matches-lightglue",
         "model": {"name": "lightglue", "match_threshold": 0.2, "width_confidence": 0.99, "depth_confidence": 0.95,

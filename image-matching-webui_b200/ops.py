@@ -161,6 +161,79 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
 
 
 # ---------------------------------------------------------------------------------------------------
+# SuperGlue
+# ---------------------------------------------------------------------------------------------------
+def _fold_bn(w, b, sd, p):
+    """Conv1d(k=1) followed by BatchNorm1d in eval mode -> one affine layer."""
+    g = sd[p + "weight"] / torch.sqrt(sd[p + "running_var"] + 1e-5)
+    return w * g[:, None], (b - sd[p + "running_mean"]) * g + sd[p + "bias"]
+
+
+def sg_pack_weights(sd, layer_names=("self", "cross") * 9, heads=4):
+    """Reference state dict (superglue.py) -> kernel layout (CPU fp32): BN folded, attention projections permuted
+    from channel order d*heads+h (superglue.py:106 `view(b, dim, heads, N)`) to h*dim+d, kenc layer 0 padded 3 -> 16."""
+    out = {}
+    for l in range(5):
+        w, b = sd[f"kenc.encoder.{3 * l}.weight"][:, :, 0].float(), sd[f"kenc.encoder.{3 * l}.bias"].float()
+        if l < 4:
+            w, b = _fold_bn(w, b, sd, f"kenc.encoder.{3 * l + 1}.")
+        if l == 0:
+            w = torch.cat([w, torch.zeros(w.shape[0], 13)], 1)
+        out[f"kenc_w{l}"], out[f"kenc_b{l}"] = w.contiguous(), b.contiguous()
+    d = sd["final_proj.weight"].shape[0]
+    hd = d // heads
+    perm_rows = lambda w: w.view(hd, heads, -1).permute(1, 0, 2).reshape(d, -1)
+    for i, _ in enumerate(layer_names):
+        p = f"gnn.layers.{i}."
+        ws = [perm_rows(sd[p + f"attn.proj.{j}.weight"][:, :, 0].float()) for j in range(3)]
+        bs = [sd[p + f"attn.proj.{j}.bias"].float().view(hd, heads).t().reshape(d) for j in range(3)]
+        out[f"l{i}.qkv_w"], out[f"l{i}.qkv_b"] = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
+        mw = sd[p + "attn.merge.weight"][:, :, 0].float()
+        out[f"l{i}.merge_w"] = mw.view(d, hd, heads).permute(0, 2, 1).reshape(d, d).contiguous()
+        out[f"l{i}.merge_b"] = sd[p + "attn.merge.bias"].float().contiguous()
+        w0, b0 = _fold_bn(sd[p + "mlp.0.weight"][:, :, 0].float(), sd[p + "mlp.0.bias"].float(), sd, p + "mlp.1.")
+        out[f"l{i}.mlp0_w"], out[f"l{i}.mlp0_b"] = w0.contiguous(), b0.contiguous()
+        out[f"l{i}.mlp1_w"], out[f"l{i}.mlp1_b"] = sd[p + "mlp.3.weight"][:, :, 0].float().contiguous(), sd[p + "mlp.3.bias"].float().contiguous()
+    out["final_w"], out["final_b"] = sd["final_proj.weight"][:, :, 0].float().contiguous(), sd["final_proj.bias"].float().contiguous()
+    return out
+
+
+def sg_weights_struct(bufs, bin_score, layer_names=("self", "cross") * 9):
+    s = L.SGWeights()
+    s.n_layers, s.bin_score = len(layer_names), float(bin_score)
+    for l in range(5):
+        s.kenc_w[l], s.kenc_b[l] = bufs[f"kenc_w{l}"].data_ptr(), bufs[f"kenc_b{l}"].data_ptr()
+    s.final_w, s.final_b = bufs["final_w"].data_ptr(), bufs["final_b"].data_ptr()
+    for i, name in enumerate(layer_names):
+        for f in ("qkv_w", "qkv_b", "merge_w", "merge_b", "mlp0_w", "mlp0_b", "mlp1_w", "mlp1_b"):
+            setattr(s.layers[i], f, bufs[f"l{i}.{f}"].data_ptr())
+        s.layers[i].is_cross = int(name == "cross")
+    return s
+
+
+def superglue_forward(bufs, bin_score, keypoints, scores, descriptors, counts, image_wh, conf):
+    """keypoints [2P,cap,2], scores [2P,cap], descriptors [2P,cap,256], counts [2P] int32, image_wh [2P,2] int32.
+    Returns matches [2P,cap] int32, matching_scores [2P,cap]."""
+    L.require_cuda(keypoints, "superglue_forward(keypoints)")
+    S, cap, _ = keypoints.shape
+    assert S % 2 == 0 and descriptors.shape == (S, cap, 256) and counts.dtype == torch.int32 and image_wh.dtype == torch.int32
+    dev = keypoints.device
+    matches = torch.empty(S, cap, dtype=torch.int32, device=dev)
+    mscores = torch.empty(S, cap, device=dev)
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_superglue_workspace_bytes(S // 2, cap), "sg")
+    c = L.SGConf(int(conf["sinkhorn_iterations"]), float(conf["match_threshold"]),
+                 int(conf.get("use_tensor_cores", 1)) if cap % 128 == 0 else 0)
+    wstruct = sg_weights_struct(bufs, bin_score)
+    with torch.cuda.device(dev):
+        rc = lib.imw_superglue_forward(C.byref(wstruct), C.byref(c), S // 2, cap, L.ptr(keypoints.contiguous()), L.ptr(scores.contiguous()),
+                                       L.ptr(descriptors.contiguous()), L.ptr(counts), L.ptr(image_wh.contiguous()), L.ptr(matches),
+                                       L.ptr(mscores), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    return matches, mscores
+
+
+# ---------------------------------------------------------------------------------------------------
 # hloc first-party matchers
 # ---------------------------------------------------------------------------------------------------
 def _matcher_common(descriptors, counts):

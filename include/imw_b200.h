@@ -113,6 +113,49 @@ int imw_lightglue_forward(const imw_lg_weights* weights, const imw_lg_conf* conf
                           imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SuperGlue matcher.
+ * Replaces: hloc/matchers/superglue.py:42-43 (SuperGlue._forward) ->
+ *           third_party/SuperGluePretrainedNetwork/models/superglue.py:228-283, batch of independent pairs.
+ * Weights are prepared by the host: BatchNorm (eval) folded into the preceding 1x1 conv, attention projection
+ * rows / merge columns permuted from the reference's channel order d*4+h to h*64+d, first keypoint-encoder
+ * layer zero-padded from 3 to 16 inputs.
+ * ---------------------------------------------------------------------------------------------- */
+#define IMW_SG_MAX_LAYERS 32
+
+typedef struct {
+  const float *qkv_w, *qkv_b;     /* [768][256]: proj[0..2] stacked */
+  const float *merge_w, *merge_b; /* [256][256] */
+  const float *mlp0_w, *mlp0_b;   /* [512][512] (BN folded), ReLU */
+  const float *mlp1_w, *mlp1_b;   /* [256][512] */
+  int is_cross;                   /* GNN_layers[i] == "cross" */
+  int pad_;
+} imw_sg_layer;
+
+typedef struct {
+  int n_layers;
+  float bin_score;
+  const float* kenc_w[5]; /* [32][16], [64][32], [128][64], [256][128], [256][256] (BN folded) */
+  const float* kenc_b[5];
+  const float *final_w, *final_b; /* [256][256] */
+  imw_sg_layer layers[IMW_SG_MAX_LAYERS];
+} imw_sg_weights;
+
+typedef struct {
+  int sinkhorn_iterations; /* conf["sinkhorn_iterations"] */
+  float match_threshold;   /* conf["match_threshold"] */
+  int use_tensor_cores;    /* as imw_lg_conf */
+} imw_sg_conf;
+
+size_t imw_superglue_workspace_bytes(int n_pairs, int cap);
+
+/* keypoints [2P][cap][2], scores [2P][cap], descriptors [2P][cap][256] token-major, counts [2P],
+ * image_wh [2P][2] = (width, height) of the image each keypoint set came from (superglue.py:65-72).
+ * Outputs: matches [2P][cap] (-1 = none), matching_scores [2P][cap]. */
+int imw_superglue_forward(const imw_sg_weights* weights, const imw_sg_conf* conf, int n_pairs, int cap, const float* keypoints,
+                          const float* scores, const float* descriptors, const int* counts, const int* image_wh, int* matches,
+                          float* matching_scores, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Mutual nearest neighbour.   Replaces hloc/matchers/nearest_neighbor.py:38-66.
  * Dual-softmax.               Replaces hloc/matchers/dual_softmax.py:50-71.
  * descriptors [2P][cap][dim] token-major (dim % 4 == 0, dim <= 256), counts [2P].

@@ -29,10 +29,35 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.LGConf) == 20 and ctypes.sizeof(_lib.SPConf) == 20
 
 
+def test_superglue_packing_is_a_relabelling():
+    """BN folding + head permutation reproduce the reference's first attention projection / keypoint encoder."""
+    import oracle
+    from oracle import superglue as osg
+    from imcui_b200 import ops
+    import ctypes
+    from imcui_b200 import _lib
+    assert ctypes.sizeof(_lib.SGLayer) == 8 * 8 + 8
+    sd = oracle.load_weights("superglue_outdoor.pt")
+    pk = ops.sg_pack_weights(sd)
+    x = torch.randn(1, 256, 7)
+    ref = torch.nn.functional.conv1d(x, sd["gnn.layers.0.attn.proj.0.weight"], sd["gnn.layers.0.attn.proj.0.bias"]).view(1, 64, 4, 7)
+    mine = (x[0].t() @ pk["l0.qkv_w"][:256].t() + pk["l0.qkv_b"][:256]).view(7, 4, 64)   # [token][head][dim]
+    assert torch.allclose(ref[0].permute(2, 1, 0), mine, atol=1e-5)
+    kin = torch.randn(1, 3, 5)
+    ref = osg._mlp(sd, "kenc.encoder", kin, 5)
+    h = torch.cat([kin[0].t(), torch.zeros(5, 13)], 1)
+    for l in range(5):
+        h = h @ pk[f"kenc_w{l}"].t() + pk[f"kenc_b{l}"]
+        if l < 4:
+            h = h.relu()
+    assert torch.allclose(ref[0].t(), h, atol=1e-4)
+
+
 def test_dynamic_load_registry():
     from imcui_b200.hloc import extractors, matchers
     from imcui_b200.hloc.utils.base_model import BaseModel, dynamic_load
-    for root, name in ((extractors, "superpoint"), (matchers, "lightglue"), (matchers, "nearest_neighbor"), (matchers, "dual_softmax")):
+    for root, name in ((extractors, "superpoint"), (matchers, "lightglue"), (matchers, "superglue"), (matchers, "nearest_neighbor"),
+                       (matchers, "dual_softmax")):
         cls = dynamic_load(root, name)
         assert issubclass(cls, BaseModel) and isinstance(cls.default_conf, dict)
     m = dynamic_load(matchers, "nearest_neighbor")({})

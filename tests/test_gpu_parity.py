@@ -258,6 +258,32 @@ def test_lightglue_batched_pairs_independent(golden, dev):
         assert np.array_equal(out["matches"][2 * p, :n0].cpu().numpy(), gg[f"cuda/{q}/matches0"])
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
+@pytest.mark.parametrize("iters", [50, 20])
+def test_superglue_matches_reference(golden, dev, iters, tc):
+    from imcui_b200.hloc import matchers
+    g = golden("sg")
+    model = _load(matchers, "superglue", {"weights": "outdoor", "sinkhorn_iterations": iters, "match_threshold": 0.2, "tensor_cores": tc}, dev)
+    for p, src in enumerate(g["sources"]):
+        f, conf, i, j = str(src).split(":")
+        b = golden(f)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        data = {"image0": torch.empty(1, 1, 480, 640, device=dev), "image1": torch.empty(1, 1, 480, 640, device=dev),
+                "keypoints0": t(b[f"{conf}/{i}/keypoints"].astype(np.float32))[None], "keypoints1": t(b[f"{conf}/{j}/keypoints"].astype(np.float32))[None],
+                "scores0": t(b[f"{conf}/{i}/scores"])[None], "scores1": t(b[f"{conf}/{j}/scores"])[None],
+                "descriptors0": t(b[f"{conf}/{i}/descriptors"])[None], "descriptors1": t(b[f"{conf}/{j}/descriptors"])[None]}
+        out = model(data)
+        pre = f"it{iters}/{p}/"
+        m0 = out["matches0"][0].cpu().numpy()
+        f1 = match_f1(m0, g[pre + "matches0"])
+        err = float(np.abs(out["matching_scores0"][0].cpu().numpy() - g[pre + "matching_scores0"]).max())
+        print(f"[sg] tc={tc} it={iters} pair {p}: F1 {f1:.4f} exact {np.array_equal(m0, g[pre + 'matches0'])} score err {err:.2e}")
+        assert np.array_equal(m0, g[pre + "matches0"]), (p, f1)
+        assert np.array_equal(out["matches1"][0].cpu().numpy(), g[pre + "matches1"])
+        assert err < SCORE_TOL
+        assert out["matches0"].dtype == torch.int64
+
+
 def _matcher_inputs(golden, p):
     g = golden("matchers")
     if p == 0:

@@ -73,6 +73,29 @@ def test_lightglue_oracle_matches_reference(golden, case, mode):
         assert np.array_equal(out["prune1"][0].numpy().astype(np.int32), g[pre + "prune1"])
 
 
+def _sg_data(golden, src):
+    f, conf, i, j = str(src).split(":")
+    b = golden(f)
+    t = torch.from_numpy
+    return {"image0": torch.empty(1, 1, 480, 640), "image1": torch.empty(1, 1, 480, 640),
+            "keypoints0": t(b[f"{conf}/{i}/keypoints"].astype(np.float32))[None], "keypoints1": t(b[f"{conf}/{j}/keypoints"].astype(np.float32))[None],
+            "scores0": t(b[f"{conf}/{i}/scores"])[None], "scores1": t(b[f"{conf}/{j}/scores"])[None],
+            "descriptors0": t(b[f"{conf}/{i}/descriptors"])[None], "descriptors1": t(b[f"{conf}/{j}/descriptors"])[None]}
+
+
+@pytest.mark.parametrize("iters", [50, 20])
+def test_superglue_oracle_matches_reference(golden, iters):
+    from oracle import superglue as osg
+    g = golden("sg")
+    w = oracle.load_weights("superglue_outdoor.pt")
+    for p, src in enumerate(g["sources"]):
+        out = osg.forward(w, _sg_data(golden, src), sinkhorn_iterations=iters, match_threshold=0.2)
+        pre = f"it{iters}/{p}/"
+        assert np.array_equal(out["matches0"][0].numpy(), g[pre + "matches0"])
+        assert np.array_equal(out["matches1"][0].numpy(), g[pre + "matches1"])
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[pre + "matching_scores0"], atol=1e-5)
+
+
 def _matcher_inputs(golden, p):
     g = golden("matchers")
     if p == 0:

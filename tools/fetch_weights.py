@@ -6,7 +6,7 @@ hloc/extractors/superpoint.py:45-49, hloc/matchers/lightglue.py:38-49); there is
 here, so SURVEY.md 8(c)'s in-tree copies are used:
   superpoint_v1.pth                      -> weights/superpoint_v1.pt
   gim_lightglue_100h.ckpt (model.*)      -> weights/superpoint_lightglue.pt   (GIM-trained SP+LG)
-  superglue_{indoor,outdoor}.pth         -> weights/superglue_{indoor,outdoor}.pt
+  superglue_outdoor.pth                  -> weights/superglue_outdoor.pt   (hloc conf default: weights=outdoor)
 Only parameters (data) are converted; no reference source code is copied.
 """
 import sys
@@ -29,7 +29,6 @@ def main(force=False):
         "superpoint_v1.pt": lambda: torch.load(str(R.SP_WEIGHTS), map_location="cpu"),
         "superpoint_lightglue.pt": R.lightglue_state_dict,
         "superglue_outdoor.pt": lambda: torch.load(str(R.SG_WEIGHTS / "superglue_outdoor.pth"), map_location="cpu"),
-        "superglue_indoor.pt": lambda: torch.load(str(R.SG_WEIGHTS / "superglue_indoor.pth"), map_location="cpu"),
     }
     for name, fn in jobs.items():
         dst = OUT / name

@@ -137,6 +137,26 @@ def lg_case(name, pairs, sources):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def sg_case(name, pairs):
+    """pairs: list of (kpts0 [N,2], scores0 [N], desc0 [256,N], kpts1, scores1, desc1, source)."""
+    blob = {"sources": np.array([p[-1] for p in pairs])}
+    for it in (50, 20):  # hloc conf "superglue": 50 (configs/matchers.py:15); a shorter run pins the iteration count
+        net = R.make_superglue({"weights": "outdoor", "sinkhorn_iterations": it, "match_threshold": 0.2})
+        for p, (k0, s0, d0, k1, s1, d1, _) in enumerate(pairs):
+            data = {"image0": torch.empty(1, 1, 480, 640), "image1": torch.empty(1, 1, 480, 640),
+                    "keypoints0": torch.from_numpy(k0)[None], "keypoints1": torch.from_numpy(k1)[None],
+                    "scores0": torch.from_numpy(s0)[None], "scores1": torch.from_numpy(s1)[None],
+                    "descriptors0": torch.from_numpy(d0)[None], "descriptors1": torch.from_numpy(d1)[None]}
+            out = net(data)
+            pre = f"it{it}/{p}/"
+            blob[pre + "matches0"] = out["matches0"][0].numpy().astype(np.int32)
+            blob[pre + "matches1"] = out["matches1"][0].numpy().astype(np.int32)
+            blob[pre + "matching_scores0"] = out["matching_scores0"][0].numpy()
+            blob[pre + "matching_scores1"] = out["matching_scores1"][0].numpy()
+            print(name, it, p, "matches", int((out["matches0"] > -1).sum()))
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def matcher_case(name, pairs):
     nn_mod, ds_mod = R.hloc_matchers()
     blob = {}
@@ -185,6 +205,12 @@ def main():
     lg_case("lg_real", [pair(rb, "api", 0, 1), pair(rb, "nocap", 0, 1)], ["sp_real:api:0:1", "sp_real:nocap:0:1"])
     lg_case("lg_synth", [pair(sb, "max1024", 0, 1), pair(sb, "max1024", 2, 3), pair(sb, "max2048", 0, 1)],
             ["sp_synth:max1024:0:1", "sp_synth:max1024:2:3", "sp_synth:max2048:0:1"])
+    def sg_pair(blob, src):
+        f, conf, i, j = src.split(":")
+        return (blob[f"{conf}/{i}/keypoints"].astype(np.float32), blob[f"{conf}/{i}/scores"], blob[f"{conf}/{i}/descriptors"],
+                blob[f"{conf}/{j}/keypoints"].astype(np.float32), blob[f"{conf}/{j}/scores"], blob[f"{conf}/{j}/descriptors"], src)
+
+    sg_case("sg", [sg_pair(rb, "sp_real:api:0:1"), sg_pair(sb, "sp_synth:max1024:0:1")])
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
 

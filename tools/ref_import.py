@@ -76,3 +76,12 @@ def hloc_matchers():
         sys.path.insert(0, str(REF))
     from imcui.hloc.matchers import nearest_neighbor, dual_softmax
     return nearest_neighbor, dual_softmax
+
+
+def make_superglue(conf):
+    import contextlib, io
+    sg = superglue_module()
+    w = conf.get("weights", "outdoor")
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = sg.SuperGlue({**conf, "weights_path": str(SG_WEIGHTS / f"superglue_{w}.pth")})
+    return net.eval()

@@ -88,6 +88,8 @@ def lib():
         L.imw_superglue_forward.restype = C.c_int
         L.imw_superglue_forward.argtypes = [C.POINTER(SGWeights), C.POINTER(SGConf), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
                                             vp, C.c_size_t, vp]
+        L.imw_magsac.restype = C.c_int
+        L.imw_magsac.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_uint, vp, vp, vp, vp, vp]
         L.imw_nearest_neighbor.restype = C.c_int
         L.imw_nearest_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp,
                                            vp, C.c_size_t, vp]

@@ -267,6 +267,24 @@ def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0)
     return m0, s0
 
 
+def magsac(pts0, pts1, counts, geometry_type="Homography", threshold=3.0, confidence=0.9999, max_iters=10000, seed=0):
+    """Batched MAGSAC++.  pts0/pts1 [n,cap,2] fp32 CUDA, counts [n] int32.
+    Returns models [n,3,3] float64, masks [n,cap] bool, n_inliers [n] int32, n_iters [n] int32 (all CUDA)."""
+    L.require_cuda(pts0, "magsac(pts0)")
+    n, cap, _ = pts0.shape
+    dev = pts0.device
+    models = torch.zeros(n, 9, dtype=torch.float64, device=dev)
+    masks = torch.zeros(n, cap, dtype=torch.uint8, device=dev)
+    n_inl = torch.zeros(n, dtype=torch.int32, device=dev)
+    n_it = torch.zeros(n, dtype=torch.int32, device=dev)
+    mt = {"Homography": 0, "Fundamental": 1}[geometry_type]
+    with torch.cuda.device(dev):
+        L.check(L.lib().imw_magsac(n, cap, L.ptr(pts0.contiguous()), L.ptr(pts1.contiguous()), L.ptr(counts), mt, float(threshold),
+                                   float(confidence), int(max_iters), int(seed) & 0xFFFFFFFF, L.ptr(models), L.ptr(masks), L.ptr(n_inl),
+                                   L.ptr(n_it), L.stream_ptr(dev)))
+    return models.view(n, 3, 3), masks.bool(), n_inl, n_it
+
+
 def debug_gemm(A, W, bias, mode="3xtf32"):
     """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32") or the CUDA-core GEMM ("fp32")."""
     L.require_cuda(A, "debug_gemm(A)")

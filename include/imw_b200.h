@@ -172,6 +172,17 @@ int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, co
                      float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
                      imw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MAGSAC++ geometric verification.
+ * Replaces: imcui/ui/utils.py:352-372 (cv2.findHomography / cv2.findFundamentalMat, method=cv2.USAC_MAGSAC) for a
+ * batch of correspondence sets.  pts0/pts1 [n_sets][cap][2] pixel coordinates, counts [n_sets].
+ * model_type 0 = homography, 1 = fundamental matrix.  Outputs: models [n_sets][9] (fp64, row-major, last element 1;
+ * all zeros = no model), masks [n_sets][cap] (1 = inlier: residual <= threshold), n_inliers / n_iters [n_sets].
+ * ---------------------------------------------------------------------------------------------- */
+int imw_magsac(int n_sets, int cap, const float* pts0, const float* pts1, const int* counts, int model_type, float threshold,
+               float confidence, int max_iters, unsigned seed, double* models, unsigned char* masks, int* n_inliers,
+               int* n_iters, imw_stream_t stream);
+
 /* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 path (split = 1: single TF32,
  * split = 3: 3xTF32 fp32-equivalent) and on the CUDA-core fp32 path. */
 int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K, int split,

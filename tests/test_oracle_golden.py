@@ -96,6 +96,26 @@ def test_superglue_oracle_matches_reference(golden, iters):
         np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[pre + "matching_scores0"], atol=1e-5)
 
 
+@pytest.mark.parametrize("tag", ["s", "m"])
+def test_loftr_oracle_matches_reference(golden, tag):
+    """Oracle == the in-tree LoFTR module (SE2LoFTR copy) with the same deterministic random weights."""
+    import importlib.util
+    from conftest import ROOT
+    from oracle import loftr as ol
+    spec = importlib.util.spec_from_file_location("synth", ROOT / "image-matching-webui_b200/utils/synth.py")
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    g = golden("loftr")
+    H, W = (int(v) for v in g[tag + "/hw"])
+    a, b, _ = synth.make_pair(0, H, W)
+    x0 = torch.from_numpy(a.astype(np.float32) / 255.0)[None, None]; x1 = torch.from_numpy(b.astype(np.float32) / 255.0)[None, None]
+    o = ol.forward(ol.random_weights(0), x0, x1, thr=float(g[tag + "/thr"]))
+    assert np.array_equal(o["i_ids"].numpy(), g[tag + "/i_ids"]) and np.array_equal(o["j_ids"].numpy(), g[tag + "/j_ids"])
+    assert np.array_equal(o["keypoints0"].numpy(), g[tag + "/keypoints0"])
+    np.testing.assert_allclose(o["keypoints1"].numpy(), g[tag + "/keypoints1"], atol=1e-4)
+    np.testing.assert_allclose(o["confidence"].numpy(), g[tag + "/confidence"], rtol=1e-4)
+    np.testing.assert_allclose(o["conf_matrix"][0].max(1)[0].numpy(), g[tag + "/conf_rowmax"], rtol=1e-4)
+
+
 def _matcher_inputs(golden, p):
     g = golden("matchers")
     if p == 0:

@@ -157,6 +157,33 @@ def sg_case(name, pairs):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def loftr_case(name):
+    """LoFTR with the deterministic random weights of oracle.loftr.random_weights loaded into the UNMODIFIED in-tree
+    LoFTR module (third_party/SE2LoFTR/src/loftr); thr lowered so that random weights still yield coarse matches."""
+    sys.path.insert(0, str(ROOT))
+    from oracle import loftr as ol
+    w = ol.random_weights(0)
+    blob = {}
+    for tag, (H, W), thr in (("s", (240, 320), 1e-5), ("m", (480, 640), 1e-6)):
+        net = R.make_loftr(0, thr=thr)
+        missing, unexpected = net.load_state_dict(w, strict=False)
+        assert not unexpected and all("num_batches_tracked" in m for m in missing), (missing, unexpected)
+        a, b, _ = synth.make_pair(0, H, W)
+        x0 = torch.from_numpy(a.astype(np.float32) / 255.0)[None, None]
+        x1 = torch.from_numpy(b.astype(np.float32) / 255.0)[None, None]
+        d = {"image0": x0, "image1": x1}
+        net(d)
+        blob[tag + "/thr"] = np.float32(thr)
+        blob[tag + "/hw"] = np.array([H, W])
+        blob[tag + "/keypoints0"] = d["mkpts0_f"].numpy(); blob[tag + "/keypoints1"] = d["mkpts1_f"].numpy()
+        blob[tag + "/confidence"] = d["mconf"].numpy()
+        blob[tag + "/i_ids"] = d["i_ids"].numpy().astype(np.int32); blob[tag + "/j_ids"] = d["j_ids"].numpy().astype(np.int32)
+        cm = d["conf_matrix"][0]
+        blob[tag + "/conf_rowmax"] = cm.max(1)[0].numpy(); blob[tag + "/conf_colmax"] = cm.max(0)[0].numpy()
+        print(name, tag, "matches", len(d["mconf"]), "conf max", float(cm.max()))
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def matcher_case(name, pairs):
     nn_mod, ds_mod = R.hloc_matchers()
     blob = {}
@@ -211,6 +238,7 @@ def main():
                 blob[f"{conf}/{j}/keypoints"].astype(np.float32), blob[f"{conf}/{j}/scores"], blob[f"{conf}/{j}/descriptors"], src)
 
     sg_case("sg", [sg_pair(rb, "sp_real:api:0:1"), sg_pair(sb, "sp_synth:max1024:0:1")])
+    loftr_case("loftr")
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
 

@@ -85,3 +85,72 @@ def make_superglue(conf):
     with contextlib.redirect_stdout(io.StringIO()):
         net = sg.SuperGlue({**conf, "weights_path": str(SG_WEIGHTS / f"superglue_{w}.pth")})
     return net.eval()
+
+
+def loftr_module():
+    """third_party/SE2LoFTR/src/loftr (the in-tree copy of zju3dv LoFTR that kornia.feature.LoFTR ports) with the
+    import stubs of SURVEY.md 8(c): e2cnn, yacs CfgNode, kornia dsnt / create_meshgrid."""
+    import torch
+    if "_ref_loftr_pkg" in sys.modules:
+        return sys.modules["_ref_loftr_pkg"]
+
+    class CfgNode(dict):
+        def __getattr__(self, k):
+            return self[k]
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    def spatial_expectation2d(heat, normalized_coordinates=True):
+        b, c, h, w = heat.shape
+        ys, xs = torch.linspace(-1, 1, h), torch.linspace(-1, 1, w)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        ex = (heat * gx).sum((-1, -2))
+        ey = (heat * gy).sum((-1, -2))
+        return torch.stack([ex, ey], -1)
+
+    def create_meshgrid(h, w, normalized_coordinates=True, device=None):
+        ys, xs = torch.linspace(-1, 1, h), torch.linspace(-1, 1, w)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        return torch.stack([gx, gy], -1)[None]
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    mod("yacs"); mod("yacs.config", CfgNode=CfgNode)
+    for n in ("e2cnn", "e2cnn.nn", "e2cnn.gspaces"):
+        mod(n)
+    dsnt = mod("kornia.geometry.subpix.dsnt", spatial_expectation2d=spatial_expectation2d)
+    mod("kornia"); mod("kornia.geometry", create_meshgrid=create_meshgrid); mod("kornia.geometry.subpix", dsnt=dsnt)
+    mod("kornia.utils", create_meshgrid=create_meshgrid)
+    src = TP / "SE2LoFTR" / "src"
+    pkg = types.ModuleType("_ref_loftr_src"); pkg.__path__ = [str(src)]
+    sys.modules["_ref_loftr_src"] = pkg
+    import importlib
+    # the package __init__ of src/loftr imports e2cnn variants; load the plain LoFTR modules directly
+    lp = types.ModuleType("_ref_loftr_src.loftr"); lp.__path__ = [str(src / "loftr")]
+    sys.modules["_ref_loftr_src.loftr"] = lp
+    bb = types.ModuleType("_ref_loftr_src.loftr.backbone"); bb.__path__ = [str(src / "loftr" / "backbone")]
+    sys.modules["_ref_loftr_src.loftr.backbone"] = bb
+    resnet = importlib.import_module("_ref_loftr_src.loftr.backbone.resnet_fpn")
+    bb.build_backbone = lambda config: resnet.ResNetFPN_8_2(config["resnetfpn"])
+    loftr = importlib.import_module("_ref_loftr_src.loftr.loftr")
+    cfg = importlib.import_module("_ref_loftr_src.loftr.utils.cvpr_ds_config")
+    out = types.SimpleNamespace(LoFTR=loftr.LoFTR, default_cfg=cfg.default_cfg)
+    sys.modules["_ref_loftr_pkg"] = out
+    return out
+
+
+def make_loftr(seed=0, thr=0.2):
+    import copy, torch
+    m = loftr_module()
+    cfg = copy.deepcopy(dict(m.default_cfg))
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}
+    cfg["match_coarse"]["thr"] = thr
+    torch.manual_seed(seed)
+    net = m.LoFTR(cfg).eval()
+    return net

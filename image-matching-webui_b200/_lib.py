@@ -52,6 +52,31 @@ class SGConf(C.Structure):
     _fields_ = [("sinkhorn_iterations", C.c_int), ("match_threshold", C.c_float), ("use_tensor_cores", C.c_int)]
 
 
+class LoftrConv(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("cin", C.c_int), ("cout", C.c_int), ("ksize", C.c_int), ("stride", C.c_int)]
+
+
+class LoftrBackbone(C.Structure):
+    _fields_ = [("conv1_w", C.c_void_p), ("conv1_b", C.c_void_p), ("l1", LoftrConv * 4), ("l2", LoftrConv * 4), ("l2_down", LoftrConv),
+                ("l3", LoftrConv * 4), ("l3_down", LoftrConv), ("l3_out", LoftrConv), ("l2_out", LoftrConv), ("l2_out2", LoftrConv * 2),
+                ("l1_out", LoftrConv), ("l1_out2", LoftrConv * 2)]
+
+
+class LoftrLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_w", "merge_w", "mlp0_w", "mlp2_w", "norm1_g", "norm1_b", "norm2_g", "norm2_b")] + \
+               [("is_cross", C.c_int), ("pad_", C.c_int)]
+
+
+class LoftrWeights(C.Structure):
+    _fields_ = [("backbone", LoftrBackbone), ("pos_enc", C.c_void_p), ("n_coarse", C.c_int), ("n_fine", C.c_int),
+                ("coarse", LoftrLayer * 8), ("fine", LoftrLayer * 2), ("down_proj_w", C.c_void_p), ("down_proj_b", C.c_void_p),
+                ("merge_feat_w", C.c_void_p), ("merge_feat_b", C.c_void_p)]
+
+
+class LoftrConf(C.Structure):
+    _fields_ = [("match_threshold", C.c_float), ("temperature", C.c_float), ("border_rm", C.c_int), ("use_tensor_cores", C.c_int)]
+
+
 class LGConf(C.Structure):
     _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
                 ("pruning_min_kpts", C.c_int), ("use_tensor_cores", C.c_int)]
@@ -78,6 +103,12 @@ def lib():
         L.imw_lightglue_workspace_bytes.argtypes = [C.c_int] * 2
         L.imw_matcher_workspace_bytes.argtypes = [C.c_int] * 2
         L.imw_superglue_workspace_bytes.argtypes = [C.c_int] * 2
+        L.imw_loftr_workspace_bytes.restype = C.c_size_t
+        L.imw_loftr_workspace_bytes.argtypes = [C.c_int] * 4
+        L.imw_loftr_forward.restype = C.c_int
+        L.imw_loftr_forward.argtypes = [C.POINTER(LoftrWeights), C.POINTER(LoftrConf), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]
         vp = C.c_void_p
         L.imw_superpoint_forward.restype = C.c_int
         L.imw_superpoint_forward.argtypes = [C.POINTER(SPWeights), C.POINTER(SPConf), C.c_int, C.c_int, C.c_int, vp,

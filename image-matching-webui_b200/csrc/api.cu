@@ -77,7 +77,7 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
   const int h = H / 8, w = W / 8;
   const bool use_tc = conf->use_tensor_cores != 0;
   if (use_tc) {
-    IMW_REQUIRE(W % 128 == 0, "imw_superpoint_forward: the tensor-core path needs W %% 128 == 0 (got %d)", W);
+    IMW_REQUIRE(W % 16 == 0, "imw_superpoint_forward: the tensor-core path needs W %% 16 == 0 (got %d)", W);
     for (int l : {1, 2, 3, 4, 5, 6, 7, 8, 10}) IMW_REQUIRE(wt->wp[l] != nullptr, "imw_superpoint_forward: bf16-plane weights missing for layer %d", l);
   }
   int rc;

@@ -28,3 +28,5 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
                int Cout, int relu, int pool, int out_fp32, cudaStream_t st);
 int tc_split_planes(const float* in, void* out_planes, size_t n, cudaStream_t st);
 int tc_merge_planes(const void* in_planes, float* out, size_t n, cudaStream_t st);
+int tc_conv_general(const void* in_planes, const void* w_planes, const float* bias, const void* res_planes, void* out, int B,
+                    int H, int W, int Cin, int Cout, int ksize, int stride, int act, int out_fp32, cudaStream_t st);

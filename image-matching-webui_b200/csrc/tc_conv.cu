@@ -32,11 +32,13 @@ constexpr int CV_A_BYTES = 128 * 128;         // one activation plane tile
 constexpr int CV_THREADS = 192;
 
 struct ConvArgs {
-  int H, W, Cin, Cout, B;
-  int relu, pool, out_fp32;
+  int H, W, Cin, Cout, B;     // H, W: INPUT size; output = ceil(H/stride) x ceil(W/stride) (then /2 if pooled)
+  int relu, pool, out_fp32;   // relu: 0 none, 1 ReLU, 2 LeakyReLU(0.01)
   const float* bias;
   __nv_bfloat16* out_planes;  // [3][B][Ho][Wo][Cout]
   float* out_f32;             // [B][Ho][Wo][Cout]
+  int ksize = 3, stride = 1;  // 3x3 (pad 1) or 1x1 (pad 0); stride 1 or 2 (TMA element strides)
+  const __nv_bfloat16* res_planes = nullptr;  // optional residual [3][B][Ho][Wo][Cout], added before the activation
 };
 
 template <int BN>
@@ -64,13 +66,15 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
-  const int tiles_x = g.W / CV_TW, tiles_y = (g.H + CV_TH - 1) / CV_TH;
+  const int Hc = (g.H + g.stride - 1) / g.stride, Wc = (g.W + g.stride - 1) / g.stride;  // conv output size
+  const int tiles_x = (Wc + CV_TW - 1) / CV_TW, tiles_y = (Hc + CV_TH - 1) / CV_TH;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y; t /= tiles_y;
   const int b = t;
   const int n0 = blockIdx.y * BN;
   const int x0 = tx * CV_TW, y0 = ty * CV_TH;
+  const int ntaps = g.ksize * g.ksize, kpad = g.ksize / 2;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -85,22 +89,22 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int chunks = g.Cin / CV_CK, steps = 9 * chunks;
+  const int chunks = g.Cin / CV_CK, steps = ntaps * chunks;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < steps; it++) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int tap = it / chunks, ck = it % chunks, dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int tap = it / chunks, ck = it % chunks, dy = tap / g.ksize - kpad, dx = tap % g.ksize - kpad;
         tc::mbar_wait(empty + s, ph ^ 1);
         tc::mbar_expect_tx(full + s, STAGE);
         uint8_t* st = smem + s * STAGE;
 #pragma unroll
-        for (int p = 0; p < 3; p++)  // activation planes: tensor dims (C, W, H, plane*B + b)
-          tc::tma_load_4d(st + p * CV_A_BYTES, &tmA, full + s, ck * CV_CK, x0 + dx, y0 + dy, p * g.B + b);
+        for (int p = 0; p < 3; p++)  // activation planes: tensor dims (C, W, H, plane*B + b); stride-2 via element strides
+          tc::tma_load_4d(st + p * CV_A_BYTES, &tmA, full + s, ck * CV_CK, x0 * g.stride + dx, y0 * g.stride + dy, p * g.B + b);
 #pragma unroll
         for (int p = 0; p < 3; p++)  // weight planes: rows (plane*9 + tap)*Cout + n, cols Cin
-          tc::tma_load_2d(st + 3 * CV_A_BYTES + p * B_BYTES, &tmW, full + s, ck * CV_CK, (p * 9 + tap) * g.Cout + n0);
+          tc::tma_load_2d(st + 3 * CV_A_BYTES + p * B_BYTES, &tmW, full + s, ck * CV_CK, (p * ntaps + tap) * g.Cout + n0);
       }
     }
   } else if (warp == 1) {
@@ -121,9 +125,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
           }
           const int tap = it / chunks, ck = it % chunks;
-          const uint32_t d_main = tmem_base + (tap / 3) * BN, d_cross = tmem_base + 3 * BN;
+          const int krow = tap / g.ksize;
+          const uint32_t d_main = tmem_base + krow * BN, d_cross = tmem_base + 3 * BN;
           if (leader) {
-            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % 3) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
+            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % g.ksize) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
             tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
             tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
             tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
@@ -143,10 +148,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc::fence_after_sync();
     const int m = q * 32 + lane;              // pixel index in the tile: row m/16, col m%16
     const int py = y0 + m / CV_TW, px = x0 + m % CV_TW;
-    const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
+    const int Ho = g.pool ? Hc / 2 : Hc, Wo = g.pool ? Wc / 2 : Wc;
     const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 16) == 0) : true;
     const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
-    const bool in_img = (py < g.H) && (px < g.W);
+    const bool in_img = (py < Hc) && (px < Wc);
     const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
     const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
 #pragma unroll 1
@@ -154,19 +159,38 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float v[32], t[32];
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
       tc::tmem_ld32(lane_base, v);
-      tc::tmem_ld32(lane_base + BN, t);
+      if (g.ksize == 3) {   // 1x1: only the first kernel-row accumulator and the cross-term accumulator are used
+        tc::tmem_ld32(lane_base + BN, t);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += t[j];
-      tc::tmem_ld32(lane_base + 2 * BN, t);
+        for (int j = 0; j < 32; j++) v[j] += t[j];
+        tc::tmem_ld32(lane_base + 2 * BN, t);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += t[j];
+        for (int j = 0; j < 32; j++) v[j] += t[j];
+      }
       tc::tmem_ld32(lane_base + 3 * BN, t);
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] += t[j];
+      if (g.res_planes && in_img) {  // residual branch of a BasicBlock (added before the activation)
+        const __nv_bfloat16* r0 = g.res_planes + opix + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 a = *reinterpret_cast<const uint4*>(r0 + j), bq = *reinterpret_cast<const uint4*>(r0 + plane_stride + j),
+                cq = *reinterpret_cast<const uint4*>(r0 + 2 * plane_stride + j);
+          const __nv_bfloat16 *pa = reinterpret_cast<const __nv_bfloat16*>(&a), *pb = reinterpret_cast<const __nv_bfloat16*>(&bq),
+                              *pc = reinterpret_cast<const __nv_bfloat16*>(&cq);
+#pragma unroll
+          for (int e = 0; e < 8; e++) t[j + e] = (__bfloat162float(pa[e]) + __bfloat162float(pb[e])) + __bfloat162float(pc[e]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) t[j] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 32; j++) {
-        float x = v[j] + g.bias[n0 + c0 + j];
-        if (g.relu) x = fmaxf(x, 0.f);
+        float x = v[j] + (g.bias ? g.bias[n0 + c0 + j] : 0.f);
+        if (g.res_planes) x += t[j];
+        if (g.relu == 1) x = fmaxf(x, 0.f);
+        else if (g.relu == 2) x = x > 0.f ? x : 0.01f * x;
         if (g.pool) {  // 2x2 window = lanes {l, l^1, l^16}: all inside this warp (2 image rows x 16 cols)
           x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
           x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
@@ -405,13 +429,14 @@ __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ in, float*
   out[i] = (__bfloat162float(in[i]) + __bfloat162float(in[n + i])) + __bfloat162float(in[2 * n + i]);
 }
 
-int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C, int box_w = CV_TW, int box_h = CV_TH) {
+int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C, int box_w = CV_TW, int box_h = CV_TH, int stride = 1) {
   PFN_encodeTiled fn = tc_get_encode_fn();
   if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B3};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {CV_CK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // with element strides the box extent is given in INPUT elements: N loaded elements <=> boxDim = N * stride
+  cuuint32_t box[4] = {CV_CK, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -440,7 +465,8 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& 
     IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid((unsigned)(g.B * ceil_div(g.H, CV_TH) * (g.W / CV_TW)), g.Cout / BN);
+  const int Hc = ceil_div(g.H, g.stride), Wc = ceil_div(g.W, g.stride);
+  dim3 grid((unsigned)(g.B * ceil_div(Hc, CV_TH) * ceil_div(Wc, CV_TW)), g.Cout / BN);
   tc_conv3x3_kernel<BN><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, g);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
@@ -452,7 +478,8 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& 
 // out: planes [3][B][Ho][Wo][Cout] bf16 or fp32 [B][Ho][Wo][Cout].
 int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,
                int Cout, int relu, int pool, int out_fp32, cudaStream_t st) {
-  IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0 && W % CV_TW == 0, "tc_conv3x3: Cin %% 64, Cout %% 64, W %% 16 (got %d,%d,%d)", Cin, Cout, W);
+  IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0, "tc_conv3x3: Cin %% 64, Cout %% 64 (got %d,%d)", Cin, Cout);
+  IMW_REQUIRE(!pool || (W % 2 == 0), "tc_conv3x3: pooled conv needs even W");
   IMW_REQUIRE(!pool || (H % 2 == 0), "tc_conv3x3: pooled conv needs even H");
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
@@ -480,6 +507,21 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
   if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin)) return e;
   if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, BN)) return e;
   ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+  return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
+}
+
+// General form used by the LoFTR backbone: 3x3 / 1x1, stride 1 / 2, optional residual, act 0 none / 1 ReLU / 2 LeakyReLU(0.01).
+// w_planes [3][k*k][Cout][Cin] bf16; bias may be NULL (bias-free convs without BatchNorm).
+int tc_conv_general(const void* in_planes, const void* w_planes, const float* bias, const void* res_planes, void* out, int B,
+                    int H, int W, int Cin, int Cout, int ksize, int stride, int act, int out_fp32, cudaStream_t st) {
+  IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0, "tc_conv_general: Cin %% 64, Cout %% 64 (got %d,%d)", Cin, Cout);
+  IMW_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "tc_conv_general: ksize 1|3, stride 1|2");
+  CUtensorMap tmA, tmW;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, CV_TW, CV_TH, stride)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, 3 * ksize * ksize * Cout, Cin, BN)) return e;
+  ConvArgs g{H, W, Cin, Cout, B, act, 0, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+  g.ksize = ksize; g.stride = stride; g.res_planes = (const __nv_bfloat16*)res_planes;
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 

@@ -72,7 +72,7 @@ def superpoint_forward(bufs, image, conf, cap, out=None, want_dense=False):
     lib = L.lib()
     nbytes = lib.imw_superpoint_workspace_bytes(B, H, W)
     ws = L.workspaces.get(dev, nbytes, "sp")
-    use_tc = bool(conf.get("tensor_cores", True)) and W % 128 == 0
+    use_tc = bool(conf.get("tensor_cores", True)) and W % 16 == 0
     c = L.SPConf(int(conf["nms_radius"]), float(conf["keypoint_threshold"]), int(conf["max_keypoints"]),
                  int(conf["remove_borders"]), int(use_tc))
     wstruct = sp_weights_struct(bufs)
@@ -231,6 +231,151 @@ def superglue_forward(bufs, bin_score, keypoints, scores, descriptors, counts, i
                                        L.ptr(mscores), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc)
     return matches, mscores
+
+
+# ---------------------------------------------------------------------------------------------------
+# LoFTR
+# ---------------------------------------------------------------------------------------------------
+def _pad_to(n, m=64):
+    return (n + m - 1) // m * m
+
+
+def _loftr_conv(sd, conv_key, bn_prefix, stride):
+    """Conv2d (bias-free) [+ BatchNorm2d eval] -> three bf16 planes [3][k*k][Cout_p][Cin_p] + fp32 bias [Cout_p];
+    channel counts zero-padded to multiples of 64 (196 -> 256)."""
+    w = sd[conv_key].float()
+    co, ci, k, _ = w.shape
+    b = None
+    if bn_prefix is not None:
+        g = sd[bn_prefix + "weight"] / torch.sqrt(sd[bn_prefix + "running_var"] + 1e-5)
+        w = w * g[:, None, None, None]
+        b = sd[bn_prefix + "bias"] - sd[bn_prefix + "running_mean"] * g
+    cop, cip = _pad_to(co), _pad_to(ci)
+    wt = torch.zeros(k * k, cop, cip)
+    wt[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(k * k, co, ci)
+    bias = torch.zeros(cop)
+    if b is not None:
+        bias[:co] = b
+    return {"w": split_bf16_planes(wt), "b": bias if b is not None else None, "cin": cip, "cout": cop, "ksize": k, "stride": stride}
+
+
+def loftr_pack_weights(sd):
+    """Reference LoFTR state dict (SE2LoFTR/src/loftr naming) -> kernel layout (CPU tensors + conv descriptors)."""
+    out = {"convs": {}}
+    g = sd["backbone.bn1.weight"] / torch.sqrt(sd["backbone.bn1.running_var"] + 1e-5)
+    w1 = sd["backbone.conv1.weight"].float() * g[:, None, None, None]
+    out["conv1_w"] = w1[:, 0].permute(1, 2, 0).reshape(49, 128).contiguous()
+    out["conv1_b"] = (sd["backbone.bn1.bias"] - sd["backbone.bn1.running_mean"] * g).float().contiguous()
+    cv = out["convs"]
+    for li in (1, 2, 3):
+        for bi in (0, 1):
+            p = f"backbone.layer{li}.{bi}."
+            s = 2 if (li > 1 and bi == 0) else 1
+            cv[f"l{li}.{2 * bi}"] = _loftr_conv(sd, p + "conv1.weight", p + "bn1.", s)
+            cv[f"l{li}.{2 * bi + 1}"] = _loftr_conv(sd, p + "conv2.weight", p + "bn2.", 1)
+        if li > 1:
+            p = f"backbone.layer{li}.0."
+            cv[f"l{li}_down"] = _loftr_conv(sd, p + "downsample.0.weight", p + "downsample.1.", 2)
+    cv["l3_out"] = _loftr_conv(sd, "backbone.layer3_outconv.weight", None, 1)
+    cv["l2_out"] = _loftr_conv(sd, "backbone.layer2_outconv.weight", None, 1)
+    cv["l2_out2.0"] = _loftr_conv(sd, "backbone.layer2_outconv2.0.weight", "backbone.layer2_outconv2.1.", 1)
+    cv["l2_out2.1"] = _loftr_conv(sd, "backbone.layer2_outconv2.3.weight", None, 1)
+    cv["l1_out"] = _loftr_conv(sd, "backbone.layer1_outconv.weight", None, 1)
+    cv["l1_out2.0"] = _loftr_conv(sd, "backbone.layer1_outconv2.0.weight", "backbone.layer1_outconv2.1.", 1)
+    cv["l1_out2.1"] = _loftr_conv(sd, "backbone.layer1_outconv2.3.weight", None, 1)
+    for prefix, n, tag in (("loftr_coarse.", 8, "c"), ("loftr_fine.", 2, "f")):
+        for i in range(n):
+            p = f"{prefix}layers.{i}."
+            out[f"{tag}{i}.qkv_w"] = torch.cat([sd[p + "q_proj.weight"], sd[p + "k_proj.weight"], sd[p + "v_proj.weight"]], 0).float().contiguous()
+            out[f"{tag}{i}.merge_w"] = sd[p + "merge.weight"].float().contiguous()
+            out[f"{tag}{i}.mlp0_w"] = sd[p + "mlp.0.weight"].float().contiguous()
+            out[f"{tag}{i}.mlp2_w"] = sd[p + "mlp.2.weight"].float().contiguous()
+            for nm, k in (("norm1.weight", "norm1_g"), ("norm1.bias", "norm1_b"), ("norm2.weight", "norm2_g"), ("norm2.bias", "norm2_b")):
+                out[f"{tag}{i}.{k}"] = sd[p + nm].float().contiguous()
+    for k in ("down_proj.weight", "down_proj.bias", "merge_feat.weight", "merge_feat.bias"):
+        out[k.replace(".weight", "_w").replace(".bias", "_b")] = sd["fine_preprocess." + k].float().contiguous()
+    return out
+
+
+def loftr_position_encoding(d_model, h, w, temp_bug_fix=False):
+    """utils/position_encoding.py:6-42 as a token table [h*w][d_model] (the default keeps the reference's 'buggy' div_term)."""
+    import math
+    pe = torch.zeros((d_model, h, w))
+    y_pos = torch.ones((h, w)).cumsum(0).float().unsqueeze(0)
+    x_pos = torch.ones((h, w)).cumsum(1).float().unsqueeze(0)
+    if temp_bug_fix:
+        div = torch.exp(torch.arange(0, d_model // 2, 2).float() * (-math.log(10000.0) / (d_model // 2)))
+    else:
+        div = torch.exp(torch.arange(0, d_model // 2, 2).float() * (-math.log(10000.0) / d_model // 2))
+    div = div[:, None, None]
+    pe[0::4] = torch.sin(x_pos * div); pe[1::4] = torch.cos(x_pos * div)
+    pe[2::4] = torch.sin(y_pos * div); pe[3::4] = torch.cos(y_pos * div)
+    return pe.permute(1, 2, 0).reshape(h * w, d_model).contiguous()
+
+
+def loftr_to_device(packed, device):
+    dev = {k: v.to(device) for k, v in packed.items() if torch.is_tensor(v)}
+    dev["convs"] = {k: {**c, "w": c["w"].to(device), "b": (c["b"].to(device) if c["b"] is not None else None)} for k, c in packed["convs"].items()}
+    return dev
+
+
+def _loftr_struct(wd, pos_enc):
+    s = L.LoftrWeights()
+    bb = s.backbone
+    bb.conv1_w, bb.conv1_b = wd["conv1_w"].data_ptr(), wd["conv1_b"].data_ptr()
+
+    def fill(dst, c):
+        dst.w = c["w"].data_ptr(); dst.b = c["b"].data_ptr() if c["b"] is not None else None
+        dst.cin, dst.cout, dst.ksize, dst.stride = c["cin"], c["cout"], c["ksize"], c["stride"]
+    cv = wd["convs"]
+    for i in range(4):
+        fill(bb.l1[i], cv[f"l1.{i}"]); fill(bb.l2[i], cv[f"l2.{i}"]); fill(bb.l3[i], cv[f"l3.{i}"])
+    fill(bb.l2_down, cv["l2_down"]); fill(bb.l3_down, cv["l3_down"]); fill(bb.l3_out, cv["l3_out"]); fill(bb.l2_out, cv["l2_out"])
+    fill(bb.l2_out2[0], cv["l2_out2.0"]); fill(bb.l2_out2[1], cv["l2_out2.1"]); fill(bb.l1_out, cv["l1_out"])
+    fill(bb.l1_out2[0], cv["l1_out2.0"]); fill(bb.l1_out2[1], cv["l1_out2.1"])
+    s.pos_enc = pos_enc.data_ptr()
+    s.n_coarse, s.n_fine = 8, 2
+    for tag, arr, n in (("c", s.coarse, 8), ("f", s.fine, 2)):
+        for i in range(n):
+            for f in ("qkv_w", "merge_w", "mlp0_w", "mlp2_w", "norm1_g", "norm1_b", "norm2_g", "norm2_b"):
+                setattr(arr[i], f, wd[f"{tag}{i}.{f}"].data_ptr())
+            arr[i].is_cross = i % 2  # layer_names = ['self', 'cross'] * n
+    s.down_proj_w, s.down_proj_b = wd["down_proj_w"].data_ptr(), wd["down_proj_b"].data_ptr()
+    s.merge_feat_w, s.merge_feat_b = wd["merge_feat_w"].data_ptr(), wd["merge_feat_b"].data_ptr()
+    return s
+
+
+def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=False):
+    """images [2P,H,W] fp32 CUDA (slot 2p = rows of the confidence matrix).  Returns dict of device tensors:
+    keypoints0/1 [P,mcap,2], confidence [P,mcap], counts [P] (+ debug features)."""
+    L.require_cuda(images, "loftr_forward(images)")
+    S, H, W = images.shape
+    assert S % 2 == 0 and H % 8 == 0 and W % 8 == 0
+    P, dev = S // 2, images.device
+    hc, wc = H // 8, W // 8
+    Lc = hc * wc
+    cap = (Lc + 127) // 128 * 128
+    mcap = int(max_matches or Lc)
+    key = ("pe", hc, wc, temp_bug_fix)
+    if key not in wd:
+        wd[key] = loftr_position_encoding(256, hc, wc, temp_bug_fix).to(dev)
+    out = {"keypoints0": torch.zeros(P, mcap, 2, device=dev), "keypoints1": torch.zeros(P, mcap, 2, device=dev),
+           "confidence": torch.zeros(P, mcap, device=dev), "counts": torch.zeros(P, dtype=torch.int32, device=dev)}
+    dbg_c = torch.zeros(S, cap, 256, device=dev) if debug else None
+    dbg_b = torch.zeros(S, Lc, 256, device=dev) if debug else None
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes(P, H, W, mcap), "loftr")
+    c = L.LoftrConf(float(conf.get("match_threshold", 0.2)), float(conf.get("temperature", 0.1)), int(conf.get("border_rm", 2)),
+                    int(conf.get("use_tensor_cores", 1)))
+    wstruct = _loftr_struct(wd, wd[key])
+    with torch.cuda.device(dev):
+        rc = lib.imw_loftr_forward(C.byref(wstruct), C.byref(c), P, H, W, L.ptr(images.contiguous()), mcap, L.ptr(out["keypoints0"]),
+                                   L.ptr(out["keypoints1"]), L.ptr(out["confidence"]), L.ptr(out["counts"]), L.ptr(dbg_c), L.ptr(dbg_b),
+                                   L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc)
+    if debug:
+        out["feat_c"], out["backbone_c"] = dbg_c[:, :Lc], dbg_b
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------

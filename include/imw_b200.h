@@ -173,6 +173,48 @@ int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, co
                      imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * LoFTR dense matcher.
+ * Replaces: hloc/matchers/loftr.py:41-71 -> kornia.feature.LoFTR == third_party/SE2LoFTR/src/loftr/loftr.py:29-75
+ * (ResNet-FPN backbone, coarse linear-attention transformer, dual-softmax coarse matching, fine refinement).
+ * Weights prepared by the host: BatchNorm folded, conv kernels as three bf16 planes [3][k*k][Cout][Cin] with the
+ * 196-channel tensors zero-padded to 256, encoder q/k/v stacked to [3*d][d].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { const void* w; const float* b; int cin, cout, ksize, stride; } imw_loftr_conv;
+typedef struct {
+  const float *conv1_w, *conv1_b;        /* 7x7 stem: [49][128] fp32 (BN folded), [128] */
+  imw_loftr_conv l1[4], l2[4], l2_down, l3[4], l3_down; /* BasicBlocks: conv1, conv2 of block 0 then block 1 */
+  imw_loftr_conv l3_out, l2_out, l2_out2[2], l1_out, l1_out2[2];
+} imw_loftr_backbone;
+typedef struct {
+  const float *qkv_w, *merge_w, *mlp0_w, *mlp2_w, *norm1_g, *norm1_b, *norm2_g, *norm2_b;
+  int is_cross, pad_;
+} imw_loftr_layer;
+typedef struct {
+  imw_loftr_backbone backbone;
+  const float* pos_enc;                  /* [hc*wc][256] for the current image size (position_encoding.py:6-42) */
+  int n_coarse, n_fine;
+  imw_loftr_layer coarse[8], fine[2];
+  const float *down_proj_w, *down_proj_b, *merge_feat_w, *merge_feat_b; /* [128][256],[128],[128][256],[128] */
+} imw_loftr_weights;
+typedef struct {
+  float match_threshold; /* match_coarse.thr */
+  float temperature;     /* match_coarse.dsmax_temperature (0.1) */
+  int border_rm;         /* match_coarse.border_rm (2) */
+  int use_tensor_cores;  /* encoder linears: 1 = 3xTF32, 2 = TF32, 0 = fp32 CUDA cores (convs are always tcgen05 bf16x3) */
+} imw_loftr_conf;
+
+size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_matches);
+
+/* images [2P][H][W] fp32 (H, W multiples of 8): slot 2p indexes the rows of the confidence matrix ("image0" of the LoFTR
+ * module), slot 2p+1 its columns; the sub-pixel refinement moves the slot-2p+1 keypoint.
+ * keypoints0/1 [P][max_matches][2], confidence [P][max_matches], counts [P] (matches in ascending row-cell order).
+ * dbg_* may be NULL: coarse features after the transformer [2P][cap][256] (cap = L rounded up to 128) / after the
+ * backbone [2P][L][256]. */
+int imw_loftr_forward(const imw_loftr_weights* weights, const imw_loftr_conf* conf, int n_pairs, int height, int width,
+                      const float* images, int max_matches, float* keypoints0, float* keypoints1, float* confidence, int* counts,
+                      float* dbg_feat_c, float* dbg_backbone_c, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * MAGSAC++ geometric verification.
  * Replaces: imcui/ui/utils.py:352-372 (cv2.findHomography / cv2.findFundamentalMat, method=cv2.USAC_MAGSAC) for a
  * batch of correspondence sets.  pts0/pts1 [n_sets][cap][2] pixel coordinates, counts [n_sets].

@@ -35,8 +35,8 @@ __device__ __forceinline__ float lf_merge3(const __nv_bfloat16* p, size_t plane,
 __global__ void __launch_bounds__(256) lf_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[49][128]*/,
                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
                                                        int H, int W) {
-  __shared__ float s_in[37][38];
-  __shared__ float s_w[49][128];
+  __shared__ __align__(16) float s_in[37][38];
+  __shared__ __align__(16) float s_w[49][128];
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int tiles_x = (Wo + 15) / 16;
   const int ox0 = (blockIdx.x % tiles_x) * 16, oy0 = (blockIdx.x / tiles_x) * 16, b = blockIdx.z, tid = threadIdx.x;

@@ -58,3 +58,25 @@ def test_loftr_plugin_contract(golden):
     out = model({"image0": x1[None, None].to(dev), "image1": x0[None, None].to(dev)})   # hloc order: the module sees (image1, image0)
     assert set(out) >= {"keypoints0", "keypoints1", "scores"}
     assert np.array_equal(out["keypoints1"].cpu().numpy(), g["s/keypoints0"]) and out["keypoints0"].shape == out["keypoints1"].shape
+
+
+def test_match_dense_with_loftr_end_to_end(golden):
+    """hloc.match_dense.match_images (row a10) driving the LoFTR plugin (row a11) from uint8 host images."""
+    import importlib.util
+    from imcui_b200.hloc import match_dense, matchers
+    from imcui_b200.hloc.configs import confs_dict
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    from oracle import loftr as ol
+    spec = importlib.util.spec_from_file_location("synth", ROOT / "image-matching-webui_b200/utils/synth.py")
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    a, b, _ = synth.make_pair(0, 480, 640)
+    g = golden("loftr")
+    conf = confs_dict["matchers"]["loftr"]
+    model = dynamic_load(matchers, "loftr")({**conf["model"], "state_dict": ol.random_weights(0), "match_threshold": float(g["m/thr"]), "max_keypoints": 30}).eval().to("cuda:0")
+    out = match_dense.match_images(model, b, a, conf["preprocessing"], device="cuda:0")   # the module sees (image_1, image_0)
+    order = np.argsort(-g["m/confidence"], kind="stable")[:30]
+    assert np.array_equal(out["mkeypoints1"], g["m/keypoints0"][order])
+    np.testing.assert_allclose(out["mkeypoints0"], g["m/keypoints1"][order], atol=2e-3)
+    np.testing.assert_allclose(out["mconf"], g["m/confidence"][order], rtol=2e-3)
+    assert np.all(np.diff(out["mconf"]) <= 1e-7)          # top-k keeps them sorted by confidence (loftr.py:58-65)
+    assert out["scale0"].tolist() == [1.0, 1.0] and np.array_equal(out["mkeypoints0_orig"], out["mkeypoints0"])

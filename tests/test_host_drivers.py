@@ -3,6 +3,7 @@ from types import SimpleNamespace
 
 import cv2
 import numpy as np
+import pytest
 import torch
 
 from conftest import GOLDEN
@@ -50,3 +51,46 @@ def test_match_images_postprocessing_with_a_fake_matcher():
     np.testing.assert_allclose(out["mkeypoints0_orig"], (np.array([[0, 1], [4, 5]]) + 0.5) * 2 - 0.5)
     np.testing.assert_allclose(out["mkeypoints1_orig"], [[2, 3], [0, 1]])
     assert out["mconf"].shape == (2,)
+
+
+def test_match_dense_postprocessing_with_a_fake_matcher():
+    """match_dense.match_images (reference :577-686): force-resize to 640x480, dfactor alignment, the swap-free output
+    keys, 'scores' adopted as mconf and the (k + 0.5) * s - 0.5 rescale with s = original / network size."""
+    from imcui_b200.hloc import match_dense as md
+    from imcui_b200.hloc.configs import confs_dict
+    seen = {}
+
+    class Fake(torch.nn.Module):
+        def forward(self, data):
+            seen["shape"] = (tuple(data["image0"].shape), tuple(data["image1"].shape))
+            return {"keypoints0": torch.tensor([[0.0, 0.0], [8.0, 16.0]]), "keypoints1": torch.tensor([[1.0, 2.0], [9.5, 18.25]]),
+                    "scores": torch.tensor([0.9, 0.4])}
+    rgb0 = np.random.RandomState(0).randint(0, 255, (960, 1280, 3), dtype=np.uint8)
+    rgb1 = np.random.RandomState(1).randint(0, 255, (480, 640, 3), dtype=np.uint8)
+    out = md.match_images(Fake(), rgb0, rgb1, confs_dict["matchers"]["loftr"]["preprocessing"], device="cpu")
+    assert seen["shape"] == ((1, 1, 480, 640), (1, 1, 480, 640))
+    assert out["scale0"].tolist() == [2.0, 2.0] and out["scale1"].tolist() == [1.0, 1.0]
+    np.testing.assert_allclose(out["mkeypoints0_orig"], (np.array([[0, 0], [8, 16]]) + 0.5) * 2 - 0.5)
+    np.testing.assert_allclose(out["mkeypoints1_orig"], [[1, 2], [9.5, 18.25]])
+    assert np.array_equal(out["keypoints0"], out["mkeypoints0"]) and out["mconf"].tolist() == pytest.approx([0.9, 0.4])
+    assert out["new_size0"].tolist() == [640, 480] and out["original_size0"].tolist() == [1280, 960]
+    # gray conversion + area resize + /255 of image 1 (no resize needed) is the plain cv2 result
+    assert np.array_equal(out["image1"], (cv2.cvtColor(rgb1, cv2.COLOR_RGB2GRAY).astype(np.float32) / 255.0))
+
+
+def test_loftr_weight_packing_layout():
+    """BN folding, 196 -> 256 zero padding and the three-plane bf16 split of the LoFTR backbone convolutions."""
+    from imcui_b200 import ops
+    from oracle import loftr as ol
+    sd = ol.random_weights(0)
+    pk = ops.loftr_pack_weights(sd)
+    c = pk["convs"]["l2.0"]
+    assert (c["cin"], c["cout"], c["ksize"], c["stride"]) == (128, 256, 3, 2) and tuple(c["w"].shape) == (3, 9, 256, 128)
+    g = sd["backbone.layer2.0.bn1.weight"] / torch.sqrt(sd["backbone.layer2.0.bn1.running_var"] + 1e-5)
+    w = (sd["backbone.layer2.0.conv1.weight"] * g[:, None, None, None]).permute(2, 3, 0, 1).reshape(9, 196, 128)
+    rec = c["w"].float().sum(0)
+    assert float((rec[:, :196] - w).abs().max()) < 1e-6 * float(w.abs().max()) + 1e-7 and float(rec[:, 196:].abs().max()) == 0.0
+    assert float(c["b"][196:].abs().max()) == 0.0 and pk["convs"]["l3_out"]["b"] is None
+    assert tuple(pk["conv1_w"].shape) == (49, 128) and tuple(pk["c0.qkv_w"].shape) == (768, 256) and tuple(pk["f1.mlp0_w"].shape) == (256, 256)
+    pe = ops.loftr_position_encoding(256, 30, 40)
+    assert torch.allclose(pe, ol.position_encoding(256, 30, 40).permute(1, 2, 0).reshape(1200, 256))

@@ -46,6 +46,14 @@ def make_pair(seed: int, height: int = 480, width: int = 640):
     return img0, img1, Hm
 
 
+def to_rgb(gray: np.ndarray) -> np.ndarray:
+    """Three correlated channels from one gray image (BASELINE config 4 uses RGB input): uint8 [...,H,W] -> [...,H,W,3]."""
+    g = gray.astype(np.float32)
+    r = np.clip(g * 1.05 + 4.0, 0, 255)
+    b = np.clip(g * 0.90 + 12.0, 0, 255)
+    return np.round(np.stack([r, g, b], -1)).astype(np.uint8)
+
+
 def make_pair_batch(seeds, height: int = 480, width: int = 640):
     """uint8 arrays [P,H,W], [P,H,W] for a list of pair seeds."""
     a, b = zip(*[make_pair(s, height, width)[:2] for s in seeds])

@@ -8,7 +8,7 @@ import oracle
 from oracle import lightglue as olg
 from oracle import matchers as om
 from oracle import superpoint as osp
-from conftest import lg_pair_from_source, match_f1
+from conftest import ROOT, lg_pair_from_source, match_f1
 
 SP_CONFS = {
     "api": {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4},
@@ -147,3 +147,32 @@ def test_matchers_oracle_empty_inputs():
         out = fn(e, d)
         assert out["matches0"].shape == (1, 128) or out["matches0"].shape == (1, 128)  # reference quirk: shape[:2]
         assert (out["matches0"] == -1).all()
+
+
+# ---- ALIKED -------------------------------------------------------------------------------------------------------
+def _aliked_input(tag):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("synth", ROOT / "image-matching-webui_b200/utils/synth.py")
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    from aliked_cases import ALIKED_CASES
+    seed, H, W, rgb, conf = ALIKED_CASES[tag]
+    a, _, _ = synth.make_pair(seed, H, W)
+    if rgb:
+        return torch.from_numpy(synth.to_rgb(a).astype(np.float32) / 255.0).permute(2, 0, 1)[None], conf
+    return torch.from_numpy(a.astype(np.float32) / 255.0)[None, None], conf
+
+
+@pytest.mark.parametrize("tag", ["s", "cap", "pad", "topk", "mean", "densecap"])
+def test_aliked_oracle_matches_reference(golden, tag):
+    from oracle import aliked as oa
+    g = golden("aliked")
+    img, conf = _aliked_input(tag)
+    with torch.no_grad():
+        o = oa.forward(oa.random_weights(0), img, **conf)
+    assert o["keypoints"].shape == g[tag + "/keypoints"].shape
+    np.testing.assert_allclose(o["keypoints"].numpy(), g[tag + "/keypoints"], atol=1e-4)
+    np.testing.assert_allclose(o["keypoint_scores"].numpy(), g[tag + "/scores"], atol=1e-6)
+    np.testing.assert_allclose(o["descriptors"].numpy(), g[tag + "/descriptors"], atol=2e-5)
+    if tag + "/score_map" in g:
+        np.testing.assert_allclose(o["score_map"][0, 0].numpy(), g[tag + "/score_map"], atol=1e-6)
+        np.testing.assert_allclose(o["feature_map"][0, :, ::40].numpy(), g[tag + "/feature_map_rows"], atol=1e-6)

@@ -184,6 +184,35 @@ def loftr_case(name):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+sys.path.insert(0, str(ROOT / "tests"))
+from aliked_cases import ALIKED_CASES  # noqa: E402
+
+
+def aliked_case(name):
+    """ALIKED (aliked-n16) with oracle.aliked.random_weights loaded into the UNMODIFIED reference module."""
+    sys.path.insert(0, str(ROOT))
+    from oracle import aliked as oa
+    w = oa.random_weights(0)
+    blob = {}
+    for tag, (seed, H, W, rgb, conf) in ALIKED_CASES.items():
+        net = R.make_aliked(w, **conf)
+        a, _, _ = synth.make_pair(seed, H, W)
+        if rgb:
+            img = torch.from_numpy(synth.to_rgb(a).astype(np.float32) / 255.0).permute(2, 0, 1)[None]
+        else:
+            img = torch.from_numpy(a.astype(np.float32) / 255.0)[None, None]
+        out = net({"image": img})
+        blob[tag + "/keypoints"] = out["keypoints"][0].numpy()
+        blob[tag + "/descriptors"] = out["descriptors"][0].numpy()[:: (8 if tag == "dense" else 1)]   # dense: every 8th row
+        blob[tag + "/scores"] = out["keypoint_scores"][0].numpy()
+        if tag in ("s", "pad"):
+            fm, sm = net.extract_dense_map(img if rgb else img.repeat(1, 3, 1, 1))
+            blob[tag + "/score_map"] = sm[0, 0].numpy()
+            blob[tag + "/feature_map_rows"] = fm[0, :, ::40].numpy()   # every 40th row of the 128-channel map
+        print(name, tag, "keypoints", out["keypoints"].shape[1], "score mean", float(out["keypoint_scores"].mean()))
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def matcher_case(name, pairs):
     nn_mod, ds_mod = R.hloc_matchers()
     blob = {}
@@ -239,9 +268,14 @@ def main():
 
     sg_case("sg", [sg_pair(rb, "sp_real:api:0:1"), sg_pair(sb, "sp_synth:max1024:0:1")])
     loftr_case("loftr")
+    aliked_case("aliked")
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:   # python make_golden.py aliked -> only that family
+        with torch.no_grad():
+            {"aliked": aliked_case, "loftr": loftr_case}[sys.argv[1]](sys.argv[1])
+    else:
+        main()

@@ -154,3 +154,36 @@ def make_loftr(seed=0, thr=0.2):
     torch.manual_seed(seed)
     net = m.LoFTR(cfg).eval()
     return net
+
+
+def aliked_module():
+    """third_party/LightGlue/lightglue/aliked.py under a stand-in `lightglue` package (its __init__ pulls every model)
+    with kornia.color.grayscale_to_rgb stubbed (kornia is not installed; the function is a channel repeat)."""
+    import torch
+    if "_ref_lg_pkg.aliked" in sys.modules:
+        return sys.modules["_ref_lg_pkg.aliked"]
+    if "kornia" not in sys.modules or not hasattr(sys.modules["kornia"], "color"):
+        k = sys.modules.get("kornia") or types.ModuleType("kornia")
+        k.__path__ = []
+        col = types.ModuleType("kornia.color")
+        col.grayscale_to_rgb = lambda x: x.repeat(1, 3, 1, 1) if x.dim() == 4 else x.repeat(3, 1, 1)
+        k.color = col
+        sys.modules["kornia"] = k
+        sys.modules["kornia.color"] = col
+    pkg = types.ModuleType("_ref_lg_pkg"); pkg.__path__ = [str(TP / "LightGlue/lightglue")]
+    sys.modules["_ref_lg_pkg"] = pkg
+    import importlib
+    return importlib.import_module("_ref_lg_pkg.aliked")
+
+
+def make_aliked(state_dict, **conf):
+    """The unmodified ALIKED module with `state_dict` loaded in place of the GitHub download (aliked.py:692-695)."""
+    import torch
+    m = aliked_module()
+    orig = torch.hub.load_state_dict_from_url
+    torch.hub.load_state_dict_from_url = lambda *a, **k: state_dict
+    try:
+        net = m.ALIKED(**conf)
+    finally:
+        torch.hub.load_state_dict_from_url = orig
+    return net.eval()

@@ -52,6 +52,20 @@ class SGConf(C.Structure):
     _fields_ = [("sinkhorn_iterations", C.c_int), ("match_threshold", C.c_float), ("use_tensor_cores", C.c_int)]
 
 
+ALIKED_FIELDS = ("b1c1_w b1c1_b b1c2_w b1c2_b b2c1_w b2c1_b b2c2_w b2c2_b b2ds_w b2ds_b "
+                 "b3o1_w b3o1_b b3c1_w b3c1_b b3o2_w b3o2_b b3c2_w b3c2_b b3ds_w b3ds_b "
+                 "b4o1_w b4o1_b b4c1_w b4c1_b b4o2_w b4o2_b b4c2_w b4c2_b b4ds_w b4ds_b "
+                 "conv1_w conv2_w conv3_w conv4_w s0_w s2_w s4_w s6_w sd_off0_w sd_off0_b sd_off2_w sd_off2_b sd_sf_w sd_agg").split()
+
+
+class AlikedWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ALIKED_FIELDS]
+
+
+class AlikedConf(C.Structure):
+    _fields_ = [("detection_threshold", C.c_float), ("max_num_keypoints", C.c_int), ("nms_radius", C.c_int)]
+
+
 class LoftrConv(C.Structure):
     _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("cin", C.c_int), ("cout", C.c_int), ("ksize", C.c_int), ("stride", C.c_int)]
 
@@ -103,6 +117,12 @@ def lib():
         L.imw_lightglue_workspace_bytes.argtypes = [C.c_int] * 2
         L.imw_matcher_workspace_bytes.argtypes = [C.c_int] * 2
         L.imw_superglue_workspace_bytes.argtypes = [C.c_int] * 2
+        L.imw_aliked_workspace_bytes.restype = C.c_size_t
+        L.imw_aliked_workspace_bytes.argtypes = [C.c_int] * 4
+        L.imw_aliked_forward.restype = C.c_int
+        L.imw_aliked_forward.argtypes = [C.POINTER(AlikedWeights), C.POINTER(AlikedConf), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]
         L.imw_loftr_workspace_bytes.restype = C.c_size_t
         L.imw_loftr_workspace_bytes.argtypes = [C.c_int] * 4
         L.imw_loftr_forward.restype = C.c_int

@@ -15,7 +15,8 @@ int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cuda
 // nms -> keypoints/scores per image (row-major order, or descending score when more than max_kpts pass)
 // keys: scratch [B][key_cap] u64.  kpts [B][cap][2] float (x,y), scores [B][cap], counts [B].
 int sp_select(const float* nms, unsigned long long* keys, int key_cap, float* kpts, float* scores, int* counts,
-              int B, int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st);
+              int B, int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st,
+              const float* thr_img = nullptr /* optional per-image thresholds [B] on the device */);
 size_t sp_select_key_cap(int H, int W);
 // in-place L2 normalisation of rows of 256 ([cells][256])
 int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st);

@@ -167,12 +167,13 @@ constexpr int SEL_SMEM_KEYS = 16384;  // 128 KB of shared memory for the in-CTA 
 
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __restrict__ nms, unsigned long long* __restrict__ keys_all,
                                                              int key_cap, float* __restrict__ kpts, float* __restrict__ scores,
-                                                             int* __restrict__ counts, int H, int W, float thr, int border,
-                                                             int max_kpts, int cap) {
+                                                             int* __restrict__ counts, int H, int W, float thr_uniform, int border,
+                                                             int max_kpts, int cap, const float* __restrict__ thr_img) {
   extern __shared__ __align__(16) unsigned long long s_keys[];
   __shared__ int s_scan[SEL_THREADS / 32];
   __shared__ int s_total;
   const int b = blockIdx.x, tid = threadIdx.x;
+  const float thr = thr_img ? thr_img[b] : thr_uniform;   // per-image threshold (ALIKED's mean fallback)
   const float* img = nms + (long long)b * H * W;
   unsigned long long* keys = keys_all + (long long)b * key_cap;
   const int npix = H * W;
@@ -334,7 +335,8 @@ int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cuda
     kern<<<grid, 256, smem, st>>>(dense, nms, H, W, radius);
     return cudaSuccess;
   };
-  if (radius == 3) IMW_CHECK_CUDA(launch(nms_kernel<3>));
+  if (radius == 2) IMW_CHECK_CUDA(launch(nms_kernel<2>));
+  else if (radius == 3) IMW_CHECK_CUDA(launch(nms_kernel<3>));
   else if (radius == 4) IMW_CHECK_CUDA(launch(nms_kernel<4>));
   else IMW_CHECK_CUDA(launch(nms_kernel<0>));
   IMW_CHECK_LAUNCH();
@@ -348,10 +350,10 @@ size_t sp_select_key_cap(int H, int W) {
 }
 
 int sp_select(const float* nms, unsigned long long* keys, int key_cap, float* kpts, float* scores, int* counts, int B,
-              int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st) {
+              int H, int W, float threshold, int border, int max_kpts, int cap, cudaStream_t st, const float* thr_img) {
   size_t smem = (size_t)SEL_SMEM_KEYS * sizeof(unsigned long long);
   IMW_CHECK_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_kernel<<<B, SEL_THREADS, smem, st>>>(nms, keys, key_cap, kpts, scores, counts, H, W, threshold, border, max_kpts, cap);
+  select_kernel<<<B, SEL_THREADS, smem, st>>>(nms, keys, key_cap, kpts, scores, counts, H, W, threshold, border, max_kpts, cap, thr_img);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

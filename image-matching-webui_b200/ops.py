@@ -234,6 +234,81 @@ def superglue_forward(bufs, bin_score, keypoints, scores, descriptors, counts, i
 
 
 # ---------------------------------------------------------------------------------------------------
+# ALIKED
+# ---------------------------------------------------------------------------------------------------
+def aliked_pack_weights(sd):
+    """Reference aliked-n16 state dict (lightglue/aliked.py naming) -> kernel layout (CPU fp32 tensors keyed by the
+    imw_aliked_weights field names): BatchNorm folded, 3x3 kernels as [tap][Cin][Cout], 1x1 kernels as [Cin][Cout]."""
+    f = lambda k: sd[k].float()
+
+    def fold(wkey, bn):
+        w = f(wkey)
+        g = f(bn + "weight") / torch.sqrt(f(bn + "running_var") + 1e-5)
+        return w * g[:, None, None, None], f(bn + "bias") - f(bn + "running_mean") * g
+
+    def taps(w, cin_pad=None, cout_pad=None):  # [Co][Ci][3][3] -> [9][Ci_p][Co_p]
+        co, ci = w.shape[:2]
+        t = torch.zeros(9, cin_pad or ci, cout_pad or co)
+        t[:, :ci, :co] = w.permute(2, 3, 1, 0).reshape(9, ci, co)
+        return t.contiguous()
+
+    def padv(b, n):
+        o = torch.zeros(n); o[: len(b)] = b
+        return o
+
+    out = {}
+    w, b = fold("block1.conv1.weight", "block1.bn1."); out["b1c1_w"], out["b1c1_b"] = taps(w, cin_pad=4), b
+    w, b = fold("block1.conv2.weight", "block1.bn2."); out["b1c2_w"], out["b1c2_b"] = taps(w), b
+    w, b = fold("block2.conv1.weight", "block2.bn1."); out["b2c1_w"], out["b2c1_b"] = taps(w), b
+    w, b = fold("block2.conv2.weight", "block2.bn2."); out["b2c2_w"], out["b2c2_b"] = taps(w), b
+    for i in (2, 3, 4):
+        out[f"b{i}ds_w"] = f(f"block{i}.downsample.weight")[:, :, 0, 0].t().contiguous()
+        out[f"b{i}ds_b"] = f(f"block{i}.downsample.bias")
+    for i in (3, 4):
+        for j in (1, 2):
+            out[f"b{i}o{j}_w"] = taps(f(f"block{i}.conv{j}.offset_conv.weight"), cout_pad=24)
+            out[f"b{i}o{j}_b"] = padv(f(f"block{i}.conv{j}.offset_conv.bias"), 24)
+            w, b = fold(f"block{i}.conv{j}.regular_conv.weight", f"block{i}.bn{j}.")
+            out[f"b{i}c{j}_w"], out[f"b{i}c{j}_b"] = taps(w), b
+    for i in (1, 2, 3, 4):
+        out[f"conv{i}_w"] = f(f"conv{i}.weight")[:, :, 0, 0].t().contiguous()
+    out["s0_w"] = f("score_head.0.weight")[:, :, 0, 0].t().contiguous()
+    out["s2_w"], out["s4_w"], out["s6_w"] = taps(f("score_head.2.weight")), taps(f("score_head.4.weight")), taps(f("score_head.6.weight"))
+    out["sd_off0_w"], out["sd_off0_b"] = taps(f("desc_head.offset_conv.0.weight")), f("desc_head.offset_conv.0.bias")
+    out["sd_off2_w"], out["sd_off2_b"] = f("desc_head.offset_conv.2.weight")[:, :, 0, 0].t().contiguous(), f("desc_head.offset_conv.2.bias")
+    out["sd_sf_w"] = f("desc_head.sf_conv.weight")[:, :, 0, 0].t().contiguous()
+    out["sd_agg"] = f("desc_head.agg_weights").contiguous()
+    assert set(out) == set(L.ALIKED_FIELDS)
+    return {k: v.contiguous() for k, v in out.items()}
+
+
+def aliked_forward(bufs, image, conf, cap, debug=False):
+    """image [B,1|3,H,W] fp32 CUDA in [0,1].  Returns batch buffers: keypoints [B,cap,2], scores [B,cap],
+    descriptors [B,cap,128], counts [2,B] int32 (written, total) (+ score_map / feature_map with debug)."""
+    L.require_cuda(image, "aliked_forward(image)")
+    assert image.dim() == 4 and image.shape[1] in (1, 3) and image.dtype == torch.float32
+    image = image.contiguous()
+    B, Cc, H, W = image.shape
+    dev = image.device
+    out = {"keypoints": torch.empty(B, cap, 2, device=dev), "scores": torch.empty(B, cap, device=dev),
+           "descriptors": torch.empty(B, cap, 128, device=dev), "counts": torch.empty(2, B, dtype=torch.int32, device=dev)}
+    smap = torch.empty(B, H, W, device=dev) if debug else None
+    fmap = torch.empty(B, H, W, 128, device=dev) if debug else None
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_aliked_workspace_bytes(B, H, W, cap), "aliked")
+    c = L.AlikedConf(float(conf["detection_threshold"]), int(conf["max_num_keypoints"]), int(conf["nms_radius"]))
+    wstruct = L.AlikedWeights(**{k: bufs[k].data_ptr() for k in L.ALIKED_FIELDS})
+    with torch.cuda.device(dev):
+        rc = lib.imw_aliked_forward(C.byref(wstruct), C.byref(c), B, Cc, H, W, L.ptr(image), cap, L.ptr(out["keypoints"]), L.ptr(out["scores"]),
+                                    L.ptr(out["descriptors"]), L.ptr(out["counts"]), L.ptr(smap), L.ptr(fmap), L.ptr(ws), ws.numel(),
+                                    L.stream_ptr(dev))
+    L.check(rc)
+    if debug:
+        out["score_map"], out["feature_map"] = smap, fmap
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # LoFTR
 # ---------------------------------------------------------------------------------------------------
 def _pad_to(n, m=64):

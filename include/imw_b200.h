@@ -173,6 +173,39 @@ int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, co
                      imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ALIKED (aliked-n16) extractor.
+ * Replaces: hloc/extractors/aliked.py:12-32 -> third_party/LightGlue/lightglue/aliked.py:757-775 (ALIKED.forward:
+ * extract_dense_map :709-740, DKD :94-261, SDDH :479-609, deformable convolutions :291-349).
+ * Weights prepared by the host (ops.aliked_pack_weights): fp32, BatchNorm folded, conv kernels as [tap][Cin][Cout]
+ * (block1.conv1 Cin padded 3 -> 4; the 18-channel offset convolutions padded to 24 outputs), 1x1 kernels as [Cin][Cout].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *b1c1_w, *b1c1_b, *b1c2_w, *b1c2_b;                                       /* block1: 3(4) -> 16 -> 16 */
+  const float *b2c1_w, *b2c1_b, *b2c2_w, *b2c2_b, *b2ds_w, *b2ds_b;                     /* block2: 16 -> 32, shortcut 1x1 (+bias) */
+  const float *b3o1_w, *b3o1_b, *b3c1_w, *b3c1_b, *b3o2_w, *b3o2_b, *b3c2_w, *b3c2_b, *b3ds_w, *b3ds_b; /* block3 (DCN): 32 -> 64 */
+  const float *b4o1_w, *b4o1_b, *b4c1_w, *b4c1_b, *b4o2_w, *b4o2_b, *b4c2_w, *b4c2_b, *b4ds_w, *b4ds_b; /* block4 (DCN): 64 -> 128 */
+  const float *conv1_w, *conv2_w, *conv3_w, *conv4_w;                                   /* aggregation heads [Cin][32] */
+  const float *s0_w, *s2_w, *s4_w, *s6_w;                                               /* score head: [128][8], [9][8][4], [9][4][4], [9][4][1] */
+  const float *sd_off0_w, *sd_off0_b, *sd_off2_w, *sd_off2_b, *sd_sf_w, *sd_agg;        /* SDDH: [9][128][32], [32], [32][32], [32], [128][128], [16][128][128] */
+} imw_aliked_weights;
+
+typedef struct {
+  float detection_threshold;   /* 0.2; <= 0: top-k mode (max_num_keypoints > 0) or mean threshold */
+  int max_num_keypoints;       /* -1: up to 20000 (n_limit_max) */
+  int nms_radius;              /* 2 */
+} imw_aliked_conf;
+
+size_t imw_aliked_workspace_bytes(int n_images, int height, int width, int cap);
+
+/* images [B][channels][H][W] fp32 in [0,1] (channels 1 = gray, repeated to RGB; 3 = RGB), same size for the batch.
+ * keypoints [B][cap][2] (x, y sub-pixel, pixel units), scores [B][cap], descriptors [B][cap][128] (L2-normalised),
+ * counts [2B]: [0,B) keypoints written, [B,2B) keypoints the reference returns (> cap = overflow).
+ * dbg_score_map [B][H][W] / dbg_feature_map [B][H][W][128]: optional copies of the dense maps (NULL to skip). */
+int imw_aliked_forward(const imw_aliked_weights* weights, const imw_aliked_conf* conf, int n_images, int channels, int height,
+                       int width, const float* images, int cap, float* keypoints, float* scores, float* descriptors, int* counts,
+                       float* dbg_score_map, float* dbg_feature_map, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LoFTR dense matcher.
  * Replaces: hloc/matchers/loftr.py:41-71 -> kornia.feature.LoFTR == third_party/SE2LoFTR/src/loftr/loftr.py:29-75
  * (ResNet-FPN backbone, coarse linear-attention transformer, dual-softmax coarse matching, fine refinement).

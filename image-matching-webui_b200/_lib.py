@@ -32,7 +32,8 @@ class LGLayer(C.Structure):
 class LGWeights(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("input_dim", C.c_int), ("posenc_wr", C.c_void_p),
                 ("token_w", C.c_void_p), ("token_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
-                ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS)]
+                ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS),
+                ("input_proj_w", C.c_void_p), ("input_proj_b", C.c_void_p)]
 
 
 IMW_SG_MAX_LAYERS = 32

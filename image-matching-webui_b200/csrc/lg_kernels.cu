@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) init_tokens_kernel(const float* __restric
     mscores[(long long)z * cap + row] = 0.f;
     prune[(long long)z * cap + row] = prune_init;
   }
-  if (row < counts[z])
+  if (desc && row < counts[z])
     reinterpret_cast<float4*>(xm + ((long long)z * cap + row) * 512)[t] =
         reinterpret_cast<const float4*>(desc + ((long long)z * cap + row) * D)[t];
 }
@@ -437,7 +437,8 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
                                      cudaStream_t st) {
   IMW_REQUIRE(W && conf && n_pairs > 0 && cap > 0, "imw_lightglue_forward: bad arguments");
   IMW_REQUIRE(W->n_layers >= 1 && W->n_layers <= IMW_LG_MAX_LAYERS, "imw_lightglue_forward: n_layers %d", W->n_layers);
-  IMW_REQUIRE(W->input_dim == 256, "imw_lightglue_forward: only 256-d descriptors (SuperPoint) in this build");
+  IMW_REQUIRE(W->input_dim == 256 || (W->input_dim == 128 && W->input_proj_w && W->input_proj_b),
+              "imw_lightglue_forward: input_dim must be 256 (identity) or 128 with input_proj weights (got %d)", W->input_dim);
   IMW_REQUIRE(cap % 4 == 0, "imw_lightglue_forward: cap %% 4");
   const int P = n_pairs, S = 2 * P, L = W->n_layers;
   Workspace ws(workspace, workspace_bytes);
@@ -453,7 +454,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   init_state_kernel<<<ceil_div(P, 128), 128, 0, st>>>(counts_in, b.counts, b.counts0, b.done, b.empty, stop, b.cnt, P, L);
   IMW_CHECK_LAUNCH();
   // prune output: 1 (+1 per surviving pruning step) when pruning is enabled, n_layers otherwise (:617-619)
-  init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(desc, b.xm[0], b.ind[0], matches, mscores, prune, b.counts, cap,
+  init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(W->input_dim == D ? desc : nullptr, b.xm[0], b.ind[0], matches, mscores, prune, b.counts, cap,
                                                                 prune_semantics ? 1 : L);
   IMW_CHECK_LAUNCH();
   posenc_kernel<<<S, 256, 0, st>>>(kpts, b.counts, W->posenc_wr, b.enc[0], cap);
@@ -509,6 +510,9 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     return IMW_OK;
   };
 
+  if (W->input_dim != D) {  // x = input_proj(desc) (lightglue.py:519-520)
+    if (int e = linear(desc, W->input_dim, W->input_proj_w, D, D, W->input_dim, EpiStore{b.xm[0], 512, sXM, W->input_proj_b, 0}, b.done, nullptr)) return e;
+  }
   for (int i = 0; i < L; i++) {
     const imw_lg_layer& ly = W->layers[i];
     float* xm = b.xm[cur];

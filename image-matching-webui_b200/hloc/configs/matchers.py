@@ -17,6 +17,12 @@ confs = {
                   "features": "superpoint", "model_name": "superpoint_lightglue.pth"},
         "preprocessing": dict(_PRE),
     },
+    "aliked-lightglue": {  # matchers.py:68-84
+        "output": "matches-aliked-lightglue",
+        "model": {"name": "lightglue", "match_threshold": 0.2, "width_confidence": 0.99, "depth_confidence": 0.95,
+                  "features": "aliked", "model_name": "aliked_lightglue.pth"},
+        "preprocessing": dict(_PRE),
+    },
     "loftr": {  # matchers.py:249-267
         "output": "matches-loftr",
         "model": {"name": "loftr", "weights": "outdoor", "max_keypoints": 2000, "match_threshold": 0.2},

@@ -22,6 +22,7 @@ class LightGlue(BaseModel):
         "mp": False,
         "add_scale_ori": False,
         "n_layers": 9,
+        "state_dict": None,  # B200 engine: in-memory checkpoint (reference key names) instead of model_name
         # B200 engine switch (not in the reference): linear layers on tcgen05.
         # True / "3xtf32": split-precision TF32 (fp32-equivalent, parity-grade); "tf32": single TF32 (fast mode,
         # match-F1 >= 0.99 but scores only within ~1.5e-2); False: fp32 CUDA cores
@@ -29,14 +30,21 @@ class LightGlue(BaseModel):
     }
     required_inputs = ["image0", "keypoints0", "scores0", "descriptors0", "image1", "keypoints1", "scores1",
                        "descriptors1"]
+    input_dims = {"superpoint": 256, "aliked": 128, "disk": 128}  # lightglue.py:350-373 (features with add_scale_ori are not built)
 
     def _init(self, conf):
         logger.info("Loading lightglue model, {}".format(conf["model_name"]))
-        if conf["features"] != "superpoint":
-            raise ValueError(f"Unsupported features: {conf['features']} (B200 engine build: superpoint)")
-        model_path = self._download_model(
-            repo_id=MODEL_REPO_ID, filename="{}/{}".format(Path(__file__).stem, self.conf["model_name"]))
-        sd = torch.load(str(model_path), map_location="cpu")
+        if conf["features"] not in self.input_dims:
+            raise ValueError(f"Unsupported features: {conf['features']} (B200 engine build: {sorted(self.input_dims)})")
+        sd = conf.get("state_dict")   # offline: no aliked_lightglue.pth / disk_lightglue.pth in the tree
+        if sd is None:
+            model_path = self._download_model(
+                repo_id=MODEL_REPO_ID, filename="{}/{}".format(Path(__file__).stem, self.conf["model_name"]))
+            sd = torch.load(str(model_path), map_location="cpu")
+        self.conf["state_dict"] = None
+        self.input_dim = self.input_dims[conf["features"]]
+        if (self.input_dim != 256) != ("input_proj.weight" in sd):
+            raise ValueError(f"features={conf['features']} needs {'an' if self.input_dim != 256 else 'no'} input_proj in the checkpoint")
         conf["filter_threshold"] = conf["match_threshold"]  # hloc/matchers/lightglue.py:50
         self.conf["filter_threshold"] = conf["match_threshold"]
         for k, v in ops.lg_pack_weights(sd, conf["n_layers"]).items():
@@ -59,12 +67,13 @@ class LightGlue(BaseModel):
         k0, k1 = data["keypoints0"], data["keypoints1"]
         d0, d1 = data["descriptors0"].permute(0, 2, 1), data["descriptors1"].permute(0, 2, 1)  # [1,N,D]
         assert k0.shape[0] == 1 and k1.shape[0] == 1, "one pair per call (reference semantics are B=1)"
-        assert d0.shape[-1] == 256 and d1.shape[-1] == 256  # lightglue.py:510-511
+        D = self.input_dim
+        assert d0.shape[-1] == D and d1.shape[-1] == D  # lightglue.py:510-511
         m, n = k0.shape[1], k1.shape[1]
         dev = k0.device
         cap = max(128, (max(m, n) + 127) // 128 * 128)  # 128-row tiles of the tcgen05 path
         kp = torch.zeros(2, cap, 2, device=dev)
-        ds = torch.zeros(2, cap, 256, device=dev)
+        ds = torch.zeros(2, cap, D, device=dev)
         kp[0, :m], kp[1, :n] = k0[0].float(), k1[0].float()
         ds[0, :m], ds[1, :n] = d0[0].float(), d1[0].float()
         counts = torch.tensor([m, n], dtype=torch.int32, device=dev)

@@ -116,12 +116,17 @@ def lg_pack_weights(sd, n_layers=9, heads=4):
     out["final_b"] = torch.stack([sd[f"log_assignment.{i}.final_proj.bias"].float() for i in range(n_layers)])
     out["match_w"] = torch.stack([sd[f"log_assignment.{i}.matchability.weight"].float().reshape(d) for i in range(n_layers)])
     out["match_b"] = torch.stack([sd[f"log_assignment.{i}.matchability.bias"].float().reshape(()) for i in range(n_layers)])
+    if "input_proj.weight" in sd:  # Linear(input_dim -> 256) for 128-d features (lightglue.py:392-395)
+        out["input_proj_w"], out["input_proj_b"] = sd["input_proj.weight"].float(), sd["input_proj.bias"].float()
     return {k: v.contiguous() for k, v in out.items()}
 
 
 def lg_weights_struct(bufs, n_layers=9):
     s = L.LGWeights()
     s.n_layers, s.input_dim = n_layers, 256
+    if "input_proj_w" in bufs:
+        s.input_dim = bufs["input_proj_w"].shape[1]
+        s.input_proj_w, s.input_proj_b = bufs["input_proj_w"].data_ptr(), bufs["input_proj_b"].data_ptr()
     s.posenc_wr = bufs["posenc_wr"].data_ptr()
     for k in ("token_w", "token_b", "final_w", "final_b", "match_w", "match_b"):
         setattr(s, k, bufs[k].data_ptr())
@@ -133,11 +138,12 @@ def lg_weights_struct(bufs, n_layers=9):
 
 
 def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=None):
-    """keypoints [2P,cap,2], descriptors [2P,cap,256], counts [2P] int32 (all CUDA, contiguous).
+    """keypoints [2P,cap,2], descriptors [2P,cap,input_dim], counts [2P] int32 (all CUDA, contiguous).
     Returns dict: matches [2P,cap] int32, scores [2P,cap], stop [P] int32, prune [2P,cap] int32."""
     L.require_cuda(keypoints, "lightglue_forward(keypoints)")
     S, cap, _ = keypoints.shape
-    assert S % 2 == 0 and descriptors.shape == (S, cap, 256) and counts.numel() == S and counts.dtype == torch.int32
+    in_dim = bufs["input_proj_w"].shape[1] if "input_proj_w" in bufs else 256
+    assert S % 2 == 0 and descriptors.shape == (S, cap, in_dim) and counts.numel() == S and counts.dtype == torch.int32
     assert keypoints.is_contiguous() and descriptors.is_contiguous() and counts.is_contiguous()
     P, dev = S // 2, keypoints.device
     if out is None:

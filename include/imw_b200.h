@@ -85,12 +85,13 @@ typedef struct {
 
 typedef struct {
   int n_layers;
-  int input_dim;              /* 256 (Identity input_proj) */
+  int input_dim;              /* 256 (Identity input_proj) or 128 (ALIKED / DISK: Linear input_proj, lightglue.py:392-395) */
   const float* posenc_wr;     /* [32][2] */
   const float *token_w, *token_b; /* [L-1][256], [L-1]   token_confidence */
   const float *final_w, *final_b; /* [L][256][256], [L][256] log_assignment.final_proj */
   const float *match_w, *match_b; /* [L][256], [L]       log_assignment.matchability */
   imw_lg_layer layers[IMW_LG_MAX_LAYERS];
+  const float *input_proj_w, *input_proj_b; /* [256][input_dim], [256]; used when input_dim != 256 */
 } imw_lg_weights;
 
 typedef struct {

@@ -21,12 +21,22 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().imw_version() >= 100
 
 
-def test_struct_sizes_match_header():
+def test_struct_sizes_match_header(tmp_path):
+    """Every ctypes mirror has the size gcc gives the C struct of include/imw_b200.h."""
+    import subprocess
     from imcui_b200 import _lib
-    assert ctypes.sizeof(_lib.SPWeights) == 36 * 8
-    assert ctypes.sizeof(_lib.LGBlock) == 10 * 8
-    assert ctypes.sizeof(_lib.LGWeights) == 8 + 7 * 8 + 16 * 20 * 8
-    assert ctypes.sizeof(_lib.LGConf) == 20 and ctypes.sizeof(_lib.SPConf) == 20
+    pairs = {"imw_sp_weights": _lib.SPWeights, "imw_sp_conf": _lib.SPConf, "imw_lg_block": _lib.LGBlock, "imw_lg_weights": _lib.LGWeights,
+             "imw_lg_conf": _lib.LGConf, "imw_sg_layer": _lib.SGLayer, "imw_aliked_weights": _lib.AlikedWeights,
+             "imw_aliked_conf": _lib.AlikedConf, "imw_loftr_conv": _lib.LoftrConv, "imw_loftr_backbone": _lib.LoftrBackbone,
+             "imw_loftr_layer": _lib.LoftrLayer, "imw_loftr_weights": _lib.LoftrWeights, "imw_loftr_conf": _lib.LoftrConf}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "imw_b200.h"\nint main(void){' +
+                   "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, cls in pairs.items():
+        assert ctypes.sizeof(cls) == int(out[n]), n
 
 
 def test_superglue_packing_is_a_relabelling():

@@ -158,6 +158,30 @@ def test_lightglue_tensor_core_path(golden, dev, case, mode, tc):
         assert err < tol, (case, mode, p, err)
 
 
+@pytest.mark.parametrize("tc", [False, "3xtf32"], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
+def test_lightglue_input_proj_128d(golden, dev, tc):
+    """features="aliked" architecture: 128-d descriptors through the Linear input_proj (lightglue.py:392-395,519-520)."""
+    import oracle
+    from imcui_b200.hloc import matchers
+    g = golden("lg_proj")
+    sd = dict(oracle.load_weights("superpoint_lightglue.pt"))
+    sd["input_proj.weight"], sd["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])
+    model = _load(matchers, "lightglue", {"match_threshold": 0.2, "features": "aliked", "state_dict": sd, "tensor_cores": tc, **LG_MODES["cuda"]}, dev)
+    for p, src in enumerate(g["sources"]):
+        k0, _, k1, _ = lg_pair_from_source(golden, src)
+        out = model(_lg_inputs(k0, np.ascontiguousarray(g[f"{p}/descriptors0"].T), k1, np.ascontiguousarray(g[f"{p}/descriptors1"].T), dev))
+        m0 = out["matches0"][0].cpu().numpy()
+        f1 = match_f1(m0, g[f"{p}/matches0"])
+        both = (m0 > -1) & (g[f"{p}/matches0"] > -1)
+        err = np.abs(out["matching_scores0"][0].cpu().numpy() - g[f"{p}/matching_scores0"])[both].max()
+        print(f"[lg-proj tc={tc}] pair {p}: F1 {f1:.4f} stop {out['stop']}/{int(g[f'{p}/stop'])} score err {err:.2e}")
+        assert out["stop"] == int(g[f"{p}/stop"]) and err < SCORE_TOL
+        if tc is False:
+            assert np.array_equal(m0, g[f"{p}/matches0"]) and np.array_equal(out["matches1"][0].cpu().numpy(), g[f"{p}/matches1"])
+        else:
+            assert f1 >= 0.999
+
+
 def test_tcgen05_gemm_unit(dev):
     """tcgen05/TMA GEMM against the CUDA-core GEMM and torch fp64."""
     from imcui_b200 import ops

@@ -73,6 +73,25 @@ def test_lightglue_oracle_matches_reference(golden, case, mode):
         assert np.array_equal(out["prune1"][0].numpy().astype(np.int32), g[pre + "prune1"])
 
 
+def _lg_proj_weights(g):
+    w = dict(oracle.load_weights("superpoint_lightglue.pt"))
+    w["input_proj.weight"], w["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])
+    return w
+
+
+def test_lightglue_input_proj_oracle_matches_reference(golden):
+    """LightGlue with a Linear(128 -> 256) input_proj (aliked / disk architecture, lightglue.py:392-395,519-520)."""
+    g = golden("lg_proj")
+    w = _lg_proj_weights(g)
+    for p, src in enumerate(g["sources"]):
+        k0, _, k1, _ = lg_pair_from_source(golden, src)
+        out = olg.forward(w, torch.from_numpy(k0)[None], torch.from_numpy(g[f"{p}/descriptors0"])[None],
+                          torch.from_numpy(k1)[None], torch.from_numpy(g[f"{p}/descriptors1"])[None], MODES["cuda"])
+        assert out["stop"] == int(g[f"{p}/stop"])
+        assert np.array_equal(out["matches0"][0].numpy(), g[f"{p}/matches0"])
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{p}/matching_scores0"], atol=1e-4)
+
+
 def _sg_data(golden, src):
     f, conf, i, j = str(src).split(":")
     b = golden(f)

@@ -137,6 +137,31 @@ def lg_case(name, pairs, sources):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def lg_proj_case(name, pairs, sources):
+    """LightGlue with a Linear input_proj (the aliked / disk architecture, lightglue.py:392-395): 128-d inputs made by
+    compressing the stored SuperPoint descriptors with the orthonormal Q of ref_import.lightglue_proj_state."""
+    lgm = R.lightglue_module()
+    blob = {"sources": np.array(sources)}
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = LG_MODES["cuda"]["prune_th"]
+    net, sd, q = R.make_lightglue_proj(128, filter_threshold=0.2, depth_confidence=0.95, width_confidence=0.99)
+    blob["input_proj_w"], blob["input_proj_b"], blob["q"] = sd["input_proj.weight"].numpy(), sd["input_proj.bias"].numpy(), q.numpy()
+    for p, (k0, d0, k1, d1) in enumerate(pairs):
+        c0 = torch.nn.functional.normalize(torch.from_numpy(d0).t() @ q.t(), dim=-1)   # [N,128]
+        c1 = torch.nn.functional.normalize(torch.from_numpy(d1).t() @ q.t(), dim=-1)
+        out = net({"image0": {"keypoints": torch.from_numpy(k0).float()[None], "descriptors": c0[None]},
+                   "image1": {"keypoints": torch.from_numpy(k1).float()[None], "descriptors": c1[None]}})
+        pre = f"{p}/"
+        blob[pre + "descriptors0"], blob[pre + "descriptors1"] = c0.numpy(), c1.numpy()
+        for k in ("matches0", "matches1", "prune0", "prune1"):
+            blob[pre + k] = out[k][0].numpy().astype(np.int32)
+        blob[pre + "matching_scores0"] = out["matching_scores0"][0].numpy()
+        blob[pre + "matching_scores1"] = out["matching_scores1"][0].numpy()
+        blob[pre + "stop"] = np.int32(out["stop"])
+        print(name, p, "stop", out["stop"], "matches", int((out["matches0"] > -1).sum()))
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = -1
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def sg_case(name, pairs):
     """pairs: list of (kpts0 [N,2], scores0 [N], desc0 [256,N], kpts1, scores1, desc1, source)."""
     blob = {"sources": np.array([p[-1] for p in pairs])}
@@ -261,6 +286,8 @@ def main():
     lg_case("lg_real", [pair(rb, "api", 0, 1), pair(rb, "nocap", 0, 1)], ["sp_real:api:0:1", "sp_real:nocap:0:1"])
     lg_case("lg_synth", [pair(sb, "max1024", 0, 1), pair(sb, "max1024", 2, 3), pair(sb, "max2048", 0, 1)],
             ["sp_synth:max1024:0:1", "sp_synth:max1024:2:3", "sp_synth:max2048:0:1"])
+    lg_proj_case("lg_proj", [pair(sb, "max1024", 0, 1), pair(rb, "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
+
     def sg_pair(blob, src):
         f, conf, i, j = src.split(":")
         return (blob[f"{conf}/{i}/keypoints"].astype(np.float32), blob[f"{conf}/{i}/scores"], blob[f"{conf}/{i}/descriptors"],
@@ -276,6 +303,12 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1:   # python make_golden.py aliked -> only that family
         with torch.no_grad():
-            {"aliked": aliked_case, "loftr": loftr_case}[sys.argv[1]](sys.argv[1])
+            if sys.argv[1] == "lg_proj":   # inputs come from the stored SuperPoint goldens
+                gb = {n: np.load(OUT / f"{n}.npz") for n in ("sp_synth", "sp_real")}
+                pr = lambda f, c, i, j: (gb[f][f"{c}/{i}/keypoints"].astype(np.float32), gb[f][f"{c}/{i}/descriptors"],
+                                         gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
+                lg_proj_case("lg_proj", [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
+            else:
+                {"aliked": aliked_case, "loftr": loftr_case}[sys.argv[1]](sys.argv[1])
     else:
         main()

@@ -69,6 +69,27 @@ def make_lightglue(**conf):
     return net.eval()
 
 
+def lightglue_proj_state(dim=128, seed=7):
+    """gim LightGlue weights + a deterministic Linear(dim -> 256) input_proj: an orthonormal lift Q^T (so that
+    256-d SuperPoint descriptors compressed with Q keep matching) and a small random bias.  Returns (state, Q [dim,256])."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(256, dim, generator=g))   # [256, dim], orthonormal columns
+    sd = dict(lightglue_state_dict())
+    sd["input_proj.weight"] = q.contiguous()
+    sd["input_proj.bias"] = 0.01 * torch.randn(256, generator=g)
+    return sd, q.t().contiguous()
+
+
+def make_lightglue_proj(dim=128, **conf):
+    lg = lightglue_module()
+    net = lg.LightGlue(features=None, input_dim=dim, weights=None, **conf)
+    sd, q = lightglue_proj_state(dim)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all("confidence_thresholds" in m for m in missing), (missing, unexpected)
+    return net.eval(), sd, q
+
+
 def hloc_matchers():
     """imcui.hloc.matchers.{nearest_neighbor,dual_softmax} import as-is (run from a scratch cwd:
     importing imcui.hloc writes log.txt)."""

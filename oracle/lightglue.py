@@ -165,7 +165,8 @@ def forward(w, kpts0, desc0, kpts1, desc1, conf=None, trace=None):
     if m == 0:
         k0 = kpts0
     d0, d1 = desc0.contiguous(), desc1.contiguous()
-    assert d0.shape[-1] == 256 and d1.shape[-1] == 256
+    in_dim = w["input_proj.weight"].shape[1] if "input_proj.weight" in w else 256   # lightglue.py:392-395,510-511
+    assert d0.shape[-1] == in_dim and d1.shape[-1] == in_dim
     if "input_proj.weight" in w:
         d0 = F.linear(d0, w["input_proj.weight"], w["input_proj.bias"])
         d1 = F.linear(d1, w["input_proj.weight"], w["input_proj.bias"])

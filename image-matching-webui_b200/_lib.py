@@ -143,10 +143,10 @@ def lib():
         L.imw_magsac.restype = C.c_int
         L.imw_magsac.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_uint, vp, vp, vp, vp, vp]
         L.imw_nearest_neighbor.restype = C.c_int
-        L.imw_nearest_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp,
+        L.imw_nearest_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp,
                                            vp, C.c_size_t, vp]
         L.imw_dual_softmax.restype = C.c_int
-        L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, vp, vp, vp,
+        L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp, vp,
                                        C.c_size_t, vp]
         L.imw_debug_gemm_tf32.restype = C.c_int
         L.imw_debug_gemm_tf32.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]

@@ -6,6 +6,7 @@
 #include "gemm_simt.cuh"
 #include "simreduce.cuh"
 #include "sp_kernels.h"
+#include "tc_simreduce.cuh"
 
 static thread_local char g_err[512] = "";
 void imw_set_error(const char* fmt, ...) {
@@ -279,8 +280,8 @@ extern "C" size_t imw_matcher_workspace_bytes(int n_pairs, int cap) {
 }
 
 extern "C" int imw_nearest_neighbor(int P, int cap, int dim, const float* desc, const int* counts, float ratio_threshold,
-                                    float distance_threshold, int do_mutual_check, int* matches0, float* scores0,
-                                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                                    float distance_threshold, int do_mutual_check, int use_tensor_cores, int* matches0,
+                                    float* scores0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   IMW_REQUIRE(P > 0 && cap > 0 && dim > 0 && dim % 4 == 0 && dim <= 256, "imw_nearest_neighbor: dim %% 4 == 0, dim <= 256 (got %d)", dim);
   Workspace ws(workspace, workspace_bytes);
   MatcherBuffers b;
@@ -289,15 +290,16 @@ extern "C" int imw_nearest_neighbor(int P, int cap, int dim, const float* desc, 
   SimArgs sa{desc, cap, dim, dim, counts, nullptr};
   OpTop2 op{b.m, b.f0, counts, cap, ratio_threshold > 0.f ? ratio_threshold * ratio_threshold : 0.f,
             distance_threshold > 0.f ? distance_threshold * distance_threshold : 0.f};
-  IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, op, st));
+  if (use_tensor_cores && tc_simreduce_ok(sa)) { if (int e = launch_tc_simreduce(sa, 2 * P, op, st)) return e; }
+  else IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, op, st));
   nn_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.m, b.f0, counts, matches0, scores0, cap, do_mutual_check);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }
 
 extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, const int* counts, float match_threshold,
-                                float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
-                                cudaStream_t st) {
+                                float inv_temperature, int use_tensor_cores, int* matches0, float* scores0, void* workspace,
+                                size_t workspace_bytes, cudaStream_t st) {
   IMW_REQUIRE(P > 0 && cap > 0 && dim > 0 && dim % 4 == 0 && dim <= 256, "imw_dual_softmax: dim %% 4 == 0, dim <= 256 (got %d)", dim);
   Workspace ws(workspace, workspace_bytes);
   MatcherBuffers b;
@@ -306,8 +308,13 @@ extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, cons
   normalize_rows_kernel<<<dim3(ceil_div(cap, 8), 2 * P), 256, 0, st>>>(desc, b.norm, counts, cap, dim);
   IMW_CHECK_LAUNCH();
   SimArgs sa{b.norm, cap, dim, dim, counts, nullptr};
-  IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st));
-  IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st));
+  if (use_tensor_cores && tc_simreduce_ok(sa)) {
+    if (int e = launch_tc_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st)) return e;
+  } else {
+    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st));
+    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st));
+  }
   dsm_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.bv, b.bj, counts, matches0, scores0, cap, match_threshold);
   IMW_CHECK_LAUNCH();
   return IMW_OK;

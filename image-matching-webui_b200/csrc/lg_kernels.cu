@@ -12,6 +12,7 @@
 #include "lg_internal.h"
 #include "simreduce.cuh"
 #include "tc_gemm.cuh"
+#include "tc_simreduce.cuh"
 #include "tc_attn.cuh"
 
 #include "token_epilogues.cuh"
@@ -558,8 +559,13 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     logsigmoid_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.zl, b.counts, b.empty, cap);
     IMW_CHECK_LAUNCH();
     SimArgs sa{b.md, cap, D, D, b.counts, b.empty};
-    IMW_CHECK_CUDA(launch_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st));
-    IMW_CHECK_CUDA(launch_simreduce(sa, S, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st));
+    if (use_tc && tc_simreduce_ok(sa)) {  // 3xTF32 similarity tiles in TMEM, same reduction functors
+      if (int e = launch_tc_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st)) return e;
+      if (int e = launch_tc_simreduce(sa, S, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st)) return e;
+    } else {
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st));
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st));
+    }
     match_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.best_v, b.best_j, b.counts, b.ind[cur], b.empty, matches, mscores,
                                                               cap, conf->filter_threshold);
     IMW_CHECK_LAUNCH();

@@ -16,6 +16,7 @@
 #include "simreduce.cuh"
 #include "sp_kernels.h"
 #include "tc_gemm.cuh"
+#include "tc_simreduce.cuh"
 
 namespace {
 
@@ -547,8 +548,13 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   {
     SimArgs sa{b.xm, cap, 512, CD, b.cntL, nullptr};
     const float scale = 1.f / (16.f * 16.f * conf->temperature);
-    IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfStats{b.rmax, b.rsum, cap, scale}, st));
-    IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfArgmax{b.rmax, b.rsum, b.best_v, b.best_j, cap, scale}, st));
+    if (conf->use_tensor_cores && tc_simreduce_ok(sa)) {
+      RUN(launch_tc_simreduce(sa, S, OpConfStats{b.rmax, b.rsum, cap, scale}, st));
+      RUN(launch_tc_simreduce(sa, S, OpConfArgmax{b.rmax, b.rsum, b.best_v, b.best_j, cap, scale}, st));
+    } else {
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfStats{b.rmax, b.rsum, cap, scale}, st));
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfArgmax{b.rmax, b.rsum, b.best_v, b.best_j, cap, scale}, st));
+    }
     int* i_ids = b.fcnt;               // [P][mcap]
     int* j_ids = b.fcnt + (size_t)P * mcap;
     lf_coarse_select_kernel<<<P, 1024, 0, st>>>(b.best_v, b.best_j, L, cap, hc, wc, conf->match_threshold, conf->border_rm, i_ids, j_ids,

@@ -55,7 +55,9 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16&
   c = __float2bfloat16_rn(r - __bfloat162float(b));
 }
 
-template <int BN>
+// KS: kernel size (3 or 1) and RES: residual input are compile-time so that the SuperPoint instantiation <BN, 3, false>
+// keeps constant tap arithmetic in the single-thread producer / MMA loops and a lean epilogue.
+template <int BN, int KS, bool RES>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g) {
   constexpr int STAGES = conv_stages<BN>(), STAGE = conv_stage_bytes<BN>(), B_BYTES = BN * 128;
@@ -74,7 +76,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int b = t;
   const int n0 = blockIdx.y * BN;
   const int x0 = tx * CV_TW, y0 = ty * CV_TH;
-  const int ntaps = g.ksize * g.ksize, kpad = g.ksize / 2;
+  constexpr int ntaps = KS * KS, kpad = KS / 2;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -93,9 +95,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < steps; it++) {
+      int tap = 0, ck = 0;
+      for (int it = 0; it < steps; it++, ck++) {
+        if (ck == chunks) { ck = 0; tap++; }
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int tap = it / chunks, ck = it % chunks, dy = tap / g.ksize - kpad, dx = tap % g.ksize - kpad;
+        const int dy = tap / KS - kpad, dx = tap % KS - kpad;
         tc::mbar_wait(empty + s, ph ^ 1);
         tc::mbar_expect_tx(full + s, STAGE);
         uint8_t* st = smem + s * STAGE;
@@ -111,7 +115,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     {
       const bool leader = tc::elect_one();
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
-      for (int it = 0; it < steps; it++) {
+      int tap = 0, ck = 0;
+      for (int it = 0; it < steps; it++, ck++) {
+        if (ck == chunks) { ck = 0; tap++; }
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         tc::mbar_wait(full + s, ph);
         tc::fence_after_sync();
@@ -124,11 +130,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ad[p] = tc::make_smem_desc_sw128(a0 + p * CV_A_BYTES + k * 32);
             bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
           }
-          const int tap = it / chunks, ck = it % chunks;
-          const int krow = tap / g.ksize;
+          const int krow = tap / KS;
           const uint32_t d_main = tmem_base + krow * BN, d_cross = tmem_base + 3 * BN;
           if (leader) {
-            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % g.ksize) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
+            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % KS) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
             tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
             tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
             tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
@@ -159,7 +164,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float v[32], t[32];
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
       tc::tmem_ld32(lane_base, v);
-      if (g.ksize == 3) {   // 1x1: only the first kernel-row accumulator and the cross-term accumulator are used
+      if (KS == 3) {   // 1x1: only the first kernel-row accumulator and the cross-term accumulator are used
         tc::tmem_ld32(lane_base + BN, t);
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += t[j];
@@ -170,7 +175,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc::tmem_ld32(lane_base + 3 * BN, t);
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] += t[j];
-      if (g.res_planes && in_img) {  // residual branch of a BasicBlock (added before the activation)
+      if (RES && in_img) {  // residual branch of a BasicBlock (added before the activation)
         const __nv_bfloat16* r0 = g.res_planes + opix + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -181,14 +186,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 8; e++) t[j + e] = (__bfloat162float(pa[e]) + __bfloat162float(pb[e])) + __bfloat162float(pc[e]);
         }
-      } else {
+      } else if (RES) {
 #pragma unroll
         for (int j = 0; j < 32; j++) t[j] = 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         float x = v[j] + (g.bias ? g.bias[n0 + c0 + j] : 0.f);
-        if (g.res_planes) x += t[j];
+        if (RES) x += t[j];
         if (g.relu == 1) x = fmaxf(x, 0.f);
         else if (g.relu == 2) x = x > 0.f ? x : 0.01f * x;
         if (g.pool) {  // 2x2 window = lanes {l, l^1, l^16}: all inside this warp (2 image rows x 16 cols)
@@ -457,19 +462,25 @@ int make_map_wgt(CUtensorMap* map, const void* base, int rows, int Cin, int BN) 
   return IMW_OK;
 }
 
-template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+template <int BN, int KS, bool RES>
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
   constexpr size_t smem = conv_smem_bytes<BN>();
   static bool attr_set = false;
   if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<BN, KS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int Hc = ceil_div(g.H, g.stride), Wc = ceil_div(g.W, g.stride);
   dim3 grid((unsigned)(g.B * ceil_div(Hc, CV_TH) * ceil_div(Wc, CV_TW)), g.Cout / BN);
-  tc_conv3x3_kernel<BN><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, g);
+  tc_conv3x3_kernel<BN, KS, RES><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, g);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+  if (g.ksize == 1) return launch_conv_t<BN, 1, false>(tmA, tmW, g, st);   // (no 1x1 conv with a residual on the path)
+  return g.res_planes ? launch_conv_t<BN, 3, true>(tmA, tmW, g, st) : launch_conv_t<BN, 3, false>(tmA, tmW, g, st);
 }
 
 }  // namespace
@@ -516,6 +527,7 @@ int tc_conv_general(const void* in_planes, const void* w_planes, const float* bi
                     int H, int W, int Cin, int Cout, int ksize, int stride, int act, int out_fp32, cudaStream_t st) {
   IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0, "tc_conv_general: Cin %% 64, Cout %% 64 (got %d,%d)", Cin, Cout);
   IMW_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "tc_conv_general: ksize 1|3, stride 1|2");
+  IMW_REQUIRE(!(ksize == 1 && res_planes), "tc_conv_general: residual input is only built for 3x3 convs");
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, CV_TW, CV_TH, stride)) return e;

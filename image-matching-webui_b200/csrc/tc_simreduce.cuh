@@ -1,0 +1,199 @@
+// Streaming similarity reductions on tcgen05 (3xTF32 split precision = fp32-equivalent products).
+//
+// Same contract and the same Op functors as simreduce.cuh: for every row i of set X (slot `own`) against all rows j
+// of the other slot of the pair, s_ij = <x_i, x_j> is produced tile by tile -- here as 128 x 128 accumulator tiles
+// in TMEM -- and folded into a per-row state; the N x M matrix never exists in memory.
+//
+//   warp 0      TMA producer: own-row tile [128 x 32 f32] and other-slot tile [128 x 32 f32] per k-block (SWIZZLE_128B)
+//   warp 1      TMEM allocation + MMA issue: hi*hi into the main accumulator, hi*lo + lo*hi into the cross accumulator
+//   warps 2..5  hi/lo splitters (x_hi = low 13 mantissa bits cleared, x_lo = x - x_hi, twin tile)
+//   warps 6..9  reduction: one TMEM lane = one row i per thread; the thread walks the 128 columns of the tile in
+//               ascending j and calls op.accum; the state lives in registers across all column tiles of the row tile
+//
+// Persistent CTAs walk the row tiles (m fastest over slots); two accumulator sets alternate so that the reduction
+// of column tile t overlaps the MMAs of tile t+1.  Needs cap % 128 == 0, K % 32 == 0, ld % 4 == 0.
+#pragma once
+#include "simreduce.cuh"
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+template <class Op>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_simreduce_kernel(const __grid_constant__ CUtensorMap tmX, SimArgs a, Op op,
+                                                                    int m_tiles) {
+  constexpr int BN = 128;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, TILE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE = 2 * TILE_BYTES;
+  constexpr int ACC_COLS = 2 * BN;
+  uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* ready = empty + TC_STAGES;
+  uint64_t* tmem_full = ready + TC_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmX);
+    for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 128); }
+    for (int i = 0; i < 2; i++) { tc::mbar_init(tmem_full + i, 1); tc::mbar_init(tmem_empty + i, 128); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int KB = a.K / TC_BK, tiles_per_slot = a.cap / TC_BM;
+
+  // every role walks the same (row tile, column tile) sequence
+  auto row_tile = [&](int mt, int& own, int& row0, int& n, int& m) -> bool {
+    own = mt / tiles_per_slot; row0 = (mt % tiles_per_slot) * TC_BM;
+    if (a.skip && a.skip[own >> 1]) return false;
+    n = a.counts[own]; m = a.counts[own ^ 1];
+    return row0 < n;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int c = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        int own, row0, n, m;
+        if (!row_tile(mt, own, row0, n, m)) continue;
+        for (int j0 = 0; j0 < m; j0 += BN)
+          for (int kb = 0; kb < KB; kb++, c++) {
+            const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+            tc::mbar_wait(empty + s, ph ^ 1);
+            tc::mbar_expect_tx(full + s, TILE_BYTES);
+            tc::tma_load_2d(smem + s * STAGE, &tmX, full + s, kb * TC_BK, own * a.cap + row0);
+            tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmX, full + s, kb * TC_BK, (own ^ 1) * a.cap + j0);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
+    int c = 0, i = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      int own, row0, n, m;
+      if (!row_tile(mt, own, row0, n, m)) continue;
+      for (int j0 = 0; j0 < m; j0 += BN, i++) {
+        const int acc = i & 1;
+        tc::mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_main = tmem_base + acc * ACC_COLS, d_cross = d_main + BN;
+        for (int kb = 0; kb < KB; kb++, c++) {
+          const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+          tc::mbar_wait(ready + s, ph);
+          tc::fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; k++) {
+            uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
+            uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
+            if (leader) {
+              tc::mma_tf32(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              tc::mma_tf32(d_cross, ad, bdl, idesc, (kb | k) ? 1u : 0u);
+              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);
+            }
+          }
+          if (leader) tc::mma_commit(empty + s);
+          __syncwarp();
+        }
+        if (leader) tc::mma_commit(tmem_full + acc);
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    const int t = threadIdx.x - 64;
+    int c = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      int own, row0, n, m;
+      if (!row_tile(mt, own, row0, n, m)) continue;
+      for (int j0 = 0; j0 < m; j0 += BN)
+        for (int kb = 0; kb < KB; kb++, c++) {
+          const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+          tc::mbar_wait(full + s, ph);
+          uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
+          uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
+#pragma unroll 8
+          for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
+            uint4 v = hi[idx], h, l;
+            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            hi[idx] = h;
+            lo[idx] = l;
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(ready + s);
+        }
+    }
+  } else {
+    const int q = warp % 4;
+    int i = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      int own, row0, n, m;
+      if (!row_tile(mt, own, row0, n, m)) continue;
+      const int row = row0 + q * 32 + lane;
+      const bool row_ok = row < n;
+      typename Op::State st;
+      op.init(st);
+      for (int j0 = 0; j0 < m; j0 += BN, i++) {
+        const int acc = i & 1;
+        tc::mbar_wait(tmem_full + acc, (i >> 1) & 1);
+        tc::fence_after_sync();
+        const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32], t[32];
+          tc::tmem_ld32(lane_addr + c0, v);
+          tc::tmem_ld32(lane_addr + BN + c0, t);
+          if (c0 + 32 >= BN) {
+            tc::fence_before_sync();
+            tc::mbar_arrive(tmem_empty + acc);
+          }
+          const int jmax = min(32, m - (j0 + c0));  // warp-uniform
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (j < jmax) op.accum(st, v[j] + t[j], row, j0 + c0 + j, own, own ^ 1);
+          }
+        }
+      }
+      if (row_ok) op.store(st, own, row);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+// true when the tensor-core version can take this problem (else call launch_simreduce)
+static inline bool tc_simreduce_ok(const SimArgs& a) {
+  return a.cap % TC_BM == 0 && a.K % TC_BK == 0 && a.ld % 4 == 0 && ((uintptr_t)a.X % 16) == 0;
+}
+
+template <class Op>
+static inline int launch_tc_simreduce(const SimArgs& a, int slots, Op op, cudaStream_t st) {
+  CUtensorMap tmX;
+  if (int e = tc_make_map_2d_f32(&tmX, a.X, (uint64_t)slots * a.cap, (uint64_t)a.K, (uint64_t)a.ld, TC_BK, TC_BM)) return e;
+  constexpr size_t smem = (size_t)TC_STAGES * 2 * (TC_BM * 128 + 128 * 128) + 1024 + 256;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_simreduce_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IMW_CHECK_CUDA(cudaGetDevice(&dev));
+    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int m_tiles = slots * (a.cap / TC_BM);
+  if (m_tiles == 0) return IMW_OK;
+  tc_simreduce_kernel<Op><<<dim3((unsigned)(m_tiles < num_sms ? m_tiles : num_sms)), TC_THREADS, smem, st>>>(tmX, a, op, m_tiles);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}

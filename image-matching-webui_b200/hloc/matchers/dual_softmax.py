@@ -12,6 +12,7 @@ class DualSoftMax(BaseModel):
     default_conf = {
         "match_threshold": 0.2,
         "inv_temperature": 20,
+        "tensor_cores": True,  # B200 engine switch (see nearest_neighbor.py)
     }
     required_inputs = ["descriptors0", "descriptors1"]
 
@@ -24,6 +25,6 @@ class DualSoftMax(BaseModel):
             matches0 = torch.full(d0.shape[:2], -1, device=d0.device)
             return {"matches0": matches0, "matching_scores0": torch.zeros_like(matches0)}
         ds, counts, n, m = _pack_pair(d0, d1)
-        m0, s0 = ops.dual_softmax(ds, counts, self.conf["match_threshold"], self.conf["inv_temperature"])
+        m0, s0 = ops.dual_softmax(ds, counts, self.conf["match_threshold"], self.conf["inv_temperature"], self.conf["tensor_cores"])
         # reference dtypes: int64 matches, float64 scores (NumPy round trip, dual_softmax.py:29-35)
         return {"matches0": m0[:, :n].long(), "matching_scores0": s0[:, :n].double()}

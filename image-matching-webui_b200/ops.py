@@ -473,22 +473,23 @@ def _matcher_common(descriptors, counts):
     return S // 2, cap, dim, dev, m0, s0, ws
 
 
-def nearest_neighbor(descriptors, counts, ratio_threshold=None, distance_threshold=None, do_mutual_check=True):
+def nearest_neighbor(descriptors, counts, ratio_threshold=None, distance_threshold=None, do_mutual_check=True, tensor_cores=True):
     """descriptors [2P,cap,dim] token-major, counts [2P].  -> matches0 [P,cap] int32, scores0 [P,cap]."""
     P, cap, dim, dev, m0, s0, ws = _matcher_common(descriptors, counts)
     with torch.cuda.device(dev):
         rc = L.lib().imw_nearest_neighbor(P, cap, dim, L.ptr(descriptors), L.ptr(counts), float(ratio_threshold or 0.0),
-                                          float(distance_threshold or 0.0), int(bool(do_mutual_check)), L.ptr(m0), L.ptr(s0),
+                                          float(distance_threshold or 0.0), int(bool(do_mutual_check)), int(bool(tensor_cores)), L.ptr(m0), L.ptr(s0),
                                           L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc)
     return m0, s0
 
 
-def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0):
+def dual_softmax(descriptors, counts, match_threshold=0.2, inv_temperature=20.0, tensor_cores=True):
     P, cap, dim, dev, m0, s0, ws = _matcher_common(descriptors, counts)
     with torch.cuda.device(dev):
         rc = L.lib().imw_dual_softmax(P, cap, dim, L.ptr(descriptors), L.ptr(counts), float(match_threshold),
-                                      float(inv_temperature), L.ptr(m0), L.ptr(s0), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+                                      float(inv_temperature), int(bool(tensor_cores)), L.ptr(m0), L.ptr(s0), L.ptr(ws), ws.numel(),
+                                      L.stream_ptr(dev))
     L.check(rc)
     return m0, s0
 

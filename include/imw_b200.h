@@ -166,12 +166,13 @@ size_t imw_matcher_workspace_bytes(int n_pairs, int cap);
 
 int imw_nearest_neighbor(int n_pairs, int cap, int dim, const float* descriptors, const int* counts,
                          float ratio_threshold /* <=0: none */, float distance_threshold /* <=0: none */,
-                         int do_mutual_check, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
-                         imw_stream_t stream);
+                         int do_mutual_check, int use_tensor_cores /* 1: 3xTF32 tcgen05 similarity tiles when cap % 128 == 0 and
+                         dim % 32 == 0 (fp32-equivalent); 0: fp32 CUDA cores */, int* matches0, float* scores0, void* workspace,
+                         size_t workspace_bytes, imw_stream_t stream);
 
 int imw_dual_softmax(int n_pairs, int cap, int dim, const float* descriptors, const int* counts, float match_threshold,
-                     float inv_temperature, int* matches0, float* scores0, void* workspace, size_t workspace_bytes,
-                     imw_stream_t stream);
+                     float inv_temperature, int use_tensor_cores, int* matches0, float* scores0, void* workspace,
+                     size_t workspace_bytes, imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ALIKED (aliked-n16) extractor.

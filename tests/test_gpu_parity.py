@@ -316,17 +316,18 @@ def _matcher_inputs(golden, p):
     return g[f"in/{p}/descriptors0"], g[f"in/{p}/descriptors1"]
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
 @pytest.mark.parametrize("p", [0, 1])
-def test_matchers_match_reference(golden, dev, p):
+def test_matchers_match_reference(golden, dev, p, tc):
     from imcui_b200.hloc import matchers
     g = golden("matchers")
     d0, d1 = (torch.from_numpy(x).to(dev)[None] for x in _matcher_inputs(golden, p))
     data = {"descriptors0": d0, "descriptors1": d1}
     cases = {
-        "nn": _load(matchers, "nearest_neighbor", {"do_mutual_check": True}, dev),
-        "nn_ratio": _load(matchers, "nearest_neighbor", {"do_mutual_check": True, "ratio_threshold": 0.9, "distance_threshold": 0.9}, dev),
-        "nn_nomutual": _load(matchers, "nearest_neighbor", {"do_mutual_check": False}, dev),
-        "dsm": _load(matchers, "dual_softmax", {"match_threshold": 0.01, "inv_temperature": 20}, dev),
+        "nn": _load(matchers, "nearest_neighbor", {"do_mutual_check": True, "tensor_cores": tc}, dev),
+        "nn_ratio": _load(matchers, "nearest_neighbor", {"do_mutual_check": True, "ratio_threshold": 0.9, "distance_threshold": 0.9, "tensor_cores": tc}, dev),
+        "nn_nomutual": _load(matchers, "nearest_neighbor", {"do_mutual_check": False, "tensor_cores": tc}, dev),
+        "dsm": _load(matchers, "dual_softmax", {"match_threshold": 0.01, "inv_temperature": 20, "tensor_cores": tc}, dev),
     }
     for tag, model in cases.items():
         out = model(data)
@@ -344,7 +345,8 @@ def test_matchers_empty(dev):
         assert (out["matches0"] == -1).all()
 
 
-def test_dual_softmax_large_property(dev):
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
+def test_dual_softmax_large_property(dev, tc):
     """BASELINE config 5 size (4096 x 4096 x 128): planted permutation is recovered and the result equals
     the oracle formula evaluated with torch on the GPU for a random subset of rows."""
     import importlib.util
@@ -355,7 +357,7 @@ def test_dual_softmax_large_property(dev):
     d0, d1 = synth.make_descriptor_pair(7, n=4096, dim=128)
     ds = torch.stack([torch.from_numpy(d0).t(), torch.from_numpy(d1).t()]).contiguous().to(dev)
     counts = torch.tensor([4096, 4096], dtype=torch.int32, device=dev)
-    m0, s0 = ops.dual_softmax(ds, counts, 0.01, 20.0)
+    m0, s0 = ops.dual_softmax(ds, counts, 0.01, 20.0, tensor_cores=tc)
     a, b = ds[0], ds[1]
     sim = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t() * 20
     P = sim.softmax(0) * sim.softmax(1)

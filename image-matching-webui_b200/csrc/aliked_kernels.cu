@@ -242,42 +242,59 @@ __device__ __forceinline__ float ak_upsample(const float* __restrict__ m, int h,
 
 // ---- feature aggregation (:723-735): warp per pixel; lane l owns channel l of each of the four 32-channel groups.
 // Writes the L2-normalised 128-channel map on the unpadded window and SELU(score_head.0 (x1234)) on the padded map. ------
-__global__ void __launch_bounds__(256) ak_fuse_kernel(const float* __restrict__ x1, const float* __restrict__ w1 /*[16][32]*/,
-                                                      const float* __restrict__ a2, const float* __restrict__ a3, const float* __restrict__ a4,
-                                                      const float* __restrict__ s0w /*[128][8]*/, float* __restrict__ feat,
-                                                      float* __restrict__ s0, int B, int Hp, int Wp, int H, int W, int pt, int pl) {
+__global__ void __launch_bounds__(256, 4) ak_fuse_kernel(const float* __restrict__ x1, const float* __restrict__ w1 /*[16][32]*/,
+                                                         const float* __restrict__ a2, const float* __restrict__ a3, const float* __restrict__ a4,
+                                                         const float* __restrict__ s0w /*[128][8]*/, float* __restrict__ feat,
+                                                         float* __restrict__ s0, int B, int Hp, int Wp, int H, int W, int pt, int pl) {
+  __shared__ __align__(16) float s_w0[128 * 8];
+  for (int i = threadIdx.x; i < 128 * 8; i += 256) s_w0[i] = s0w[i];
+  __syncthreads();
   const int lane = threadIdx.x % 32;
-  float w1r[16], w0r[4][8];
+  float w1r[16];
 #pragma unroll
   for (int c = 0; c < 16; c++) w1r[c] = w1[c * 32 + lane];
-#pragma unroll
-  for (int g = 0; g < 4; g++)
-#pragma unroll
-    for (int o = 0; o < 8; o++) w0r[g][o] = s0w[(g * 32 + lane) * 8 + o];
   const long long npix = (long long)B * Hp * Wp;
   for (long long p = (long long)blockIdx.x * 8 + threadIdx.x / 32; p < npix; p += (long long)gridDim.x * 8) {
     const int x = (int)(p % Wp), y = (int)((p / Wp) % Hp), b = (int)(p / ((long long)Wp * Hp));
-    const float* px1 = x1 + p * 16;
-    const float xv = lane < 16 ? px1[lane] : 0.f;
+    const float xv = lane < 16 ? x1[p * 16 + lane] : 0.f;
     float v[4];
+    v[1] = ak_upsample(a2 + (long long)b * (Hp / 2) * (Wp / 2) * 32, Hp / 2, Wp / 2, Hp, Wp, y, x, lane);
+    v[2] = ak_upsample(a3 + (long long)b * (Hp / 8) * (Wp / 8) * 32, Hp / 8, Wp / 8, Hp, Wp, y, x, lane);
+    v[3] = ak_upsample(a4 + (long long)b * (Hp / 32) * (Wp / 32) * 32, Hp / 32, Wp / 32, Hp, Wp, y, x, lane);
     v[0] = 0.f;
 #pragma unroll
     for (int c = 0; c < 16; c++) v[0] = fmaf(__shfl_sync(0xffffffffu, xv, c), w1r[c], v[0]);
     v[0] = ak_selu(v[0]);
-    v[1] = ak_upsample(a2 + (long long)b * (Hp / 2) * (Wp / 2) * 32, Hp / 2, Wp / 2, Hp, Wp, y, x, lane);
-    v[2] = ak_upsample(a3 + (long long)b * (Hp / 8) * (Wp / 8) * 32, Hp / 8, Wp / 8, Hp, Wp, y, x, lane);
-    v[3] = ak_upsample(a4 + (long long)b * (Hp / 32) * (Wp / 32) * 32, Hp / 32, Wp / 32, Hp, Wp, y, x, lane);
+    // score_head.0: 8 partial dot products per lane, then a transposing butterfly (9 shuffles instead of 8 x 5):
+    // after the xor-16 / 8 / 4 exchanges lane l holds output o = bit4*4 + bit3*2 + bit2 summed over its 8-lane class
     float part[8];
 #pragma unroll
-    for (int o = 0; o < 8; o++) part[o] = v[0] * w0r[0][o] + v[1] * w0r[1][o] + v[2] * w0r[2][o] + v[3] * w0r[3][o];
+    for (int o = 0; o < 8; o++) part[o] = 0.f;
 #pragma unroll
-    for (int o = 0; o < 8; o++) part[o] = ak_warp_sum(part[o]);
-    if (lane < 8) {
-      float r = part[0];
-#pragma unroll
-      for (int o = 1; o < 8; o++) r = lane == o ? part[o] : r;
-      s0[p * 8 + lane] = ak_selu(r);
+    for (int g = 0; g < 4; g++) {
+      const float4 wa = *reinterpret_cast<const float4*>(&s_w0[(g * 32 + lane) * 8]), wb = *reinterpret_cast<const float4*>(&s_w0[(g * 32 + lane) * 8 + 4]);
+      part[0] = fmaf(v[g], wa.x, part[0]); part[1] = fmaf(v[g], wa.y, part[1]); part[2] = fmaf(v[g], wa.z, part[2]); part[3] = fmaf(v[g], wa.w, part[3]);
+      part[4] = fmaf(v[g], wb.x, part[4]); part[5] = fmaf(v[g], wb.y, part[5]); part[6] = fmaf(v[g], wb.z, part[6]); part[7] = fmaf(v[g], wb.w, part[7]);
     }
+    float k4[4], k2[2], k1;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const float send = hi ? part[q] : part[q + 4], keep = hi ? part[q + 4] : part[q]; k4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int q = 0; q < 2; q++) { const float send = hi ? k4[q] : k4[q + 2], keep = hi ? k4[q + 2] : k4[q]; k2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+    }
+    {
+      const bool hi = lane & 4;
+      const float send = hi ? k2[0] : k2[1], keep = hi ? k2[1] : k2[0];
+      k1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    k1 += __shfl_xor_sync(0xffffffffu, k1, 2);
+    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+    if ((lane & 3) == 0) s0[p * 8 + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))] = ak_selu(k1);
     const int uy = y - pt, ux = x - pl;
     if (uy >= 0 && uy < H && ux >= 0 && ux < W) {
       const float ss = ak_warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
@@ -635,7 +652,7 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     IMW_CHECK_LAUNCH();
     ak_conv1x1_selu_kernel<<<(unsigned)((P / 1024 * 32 + 255) / 256), 256, 0, st>>>(b.x4, w.conv4_w, b.a4, P / 1024, 128);
     IMW_CHECK_LAUNCH();
-    ak_fuse_kernel<<<148 * 8, 256, 0, st>>>(b.x1, w.conv1_w, b.a2, b.a3, b.a4, w.s0_w, b.feat, b.s0, SB, Hp, Wp, H, W, pt, pl);
+    ak_fuse_kernel<<<148 * 16, 256, 0, st>>>(b.x1, w.conv1_w, b.a2, b.a3, b.a4, w.s0_w, b.feat, b.s0, SB, Hp, Wp, H, W, pt, pl);
     IMW_CHECK_LAUNCH();
     // score head tail (3x3 8 -> 4, 4 -> 4, 4 -> 1 + sigmoid, cropped to the unpadded window)
     RUN((ak_conv<4, 8>(ak_args(b.s0, SB, Hp, Wp, 8, w.s2_w, nullptr, b.s1, 4, 4, 1), st)));

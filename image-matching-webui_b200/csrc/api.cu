@@ -225,26 +225,30 @@ struct OpRowMaxSum {  // softmax statistics of inv_temperature * sim along the o
 
 // P = softmax(sim, dim=-2) * softmax(sim, dim=-1) (dual_softmax.py:23); arg-max along the other image.
 struct OpDSMArgmax {
-  using State = ArgMaxState;
+  // arg-max over the other image of softmax(x, dim 1)[i,j] * softmax(x, dim 2)[i,j].  The factor normalised along the
+  // OTHER image's statistics is <= 1, so exp(x - max_own) / sum_own bounds the product: once a candidate is held, any
+  // x below  max_own + log(best * sum_own)  (minus a safety margin) cannot win and skips the exp / divide work.
+  struct State { float v; int j; float xmin; };
   const float *rmax, *rsum; float* best_v; int* best_j; int cap; float scale;
-  __device__ void init(State& s) const { s.v = -INFINITY; s.j = 0x7fffffff; }
+  __device__ void init(State& s) const { s.v = -INFINITY; s.j = 0x7fffffff; s.xmin = -INFINITY; }
   __device__ void accum(State& s, float v, int i, int j, int own, int other) const {
-    float x = v * scale;
-    long long io = (long long)own * cap + i, jo = (long long)other * cap + j;
-    // image-1 statistics normalise dim=-2 (over image-0 rows), image-0 statistics dim=-1
-    long long i0 = (own & 1) ? jo : io, i1 = (own & 1) ? io : jo;
-    float p_col = __fdiv_rn(expf(x - rmax[i1]), rsum[i1]);
-    float p_row = __fdiv_rn(expf(x - rmax[i0]), rsum[i0]);
-    argmax_accum(s, __fmul_rn(p_col, p_row), j);
+    const float x = v * scale;
+    if (x < s.xmin) return;
+    const long long io = (long long)own * cap + i, jo = (long long)other * cap + j;
+    const long long i0 = (own & 1) ? jo : io, i1 = (own & 1) ? io : jo;   // image-0 / image-1 statistics
+    // softmax over image-0 positions (statistics kept per image-1 column) times softmax over image-1 positions
+    const float p1 = __fdiv_rn(expf(x - rmax[i1]), rsum[i1]), p2 = __fdiv_rn(expf(x - rmax[i0]), rsum[i0]);
+    const float p = __fmul_rn(p1, p2);
+    if (p > s.v || (p == s.v && j < s.j)) {
+      s.v = p; s.j = j;
+      s.xmin = rmax[io] + logf(p * rsum[io]) - 1e-3f;   // -inf while p underflows to 0: nothing is skipped
+    }
   }
   __device__ State shfl_xor(const State& s, int o) const {
-    State t; t.v = __shfl_xor_sync(0xffffffffu, s.v, o); t.j = __shfl_xor_sync(0xffffffffu, s.j, o); return t;
+    State t; t.v = __shfl_xor_sync(0xffffffffu, s.v, o); t.j = __shfl_xor_sync(0xffffffffu, s.j, o); t.xmin = s.xmin; return t;
   }
-  __device__ void merge(State& a, const State& b) const { argmax_accum(a, b.v, b.j); }
-  __device__ void store(const State& s, int own, int i) const {
-    best_v[(long long)own * cap + i] = s.v;
-    best_j[(long long)own * cap + i] = s.j;
-  }
+  __device__ void merge(State& a, const State& b) const { if (b.v > a.v || (b.v == a.v && b.j < a.j)) { a.v = b.v; a.j = b.j; } }
+  __device__ void store(const State& s, int own, int i) const { best_v[(long long)own * cap + i] = s.v; best_j[(long long)own * cap + i] = s.j; }
 };
 
 // (P == row max) & (P == col max) & (P > thr)  (dual_softmax.py:24-28)

@@ -213,6 +213,7 @@ struct OpRowMaxSum {  // softmax statistics of inv_temperature * sim along the o
   float* rmax; float* rsum; int cap; float scale;
   __device__ void init(State& s) const { s.m = -INFINITY; s.s = 0.f; }
   __device__ void accum(State& s, float v, int, int, int, int) const { lse_accum(s, v * scale); }
+  __device__ void accum32(State& s, const float (&v)[32], int, int, int jn, int, int) const { lse_accum32(s, v, jn, scale); }
   __device__ State shfl_xor(const State& s, int o) const {
     State t; t.m = __shfl_xor_sync(0xffffffffu, s.m, o); t.s = __shfl_xor_sync(0xffffffffu, s.s, o); return t;
   }

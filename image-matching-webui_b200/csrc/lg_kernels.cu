@@ -295,6 +295,7 @@ struct OpRowLSE {
   float* rmax; float* rlse; int cap;
   __device__ void init(State& s) const { s.m = -CUDART_INF_F; s.s = 0.f; }
   __device__ void accum(State& s, float v, int, int, int, int) const { lse_accum(s, v); }
+  __device__ void accum32(State& s, const float (&v)[32], int, int, int jn, int, int) const { lse_accum32(s, v, jn, 1.f); }
   __device__ State shfl_xor(const State& s, int o) const {
     State t; t.m = __shfl_xor_sync(0xffffffffu, s.m, o); t.s = __shfl_xor_sync(0xffffffffu, s.s, o); return t;
   }

@@ -127,6 +127,17 @@ __device__ __forceinline__ void lse_merge(MaxSumState& a, const MaxSumState& b) 
   a.s = a.s * expf(a.m - m) + b.s * expf(b.m - m);
   a.m = m;
 }
+// chunked form for the tensor-core kernel: fold 32 (scaled) values at once -- one rescale per chunk, no per-element branch
+__device__ __forceinline__ void lse_accum32(MaxSumState& st, const float (&v)[32], int jn, float scale) {
+  float x[32], cm = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j++) { x[j] = j < jn ? v[j] * scale : -INFINITY; cm = fmaxf(cm, x[j]); }
+  if (cm > st.m) { st.s *= expf(st.m - cm); st.m = cm; }   // st.s == 0 while st.m == -inf
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) a += expf(x[j] - st.m);
+  st.s += a;
+}
 // first-index arg-max (torch.max(dim) semantics: lowest index among equal maxima)
 __device__ __forceinline__ void argmax_accum(ArgMaxState& st, float v, int j) {
   if (v > st.v || (v == st.v && j < st.j)) { st.v = v; st.j = j; }

@@ -7,18 +7,30 @@
 //   warp 0      TMA producer: own-row tile [128 x 32 f32] and other-slot tile [128 x 32 f32] per k-block (SWIZZLE_128B)
 //   warp 1      TMEM allocation + MMA issue: hi*hi into the main accumulator, hi*lo + lo*hi into the cross accumulator
 //   warps 2..5  hi/lo splitters (x_hi = low 13 mantissa bits cleared, x_lo = x - x_hi, twin tile)
-//   warps 6..9  reduction: one TMEM lane = one row i per thread; the thread walks the 128 columns of the tile in
-//               ascending j and calls op.accum; the state lives in registers across all column tiles of the row tile
+//   warps 6..13 reduction: one TMEM lane = one row i per thread, two warps per TMEM sub-partition (columns 0..63 /
+//               64..127 of the tile); a thread walks its columns in 32-wide chunks (op.accum32 when the functor has a
+//               chunked form, else op.accum per element); the state lives in registers across all column tiles of the
+//               row tile and the two half-states are merged through shared memory at the end
 //
 // Persistent CTAs walk the row tiles (m fastest over slots); two accumulator sets alternate so that the reduction
 // of column tile t overlaps the MMAs of tile t+1.  Needs cap % 128 == 0, K % 32 == 0, ld % 4 == 0.
 #pragma once
+#include <type_traits>
+
 #include "simreduce.cuh"
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
+constexpr int TCS_THREADS = 64 + 128 + 256;
+
+// functors may provide a chunked form  accum32(State&, const float (&s)[32], int i, int j0, int jn, int own, int other)
+template <class Op, class = void>
+struct tcs_has_accum32 : std::false_type {};
 template <class Op>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_simreduce_kernel(const __grid_constant__ CUtensorMap tmX, SimArgs a, Op op,
+struct tcs_has_accum32<Op, std::void_t<decltype(&Op::accum32)>> : std::true_type {};
+
+template <class Op>
+__global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __grid_constant__ CUtensorMap tmX, SimArgs a, Op op,
                                                                     int m_tiles) {
   constexpr int BN = 128;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -32,12 +44,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_simreduce_kernel(const __gri
   uint64_t* tmem_full = ready + TC_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  typename Op::State* half_state = (typename Op::State*)(smem + TC_STAGES * STAGE + 256);   // [128]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmX);
     for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 128); }
-    for (int i = 0; i < 2; i++) { tc::mbar_init(tmem_full + i, 1); tc::mbar_init(tmem_empty + i, 128); }
+    for (int i = 0; i < 2; i++) { tc::mbar_init(tmem_full + i, 1); tc::mbar_init(tmem_empty + i, 256); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_simreduce_kernel(const __gri
         }
     }
   } else {
-    const int q = warp % 4;
+    const int q = warp % 4, half = (warp - 6) / 4;   // TMEM sub-partition, column half of the tile
     int i = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       int own, row0, n, m;
@@ -146,25 +159,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_simreduce_kernel(const __gri
         const int acc = i & 1;
         tc::mbar_wait(tmem_full + acc, (i >> 1) & 1);
         tc::fence_after_sync();
-        const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + half * 64;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
           float v[32], t[32];
           tc::tmem_ld32(lane_addr + c0, v);
           tc::tmem_ld32(lane_addr + BN + c0, t);
-          if (c0 + 32 >= BN) {
+          if (c0 == 32) {
             tc::fence_before_sync();
             tc::mbar_arrive(tmem_empty + acc);
           }
-          const int jmax = min(32, m - (j0 + c0));  // warp-uniform
-          if (row_ok) {
+          const int jc = j0 + half * 64 + c0, jn = min(32, m - jc);  // warp-uniform; may be <= 0
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (j < jmax) op.accum(st, v[j] + t[j], row, j0 + c0 + j, own, own ^ 1);
+          for (int j = 0; j < 32; j++) v[j] += t[j];
+          if (row_ok && jn > 0) {
+            if constexpr (tcs_has_accum32<Op>::value) {
+              op.accum32(st, v, row, jc, jn, own, own ^ 1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < jn) op.accum(st, v[j], row, jc + j, own, own ^ 1);
+            }
           }
         }
       }
-      if (row_ok) op.store(st, own, row);
+      // merge the two column halves of every row (functor merges are order-insensitive, ties included)
+      if (half == 1) half_state[q * 32 + lane] = st;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && row_ok) {
+        op.merge(st, half_state[q * 32 + lane]);
+        op.store(st, own, row);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
   tc::fence_before_sync();
@@ -181,7 +207,7 @@ template <class Op>
 static inline int launch_tc_simreduce(const SimArgs& a, int slots, Op op, cudaStream_t st) {
   CUtensorMap tmX;
   if (int e = tc_make_map_2d_f32(&tmX, a.X, (uint64_t)slots * a.cap, (uint64_t)a.K, (uint64_t)a.ld, TC_BK, TC_BM)) return e;
-  constexpr size_t smem = (size_t)TC_STAGES * 2 * (TC_BM * 128 + 128 * 128) + 1024 + 256;
+  constexpr size_t smem = (size_t)TC_STAGES * 2 * (TC_BM * 128 + 128 * 128) + 1024 + 256 + 128 * sizeof(typename Op::State);
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
@@ -193,7 +219,7 @@ static inline int launch_tc_simreduce(const SimArgs& a, int slots, Op op, cudaSt
   }
   const int m_tiles = slots * (a.cap / TC_BM);
   if (m_tiles == 0) return IMW_OK;
-  tc_simreduce_kernel<Op><<<dim3((unsigned)(m_tiles < num_sms ? m_tiles : num_sms)), TC_THREADS, smem, st>>>(tmX, a, op, m_tiles);
+  tc_simreduce_kernel<Op><<<dim3((unsigned)(m_tiles < num_sms ? m_tiles : num_sms)), TCS_THREADS, smem, st>>>(tmX, a, op, m_tiles);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -134,11 +134,48 @@ def row_magsac(dev, iters):
              mean_inliers=float(ninl.float().mean()), mean_iterations=float(nit.float().mean()))
 
 
-ROWS = {"sg": row_superglue, "loftr": row_loftr, "aliked": row_aliked, "nn": row_nn, "magsac": row_magsac}
+def row_config4(dev, iters):
+    """BASELINE configs[3] on one GPU: ALIKED (RGB 640x480, 1024 keypoints) -> LightGlue (128-d input_proj) -> MAGSAC++ F.
+    Random ALIKED weights and GIM LightGlue weights with the synthetic input_proj of the goldens (no checkpoints offline):
+    a throughput configuration, parity is covered by the per-stage tests."""
+    from oracle import aliked as oa
+    P, cap = 32, 1024
+    aw = {k: v.to(dev) for k, v in ops.aliked_pack_weights(oa.random_weights(0)).items()}
+    g = np.load(ROOT / "tests/golden/lg_proj.npz")
+    sd = dict(torch.load(str(ROOT / "weights/superpoint_lightglue.pt"), map_location="cpu"))
+    sd["input_proj.weight"], sd["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])
+    lw = {k: v.to(dev) for k, v in ops.lg_pack_weights(sd, 9).items()}
+    a, b = synth.make_pair_batch(list(range(P)))
+    rgb = torch.from_numpy(synth.to_rgb(np.stack([a, b], 1).reshape(2 * P, 480, 640)).astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(dev)
+    aconf = {"detection_threshold": 0.1, "max_num_keypoints": cap, "nms_radius": 2}
+    lconf = {"depth_confidence": 0.95, "width_confidence": 0.99, "filter_threshold": 0.2, "pruning_min_kpts": 1536, "use_tensor_cores": 1}
+    ar = torch.arange(cap, device=dev)
+
+    def step():
+        f = ops.aliked_forward(aw, rgb, aconf, cap)
+        counts = f["counts"][0].contiguous()
+        lg = ops.lightglue_forward(lw, 9, f["keypoints"], f["descriptors"], counts, lconf)
+        m0 = lg["matches"][0::2]                                       # [P,cap] matches0 per pair
+        valid = (m0 > -1) & (ar[None] < counts[0::2, None])
+        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)   # matched keypoints first (device-side compaction)
+        k0 = torch.gather(f["keypoints"][0::2], 1, order[..., None].expand(-1, -1, 2))
+        j = torch.gather(m0, 1, order).clamp(min=0).long()
+        k1 = torch.gather(f["keypoints"][1::2], 1, j[..., None].expand(-1, -1, 2))
+        nm = valid.sum(1).to(torch.int32)
+        _, masks, ninl, _ = ops.magsac(k0.contiguous(), k1.contiguous(), nm, "Fundamental", 3.0, 0.9999, 10000)
+        return nm, ninl, lg["stop"]
+    ms, nl = timed(step, iters)
+    nm, ninl, stop = step()
+    emit("config 4: ALIKED + LightGlue(128-d) + MAGSAC++ F", pairs=P, keypoints=cap, ms=round(ms, 2), pairs_per_s=round(P / ms * 1e3, 1), launches=nl,
+         mean_matches=float(nm.float().mean()), mean_inliers=float(ninl.float().mean()), mean_stop_layer=float(stop.float().mean()),
+         weights="random ALIKED, GIM LightGlue + synthetic input_proj")
+
+
+ROWS = {"config4": row_config4, "sg": row_superglue, "loftr": row_loftr, "aliked": row_aliked, "nn": row_nn, "magsac": row_magsac}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="sg,loftr,aliked,nn,magsac")
+    ap.add_argument("--rows", default="sg,loftr,aliked,nn,magsac,config4")
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
     dev = torch.device("cuda:0")

@@ -36,17 +36,17 @@ struct TcGemmArgs {
                          //    only even slots produce output: C[pair] = X_0 X_1^T (score matrices)
 };
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 320;
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 448;
 
 template <int BN, int SPLIT>
 constexpr size_t tc_gemm_smem_bytes() {
   return (size_t)TC_STAGES * (SPLIT == 3 ? 2 : 1) * (TC_BM * 128 + BN * 128) + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-         4 * 32 * 33 * sizeof(float) /*epilogue transpose tiles*/;
+         8 * 32 * 33 * sizeof(float) /*epilogue transpose tiles*/;
 }
 
 // Persistent: one CTA per SM walks the (m-tile, n-tile) list (n fastest, so the CTAs that share an A tile run
 // together and hit L2).  Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 hi/lo splitters (SPLIT == 3),
-// 6-9 epilogue.  The smem ring runs across tile boundaries and two TMEM accumulator sets alternate, so the
+// 6-13 epilogue (two warps per TMEM sub-partition, half of the tile's columns each).  The smem ring runs across tile boundaries and two TMEM accumulator sets alternate, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int SPLIT, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
     for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 128); }
-    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 256); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
     }
   } else {
     const int q = warp % 4;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    const int half = (warp - 6) / 4;  // two warps per sub-partition: columns [0, BN/2) and [BN/2, BN)
     // TMEM gives one output ROW per thread; global memory wants one row per warp instruction.  Transpose each
     // 32x32 block through a padded smem tile so that lanes run along the columns: every load/store of the
     // functor epilogue is one fully coalesced 128-byte line.
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
       const int row_base = row0 + q * 32;
       const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         float v[32];
         tc::tmem_ld32(lane_addr + c0, v);
         if (SPLIT == 3) {
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] += t[j];
         }
-        if (c0 + 32 >= BN) {  // last TMEM read of this accumulator set: hand it back to the MMA warp
+        if (c0 + 32 >= (half + 1) * (BN / 2)) {  // this warp's last TMEM read of the accumulator set: hand it back to the MMA warp
           tc::fence_before_sync();
           tc::mbar_arrive(tmem_empty + acc);
         }

@@ -148,7 +148,9 @@ def row_config4(dev, iters):
     a, b = synth.make_pair_batch(list(range(P)))
     rgb = torch.from_numpy(synth.to_rgb(np.stack([a, b], 1).reshape(2 * P, 480, 640)).astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(dev)
     aconf = {"detection_threshold": 0.1, "max_num_keypoints": cap, "nms_radius": 2}
-    lconf = {"depth_confidence": 0.95, "width_confidence": 0.99, "filter_threshold": 0.2, "pruning_min_kpts": 1536, "use_tensor_cores": 1}
+    # no trained ALIKED / ALIKED-LightGlue weights offline: with random descriptors the early exit fires at layer 1, so the
+    # matcher is forced to full depth (9 layers, no pruning) = an upper bound of its cost
+    lconf = {"depth_confidence": -1.0, "width_confidence": -1.0, "filter_threshold": 0.2, "pruning_min_kpts": 1536, "use_tensor_cores": 1}
     ar = torch.arange(cap, device=dev)
 
     def step():
@@ -168,7 +170,7 @@ def row_config4(dev, iters):
     nm, ninl, stop = step()
     emit("config 4: ALIKED + LightGlue(128-d) + MAGSAC++ F", pairs=P, keypoints=cap, ms=round(ms, 2), pairs_per_s=round(P / ms * 1e3, 1), launches=nl,
          mean_matches=float(nm.float().mean()), mean_inliers=float(ninl.float().mean()), mean_stop_layer=float(stop.float().mean()),
-         weights="random ALIKED, GIM LightGlue + synthetic input_proj")
+         weights="random ALIKED, GIM LightGlue + synthetic input_proj; LightGlue forced to full depth")
 
 
 ROWS = {"config4": row_config4, "sg": row_superglue, "loftr": row_loftr, "aliked": row_aliked, "nn": row_nn, "magsac": row_magsac}

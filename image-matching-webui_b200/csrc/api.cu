@@ -44,9 +44,9 @@ size_t sp_carve(Workspace& ws, SPBuffers& b, int B, int H, int W) {
   b.a6 = ws.take<float>(sb * h * w * 128 * 3 / 2);
   b.a7 = ws.take<float>(sb * h * w * 128 * 3 / 2);
   b.a8 = ws.take<float>(sb * h * w * 128 * 3 / 2);
-  b.pa = ws.take<float>(sb * h * w * 256);
-  b.logits = ws.take<float>(sb * h * w * 65 + 64);
-  b.da = ws.take<float>(sb * h * w * 256);
+  b.pa = ws.take<float>(sb * h * w * 256 * 3 / 2);
+  b.logits = ws.take<float>(sb * h * w * 128);
+  b.da = ws.take<float>(sb * h * w * 256 * 3 / 2);
   b.dense = ws.take<float>((size_t)B * H * W);
   b.nms = ws.take<float>((size_t)B * H * W);
   b.dd = ws.take<float>((size_t)B * h * w * 256);
@@ -81,6 +81,7 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
     IMW_REQUIRE(W % 16 == 0, "imw_superpoint_forward: the tensor-core path needs W %% 16 == 0 (got %d)", W);
     for (int l : {1, 2, 3, 4, 5, 6, 7, 8, 10}) IMW_REQUIRE(wt->wp[l] != nullptr, "imw_superpoint_forward: bf16-plane weights missing for layer %d", l);
   }
+  const bool tc_heads = use_tc && wt->wp[9] && wt->wp[11];
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
   for (int b0 = 0; b0 < B; b0 += SP_SUB) {
@@ -96,8 +97,9 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
       RUN(tc_conv3x3(b.a5, wt->wp[5], wt->b[5], b.a6, nb, H / 4, W / 4, 128, 128, 1, 1, 0, st));
       RUN(tc_conv3x3(b.a6, wt->wp[6], wt->b[6], b.a7, nb, h, w, 128, 128, 1, 0, 0, st));
       RUN(tc_conv3x3(b.a7, wt->wp[7], wt->b[7], b.a8, nb, h, w, 128, 128, 1, 0, 0, st));
-      RUN(tc_conv3x3(b.a8, wt->wp[8], wt->b[8], b.pa, nb, h, w, 128, 256, 1, 0, 1, st));
-      RUN(tc_conv3x3(b.a8, wt->wp[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, 1, st));
+      const int head_planes = tc_heads ? 0 : 1;   // 1x1 heads on tcgen05 too: keep the 3x3 head outputs as planes
+      RUN(tc_conv3x3(b.a8, wt->wp[8], wt->b[8], b.pa, nb, h, w, 128, 256, 1, 0, head_planes, st));
+      RUN(tc_conv3x3(b.a8, wt->wp[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, head_planes, st));
     } else {
       RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], b.a1, nullptr, nb, H, W, st));
       RUN(sp_conv3x3(b.a1, wt->w[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, st));
@@ -111,18 +113,25 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
       RUN(sp_conv3x3(b.a8, wt->w[10], wt->b[10], b.da, nb, h, w, 128, 256, 1, 0, st)); // descriptor head (superpoint.py:194)
     }
     // detector head 1x1 + softmax + depth-to-space (superpoint.py:166-170)
-    {
+    if (tc_heads) {  // 65 outputs zero-padded to 128 (weights and bias padded by the host)
+      RUN(tc_conv_general(b.pa, wt->wp[9], wt->b[9], nullptr, b.logits, nb, h, w, 256, 128, 1, 1, 0, 1, st));
+      RUN(sp_softmax_d2s(b.logits, b.dense + (size_t)b0 * H * W, nb, h, w, st, 128));
+    } else {
       GemmArgs g{};
       g.A = b.pa; g.lda = 256; g.W = wt->w[9]; g.ldw = 256; g.M = nb * h * w; g.N = 65; g.K = 256;
       IMW_CHECK_CUDA(launch_gemm(g, 1, EpiBias{b.logits, 0, 65, wt->b[9], 0}, st));
+      RUN(sp_softmax_d2s(b.logits, b.dense + (size_t)b0 * H * W, nb, h, w, st));
     }
-    RUN(sp_softmax_d2s(b.logits, b.dense + (size_t)b0 * H * W, nb, h, w, st));
     // descriptor head 1x1 + channel L2 norm (superpoint.py:195-196)
     {
       float* dd = b.dd + (size_t)b0 * h * w * 256;
-      GemmArgs g{};
-      g.A = b.da; g.lda = 256; g.W = wt->w[11]; g.ldw = 256; g.M = nb * h * w; g.N = 256; g.K = 256;
-      IMW_CHECK_CUDA(launch_gemm(g, 1, EpiBias{dd, 0, 256, wt->b[11], 0}, st));
+      if (tc_heads) {
+        RUN(tc_conv_general(b.da, wt->wp[11], wt->b[11], nullptr, dd, nb, h, w, 256, 256, 1, 1, 0, 1, st));
+      } else {
+        GemmArgs g{};
+        g.A = b.da; g.lda = 256; g.W = wt->w[11]; g.ldw = 256; g.M = nb * h * w; g.N = 256; g.K = 256;
+        IMW_CHECK_CUDA(launch_gemm(g, 1, EpiBias{dd, 0, 256, wt->b[11], 0}, st));
+      }
       RUN(sp_l2norm_rows(dd, (long long)nb * h * w, 256, st));
     }
   }

@@ -8,8 +8,8 @@ int sp_conv3x3(const float* in, const float* w, const float* bias, float* out, i
 int sp_conv3x3_c1(const float* img, const float* w, const float* bias, float* out, void* out_planes, int B, int H, int W,
                   cudaStream_t st);
 
-// logits [B][h][w][65] (NHWC) -> dense scores [B][8h][8w]
-int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st);
+// logits [B][h][w][ld >= 65] (NHWC, 65 used) -> dense scores [B][8h][8w]
+int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st, int ld = 65);
 // dense [B][H][W] -> nms [B][H][W] (scores kept at surviving maxima, 0 elsewhere)
 int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cudaStream_t st);
 // nms -> keypoints/scores per image (row-major order, or descending score when more than max_kpts pass)

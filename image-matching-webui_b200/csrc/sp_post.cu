@@ -15,12 +15,12 @@ namespace {
 // ---- softmax over 65 channels + depth-to-space -----------------------------------------------
 // one warp per 8x8 cell; lane l owns channels l, l+32 (and lane 0 the dustbin, channel 64).
 __global__ void __launch_bounds__(256) softmax_d2s_kernel(const float* __restrict__ logits, float* __restrict__ dense,
-                                                          int B, int h, int w) {
+                                                          int B, int h, int w, int ld) {
   const long long cell = (long long)blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const long long ncell = (long long)B * h * w;
   if (cell >= ncell) return;
-  const float* p = logits + cell * 65;
+  const float* p = logits + cell * ld;
   float a = p[lane], b = p[lane + 32];
   float d = (lane == 0) ? p[64] : -CUDART_INF_F;
   float m = warp_max(fmaxf(fmaxf(a, b), d));
@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restric
 
 }  // namespace
 
-int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st) {
+int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaStream_t st, int ld) {
   long long ncell = (long long)B * h * w;
-  softmax_d2s_kernel<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(logits, dense, B, h, w);
+  softmax_d2s_kernel<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(logits, dense, B, h, w, ld);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -29,6 +29,13 @@ def sp_pack_weights(state_dict):
         if name in SP_TC_LAYERS:  # [3 planes][tap][Cout][Cin] bf16, w = p0 + p1 + p2 (tcgen05 split-precision path)
             wt = state_dict[name + ".weight"].float().permute(2, 3, 0, 1).reshape(9, w.shape[2], w.shape[1]).contiguous()
             out[name + "_wp"] = split_bf16_planes(wt)
+        elif name in ("convPb", "convDb"):  # 1x1 heads on the same path: [3][1][Cout_p][Cin], the 65 detector outputs padded to 128
+            co, ci = w.shape
+            cop = (co + 127) // 128 * 128
+            wt = torch.zeros(1, cop, ci); wt[0, :co] = w
+            out[name + "_wp"] = split_bf16_planes(wt)
+            bp = torch.zeros(cop); bp[:co] = out[name + "_b"]
+            out[name + "_b"] = bp
     return out
 
 

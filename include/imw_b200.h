@@ -41,7 +41,9 @@ typedef struct {
   const float* w[12]; /* conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db */
   const float* b[12];
   /* optional: 3x3 kernels of conv1b..conv4b, convPa, convDa as three bf16 planes [3][9][Cout][Cin]
-     (w = p0 + p1 + p2) for the tcgen05 split-precision path; NULL entries -> CUDA-core path only */
+     (w = p0 + p1 + p2) for the tcgen05 split-precision path; NULL entries -> CUDA-core path only.
+     wp[9] / wp[11] (optional): the 1x1 heads as planes [3][1][Cout_p][256], convPb's 65 outputs zero-padded to
+     Cout_p = 128 -- then b[9] must hold 128 values (65 + zeros) */
   const void* wp[12];
 } imw_sp_weights;
 

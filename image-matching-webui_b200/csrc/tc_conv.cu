@@ -114,7 +114,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     {
       const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_BF16, 128, 2 * BN);
       int tap = 0, ck = 0;
       for (int it = 0; it < steps; it++, ck++) {
         if (ck == chunks) { ck = 0; tap++; }
@@ -130,15 +130,16 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ad[p] = tc::make_smem_desc_sw128(a0 + p * CV_A_BYTES + k * 32);
             bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
           }
-          const int krow = tap / KS;
-          const uint32_t d_main = tmem_base + krow * BN, d_cross = tmem_base + 3 * BN;
+          // The three weight planes are contiguous in N ([b0 | b1 | b2] rows), so the six partial products of the
+          // split are issued as four MMAs that read each operand tile less often (shared-memory operand bandwidth is
+          // what bounds this kernel): a0 x b0 -> main, a0 x [b1|b2] and a1 x [b0|b1] -> [c1|c2], a2 x b0 -> c2.
+          // main alternates between two accumulators step by step: shorter truncating-add chains.
+          const uint32_t d_main = tmem_base + (it & 1) * BN, d_c1 = tmem_base + 2 * BN, d_c2 = tmem_base + 3 * BN;
           if (leader) {
-            tc::mma_f16(d_main, ad[0], bd[0], idesc, ((tap % KS) | ck | k) ? 1u : 0u);  // first MMA of this kernel row
-            tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
-            tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
-            tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
-            tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
-            tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+            tc::mma_f16(d_main, ad[0], bd[0], idesc, (it >= 2 || k) ? 1u : 0u);
+            tc::mma_f16(d_c1, ad[0], bd[1], idesc2, (it | k) ? 1u : 0u);
+            tc::mma_f16(d_c1, ad[1], bd[0], idesc2, 1u);
+            tc::mma_f16(d_c2, ad[2], bd[0], idesc, 1u);
           }
         }
         if (leader) tc::mma_commit(empty + s);
@@ -164,14 +165,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float v[32], t[32];
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
       tc::tmem_ld32(lane_base, v);
-      if (KS == 3) {   // 1x1: only the first kernel-row accumulator and the cross-term accumulator are used
+      if (steps >= 2) {   // second main accumulator (odd k-steps)
         tc::tmem_ld32(lane_base + BN, t);
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += t[j];
-        tc::tmem_ld32(lane_base + 2 * BN, t);
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += t[j];
       }
+      tc::tmem_ld32(lane_base + 2 * BN, t);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += t[j];
       tc::tmem_ld32(lane_base + 3 * BN, t);
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] += t[j];
@@ -305,7 +306,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     {
       const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN);
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_BF16, 128, 2 * BN);
       int i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
         const int acc = i & 1;
@@ -319,7 +320,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc::mbar_wait(b_full + s, ph);
           tc::fence_after_sync();
           const uint32_t a0 = tc::smem_u32(sA + dxi * 3 * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
-          const uint32_t d_main = d_base + dyi * BN, d_cross = d_base + 3 * BN;
+          const uint32_t d_main = d_base + (it & 1) * BN, d_c1 = d_base + 2 * BN, d_c2 = d_base + 3 * BN;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             uint64_t ad[3], bd[3];
@@ -328,13 +329,11 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
               bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
             }
-            if (leader) {
-              tc::mma_f16(d_main, ad[0], bd[0], idesc, (dxi | k) ? 1u : 0u);  // first MMA into this kernel row's accumulator
-              tc::mma_f16(d_cross, ad[0], bd[1], idesc, (it | k) ? 1u : 0u);
-              tc::mma_f16(d_cross, ad[1], bd[0], idesc, 1u);
-              tc::mma_f16(d_cross, ad[0], bd[2], idesc, 1u);
-              tc::mma_f16(d_cross, ad[1], bd[1], idesc, 1u);
-              tc::mma_f16(d_cross, ad[2], bd[0], idesc, 1u);
+            if (leader) {  // four MMAs for the six partial products ([b0|b1|b2] contiguous in N), see tc_conv3x3_kernel
+              tc::mma_f16(d_main, ad[0], bd[0], idesc, (it >= 2 || k) ? 1u : 0u);
+              tc::mma_f16(d_c1, ad[0], bd[1], idesc2, (it | k) ? 1u : 0u);
+              tc::mma_f16(d_c1, ad[1], bd[0], idesc2, 1u);
+              tc::mma_f16(d_c2, ad[2], bd[0], idesc, 1u);
             }
           }
           if (leader) {

@@ -9,8 +9,10 @@
 //              softmax_j and P_j V_j run, V_{j+1} while S_{j+1} and softmax_{j+1} run)
 //   warp 1     MMA issuer: S_j = Q K_j^T into one of two TMEM buffers (main hi*hi and cross-term accumulators),
 //              O_j = P_j V_j into a fresh TMEM tile (never rescaled in place)
-//   warps 2-5  one q row per thread: tcgen05.ld S_j, mask, running max / sum, P_j = exp(S_j - m) written to shared
-//              memory as hi/lo K-major SWIZZLE_128B tiles for the second MMA, and the running output
+//   warps 2-9  softmax / correction, two warps per TMEM sub-partition: a thread owns one q row and HALF of the columns
+//              (32 of the 64 keys of S_j, 32 of the 64 output dims of O): tcgen05.ld S_j, mask, row max (exchanged
+//              with the partner thread through shared memory), P_j = exp(S_j - m) written to shared memory as
+//              hi/lo K-major SWIZZLE_128B tiles for the second MMA, and the running output
 //              acc = (acc + O_{j-1}) * exp(m_{j-1} - m_j) kept in registers.
 #pragma once
 #include "common.cuh"
@@ -27,12 +29,12 @@ struct TcAttnArgs {
   long long plane_rows_vt;  // slots*4*64
 };
 
-constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 192;
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 64 + 256;
 constexpr int TA_Q_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 k-subtiles x [128 x 32 f32]  = 64 KB
 constexpr int TA_K_BYTES = 2 * 2 * TA_BKV * 128;    // hi/lo x 2 subtiles x [64 x 32]        = 32 KB
 constexpr int TA_V_BYTES = 2 * 2 * 64 * 128;        // hi/lo x 2 kv-subtiles x [64 d x 32 kv] = 32 KB
 constexpr int TA_P_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 kv-subtiles x [128 x 32]     = 64 KB
-constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256;
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256 + 2 * 2 * 128 * sizeof(float);
 
 // TMEM columns: S buffers 2 x (main 64 + cross 64) = 256, O main 64 + cross 64 -> 384 (allocate 512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
@@ -62,11 +64,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
            *s_full = bars + 5 /*[2]*/, *p_full = bars + 7, *o_full = bars + 8;
   uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  float* xchg = (float*)(sP + TA_P_BYTES + 256);   // [tile parity][half][128 rows]: row maxima / final sums of the partner thread
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
     tc::mbar_init(q_full, 1); tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
-    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, 128);
+    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, 256);
     tc::mbar_init(o_full, 1);
     tc::fence_barrier_init();
   }
@@ -153,64 +156,64 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     const int q = warp % 4, r = q * 32 + lane;           // TMEM lane = q row inside the tile
+    const int half = (warp - 2) / 4;                     // keys [32 half, +32) of S_j and dims [32 half, +32) of O
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f, acc[64];
+    float m = -INFINITY, l = 0.f, acc[32];
 #pragma unroll
-    for (int c = 0; c < 64; c++) acc[c] = 0.f;
+    for (int c = 0; c < 32; c++) acc[c] = 0.f;
     for (int j = 0; j < T; j++) {
       tc::mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc::fence_after_sync();
-      float s[64];
+      float s[32];
       {
         float t[32];
-        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128;
-        tc::tmem_ld32(a, *reinterpret_cast<float(*)[32]>(&s[0]));
-        tc::tmem_ld32(a + 32, *reinterpret_cast<float(*)[32]>(&s[32]));
+        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128 + half * 32;
+        tc::tmem_ld32(a, s);
         tc::tmem_ld32(a + 64, t);
 #pragma unroll
         for (int c = 0; c < 32; c++) s[c] += t[c];
-        tc::tmem_ld32(a + 96, t);
-#pragma unroll
-        for (int c = 0; c < 32; c++) s[32 + c] += t[c];
       }
-      const int kv0 = j * TA_BKV;
+      const int kv0 = j * TA_BKV + half * 32;
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; c++) {
+      for (int c = 0; c < 32; c++) {
         s[c] = (kv0 + c < nk) ? s[c] * g.scale : -INFINITY;
         mx = fmaxf(mx, s[c]);
       }
-      const float m_new = fmaxf(m, mx);          // finite: at least one key of this tile is valid
+      // row maximum over both halves (partner thread = same row, other column half)
+      float* xb = xchg + (j & 1) * 256;
+      xb[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m, fmaxf(mx, xb[(half ^ 1) * 128 + r]));   // finite: the tile holds at least one valid key
       const float alpha = __expf(m - m_new);     // 0 on the first tile (m = -inf)
       float ps = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
-      l = l * alpha + ps;
+      for (int c = 0; c < 32; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
+      l = l * alpha + ps;                        // partial sum over this thread's columns
       m = m_new;
       if (j > 0) {  // fold in O_{j-1} (computed relative to m_{j-1}), then move the reference to m_j
         tc::mbar_wait(o_full, (j - 1) & 1);
         tc::fence_after_sync();
         float t[32];
+        tc::tmem_ld32(lane_addr + TA_O_COL + half * 32, t);        // main
 #pragma unroll
-        for (int h = 0; h < 4; h++) {
-          tc::tmem_ld32(lane_addr + TA_O_COL + h * 32, t);  // h 0,1: main cols 0..63; h 2,3: cross
+        for (int c = 0; c < 32; c++) acc[c] += t[c];
+        tc::tmem_ld32(lane_addr + TA_O_COL + 64 + half * 32, t);   // cross terms
 #pragma unroll
-          for (int c = 0; c < 32; c++) acc[(h & 1) * 32 + c] += t[c];
-        }
+        for (int c = 0; c < 32; c++) acc[c] += t[c];
       }
 #pragma unroll
-      for (int c = 0; c < 64; c++) acc[c] *= alpha;
+      for (int c = 0; c < 32; c++) acc[c] *= alpha;
       // P_j -> shared memory, hi/lo planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk c of
       // row r lives at chunk c ^ (r & 7)); the previous P V MMA has completed (o_full above)
       tc::fence_before_sync();
-#pragma unroll
-      for (int sub = 0; sub < 2; sub++) {
-        uint8_t* ph = sP + (0 * 2 + sub) * TA_BQ * 128 + r * 128;
-        uint8_t* pl = sP + (1 * 2 + sub) * TA_BQ * 128 + r * 128;
+      {
+        uint8_t* ph = sP + (0 * 2 + half) * TA_BQ * 128 + r * 128;
+        uint8_t* pl = sP + (1 * 2 + half) * TA_BQ * 128 + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ch++) {
           uint4 h4, l4;
-          const float* v = &s[sub * 32 + ch * 4];
+          const float* v = &s[ch * 4];
           h4.x = __float_as_uint(v[0]) & 0xFFFFE000u; h4.y = __float_as_uint(v[1]) & 0xFFFFE000u;
           h4.z = __float_as_uint(v[2]) & 0xFFFFE000u; h4.w = __float_as_uint(v[3]) & 0xFFFFE000u;
           l4.x = __float_as_uint(v[0] - __uint_as_float(h4.x)); l4.y = __float_as_uint(v[1] - __uint_as_float(h4.y));
@@ -228,19 +231,22 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc::fence_after_sync();
     {
       float t[32];
+      tc::tmem_ld32(lane_addr + TA_O_COL + half * 32, t);
 #pragma unroll
-      for (int h = 0; h < 4; h++) {
-        tc::tmem_ld32(lane_addr + TA_O_COL + h * 32, t);
+      for (int c = 0; c < 32; c++) acc[c] += t[c];
+      tc::tmem_ld32(lane_addr + TA_O_COL + 64 + half * 32, t);
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[(h & 1) * 32 + c] += t[c];
-      }
+      for (int c = 0; c < 32; c++) acc[c] += t[c];
     }
+    float* xb = xchg + (T & 1) * 256;   // the buffer the last tile did not use
+    xb[half * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int row = q0 + r;
     if (row < nq) {
-      const float inv = 1.f / l;
-      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64);
+      const float inv = 1.f / (l + xb[(half ^ 1) * 128 + r]);
+      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + half * 32);
 #pragma unroll
-      for (int c = 0; c < 16; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      for (int c = 0; c < 8; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
     }
   }
   tc::fence_before_sync();

@@ -57,8 +57,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ uint8_t ta_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)ta_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                 // [plane][sub][128 rows][128 B]
-  uint8_t* sK = sQ + TA_Q_BYTES;      // [plane][sub][64 rows][128 B]
-  uint8_t* sV = sK + TA_K_BYTES;      // [plane][sub][64 d rows][128 B]
+  uint8_t* sK = sQ + TA_Q_BYTES;      // [sub][plane][64 rows][128 B]   (hi | lo of one k-subtile adjacent: one N = 128 operand)
+  uint8_t* sV = sK + TA_K_BYTES;      // [sub][plane][64 d rows][128 B]
   uint8_t* sP = sV + TA_V_BYTES;      // [plane][sub][128 rows][128 B]
   uint64_t* bars = (uint64_t*)(sP + TA_P_BYTES);
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
@@ -94,18 +94,18 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::mbar_expect_tx(k_full, TA_K_BYTES);
         for (int p = 0; p < 2; p++)
           for (int sub = 0; sub < 2; sub++)
-            tc::tma_load_2d(sK + (p * 2 + sub) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + j * TA_BKV);
+            tc::tma_load_2d(sK + (sub * 2 + p) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + j * TA_BKV);
         if (j > 0) tc::mbar_wait(v_empty, (j - 1) & 1);
         tc::mbar_expect_tx(v_full, TA_V_BYTES);
         for (int p = 0; p < 2; p++)
           for (int sub = 0; sub < 2; sub++)
-            tc::tma_load_2d(sV + (p * 2 + sub) * 64 * 128, &tmV, v_full, j * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
+            tc::tma_load_2d(sV + (sub * 2 + p) * 64 * 128, &tmV, v_full, j * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
       }
     }
   } else if (warp == 1) {
     {
       const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64), idesc2 = tc::make_idesc(tc::FMT_TF32, 128, 128);
       const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
       auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi
         tc::mbar_wait(k_full, j & 1);
@@ -115,11 +115,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int ks = 0; ks < 8; ks++) {
           const int sub = ks / 4, ko = (ks % 4) * 32;
           uint64_t qh = tc::make_smem_desc_sw128(aQ + (0 * 2 + sub) * TA_BQ * 128 + ko), ql = tc::make_smem_desc_sw128(aQ + (1 * 2 + sub) * TA_BQ * 128 + ko);
-          uint64_t kh = tc::make_smem_desc_sw128(aK + (0 * 2 + sub) * TA_BKV * 128 + ko), kl = tc::make_smem_desc_sw128(aK + (1 * 2 + sub) * TA_BKV * 128 + ko);
+          uint64_t kh = tc::make_smem_desc_sw128(aK + (sub * 2 + 0) * TA_BKV * 128 + ko);   // [K_hi | K_lo]: 128 adjacent rows
           if (leader) {
-            tc::mma_tf32(d_main, qh, kh, idesc, ks ? 1u : 0u);
-            tc::mma_tf32(d_cross, qh, kl, idesc, ks ? 1u : 0u);
-            tc::mma_tf32(d_cross, ql, kh, idesc, 1u);
+            tc::mma_tf32(d_main, qh, kh, idesc2, ks ? 1u : 0u);   // Q_hi x [K_hi | K_lo] -> [main | cross]
+            tc::mma_tf32(d_cross, ql, kh, idesc, 1u);             // Q_lo x K_hi -> cross
           }
         }
         if (leader) {
@@ -140,10 +139,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int ks = 0; ks < 8; ks++) {  // O_j = P_j V_j, K = 64 keys
           const int sub = ks / 4, ko = (ks % 4) * 32;
           uint64_t ph = tc::make_smem_desc_sw128(aP + (0 * 2 + sub) * TA_BQ * 128 + ko), pl = tc::make_smem_desc_sw128(aP + (1 * 2 + sub) * TA_BQ * 128 + ko);
-          uint64_t vh = tc::make_smem_desc_sw128(aV + (0 * 2 + sub) * 64 * 128 + ko), vl = tc::make_smem_desc_sw128(aV + (1 * 2 + sub) * 64 * 128 + ko);
+          uint64_t vh = tc::make_smem_desc_sw128(aV + (sub * 2 + 0) * 64 * 128 + ko);       // [V_hi | V_lo]
           if (leader) {
-            tc::mma_tf32(d_main, ph, vh, idesc, ks ? 1u : 0u);
-            tc::mma_tf32(d_cross, ph, vl, idesc, ks ? 1u : 0u);
+            tc::mma_tf32(d_main, ph, vh, idesc2, ks ? 1u : 0u);
             tc::mma_tf32(d_cross, pl, vh, idesc, 1u);
           }
         }

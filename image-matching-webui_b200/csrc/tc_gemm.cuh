@@ -54,9 +54,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
                                                                     int m_tiles) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-  // stage layout: [A | W] (TMA destination, becomes hi in place) and for SPLIT == 3 [A_lo | W_lo] behind it
+  // stage layout, SPLIT == 3: [A_hi | A_lo | W_hi | W_lo] -- TMA lands the fp32 tiles in the hi slots, the splitters rewrite
+  // them in place and fill the lo slots; W_hi and W_lo are adjacent so that A_hi x [W_hi | W_lo] is ONE MMA of N = 2 BN
+  // (fewer shared-memory operand reads than three MMAs).  SPLIT == 1: [A | W].
   constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, TILE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGE = (SPLIT == 3 ? 2 : 1) * TILE_BYTES;
+  constexpr int W_OFF = (SPLIT == 3 ? 2 : 1) * A_BYTES;
   constexpr int ACC_COLS = (SPLIT == 3 ? 2 : 1) * BN;   // SPLIT == 3: hi*hi and cross-term accumulators (see header)
   uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
   uint64_t* empty = full + TC_STAGES;
@@ -105,13 +108,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
           tc::mbar_wait(empty + s, ph ^ 1);
           tc::mbar_expect_tx(full + s, TILE_BYTES);
           tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
-          tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmW, full + s, kb * TC_BK, w_row0);
+          tc::tma_load_2d(smem + s * STAGE + W_OFF, &tmW, full + s, kb * TC_BK, w_row0);
         }
       }
     }
   } else if (warp == 1) {
     const bool leader = tc::elect_one();
-    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN), idesc2 = tc::make_idesc(tc::FMT_TF32, TC_BM, 2 * BN);
     int c = 0, i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int m_tile, n0, z, row0, nrows;
@@ -124,17 +127,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
         const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
         tc::mbar_wait(SPLIT == 3 ? ready + s : full + s, ph);
         tc::fence_after_sync();
-        const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+        const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + W_OFF;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; k++) {
           // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
           uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
-          uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
+          uint64_t adl = tc::make_smem_desc_sw128(a_addr + A_BYTES + k * 32);
           if (leader) {
-            tc::mma_tf32(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
             if (SPLIT == 3) {
-              tc::mma_tf32(d_cross, ad, bdl, idesc, (kb | k) ? 1u : 0u);
-              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);
+              tc::mma_tf32(d_main, ad, bd, idesc2, (kb | k) ? 1u : 0u);   // A_hi x [W_hi | W_lo] -> [main | cross]
+              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);                  // A_lo x W_hi -> cross
+            } else {
+              tc::mma_tf32(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
             }
           }
         }
@@ -156,18 +160,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
         for (int kb = 0; kb < KB; kb++, c++) {
           const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
           tc::mbar_wait(full + s, ph);
-          uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
-          uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
+          uint4* base = reinterpret_cast<uint4*>(smem + s * STAGE);
 #pragma unroll 8
           for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
-            uint4 v = hi[idx], h, l;
+            // A region: hi at idx, lo A_BYTES behind; W region: hi at W_OFF + .., lo B_BYTES behind
+            const bool in_a = idx < A_BYTES / 16;
+            uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
+            uint4* lo = hi + (in_a ? A_BYTES : B_BYTES) / 16;
+            uint4 v = *hi, h, l;
             h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
             l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
             l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
             l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
             l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            hi[idx] = h;
-            lo[idx] = l;
+            *hi = h;
+            *lo = l;
           }
           tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
           tc::mbar_arrive(ready + s);

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __gr
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, TILE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGE = 2 * TILE_BYTES;
+  constexpr int STAGE = 2 * TILE_BYTES;   // [A_hi | A_lo | B_hi | B_lo] (see tc_gemm.cuh)
+  constexpr int W_OFF = 2 * A_BYTES;
   constexpr int ACC_COLS = 2 * BN;
   uint64_t* full = (uint64_t*)(smem + TC_STAGES * STAGE);
   uint64_t* empty = full + TC_STAGES;
@@ -80,13 +81,13 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __gr
             tc::mbar_wait(empty + s, ph ^ 1);
             tc::mbar_expect_tx(full + s, TILE_BYTES);
             tc::tma_load_2d(smem + s * STAGE, &tmX, full + s, kb * TC_BK, own * a.cap + row0);
-            tc::tma_load_2d(smem + s * STAGE + A_BYTES, &tmX, full + s, kb * TC_BK, (own ^ 1) * a.cap + j0);
+            tc::tma_load_2d(smem + s * STAGE + W_OFF, &tmX, full + s, kb * TC_BK, (own ^ 1) * a.cap + j0);
           }
       }
     }
   } else if (warp == 1) {
     const bool leader = tc::elect_one();
-    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN);
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, TC_BM, BN), idesc2 = tc::make_idesc(tc::FMT_TF32, TC_BM, 2 * BN);
     int c = 0, i = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       int own, row0, n, m;
@@ -100,15 +101,14 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __gr
           const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
           tc::mbar_wait(ready + s, ph);
           tc::fence_after_sync();
-          const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+          const uint32_t a_addr = tc::smem_u32(smem + s * STAGE), b_addr = a_addr + W_OFF;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; k++) {
             uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
-            uint64_t adl = tc::make_smem_desc_sw128(a_addr + TILE_BYTES + k * 32), bdl = tc::make_smem_desc_sw128(b_addr + TILE_BYTES + k * 32);
+            uint64_t adl = tc::make_smem_desc_sw128(a_addr + A_BYTES + k * 32);
             if (leader) {
-              tc::mma_tf32(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
-              tc::mma_tf32(d_cross, ad, bdl, idesc, (kb | k) ? 1u : 0u);
-              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);
+              tc::mma_tf32(d_main, ad, bd, idesc2, (kb | k) ? 1u : 0u);   // X_hi x [Y_hi | Y_lo] -> [main | cross]
+              tc::mma_tf32(d_cross, adl, bd, idesc, 1u);                  // X_lo x Y_hi -> cross
             }
           }
           if (leader) tc::mma_commit(empty + s);
@@ -128,18 +128,20 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __gr
         for (int kb = 0; kb < KB; kb++, c++) {
           const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
           tc::mbar_wait(full + s, ph);
-          uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE);
-          uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE + TILE_BYTES);
+          uint4* base = reinterpret_cast<uint4*>(smem + s * STAGE);
 #pragma unroll 8
           for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
-            uint4 v = hi[idx], h, l;
+            const bool in_a = idx < A_BYTES / 16;
+            uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
+            uint4* lo = hi + (in_a ? A_BYTES : B_BYTES) / 16;
+            uint4 v = *hi, h, l;
             h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
             l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
             l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
             l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
             l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            hi[idx] = h;
-            lo[idx] = l;
+            *hi = h;
+            *lo = l;
           }
           tc::fence_proxy_async();
           tc::mbar_arrive(ready + s);

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256) lf_conv1_kernel(const float* __restrict__
 // ---- FPN: out = a + bilinear_2x(b) (align_corners=True), resnet_fpn.py:110-115 -- bf16 planes in / out -------------------
 __global__ void __launch_bounds__(256) lf_upsample_add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ bsrc,
                                                               __nv_bfloat16* __restrict__ out, int B, int Ho, int Wo, int C) {
-  const size_t n = (size_t)B * Ho * Wo * C, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread = 8 consecutive channels of one output pixel (16-byte loads / stores per plane)
+  const size_t n = (size_t)B * Ho * Wo * C, i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   const int c = (int)(i % C);
   size_t t = i / C;
@@ -87,12 +88,29 @@ __global__ void __launch_bounds__(256) lf_upsample_add_kernel(const __nv_bfloat1
   const int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
   const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
   const size_t ps = (size_t)B * hs * ws * C;
-  auto src = [&](int yy, int xx) { return lf_merge3(bsrc, ps, (((size_t)b * hs + yy) * ws + xx) * C + c); };
-  const float up = hy * (hx * src(y0, x0) + lx * src(y0, x1)) + ly * (hx * src(y1, x0) + lx * src(y1, x1));
-  const float v = lf_merge3(a, n, i) + up;
-  __nv_bfloat16 p0, p1, p2;
-  lf_split3(v, p0, p1, p2);
-  out[i] = p0; out[n + i] = p1; out[2 * n + i] = p2;
+  auto load8 = [](const __nv_bfloat16* base, size_t plane, size_t off, float (&v)[8]) {   // p0 + p1 + p2 of 8 channels
+    const uint4 q0 = *reinterpret_cast<const uint4*>(base + off), q1 = *reinterpret_cast<const uint4*>(base + plane + off),
+                q2 = *reinterpret_cast<const uint4*>(base + 2 * plane + off);
+    const __nv_bfloat16 *e0 = reinterpret_cast<const __nv_bfloat16*>(&q0), *e1 = reinterpret_cast<const __nv_bfloat16*>(&q1),
+                        *e2 = reinterpret_cast<const __nv_bfloat16*>(&q2);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (__bfloat162float(e0[k]) + __bfloat162float(e1[k])) + __bfloat162float(e2[k]);
+  };
+  float s00[8], s01[8], s10[8], s11[8], av[8];
+  load8(bsrc, ps, (((size_t)b * hs + y0) * ws + x0) * C + c, s00);
+  load8(bsrc, ps, (((size_t)b * hs + y0) * ws + x1) * C + c, s01);
+  load8(bsrc, ps, (((size_t)b * hs + y1) * ws + x0) * C + c, s10);
+  load8(bsrc, ps, (((size_t)b * hs + y1) * ws + x1) * C + c, s11);
+  load8(a, n, i, av);
+  __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float up = hy * (hx * s00[k] + lx * s01[k]) + ly * (hx * s10[k] + lx * s11[k]);
+    lf_split3(av[k] + up, o0[k], o1[k], o2[k]);
+  }
+  *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(o0);
+  *reinterpret_cast<uint4*>(out + n + i) = *reinterpret_cast<const uint4*>(o1);
+  *reinterpret_cast<uint4*>(out + 2 * n + i) = *reinterpret_cast<const uint4*>(o2);
 }
 
 // bf16 planes -> fp32 (fine feature map used by the window gather)
@@ -134,10 +152,14 @@ template <int DH>
 __global__ void __launch_bounds__(DH * DH > 256 ? 1024 : 256)
 la_kv_kernel(const float* __restrict__ K, const float* __restrict__ V, float* __restrict__ KV, float* __restrict__ Ksum,
              const int* __restrict__ counts, int n_static, long long group_stride, int dm, const int* __restrict__ skip, int group_xor) {
+  // gridDim.z > 1: the token range is cut into gridDim.z chunks and KV / Ksum are PARTIAL sums laid out
+  // [g][h][split][...] (summed in a fixed order by la_kv_reduce_kernel: deterministic)
   const int g = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   if (skip && skip[g]) return;
   const int src = g ^ group_xor;                // cross layers: keys / values of the paired group
-  const int n = counts ? counts[src] : n_static;
+  const int n_all = counts ? counts[src] : n_static;
+  const int chunk = (n_all + gridDim.z - 1) / gridDim.z;
+  const int s_begin = blockIdx.z * chunk, n = min(n_all, s_begin + chunk);
   constexpr int NT = DH * DH > 256 ? 1024 : 256;
   constexpr int TS = 64;
   __shared__ float sK[TS][DH + 1], sV[TS][DH + 1];
@@ -146,7 +168,7 @@ la_kv_kernel(const float* __restrict__ K, const float* __restrict__ V, float* __
   float acc = 0.f, ks = 0.f;
   const float* Kb = K + src * group_stride + h * DH;
   const float* Vb = V + src * group_stride + h * DH;
-  for (int s0 = 0; s0 < n; s0 += TS) {
+  for (int s0 = s_begin; s0 < n; s0 += TS) {
     __syncthreads();
     for (int i = tid; i < TS * DH; i += NT) {
       const int s = i / DH, c = i % DH;
@@ -161,9 +183,23 @@ la_kv_kernel(const float* __restrict__ K, const float* __restrict__ V, float* __
     }
   }
   if (active) {
-    KV[(((long long)g * gridDim.y + h) * DH + d) * DH + v] = acc;
-    if (v == 0) Ksum[((long long)g * gridDim.y + h) * DH + d] = ks;
+    const long long gh = ((long long)g * gridDim.y + h) * gridDim.z + blockIdx.z;
+    KV[(gh * DH + d) * DH + v] = acc;
+    if (v == 0) Ksum[gh * DH + d] = ks;
   }
+}
+
+// KV[gh][e] = sum_split part[gh][split][e] (fixed order)
+__global__ void __launch_bounds__(256) la_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n_gh, int elems,
+                                                           int nsplit, const int* __restrict__ skip, int gh_per_group) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_gh * elems) return;
+  const long long gh = i / elems;
+  if (skip && skip[gh / gh_per_group]) return;
+  const int e = (int)(i % elems);
+  float s = 0.f;
+  for (int k = 0; k < nsplit; k++) s += part[(gh * nsplit + k) * elems + e];
+  out[i] = s;
 }
 
 // msg[l][h*DH + v] = (sum_d Q[l][h][d] KV[h][d][v]) / (sum_d Q[l][h][d] Ksum[h][d] + eps) * S
@@ -401,9 +437,11 @@ __global__ void lf_scale_counts_kernel(const int* mcount, int* rows25, int P) { 
   if (i < 2 * P) rows25[i] = mcount[i % P] * 25;
 }
 
+constexpr int LF_KV_SPLIT = 32;   // token chunks per (slot, head) in the coarse K^T V reduction
+
 struct LFBuffers {
   void *pa, *pb, *pc, *pd, *pe2;   // backbone plane scratch
-  float *fc, *ff, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *rmax, *rsum, *best_v;
+  float *fc, *ff, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *kv_part, *ksum_part, *rmax, *rsum, *best_v;
   int *best_j, *skip_even, *skip_odd, *cntL, *rows25, *fcnt;
   float *U, *G, *ctx, *fx, *fq, *fk, *fv, *fmsg, *ftmp, *fh, *fkv, *fksum;
 };
@@ -419,6 +457,7 @@ size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H, int W, int cap, int m
   b.xm = ws.take<float>(T * 512); b.q = ws.take<float>(T * CD); b.k = ws.take<float>(T * CD); b.v = ws.take<float>(T * CD);
   b.msg = ws.take<float>(T * CD); b.tmp = ws.take<float>(T * CD); b.h = ws.take<float>(T * 512);
   b.kv = ws.take<float>(S * NH * 32 * 32); b.ksum = ws.take<float>(S * NH * 32);
+  b.kv_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32 * 32); b.ksum_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32);
   b.rmax = ws.take<float>(T); b.rsum = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
   b.skip_even = ws.take<int>(S); b.skip_odd = ws.take<int>(S); b.cntL = ws.take<int>(S); b.rows25 = ws.take<int>(S); b.fcnt = ws.take<int>(S * mcap);
   const size_t FT = 2 * (size_t)P * mcap * 25;  // fine tokens
@@ -487,7 +526,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   RUN(conv(x2a, bb.l2_out, nullptr, b.pe2, h4, w4, 0, 0));                // layer2_outconv(x2) -> pe2
   {
     const size_t n = (size_t)S * h4 * w4 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pe2, (const __nv_bfloat16*)x3_out,
+    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pe2, (const __nv_bfloat16*)x3_out,
                                                                        (__nv_bfloat16*)b.pb, S, h4, w4, 256);
     IMW_CHECK_LAUNCH();
   }
@@ -495,7 +534,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   RUN(conv(b.pa, bb.l1_out, nullptr, b.pb, h2, w2, 0, 0));                // layer1_outconv(x1) -> pb (256 padded)
   {
     const size_t n = (size_t)S * h2 * w2 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pb, (const __nv_bfloat16*)x2a,
+    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pb, (const __nv_bfloat16*)x2a,
                                                                        (__nv_bfloat16*)b.pc, S, h2, w2, 256);
     IMW_CHECK_LAUNCH();
   }
@@ -511,6 +550,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   lf_parity_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.skip_even, b.skip_odd, S);
   IMW_CHECK_LAUNCH();
   const int use_tc = conf->use_tensor_cores;
+  const int kv_split = LF_KV_SPLIT;
   auto tok_linear = [&](const float* A, int lda, const float* Wt, int N, int K, auto epi, const int* skip) -> int {
     if (use_tc) {
       TcGemmArgs t{};
@@ -528,7 +568,11 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   auto encoder = [&](const imw_loftr_layer& ly, const int* skip_q, int kv_xor) -> int {
     // projections for every slot (q of the updated slots, k/v of their sources)
     if (int e = tok_linear(b.xm, 512, ly.qkv_w, 3 * CD, CD, EpiLinAttnQKV{b.q, b.k, b.v, CD, (long long)cap * CD, (float)L}, nullptr)) return e;
-    la_kv_kernel<32><<<dim3(S, NH), 1024, 0, st>>>(b.k, b.v, b.kv, b.ksum, nullptr, L, (long long)cap * CD, CD, skip_q, kv_xor);
+    la_kv_kernel<32><<<dim3(S, NH, kv_split), 1024, 0, st>>>(b.k, b.v, b.kv_part, b.ksum_part, nullptr, L, (long long)cap * CD, CD, skip_q, kv_xor);
+    IMW_CHECK_LAUNCH();
+    la_kv_reduce_kernel<<<ceil_div(S * NH * 32 * 32, 256), 256, 0, st>>>(b.kv_part, b.kv, (long long)S * NH, 32 * 32, kv_split, skip_q, NH);
+    IMW_CHECK_LAUNCH();
+    la_kv_reduce_kernel<<<ceil_div(S * NH * 32, 256), 256, 0, st>>>(b.ksum_part, b.ksum, (long long)S * NH, 32, kv_split, skip_q, NH);
     IMW_CHECK_LAUNCH();
     la_apply_kernel<32><<<dim3(ceil_div(L, 8 * 16), S), 256, 0, st>>>(b.q, b.kv, b.ksum, b.msg, nullptr, L, (long long)cap * CD, CD, CD,
                                                                     (long long)cap * CD, skip_q, kv_xor);

@@ -433,7 +433,7 @@ def _loftr_struct(wd, pos_enc):
     return s
 
 
-def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=False):
+def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=False, max_workspace_bytes=48 << 30):
     """images [2P,H,W] fp32 CUDA (slot 2p = rows of the confidence matrix).  Returns dict of device tensors:
     keypoints0/1 [P,mcap,2], confidence [P,mcap], counts [P] (+ debug features)."""
     L.require_cuda(images, "loftr_forward(images)")
@@ -452,15 +452,22 @@ def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=
     dbg_c = torch.zeros(S, cap, 256, device=dev) if debug else None
     dbg_b = torch.zeros(S, Lc, 256, device=dev) if debug else None
     lib = L.lib()
-    ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes(P, H, W, mcap), "loftr")
+    # pairs per library call: bound the workspace (~4 GB per 1024x1024 pair) -- BASELINE configs[2] is batch = 32
+    per_pair = lib.imw_loftr_workspace_bytes(1, H, W, mcap)
+    chunk = max(1, min(P, int(max_workspace_bytes // max(per_pair, 1))))
+    ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes(chunk, H, W, mcap), "loftr")
     c = L.LoftrConf(float(conf.get("match_threshold", 0.2)), float(conf.get("temperature", 0.1)), int(conf.get("border_rm", 2)),
                     int(conf.get("use_tensor_cores", 1)))
     wstruct = _loftr_struct(wd, wd[key])
+    images = images.contiguous()
     with torch.cuda.device(dev):
-        rc = lib.imw_loftr_forward(C.byref(wstruct), C.byref(c), P, H, W, L.ptr(images.contiguous()), mcap, L.ptr(out["keypoints0"]),
-                                   L.ptr(out["keypoints1"]), L.ptr(out["confidence"]), L.ptr(out["counts"]), L.ptr(dbg_c), L.ptr(dbg_b),
-                                   L.ptr(ws), ws.numel(), L.stream_ptr(dev))
-    L.check(rc)
+        for p0 in range(0, P, chunk):
+            n = min(chunk, P - p0)
+            rc = lib.imw_loftr_forward(C.byref(wstruct), C.byref(c), n, H, W, L.ptr(images[2 * p0:]), mcap, L.ptr(out["keypoints0"][p0:]),
+                                       L.ptr(out["keypoints1"][p0:]), L.ptr(out["confidence"][p0:]), L.ptr(out["counts"][p0:]),
+                                       L.ptr(dbg_c[2 * p0:]) if debug else None, L.ptr(dbg_b[2 * p0:]) if debug else None,
+                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+            L.check(rc)
     if debug:
         out["feat_c"], out["backbone_c"] = dbg_c[:, :Lc], dbg_b
     return out

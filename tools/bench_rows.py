@@ -66,7 +66,7 @@ def row_superglue(dev, iters):
 def row_loftr(dev, iters):
     from oracle import loftr as ol  # deterministic random weights only (no checkpoint offline); not the measured path
     wd = ops.loftr_to_device(ops.loftr_pack_weights(ol.random_weights(0)), dev)
-    for (H, W, P, thr) in ((480, 640, 8, 1e-6), (1024, 1024, 4, 1e-7)):
+    for (H, W, P, thr) in ((480, 640, 16, 1e-6), (1024, 1024, 32, 1e-7)):   # BASELINE configs[2]: batch = 32 at 1024x1024
         a, b = synth.make_pair_batch(list(range(P)), H, W)
         imgs = torch.from_numpy(np.stack([a, b], 1).reshape(2 * P, H, W).astype(np.float32) / 255.0).to(dev)
         for tc in (1,):

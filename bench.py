@@ -340,7 +340,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.fp32 else ("f32-equivalent: bf16x3 split tcgen05 convs (SuperPoint), " +
-                                          ("single-TF32" if args.tf32 else "3xTF32 split") + " tcgen05 linears (LightGlue), f32 attention/assignment"),
+                                          ("single-TF32" if args.tf32 else "3xTF32 split") + " tcgen05 linears / attention / assignment (LightGlue), f32 detector post-processing"),
         "data": "synthetic",
         "config": {"workload": "SuperPoint+LightGlue, batch=64 synthetic 640x480 pairs per GPU (BASELINE configs[1])",
                    "pairs_per_gpu": P, "max_keypoints": 1024, "weights": "superpoint_v1 + GIM SP-LightGlue (real)",

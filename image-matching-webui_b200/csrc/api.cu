@@ -89,8 +89,12 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
     const float* img = image + (size_t)b0 * H * W;
     if (use_tc) {
       // encoder + both 3x3 head convs on tcgen05, activations carried as three bf16 planes
-      RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], nullptr, b.a1, nb, H, W, st));
-      RUN(tc_conv3x3(b.a1, wt->wp[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, 0, st));
+      if (conf->use_tensor_cores == 1) {   // conv1a evaluated inside the conv1b kernel (no plane traffic for the first layer)
+        RUN(tc_conv1ab_fused(img, wt->w[0], wt->b[0], wt->wp[1], wt->b[1], b.a2, nb, H, W, 1, st));
+      } else {                             // 2: unfused pair (kept for A/B measurements)
+        RUN(sp_conv3x3_c1(img, wt->w[0], wt->b[0], nullptr, b.a1, nb, H, W, st));
+        RUN(tc_conv3x3(b.a1, wt->wp[1], wt->b[1], b.a2, nb, H, W, 64, 64, 1, 1, 0, st));
+      }
       RUN(tc_conv3x3(b.a2, wt->wp[2], wt->b[2], b.a3, nb, H / 2, W / 2, 64, 64, 1, 0, 0, st));
       RUN(tc_conv3x3(b.a3, wt->wp[3], wt->b[3], b.a4, nb, H / 2, W / 2, 64, 64, 1, 1, 0, st));
       RUN(tc_conv3x3(b.a4, wt->wp[4], wt->b[4], b.a5, nb, H / 4, W / 4, 64, 128, 1, 0, 0, st));

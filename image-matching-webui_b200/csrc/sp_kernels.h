@@ -27,6 +27,8 @@ int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts
 // tcgen05 split-precision conv (tc_conv.cu): activations / weights as three bf16 planes
 int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,
                int Cout, int relu, int pool, int out_fp32, cudaStream_t st);
+int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b, void* out, int B,
+                     int H, int W, int pool, cudaStream_t st);
 int tc_split_planes(const float* in, void* out_planes, size_t n, cudaStream_t st);
 int tc_merge_planes(const void* in_planes, float* out, size_t n, cudaStream_t st);
 int tc_conv_general(const void* in_planes, const void* w_planes, const float* bias, const void* res_planes, void* out, int B,

@@ -39,6 +39,10 @@ struct ConvArgs {
   float* out_f32;             // [B][Ho][Wo][Cout]
   int ksize = 3, stride = 1;  // 3x3 (pad 1) or 1x1 (pad 0); stride 1 or 2 (TMA element strides)
   const __nv_bfloat16* res_planes = nullptr;  // optional residual [3][B][Ho][Wo][Cout], added before the activation
+  // fused first layer (tc_conv3x3_c64_kernel<true>): the activation operand is conv1a(image) computed in the CTA
+  const float* img = nullptr;   // [B][H][W] fp32
+  const float* w1a = nullptr;   // [9][64]
+  const float* b1a = nullptr;   // [64]
 };
 
 template <int BN>
@@ -242,12 +246,17 @@ constexpr int C64_COPY = 18 * 8 * 128;            // one (plane, dx) halo copy: 
 constexpr int C64_A_BYTES = 9 * C64_COPY;         // 3 planes x 3 dx
 constexpr int C64_B_STAGE = 3 * 64 * 128;         // 3 weight planes of one tap
 constexpr int C64_B_STAGES = 2;
-constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256;
+constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256 + 2 * 240 * sizeof(float) /*fused: image patches*/;
+constexpr int C64_FUSE_THREADS = CV_THREADS + 128;
 
 // Persistent: one CTA per SM walks the tile list.  The three dx-copy slots, the weight ring and two TMEM
 // accumulator sets (2 x 4 x 64 = 512 columns) are all recycled through mbarriers, so the next tile's loads and
 // MMAs run while the epilogue warps drain the previous tile.
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// FUSE: the input is the 1-channel image; warps 6..9 evaluate conv1a (3x3, Cin = 1, bias, ReLU; superpoint.py:152) on the halo
+// patch of every tile, split the result into the three bf16 planes and write the three dx-shifted SWIZZLE_128B copies
+// themselves (the layout TMA would have produced) -- conv1a's 118 MB / image of plane traffic never touches HBM.
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? C64_FUSE_THREADS : CV_THREADS, 1)
 tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles) {
   constexpr int BN = 64;
   extern __shared__ uint8_t cv_smem_raw[];
@@ -267,7 +276,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
-    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, FUSE ? 128 : 1); tc::mbar_init(a_empty + i, 1); }
     for (int s = 0; s < C64_B_STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
     for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
     tc::fence_barrier_init();
@@ -287,7 +296,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int x0 = tx * C64_TW, y0 = ty * C64_TH;
         for (int it = 0; it < 9; it++) {
           const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
-          if (dyi == 0) {
+          if (!FUSE && dyi == 0) {
             tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);
             tc::mbar_expect_tx(a_full + dxi, 3 * C64_COPY);
 #pragma unroll
@@ -344,6 +353,64 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         if (leader) tc::mma_commit(tmem_full + acc);
         __syncwarp();
+      }
+    }
+  } else if (FUSE && warp >= 6) {
+    const int t = threadIdx.x - CV_THREADS;   // 0..127
+    const int chunk = t % 8;                  // output channels [8 chunk, +8) = one 16-byte unit of a pixel's 128-byte row
+    float w[9][8], bv[8];
+#pragma unroll
+    for (int tp = 0; tp < 9; tp++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) w[tp][k] = g.w1a[tp * 64 + chunk * 8 + k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) bv[k] = g.b1a[chunk * 8 + k];
+    float* s_img = (float*)((uint8_t*)tmem_slot + 64);   // [2][20 rows][12 cols], double-buffered by tile parity
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int x0 = tx * C64_TW, y0 = ty * C64_TH;
+      float* im = s_img + (i & 1) * 240;
+      const float* src = g.img + (size_t)b * g.H * g.W;
+      for (int idx = t; idx < 240; idx += 128) {   // image rows y0-2 .. y0+17, cols x0-2 .. x0+9, zeros outside (conv1a padding)
+        const int gy = y0 - 2 + idx / 12, gx = x0 - 2 + idx % 12;
+        im[idx] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? src[(size_t)gy * g.W + gx] : 0.f;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int dxi = 0; dxi < 3; dxi++) {
+        tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);   // the MMAs of the previous tile have read this dx slot
+        uint8_t* copy = sA + dxi * 3 * C64_COPY;
+#pragma unroll 1
+        for (int k = 0; k < 9; k++) {
+          const int pidx = t / 8 + 16 * k;             // pixel of the copy: halo row pidx / 8, column pidx % 8
+          const int hy = pidx / 8, cx = pidx % 8;
+          const int gy = y0 - 1 + hy, gx = x0 + dxi - 1 + cx;   // conv1a output position held by this operand row
+          float a[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) a[c] = 0.f;
+          const bool inside = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;   // conv1b's zero padding: outside -> 0
+          if (inside) {
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+              for (int dx = 0; dx < 3; dx++) {
+                const float v = im[(hy + dy) * 12 + cx + dxi + dx];
+#pragma unroll
+                for (int c = 0; c < 8; c++) a[c] = fmaf(v, w[dy * 3 + dx][c], a[c]);
+              }
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = fmaxf(a[c] + bv[c], 0.f);
+          }
+          __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) split3(a[c], p0[c], p1[c], p2[c]);
+          const int off = pidx * 128 + ((chunk ^ (pidx & 7)) * 16);   // SWIZZLE_128B: 16-byte unit c of row r sits at c ^ (r & 7)
+          *reinterpret_cast<uint4*>(copy + off) = *reinterpret_cast<const uint4*>(p0);
+          *reinterpret_cast<uint4*>(copy + C64_COPY + off) = *reinterpret_cast<const uint4*>(p1);
+          *reinterpret_cast<uint4*>(copy + 2 * C64_COPY + off) = *reinterpret_cast<const uint4*>(p2);
+        }
+        tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
+        tc::mbar_arrive(a_full + dxi);
       }
     }
   } else {
@@ -499,7 +566,7 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
     static bool attr_set = false;
     if (!attr_set) {
-      IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
+      IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
       attr_set = true;
     }
     const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
@@ -510,7 +577,7 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
       IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     dim3 grid((unsigned)(total < num_sms ? total : num_sms), 1);
-    tc_conv3x3_c64_kernel<<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
+    tc_conv3x3_c64_kernel<false><<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   }
@@ -518,6 +585,29 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
   if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, BN)) return e;
   ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
+}
+
+// SuperPoint conv1a + conv1b in one kernel: image [B][H][W] fp32 -> conv1b output planes (2x2 max-pooled when pool).
+int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b, void* out, int B,
+                     int H, int W, int pool, cudaStream_t st) {
+  IMW_REQUIRE(W % C64_TW == 0 && (!pool || (H % 2 == 0)), "tc_conv1ab_fused: W %% 8 == 0 (even H when pooled)");
+  CUtensorMap tmW;
+  if (int e = make_map_wgt(&tmW, w1b_planes, 3 * 9 * 64, 64, 64)) return e;
+  ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (__nv_bfloat16*)out, (float*)out};
+  g.img = img; g.w1a = w1a; g.b1a = b1a;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
+    int dev = 0;
+    IMW_CHECK_CUDA(cudaGetDevice(&dev));
+    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
+  tc_conv3x3_c64_kernel<true><<<dim3((unsigned)(total < num_sms ? total : num_sms)), C64_FUSE_THREADS, C64_SMEM, st>>>(tmW, tmW, g, total);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
 }
 
 // General form used by the LoFTR backbone: 3x3 / 1x1, stride 1 / 2, optional residual, act 0 none / 1 ReLU / 2 LeakyReLU(0.01).

@@ -247,7 +247,8 @@ constexpr int C64_A_BYTES = 9 * C64_COPY;         // 3 planes x 3 dx
 constexpr int C64_B_STAGE = 3 * 64 * 128;         // 3 weight planes of one tap
 constexpr int C64_B_STAGES = 2;
 constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256 + 2 * 240 * sizeof(float) /*fused: image patches*/;
-constexpr int C64_FUSE_THREADS = CV_THREADS + 128;
+constexpr int C64_FUSE_PROD = 256;   // conv1a producer threads (8 warps)
+constexpr int C64_FUSE_THREADS = CV_THREADS + C64_FUSE_PROD;
 
 // Persistent: one CTA per SM walks the tile list.  The three dx-copy slots, the weight ring and two TMEM
 // accumulator sets (2 x 4 x 64 = 512 columns) are all recycled through mbarriers, so the next tile's loads and
@@ -276,7 +277,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
-    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, FUSE ? 128 : 1); tc::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, FUSE ? C64_FUSE_PROD : 1); tc::mbar_init(a_empty + i, 1); }
     for (int s = 0; s < C64_B_STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
     for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
     tc::fence_barrier_init();
@@ -356,7 +357,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (FUSE && warp >= 6) {
-    const int t = threadIdx.x - CV_THREADS;   // 0..127
+    const int t = threadIdx.x - CV_THREADS;   // 0..C64_FUSE_PROD-1
     const int chunk = t % 8;                  // output channels [8 chunk, +8) = one 16-byte unit of a pixel's 128-byte row
     float w[9][8], bv[8];
 #pragma unroll
@@ -372,17 +373,18 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int x0 = tx * C64_TW, y0 = ty * C64_TH;
       float* im = s_img + (i & 1) * 240;
       const float* src = g.img + (size_t)b * g.H * g.W;
-      for (int idx = t; idx < 240; idx += 128) {   // image rows y0-2 .. y0+17, cols x0-2 .. x0+9, zeros outside (conv1a padding)
+      for (int idx = t; idx < 240; idx += C64_FUSE_PROD) {   // image rows y0-2 .. y0+17, cols x0-2 .. x0+9, zeros outside (conv1a padding)
         const int gy = y0 - 2 + idx / 12, gx = x0 - 2 + idx % 12;
         im[idx] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? src[(size_t)gy * g.W + gx] : 0.f;
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");
       for (int dxi = 0; dxi < 3; dxi++) {
         tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);   // the MMAs of the previous tile have read this dx slot
         uint8_t* copy = sA + dxi * 3 * C64_COPY;
 #pragma unroll 1
-        for (int k = 0; k < 9; k++) {
-          const int pidx = t / 8 + 16 * k;             // pixel of the copy: halo row pidx / 8, column pidx % 8
+        for (int k = 0; k < (144 + C64_FUSE_PROD / 8 - 1) / (C64_FUSE_PROD / 8); k++) {
+          const int pidx = t / 8 + (C64_FUSE_PROD / 8) * k;   // pixel of the copy: halo row pidx / 8, column pidx % 8
+          if (pidx >= 144) break;
           const int hy = pidx / 8, cx = pidx % 8;
           const int gy = y0 - 1 + hy, gx = x0 + dxi - 1 + cx;   // conv1a output position held by this operand row
           float a[8];

@@ -664,6 +664,12 @@ extern "C" int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout
   return tc_conv3x3(in_p, w_p, bias, out, B, H, W, Cin, Cout, relu, pool, 1, st);
 }
 
+// bench hook: SuperPoint conv1a + conv1b fused (image in, pooled conv1b planes out)
+extern "C" int imw_debug_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,
+                                       void* out_planes, int B, int H, int W, int pool, cudaStream_t st) {
+  return tc_conv1ab_fused(img, w1a, b1a, w1b_planes, b1b, out_planes, B, H, W, pool, st);
+}
+
 // bench hook: the tcgen05 conv alone on pre-split operands (planes in, planes out)
 extern "C" int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, const float* bias, void* out_planes, int B,
                                            int H, int W, int Cin, int Cout, int relu, int pool, cudaStream_t st) {

@@ -24,7 +24,7 @@ extern "C" unsigned long long imw_launch_count(void) { return g_imw_launches; }
 // SuperPoint
 // =====================================================================================================
 namespace {
-constexpr int SP_SUB = 8;  // images per pass through the conv stack (bounds the activation workspace)
+int SP_SUB = 8;  // images per pass through the conv stack (bounds the activation workspace); imw_debug_set_sp_sub
 
 struct SPBuffers {
   float *a1, *a2, *a3, *a4, *a5, *a6, *a7, *a8, *pa, *logits, *da, *dense, *nms, *dd;
@@ -55,6 +55,11 @@ size_t sp_carve(Workspace& ws, SPBuffers& b, int B, int H, int W) {
   return ws.off;
 }
 }  // namespace
+
+extern "C" int imw_debug_set_sp_sub(int n) {   // tuning hook: images per pass of the SuperPoint conv stack
+  if (n > 0) SP_SUB = n;
+  return SP_SUB;
+}
 
 extern "C" size_t imw_superpoint_workspace_bytes(int batch, int height, int width) {
   Workspace ws(nullptr, 0);

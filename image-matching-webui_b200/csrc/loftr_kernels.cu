@@ -484,6 +484,8 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
                                  cudaStream_t st) {
   IMW_REQUIRE(W && conf && n_pairs > 0 && height % 8 == 0 && width % 8 == 0, "imw_loftr_forward: H, W must be multiples of 8");
   IMW_REQUIRE(max_matches > 0, "imw_loftr_forward: max_matches must be positive");
+  IMW_REQUIRE((long long)n_pairs * max_matches <= 65535, "imw_loftr_forward: n_pairs * max_matches must not exceed 65535 (got %d x %d); "
+              "split the batch (ops.loftr_forward does)", n_pairs, max_matches);
   const int P = n_pairs, S = 2 * P, H = height, Wd = width;
   const int h2 = H / 2, w2 = Wd / 2, h4 = H / 4, w4 = Wd / 4, hc = H / 8, wc = Wd / 8, L = hc * wc, cap = (L + 127) / 128 * 128, mcap = max_matches;
   Workspace ws(workspace, workspace_bytes);

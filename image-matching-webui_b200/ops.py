@@ -454,7 +454,7 @@ def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=
     lib = L.lib()
     # pairs per library call: bound the workspace (~4 GB per 1024x1024 pair) -- BASELINE configs[2] is batch = 32
     per_pair = lib.imw_loftr_workspace_bytes(1, H, W, mcap)
-    chunk = max(1, min(P, int(max_workspace_bytes // max(per_pair, 1))))
+    chunk = max(1, min(P, int(max_workspace_bytes // max(per_pair, 1)), 65535 // mcap))   # grid.y of the fine stage = pairs * mcap
     ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes(chunk, H, W, mcap), "loftr")
     c = L.LoftrConf(float(conf.get("match_threshold", 0.2)), float(conf.get("temperature", 0.1)), int(conf.get("border_rm", 2)),
                     int(conf.get("use_tensor_cores", 1)))

@@ -282,6 +282,8 @@ int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, con
                                 int height, int width, int cin, int cout, int relu, int pool, imw_stream_t stream);
 /* SuperPoint conv1a (1 -> 64) evaluated inside the conv1b (64 -> 64) tcgen05 kernel: image [B][H][W] fp32, w1a [9][64],
  * w1b_planes [3][9][64][64] bf16 -> conv1b output planes [3][B][H/2][W/2][64] (pool = 1) */
+/* tuning hook: images per pass of the SuperPoint conv stack (default 8); returns the value in effect */
+int imw_debug_set_sp_sub(int n);
 int imw_debug_conv1ab_fused(const float* image, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,
                             void* out_planes, int batch, int height, int width, int pool, imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,

@@ -24,7 +24,7 @@ extern "C" unsigned long long imw_launch_count(void) { return g_imw_launches; }
 // SuperPoint
 // =====================================================================================================
 namespace {
-int SP_SUB = 8;  // images per pass through the conv stack (bounds the activation workspace); imw_debug_set_sp_sub
+int SP_SUB = 32;  // images per pass through the conv stack (bounds the activation workspace); imw_debug_set_sp_sub
 
 struct SPBuffers {
   float *a1, *a2, *a3, *a4, *a5, *a6, *a7, *a8, *pa, *logits, *da, *dense, *nms, *dd;

@@ -350,7 +350,7 @@ def main():
                    "pairs_per_gpu": P, "max_keypoints": 1024, "weights": "superpoint_v1 + GIM SP-LightGlue (real)",
                    "lightglue": "depth_confidence 0.95, width_confidence 0.99, CUDA pruning threshold 1536 (reference CUDA semantics)",
                    "mean_keypoints": mean_kpts, "mean_stop_layer": mean_stop, "mean_matches": mean_matches,
-                   "l2": "per-step working set (>= 1.3 GB of activations per 8-image sub-batch) >> 126 MB L2; no explicit flush",
+                   "l2": "per-step working set (> 1 GB of activations per 32-image conv pass) >> 126 MB L2; no explicit flush",
                    "parallelism": f"pair shard x{world}, NCCL all_gather of match counts" if world > 1 else "single GPU"},
         "achieved_tflops": value * pair_gflop / 1e3,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},

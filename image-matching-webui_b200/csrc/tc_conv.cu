@@ -5,19 +5,25 @@
 // value is carried as three bf16 planes x = x1 + x2 + x3 (8 + 8 + 8 mantissa bits, exact to 2^-24 relative)
 // and the product is assembled from the six leading partial products
 //     a1b1 + a1b2 + a2b1 + a1b3 + a2b2 + a3b1        (dropped terms <= 2^-24 |a||b|)
-// accumulated in fp32 in TMEM: six kind::f16 (bf16) MMAs per k-step = 1/6 of the bf16 tensor peak.
+// accumulated in fp32 in TMEM = 1/6 of the bf16 tensor peak.  The three weight planes of a stage are contiguous in N
+// ([b1 | b2 | b3] rows), so the six products are issued as FOUR kind::f16 MMAs per k-step
+//     a1 x b1 -> main          a1 x [b2|b3] -> [c1|c2]          a2 x [b1|b2] -> [c1|c2]          a3 x b1 -> c2
+// which reads the activation tile four times instead of six (shared-memory operand reads bound these kernels).
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
 // accumulating MMAs (measured: ~1e-5 relative after 216 MMAs into one accumulator).  The accumulation is therefore
-// spread over FOUR TMEM accumulators -- the leading a1*b1 term per kernel row dy (12-24 MMAs each) and one for all
-// cross terms (2^-8 of the magnitude, so its truncation error is negligible) -- summed in fp32 in the epilogue.
+// spread over FOUR TMEM accumulators -- the leading a1*b1 term alternates between two of them k-step by k-step, the
+// first-order (2^-8) and second-order (2^-16) cross terms have their own -- summed in fp32 in the epilogue.
 //
-// GEMM view: M = 128 output pixels (8 rows x 16 cols of one image), N = Cout tile (64 / 128), K = 9 taps x Cin.
-// The nine taps are nine shifted TMA box loads of the NHWC activation planes (4-D tensor map, out-of-bounds
-// coordinates zero-filled = the conv's zero padding), 64 channels = one 128-byte swizzled row per pixel.
+// Generic kernel (tc_conv3x3_kernel<BN, KS, RES>): GEMM view M = 128 output pixels (8 rows x 16 cols of one image),
+// N = Cout tile (64 / 128), K = taps x Cin; 3x3 (pad 1) or 1x1, stride 1 or 2.  The taps are shifted TMA box loads of
+// the NHWC activation planes (4-D tensor map, element strides for stride 2, out-of-bounds coordinates zero-filled =
+// the conv's zero padding), 64 channels = one 128-byte swizzled row per pixel.
 //   warp 0: TMA producer (3 activation planes + 3 weight planes per (tap, 64-channel chunk) stage)
-//   warp 1: TMEM alloc + tcgen05.mma issue (24 MMAs per stage)
-//   warps 2-5: epilogue: tcgen05.ld, bias, ReLU, optional fused 2x2 max-pool (lane shuffles: the 2x2
-//              window lives in one warp), re-split into bf16 planes (or fp32) and store NHWC.
+//   warp 1: TMEM alloc + tcgen05.mma issue (16 MMAs per stage)
+//   warps 2-5: epilogue: tcgen05.ld, bias, optional residual planes, ReLU / LeakyReLU, optional fused 2x2 max-pool
+//              (lane shuffles: the 2x2 window lives in one warp), re-split into bf16 planes (or fp32) and store NHWC.
+// Cin = Cout = 64 specialisation (tc_conv3x3_c64_kernel<FUSE>): persistent, halo tile as three dx-shifted copies,
+// double-buffered TMEM; FUSE evaluates SuperPoint's conv1a inside the CTA (see below).
 #include <cuda_bf16.h>
 
 #include "../../include/imw_b200.h"

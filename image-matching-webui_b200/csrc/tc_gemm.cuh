@@ -1,23 +1,24 @@
 // tcgen05 TF32 GEMM   C[M,N] = A[M,K] * W[N,K]^T   (fp32 accumulate in TMEM).
 //
 // SPLIT = 1: operands read as single TF32 (10-bit mantissa): fast mode.
-// SPLIT = 3: 3xTF32 split precision = fp32-equivalent products: after TMA lands the fp32 tiles, the four
-//            epilogue warps rewrite them in shared memory as x_hi (low 13 mantissa bits cleared, exactly
-//            TF32-representable) and x_lo = x - x_hi in a twin tile (same swizzled offsets), and the MMA warp
-//            issues  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (dropped lo*lo term and the TF32 rounding of the lo
-//            parts are <= 2^-21 relative).  This is the default: LightGlue scores stay within the 1e-3 parity
-//            tolerance, which single TF32 does not (measured 1.4e-2 on the golden pairs).
+// SPLIT = 3: 3xTF32 split precision = fp32-equivalent products: after TMA lands the fp32 tiles, four splitter warps
+//            rewrite them in shared memory as x_hi (low 13 mantissa bits cleared, exactly TF32-representable) and
+//            x_lo = x - x_hi (same swizzled offsets, lo slot right behind the hi slot), and the MMA warp issues
+//            A_hi x [W_hi | W_lo] (one MMA of N = 2 BN) and A_lo x W_hi  (dropped lo*lo term and the TF32 rounding
+//            of the lo parts are <= 2^-21 relative).  This is the default: LightGlue scores stay within the 1e-3
+//            parity tolerance, which single TF32 does not (measured 1.4e-2 on the golden pairs).
 //
-//   warp 0      TMA producer: A tile [128 x 32 f32] and W tile [BN x 32 f32] per k-block, SWIZZLE_128B,
-//               through a STAGES-deep full/empty mbarrier ring
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=8 per instruction)
-//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one TMEM lane = one output row per
-//               thread), apply the same functor epilogues as the CUDA-core GEMM, store
-//
-// One output tile per CTA; two CTAs are co-resident per SM (smem <= 100 KB, <= 256 TMEM columns each)
-// so one CTA's epilogue overlaps the other's main loop.  Rows are [slots][cap] with cap % 128 == 0:
-// a tile never straddles two slots, finished pairs / rows beyond the slot's count are skipped on the
-// device.
+// Persistent: one CTA per SM walks the (m-tile, n-tile) list; the smem ring runs across tile boundaries and two TMEM
+// accumulator sets alternate, so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 0       TMA producer: A tile [128 x 32 f32] and W tile [BN x 32 f32] per k-block, SWIZZLE_128B,
+//                through a STAGES-deep full/empty mbarrier ring
+//   warp 1       TMEM allocation + single-thread tcgen05.mma issue (M = 128, K = 8 per instruction)
+//   warps 2..5   hi/lo splitters (SPLIT == 3)
+//   warps 6..13  epilogue, two warps per TMEM sub-partition (half of the tile's columns each): tcgen05.ld (one TMEM
+//                lane = one output row per thread), transpose through a padded smem tile so that global accesses
+//                run along the columns, apply the same functor epilogues as the CUDA-core GEMM, store
+// Rows are [slots][cap] with cap % 128 == 0: a tile never straddles two slots; finished pairs / rows beyond the
+// slot's count are skipped on the device.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"

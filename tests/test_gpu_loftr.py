@@ -80,3 +80,23 @@ def test_match_dense_with_loftr_end_to_end(golden):
     np.testing.assert_allclose(out["mconf"], g["m/confidence"][order], rtol=2e-3)
     assert np.all(np.diff(out["mconf"]) <= 1e-7)          # top-k keeps them sorted by confidence (loftr.py:58-65)
     assert out["scale0"].tolist() == [1.0, 1.0] and np.array_equal(out["mkeypoints0_orig"], out["mkeypoints0"])
+
+
+@pytest.mark.parametrize("hw", [(200, 264), (136, 328)], ids=lambda v: f"{v[0]}x{v[1]}")
+def test_loftr_ragged_sizes_vs_oracle(hw):
+    """Sizes whose coarse grid is not a multiple of the 128-token tile (partial GEMM / conv / similarity tiles)."""
+    from imcui_b200 import ops
+    from oracle import loftr as ol
+    dev = torch.device("cuda:0")
+    H, W = hw
+    x0, x1 = _pair(H, W)
+    sd = ol.random_weights(0)
+    thr = 1e-5
+    o = ol.forward(sd, x0[None, None], x1[None, None], thr=thr)
+    out = ops.loftr_forward(ops.loftr_to_device(ops.loftr_pack_weights(sd), dev), torch.stack([x0, x1]).to(dev), {"match_threshold": thr})
+    n = int(out["counts"][0])
+    print(f"[loftr ragged] {hw}: matches {n} (oracle {len(o['confidence'])})")
+    assert n == len(o["confidence"]) and n > 0
+    assert np.array_equal(out["keypoints0"][0, :n].cpu().numpy(), o["keypoints0"].numpy())
+    np.testing.assert_allclose(out["keypoints1"][0, :n].cpu().numpy(), o["keypoints1"].numpy(), atol=2e-3)
+    np.testing.assert_allclose(out["confidence"][0, :n].cpu().numpy(), o["confidence"].numpy(), rtol=2e-3)

@@ -48,6 +48,26 @@ def test_superpoint_matches_reference(golden, dev, case, confs, tc):
                 assert moved == 0  # row-major order: exact
 
 
+@pytest.mark.parametrize("hw", [(136, 208), (200, 336), (136, 200), (64, 64)], ids=lambda v: f"{v[0]}x{v[1]}")
+def test_superpoint_ragged_sizes_vs_oracle(dev, hw):
+    """Sizes that leave partial tiles in every conv kernel (H % 16 != 0, W % 16 != 0 -> CUDA-core convs, tiny maps):
+    no cap, so the keypoint list is the exact row-major set; checked against the CPU oracle on the same image."""
+    import oracle
+    from oracle import superpoint as osp
+    from imcui_b200.hloc import extractors
+    from imcui_b200.utils import synth
+    H, W = hw
+    a, _, _ = synth.make_pair(5, H, W)
+    img = torch.from_numpy(a.astype(np.float32) / 255.0)[None, None]
+    conf = {"nms_radius": 3, "max_keypoints": -1, "keypoint_threshold": 0.01, "remove_borders": 4}
+    ref = osp.forward(oracle.load_weights("superpoint_v1.pt"), img, conf)
+    out = _load(extractors, "superpoint", conf, dev)({"image": img.to(dev)})
+    k, rk = out["keypoints"][0].cpu(), ref["keypoints"][0]
+    assert k.shape == rk.shape and torch.equal(k, rk), f"{hw}: {k.shape[0]} vs {rk.shape[0]} keypoints"
+    assert (out["scores"][0].cpu() - ref["scores"][0]).abs().max() < 1e-4
+    assert (out["descriptors"][0].cpu() - ref["descriptors"][0]).abs().max() < 1e-3
+
+
 @pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-bf16x3"])
 def test_superpoint_dense_scores(golden, dev, tc):
     from imcui_b200 import ops

@@ -176,39 +176,17 @@ def forward(w, image, detection_threshold=0.2, max_num_keypoints=-1, nms_radius=
             "score_map": score, "feature_map": feat, "offsets": off}
 
 
+def _synth_weights():
+    """image-matching-webui_b200/utils/synth_weights.py loaded by path (no import of the product package)."""
+    import importlib.util
+    from pathlib import Path
+    p = Path(__file__).resolve().parent.parent / "image-matching-webui_b200" / "utils" / "synth_weights.py"
+    spec = importlib.util.spec_from_file_location("_imw_synth_weights", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 def random_weights(seed=0):
-    """Deterministic random aliked-n16 parameters (reference key names), generated key by key from a CPU Generator."""
-    g = torch.Generator().manual_seed(4321 + seed)
-    w = {}
-    c1, c2, c3, c4 = CFG["c"]
-    dim, K, M = CFG["dim"], CFG["K"], CFG["M"]
-
-    def conv(name, co, ci, k, bias=False, gain=1.0):
-        w[name + ".weight"] = torch.randn(co, ci, k, k, generator=g) * (gain * math.sqrt(1.0 / (k * k * ci)))
-        if bias:
-            w[name + ".bias"] = 0.1 * torch.randn(co, generator=g)
-
-    def bn(p, c):
-        w[p + "weight"] = 0.9 + 0.2 * torch.rand(c, generator=g)
-        w[p + "bias"] = 0.05 * torch.randn(c, generator=g)
-        w[p + "running_mean"] = 0.05 * torch.randn(c, generator=g)
-        w[p + "running_var"] = 0.9 + 0.2 * torch.rand(c, generator=g)
-        w[p + "num_batches_tracked"] = torch.tensor(0)
-
-    conv("block1.conv1", c1, 3, 3, gain=3.0); bn("block1.bn1.", c1); conv("block1.conv2", c1, c1, 3); bn("block1.bn2.", c1)
-    for name, ci, co, dcn in (("block2", c1, c2, False), ("block3", c2, c3, True), ("block4", c3, c4, True)):
-        for j, cin in ((1, ci), (2, co)):
-            if dcn:
-                conv(f"{name}.conv{j}.offset_conv", 18, cin, 3, bias=True, gain=2.0)
-                conv(f"{name}.conv{j}.regular_conv", co, cin, 3)
-            else:
-                conv(f"{name}.conv{j}", co, cin, 3)
-            bn(f"{name}.bn{j}.", co)
-        conv(f"{name}.downsample", co, ci, 1, bias=True)
-    conv("conv1", dim // 4, c1, 1); conv("conv2", dim // 4, c2, 1); conv("conv3", dim // 4, c3, 1); conv("conv4", dim // 4, dim, 1)
-    conv("score_head.0", 8, dim, 1); conv("score_head.2", 4, 8, 3); conv("score_head.4", 4, 4, 3)
-    conv("score_head.6", 1, 4, 3, gain=-1.0)   # sign chosen so that the score map is sparse (mean ~0.09, a few hundred maxima > 0.2)
-    conv("desc_head.offset_conv.0", 2 * M, dim, K, bias=True, gain=6.0); conv("desc_head.offset_conv.2", 2 * M, 2 * M, 1, bias=True, gain=4.0)
-    conv("desc_head.sf_conv", dim, dim, 1, gain=3.0)
-    w["desc_head.agg_weights"] = torch.rand(M, dim, dim, generator=g)
-    return w
+    """Deterministic random aliked-n16 parameters (reference key names): see utils/synth_weights.py."""
+    return _synth_weights().aliked_random_weights(seed)

@@ -174,54 +174,17 @@ def forward(w, image0, image1, thr=0.2, cfg=None):
             "feat_c0": t0, "feat_c1": t1, "feat_f0": ff0, "feat_f1": ff1, "backbone_c": fc, "conf_matrix": conf}
 
 
+def _synth_weights():
+    """image-matching-webui_b200/utils/synth_weights.py loaded by path (no import of the product package)."""
+    import importlib.util
+    from pathlib import Path
+    p = Path(__file__).resolve().parent.parent / "image-matching-webui_b200" / "utils" / "synth_weights.py"
+    spec = importlib.util.spec_from_file_location("_imw_synth_weights", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 def random_weights(seed=0):
-    """Deterministic random LoFTR parameters (no standard checkpoint exists offline).  Generated key by key from a CPU
-    torch.Generator so that the GPU box reproduces them without shipping a 46 MB file; tools/make_golden.py loads the
-    very same dict into the reference module.  BatchNorm statistics / affine terms are randomised (not the identity
-    defaults) so that BN folding is exercised."""
-    g = torch.Generator().manual_seed(1234 + seed)
-    w = {}
-
-    def conv(name, co, ci, k):
-        w[name] = torch.randn(co, ci, k, k, generator=g) * math.sqrt(2.0 / (k * k * co))
-
-    def bn(p, c):
-        w[p + "weight"] = 0.9 + 0.2 * torch.rand(c, generator=g)
-        w[p + "bias"] = 0.02 * torch.randn(c, generator=g)
-        w[p + "running_mean"] = 0.02 * torch.randn(c, generator=g)
-        w[p + "running_var"] = 0.9 + 0.2 * torch.rand(c, generator=g)
-
-    def lin(name, o, i, bias=False):
-        w[name + ".weight"] = torch.randn(o, i, generator=g) * math.sqrt(2.0 / (o + i))
-        if bias:
-            w[name + ".bias"] = 0.05 * torch.randn(o, generator=g)
-
-    conv("backbone.conv1.weight", 128, 1, 7); bn("backbone.bn1.", 128)
-    dims = [(128, 128), (128, 196), (196, 256)]
-    for li, (ci, co) in enumerate(dims, 1):
-        for bi in range(2):
-            p = f"backbone.layer{li}.{bi}."
-            cin = ci if bi == 0 else co
-            conv(p + "conv1.weight", co, cin, 3); conv(p + "conv2.weight", co, co, 3)
-            bn(p + "bn1.", co); bn(p + "bn2.", co)
-            if bi == 0 and li > 1:
-                conv(p + "downsample.0.weight", co, cin, 1); bn(p + "downsample.1.", co)
-    conv("backbone.layer3_outconv.weight", 256, 256, 1)
-    conv("backbone.layer2_outconv.weight", 256, 196, 1)
-    conv("backbone.layer2_outconv2.0.weight", 256, 256, 3); bn("backbone.layer2_outconv2.1.", 256)
-    conv("backbone.layer2_outconv2.3.weight", 196, 256, 3)
-    conv("backbone.layer1_outconv.weight", 196, 128, 1)
-    conv("backbone.layer1_outconv2.0.weight", 196, 196, 3); bn("backbone.layer1_outconv2.1.", 196)
-    conv("backbone.layer1_outconv2.3.weight", 128, 196, 3)
-    for prefix, n, d in (("loftr_coarse.", 8, 256), ("loftr_fine.", 2, 128)):
-        for i in range(n):
-            p = f"{prefix}layers.{i}."
-            for nm in ("q_proj", "k_proj", "v_proj", "merge"):
-                lin(p + nm, d, d)
-            lin(p + "mlp.0", 2 * d, 2 * d); lin(p + "mlp.2", d, 2 * d)
-            for nm in ("norm1", "norm2"):
-                w[p + nm + ".weight"] = 1.0 + 0.05 * torch.randn(d, generator=g)
-                w[p + nm + ".bias"] = 0.02 * torch.randn(d, generator=g)
-    lin("fine_preprocess.down_proj", 128, 256, bias=True)
-    lin("fine_preprocess.merge_feat", 128, 256, bias=True)
-    return w
+    """Deterministic random LoFTR parameters (no standard checkpoint exists offline): see utils/synth_weights.py."""
+    return _synth_weights().loftr_random_weights(seed)

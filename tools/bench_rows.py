@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import imcui_b200  # noqa: E402,F401
 from imcui_b200 import _lib as L, engine, ops  # noqa: E402
-from imcui_b200.utils import synth  # noqa: E402
+from imcui_b200.utils import synth, synth_weights  # noqa: E402
 
 
 def timed(fn, iters, warmup=2):
@@ -64,8 +64,7 @@ def row_superglue(dev, iters):
 
 
 def row_loftr(dev, iters):
-    from oracle import loftr as ol  # deterministic random weights only (no checkpoint offline); not the measured path
-    wd = ops.loftr_to_device(ops.loftr_pack_weights(ol.random_weights(0)), dev)
+    wd = ops.loftr_to_device(ops.loftr_pack_weights(synth_weights.loftr_random_weights(0)), dev)   # no checkpoint offline
     for (H, W, P, thr) in ((480, 640, 16, 1e-6), (1024, 1024, 32, 1e-7)):   # BASELINE configs[2]: batch = 32 at 1024x1024
         a, b = synth.make_pair_batch(list(range(P)), H, W)
         imgs = torch.from_numpy(np.stack([a, b], 1).reshape(2 * P, H, W).astype(np.float32) / 255.0).to(dev)
@@ -80,8 +79,7 @@ def row_loftr(dev, iters):
 
 
 def row_aliked(dev, iters):
-    from oracle import aliked as oa
-    w = {k: v.to(dev) for k, v in ops.aliked_pack_weights(oa.random_weights(0)).items()}
+    w = {k: v.to(dev) for k, v in ops.aliked_pack_weights(synth_weights.aliked_random_weights(0)).items()}
     B = 32
     a, _ = synth.make_pair_batch(list(range(B)))
     rgb = torch.from_numpy(synth.to_rgb(a).astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(dev)
@@ -138,9 +136,8 @@ def row_config4(dev, iters):
     """BASELINE configs[3] on one GPU: ALIKED (RGB 640x480, 1024 keypoints) -> LightGlue (128-d input_proj) -> MAGSAC++ F.
     Random ALIKED weights and GIM LightGlue weights with the synthetic input_proj of the goldens (no checkpoints offline):
     a throughput configuration, parity is covered by the per-stage tests."""
-    from oracle import aliked as oa
     P, cap = 32, 1024
-    aw = {k: v.to(dev) for k, v in ops.aliked_pack_weights(oa.random_weights(0)).items()}
+    aw = {k: v.to(dev) for k, v in ops.aliked_pack_weights(synth_weights.aliked_random_weights(0)).items()}
     g = np.load(ROOT / "tests/golden/lg_proj.npz")
     sd = dict(torch.load(str(ROOT / "weights/superpoint_lightglue.pt"), map_location="cpu"))
     sd["input_proj.weight"], sd["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])

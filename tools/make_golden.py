@@ -21,6 +21,9 @@ import ref_import as R  # noqa: E402
 spec = importlib.util.spec_from_file_location("synth", ROOT / "image-matching-webui_b200/utils/synth.py")
 synth = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(synth)
+spec = importlib.util.spec_from_file_location("synth_weights", ROOT / "image-matching-webui_b200/utils/synth_weights.py")
+synth_weights = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(synth_weights)
 
 OUT = ROOT / "tests" / "golden"
 torch.set_grad_enabled(False)
@@ -183,11 +186,9 @@ def sg_case(name, pairs):
 
 
 def loftr_case(name):
-    """LoFTR with the deterministic random weights of oracle.loftr.random_weights loaded into the UNMODIFIED in-tree
+    """LoFTR with the deterministic random weights of utils/synth_weights.py loaded into the UNMODIFIED in-tree
     LoFTR module (third_party/SE2LoFTR/src/loftr); thr lowered so that random weights still yield coarse matches."""
-    sys.path.insert(0, str(ROOT))
-    from oracle import loftr as ol
-    w = ol.random_weights(0)
+    w = synth_weights.loftr_random_weights(0)
     blob = {}
     for tag, (H, W), thr in (("s", (240, 320), 1e-5), ("m", (480, 640), 1e-6)):
         net = R.make_loftr(0, thr=thr)
@@ -214,10 +215,8 @@ from aliked_cases import ALIKED_CASES  # noqa: E402
 
 
 def aliked_case(name):
-    """ALIKED (aliked-n16) with oracle.aliked.random_weights loaded into the UNMODIFIED reference module."""
-    sys.path.insert(0, str(ROOT))
-    from oracle import aliked as oa
-    w = oa.random_weights(0)
+    """ALIKED (aliked-n16) with utils/synth_weights.aliked_random_weights loaded into the UNMODIFIED reference module."""
+    w = synth_weights.aliked_random_weights(0)
     blob = {}
     for tag, (seed, H, W, rgb, conf) in ALIKED_CASES.items():
         net = R.make_aliked(w, **conf)

@@ -94,3 +94,34 @@ def test_loftr_weight_packing_layout():
     assert tuple(pk["conv1_w"].shape) == (49, 128) and tuple(pk["c0.qkv_w"].shape) == (768, 256) and tuple(pk["f1.mlp0_w"].shape) == (256, 256)
     pe = ops.loftr_position_encoding(256, 30, 40)
     assert torch.allclose(pe, ol.position_encoding(256, 30, 40).permute(1, 2, 0).reshape(1200, 256))
+
+
+def test_conf_registry_equals_reference():
+    """Every conf name of the package has the reference's output / model / preprocessing values (golden: the
+    reference's imcui/hloc/configs entries dumped by tools/make_golden.py confs)."""
+    import json
+    from imcui_b200.hloc.configs import confs_dict
+    ref = json.loads((GOLDEN / "confs.json").read_text())
+    for kind in ("extractors", "matchers"):
+        assert set(confs_dict[kind]) == set(ref[kind]), kind   # no invented names, none missing from the dump
+        for name, c in confs_dict[kind].items():
+            for k in ("output", "model", "preprocessing", "max_error", "cell_size"):
+                assert c.get(k) == ref[kind][name].get(k), (kind, name, k)
+
+
+def test_plugin_classes_keep_the_reference_contract():
+    """Class names, default_conf values and required_inputs of the plugins == the reference's (golden: read from the
+    reference sources with `ast` by tools/make_golden.py plugins).  Extra keys are allowed only for engine switches."""
+    import json
+    from imcui_b200.hloc import extractors, matchers
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    ref = json.loads((GOLDEN / "plugins.json").read_text())
+    engine_keys = {"tensor_cores", "state_dict", "max_matches", "pruning_min_kpts", "n_layers"}  # n_layers: lightglue.py default
+    for key, r in ref.items():
+        kind, mod = key.split("/")
+        cls = dynamic_load({"extractors": extractors, "matchers": matchers}[kind], mod)
+        assert cls.__name__ == r["class"]
+        assert list(cls.required_inputs) == r["required_inputs"], key
+        for k, v in r["default_conf"].items():
+            assert cls.default_conf[k] == v, (key, k, cls.default_conf.get(k), v)
+        assert set(cls.default_conf) - set(r["default_conf"]) <= engine_keys, (key, set(cls.default_conf) - set(r["default_conf"]))

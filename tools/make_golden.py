@@ -237,6 +237,41 @@ def aliked_case(name):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def confs_case(name):
+    """The reference's registry entries (imcui/hloc/configs) for every conf name the B200 package provides."""
+    import json
+    if str(R.REF) not in sys.path:
+        sys.path.insert(0, str(R.REF))
+    from imcui.hloc.configs import confs_dict as ref
+    sys.path.insert(0, str(ROOT))
+    from imcui_b200.hloc.configs import confs_dict as mine
+    out = {kind: {n: ref[kind][n] for n in mine[kind] if n in ref[kind]} for kind in ("extractors", "matchers")}
+    (OUT / f"{name}.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    print(name, {k: len(v) for k, v in out.items()})
+
+
+PLUGIN_FILES = {"extractors": ["superpoint", "aliked"], "matchers": ["lightglue", "superglue", "loftr", "nearest_neighbor", "dual_softmax"]}
+
+
+def plugin_contract_case(name):
+    """default_conf / required_inputs of the reference plugin classes, read from the source with `ast` (several of the
+    modules cannot be imported here: kornia)."""
+    import ast, json
+    out = {}
+    for kind, mods in PLUGIN_FILES.items():
+        for m in mods:
+            tree = ast.parse((R.REF / "imcui/hloc" / kind / f"{m}.py").read_text())
+            for node in ast.walk(tree):
+                if isinstance(node, ast.ClassDef) and any(getattr(b, "id", "") == "BaseModel" for b in node.bases):
+                    d = {"class": node.name}
+                    for st in node.body:
+                        if isinstance(st, ast.Assign) and st.targets[0].id in ("default_conf", "required_inputs"):
+                            d[st.targets[0].id] = ast.literal_eval(st.value)
+                    out[f"{kind}/{m}"] = d
+    (OUT / f"{name}.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    print(name, {k: v["class"] for k, v in out.items()})
+
+
 def matcher_case(name, pairs):
     nn_mod, ds_mod = R.hloc_matchers()
     blob = {}
@@ -295,6 +330,8 @@ def main():
     sg_case("sg", [sg_pair(rb, "sp_real:api:0:1"), sg_pair(sb, "sp_synth:max1024:0:1")])
     loftr_case("loftr")
     aliked_case("aliked")
+    confs_case("confs")
+    plugin_contract_case("plugins")
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
 
@@ -308,6 +345,6 @@ if __name__ == "__main__":
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
                 lg_proj_case("lg_proj", [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
             else:
-                {"aliked": aliked_case, "loftr": loftr_case}[sys.argv[1]](sys.argv[1])
+                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case}[sys.argv[1]](sys.argv[1])
     else:
         main()

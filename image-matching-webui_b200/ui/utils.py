@@ -11,6 +11,36 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..hloc import extract_features, extractors, match_dense, match_features, matchers
+from ..hloc.utils.base_model import dynamic_load
+
+DEVICE = "cuda" if torch.cuda.is_available() else "cpu"   # ui/utils.py:38
+
+
+def parse_match_config(conf):
+    """ui/utils.py:87-109: zoo entry {matcher, feature, dense/standalone} -> conf dicts of the registry."""
+    if conf["standalone"]:
+        return {"matcher": match_dense.confs.get(conf["matcher"]), "standalone": True, "info": conf.get("info", {})}
+    return {"feature": extract_features.confs.get(conf["feature"]), "matcher": match_features.confs.get(conf["matcher"]),
+            "standalone": False, "info": conf.get("info", {})}
+
+
+def get_matcher_zoo(matcher_zoo):
+    """ui/utils.py:66-84."""
+    return {k: parse_match_config(v) for k, v in matcher_zoo.items()}
+
+
+def get_model(match_conf: Dict[str, Any], device=None):
+    """ui/utils.py:112-124 (the registry call site: dynamic_load over the plugin root)."""
+    Model = dynamic_load(matchers, match_conf["model"]["name"])
+    return Model(match_conf["model"]).eval().to(device or DEVICE)
+
+
+def get_feature_model(conf: Dict[str, Dict[str, Any]], device=None):
+    """ui/utils.py:127-139."""
+    Model = dynamic_load(extractors, conf["model"]["name"])
+    return Model(conf["model"]).eval().to(device or DEVICE)
+
 
 DEFAULT_RANSAC_METHOD = "B200_MAGSAC"
 DEFAULT_RANSAC_REPROJ_THRESHOLD = 8

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_keypoints_equivalent, lg_pair_from_source, match_f1
+from conftest import GOLDEN, assert_keypoints_equivalent, lg_pair_from_source, match_f1
 
 pytestmark = pytest.mark.gpu
 
@@ -386,3 +386,22 @@ def test_dual_softmax_large_property(dev, tc):
     agree = (ref == m0[0].long()).float().mean().item()
     assert agree > 0.999, agree
     assert (m0[0] > -1).sum() > 1500
+
+
+def test_api_pipeline_end_to_end(golden, dev):
+    """ImageMatchingAPI mirror (api/core.py): uint8 RGB pair -> extract x2 -> LightGlue -> MAGSAC++ on the GPU; the raw
+    match count equals the reference LightGlue result on the same pair (golden lg_real, CUDA semantics)."""
+    from imcui_b200.api import ImageMatchingAPI
+    from imcui_b200.ui.utils import get_matcher_zoo
+    conf = get_matcher_zoo({"superpoint+lightglue": {"matcher": "superpoint-lightglue", "feature": "superpoint_max", "dense": False,
+                                                     "standalone": False}})["superpoint+lightglue"]
+    api = ImageMatchingAPI(conf={**conf, "ransac": {"enable": True, "method": "B200_MAGSAC", "reproj_threshold": 8, "confidence": 0.9999,
+                                                    "max_iter": 10000}}, device="cuda:0")
+    rgb0 = np.load(GOLDEN / "data" / "02928139_3448003521.npz")["rgb"]
+    rgb1 = np.load(GOLDEN / "data" / "17295357_9106075285.npz")["rgb"]
+    pred = api(rgb0, rgb1)
+    n_ref = int((golden("lg_real")["cuda/0/matches0"] > -1).sum())
+    n = len(pred["mkeypoints0_orig"])
+    print(f"[api] raw matches {n} (reference {n_ref}), verified {len(pred['mmkeypoints0_orig'])}")
+    assert abs(n - n_ref) <= 2 and pred["mconf"].shape == (n,)
+    assert 8 <= len(pred["mmkeypoints0_orig"]) <= n and "geom_info" in pred and "Fundamental" in pred["geom_info"]

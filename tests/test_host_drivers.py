@@ -125,3 +125,20 @@ def test_plugin_classes_keep_the_reference_contract():
         for k, v in r["default_conf"].items():
             assert cls.default_conf[k] == v, (key, k, cls.default_conf.get(k), v)
         assert set(cls.default_conf) - set(r["default_conf"]) <= engine_keys, (key, set(cls.default_conf) - set(r["default_conf"]))
+
+
+def test_api_pipeline_builds_from_the_registry_and_refuses_cpu():
+    """ImageMatchingAPI mirror: zoo entry -> conf dicts -> plugins through dynamic_load; the product path has no CPU
+    fallback, so a forward on a machine without CUDA raises instead of silently computing elsewhere."""
+    from imcui_b200.api import ImageMatchingAPI
+    from imcui_b200.ui.utils import get_matcher_zoo
+    zoo = get_matcher_zoo({"superpoint+mnn": {"matcher": "NN-mutual", "feature": "superpoint_max", "dense": False, "standalone": False}})
+    conf = zoo["superpoint+mnn"]
+    assert conf["feature"]["model"]["name"] == "superpoint" and conf["matcher"]["model"]["name"] == "nearest_neighbor"
+    api = ImageMatchingAPI(conf={**conf, "ransac": {"enable": False}}, device="cpu", max_keypoints=512)
+    assert type(api.extractor).__name__ == "SuperPoint" and type(api.matcher).__name__ == "NearestNeighbor"
+    assert api.extractor.conf["max_keypoints"] == 512 and api.extractor.conf["keypoint_threshold"] == 0.015   # core.py:78-96
+    rgb = np.load(GOLDEN / "data" / "02928139_3448003521.npz")["rgb"]
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception, match="CUDA|cuda"):
+            api(rgb, rgb)

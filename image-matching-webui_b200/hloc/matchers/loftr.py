@@ -55,7 +55,7 @@ class LoFTR(BaseModel):
         n = int(out["counts"][0])
         k0, k1, scores = out["keypoints0"][0, :n], out["keypoints1"][0, :n], out["confidence"][0, :n]
         top_k = self.conf["max_keypoints"]
-        if top_k is not None and len(scores) > top_k:  # hloc/matchers/loftr.py:58-65 (note: -1 keeps nothing... as the reference)
+        if top_k is not None and len(scores) > top_k:  # hloc/matchers/loftr.py:58-65 (sic: with -1 the slice [:-1] drops the lowest-confidence match, as in the reference)
             keep = torch.argsort(scores, descending=True)[:top_k]
             k0, k1, scores = k0[keep], k1[keep], scores[keep]
         # switch back: module keypoints0 belong to hloc's image1

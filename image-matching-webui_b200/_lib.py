@@ -92,6 +92,10 @@ class LoftrConf(C.Structure):
     _fields_ = [("match_threshold", C.c_float), ("temperature", C.c_float), ("border_rm", C.c_int), ("use_tensor_cores", C.c_int)]
 
 
+class PreConf(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("grayscale", "resize_max", "force_resize", "width", "height", "dfactor")]
+
+
 class LGConf(C.Structure):
     _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
                 ("pruning_min_kpts", C.c_int), ("use_tensor_cores", C.c_int)]
@@ -162,8 +166,50 @@ def lib():
         L.imw_debug_attention.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]
         L.imw_debug_conv3x3_tc.restype = C.c_int
         L.imw_debug_conv3x3_tc.argtypes = [vp] * 4 + [C.c_int] * 7 + [vp, C.c_size_t, vp]
+        L.imw_preprocess_plan.restype = C.c_int
+        L.imw_preprocess_plan.argtypes = [C.POINTER(PreConf), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.imw_preprocess_workspace_bytes.restype = C.c_size_t
+        L.imw_preprocess_workspace_bytes.argtypes = [C.POINTER(PreConf), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.imw_preprocess.restype = C.c_int
+        L.imw_preprocess.argtypes = [C.POINTER(PreConf), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]
+        L.imw_gather_matches.restype = C.c_int
+        L.imw_gather_matches.argtypes = [C.c_int, C.c_int] + [vp] * 12
+        L.imw_prof_begin.restype = C.c_int
+        L.imw_prof_begin.argtypes = [vp]
+        L.imw_prof_end.restype = C.c_longlong
+        L.imw_prof_end.argtypes = [C.c_char_p, C.c_size_t]
         _lib = L
     return _lib
+
+
+class launch_profile:
+    """with launch_profile(device) as p: step()  ->  p.sites = [(site, launches, total_ms)] sorted by time, p.total_ms.
+    Library-side CUDA events behind every launch on the current stream (include/imw_b200.h: imw_prof_begin/end)."""
+
+    def __init__(self, device=None):
+        self.device, self.sites, self.total_ms, self.launches = device, [], 0.0, 0
+
+    def __enter__(self):
+        check(lib().imw_prof_begin(stream_ptr(self.device)))
+        return self
+
+    def __exit__(self, *exc):
+        buf = C.create_string_buffer(1 << 18)
+        n = lib().imw_prof_end(buf, len(buf))
+        if n < 0:
+            check(int(n))
+        self.launches = int(n)
+        for line in buf.value.decode().splitlines():
+            site, cnt, ms = line.rsplit("\t", 2)
+            self.sites.append((site, int(cnt), float(ms)))
+        self.sites.sort(key=lambda t: -t[2])
+        self.total_ms = sum(t[2] for t in self.sites)
+        return False
+
+    def find(self, *needles):
+        """Sites whose signature contains every needle (kernel family / template arguments)."""
+        return [t for t in self.sites if all(n in t[0] for n in needles)]
 
 
 class ImwError(RuntimeError):

@@ -1,5 +1,6 @@
 // C-ABI entry points (include/imw_b200.h): SuperPoint forward and the hloc first-party matchers.
 #include <stdarg.h>
+#include <string.h>
 
 #include "../../include/imw_b200.h"
 #include "common.cuh"
@@ -19,6 +20,66 @@ extern "C" const char* imw_last_error(void) { return g_err; }
 extern "C" int imw_version(void) { return 100; }
 unsigned long long g_imw_launches = 0;
 extern "C" unsigned long long imw_launch_count(void) { return g_imw_launches; }
+
+int imw_num_sms() {
+  static int sms[64] = {0};
+  const int d = imw_cur_device() & 63;
+  if (!sms[d]) cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+  return sms[d] > 0 ? sms[d] : 148;
+}
+
+// ---- launch-site profiler ---------------------------------------------------------------------------
+// imw_prof_begin(stream): record a start event and switch marking on; every launch of the library then records one
+// event behind itself (IMW_COUNT_LAUNCH).  imw_prof_end(): synchronise the events, attribute each interval to the
+// launch that ended it, aggregate per launch site (host launcher signature incl. template arguments + line) and
+// render "site<TAB>launches<TAB>total_ms" lines into a caller buffer.  Used by bench.py for the live per-kernel
+// share of the step and the roofline of the dominant kernel; off (zero cost beyond one branch) otherwise.
+#include <map>
+#include <string>
+#include <vector>
+int g_imw_prof_on = 0;
+namespace {
+struct ProfMark { cudaEvent_t ev; const char* site; int line; };
+std::vector<cudaEvent_t> g_prof_pool;
+std::vector<ProfMark> g_prof_marks;
+cudaEvent_t g_prof_start = nullptr;
+cudaEvent_t prof_event(size_t i) {
+  while (g_prof_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); g_prof_pool.push_back(e); }
+  return g_prof_pool[i];
+}
+}  // namespace
+void imw_prof_mark(const char* site, int line, cudaStream_t st) {
+  cudaEvent_t e = prof_event(g_prof_marks.size() + 1);
+  cudaEventRecord(e, st);
+  g_prof_marks.push_back({e, site, line});
+}
+extern "C" int imw_prof_begin(cudaStream_t st) {
+  g_prof_marks.clear();
+  g_prof_start = prof_event(0);
+  IMW_CHECK_CUDA(cudaEventRecord(g_prof_start, st));
+  g_imw_prof_on = 1;
+  return IMW_OK;
+}
+extern "C" long long imw_prof_end(char* buf, size_t buf_bytes) {
+  g_imw_prof_on = 0;
+  if (g_prof_marks.empty()) { if (buf && buf_bytes) buf[0] = 0; return 0; }
+  if (cudaEventSynchronize(g_prof_marks.back().ev) != cudaSuccess) return IMW_ERR_CUDA;
+  std::map<std::string, std::pair<long long, double>> agg;
+  cudaEvent_t prev = g_prof_start;
+  for (const ProfMark& m : g_prof_marks) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prev, m.ev);
+    prev = m.ev;
+    auto& a = agg[std::string(m.site) + ":" + std::to_string(m.line)];
+    a.first += 1; a.second += ms;
+  }
+  std::string out;
+  for (auto& kv : agg) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+  if (buf && buf_bytes) { size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+  const long long n = (long long)g_prof_marks.size();
+  g_prof_marks.clear();
+  return n;
+}
 
 // =====================================================================================================
 // SuperPoint
@@ -191,6 +252,7 @@ struct OpTop2 {
     bool ok = true;
     if (ratio2 > 0.f && n > 1 && m > 1) ok = ok && (d0 <= ratio2 * d1);  // :52-53: ratio test off for single descriptors
     if (dist2 > 0.f) ok = ok && (d0 <= dist2);
+    ok = ok && (unsigned)s.j1 < (unsigned)m;   // NaN similarities leave j1 at its init value
     match[(long long)own * cap + i] = ok ? s.j1 : -1;
     score[(long long)own * cap + i] = ok ? (s.v1 + 1.f) / 2.f : 0.f;
   }
@@ -281,7 +343,8 @@ __global__ void dsm_finish_kernel(const float* __restrict__ best_v, const int* _
     long long io = (long long)(2 * p) * cap + i;
     int j = best_j[io];
     float v = best_v[io];
-    if (best_j[(long long)(2 * p + 1) * cap + j] == i && v > thr) { out = j; s = v; }
+    // NaN rows (zero-norm descriptors) leave the arg-max at its init value: "no match", as the reference returns
+    if ((unsigned)j < (unsigned)counts[2 * p + 1] && best_j[(long long)(2 * p + 1) * cap + j] == i && v > thr) { out = j; s = v; }
   }
   matches0[(long long)p * cap + i] = out;
   scores0[(long long)p * cap + i] = s;

@@ -24,9 +24,18 @@ void imw_set_error(const char* fmt, ...);
 
 // every kernel launch of the library is counted (bench.py reports it as gpu_launches)
 extern unsigned long long g_imw_launches;
+// launch-site profiler (imw_prof_begin / imw_prof_end, api.cu): when enabled, a CUDA event is recorded on the launching
+// stream after every launch; the interval between consecutive events is that launch's duration inside the real step
+extern int g_imw_prof_on;
+void imw_prof_mark(const char* site, int line, cudaStream_t st);
+#define IMW_COUNT_LAUNCH(stream_)                                             \
+  do {                                                                        \
+    ++g_imw_launches;                                                         \
+    if (g_imw_prof_on) imw_prof_mark(__PRETTY_FUNCTION__, __LINE__, stream_); \
+  } while (0)
 #define IMW_CHECK_LAUNCH()               \
   do {                                   \
-    ++g_imw_launches;                    \
+    IMW_COUNT_LAUNCH(st);                \
     IMW_CHECK_CUDA(cudaGetLastError());  \
   } while (0)
 
@@ -36,6 +45,20 @@ extern unsigned long long g_imw_launches;
       imw_set_error(__VA_ARGS__);                                                         \
       return IMW_ERR_ARG;                                                                 \
     }                                                                                     \
+  } while (0)
+
+// Function attributes and the SM count are per DEVICE: cache them per device ordinal, not per process
+// (one process may drive several GPUs through torch.cuda.device(dev)).
+static inline int imw_cur_device() { int d = 0; cudaGetDevice(&d); return d; }
+int imw_num_sms();  // SM count of the current device (api.cu, cached per ordinal)
+#define IMW_SMEM_ATTR_ONCE(kernel, bytes)                                                                       \
+  do {                                                                                                          \
+    static unsigned long long done_ = 0;                                                                        \
+    const int d_ = imw_cur_device() & 63;                                                                       \
+    if (!((done_ >> d_) & 1ull)) {                                                                              \
+      IMW_CHECK_CUDA(cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      done_ |= 1ull << d_;                                                                                      \
+    }                                                                                                           \
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

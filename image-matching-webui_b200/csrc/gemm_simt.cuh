@@ -96,7 +96,7 @@ static inline cudaError_t launch_gemm(const GemmArgs& g, int batches, Epi epi, c
   dim3 grid(ceil_div(g.N, GEMM_TN), ceil_div(g.M, GEMM_TM), batches);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
   gemm_nt_kernel<Epi><<<grid, GEMM_THREADS, 0, st>>>(g, epi);
-  ++g_imw_launches;
+  IMW_COUNT_LAUNCH(st);
   return cudaGetLastError();
 }
 

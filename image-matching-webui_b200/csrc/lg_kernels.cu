@@ -347,9 +347,11 @@ __global__ void __launch_bounds__(256) match_kernel(const float* __restrict__ be
   const int z = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, zo = z ^ 1;
   if (empty[z >> 1] || i >= counts[z]) return;
   const long long io = (long long)z * cap + i;
-  const int j = best_j[io];
+  const int jr = best_j[io];
+  const bool j_ok = (unsigned)jr < (unsigned)counts[zo];   // NaN rows leave the arg-max at its init value: unmatched
+  const int j = j_ok ? jr : 0;
   const long long jo = (long long)zo * cap + j;
-  const bool mutual = best_j[jo] == i;
+  const bool mutual = j_ok && best_j[jo] == i;
   // mscores0 = exp(max0) where mutual; mscores1[j] = mscores0[m1[j]] where mutual
   const float sc0 = (z & 1) ? expf(best_v[jo]) : expf(best_v[io]);
   const float ms = mutual ? sc0 : 0.f;

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(1024) lf_coarse_select_kernel(const float* __r
     if (i < L) {
       v = best_v[(long long)(2 * p) * cap + i];
       j = best_j[(long long)(2 * p) * cap + i];
-      ok = v > thr && inner(i) && inner(j) && best_j[(long long)(2 * p + 1) * cap + j] == i;
+      ok = v > thr && (unsigned)j < (unsigned)L && inner(i) && inner(j) && best_j[(long long)(2 * p + 1) * cap + j] == i;   // NaN rows: j = init
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (lane == 0) s_w[wid] = __popc(bal);

@@ -167,9 +167,11 @@ __global__ void __launch_bounds__(256) sg_match_kernel(const float* __restrict__
   const int z = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, zo = z ^ 1;
   if (empty[z >> 1] || i >= counts[z]) return;
   const long long io = (long long)z * cap + i;
-  const int j = best_j[io];
+  const int jr = best_j[io];
+  const bool j_ok = (unsigned)jr < (unsigned)counts[zo];   // NaN scores leave the arg-max at its init value: unmatched
+  const int j = j_ok ? jr : 0;
   const long long jo = (long long)zo * cap + j;
-  const bool mutual = best_j[jo] == i;
+  const bool mutual = j_ok && best_j[jo] == i;
   const float sc0 = (z & 1) ? __expf(best_v[jo]) : __expf(best_v[io]);
   const float ms = mutual ? sc0 : 0.f;
   matches[io] = (mutual && ms > th) ? j : -1;

@@ -109,7 +109,7 @@ static inline cudaError_t launch_simreduce(const SimArgs& a, int slots, Op op, c
   dim3 grid(ceil_div(a.cap, SR_T), slots);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
   simreduce_kernel<Op><<<grid, SR_THREADS, smem, st>>>(a, op);
-  ++g_imw_launches;
+  IMW_COUNT_LAUNCH(st);
   return cudaGetLastError();
 }
 

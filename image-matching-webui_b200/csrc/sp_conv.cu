@@ -197,11 +197,7 @@ int sp_conv3x3(const float* in, const float* w, const float* bias, float* out, i
   IMW_REQUIRE(Cin % CH == 0 && Cout % COUT_T == 0, "sp_conv3x3: Cin %% 16 / Cout %% 64 (got %d,%d)", Cin, Cout);
   IMW_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "sp_conv3x3: pooled conv needs even H,W");
   size_t smem = (size_t)(CH * IN_PLANE + 9 * CH * COUT_T) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE(conv3x3_nhwc_kernel, smem);
   dim3 grid(ceil_div(W, TILE) * ceil_div(H, TILE), Cout / COUT_T, B);
   conv3x3_nhwc_kernel<<<grid, 256, smem, st>>>(in, w, bias, out, H, W, Cin, Cout, relu, pool);
   IMW_CHECK_LAUNCH();

@@ -259,11 +259,7 @@ static inline int launch_tc_attn(const float* q_planes, const float* k_planes, c
   if (int e = tc_make_map_2d_f32(&tmQ, q_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BQ)) return e;
   if (int e = tc_make_map_2d_f32(&tmK, k_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BKV)) return e;
   if (int e = tc_make_map_2d_f32(&tmV, vt_planes, (uint64_t)rows_vt, (uint64_t)g.cap, (uint64_t)g.cap, 32, 64)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE(tc_attn_kernel, TA_SMEM);
   dim3 grid(g.cap / TA_BQ, 4, g.slots);
   tc_attn_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(tmQ, tmK, tmV, g);
   IMW_CHECK_LAUNCH();

@@ -539,11 +539,7 @@ int make_map_wgt(CUtensorMap* map, const void* base, int rows, int Cin, int BN) 
 template <int BN, int KS, bool RES>
 int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
   constexpr size_t smem = conv_smem_bytes<BN>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<BN, KS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE((tc_conv3x3_kernel<BN, KS, RES>), smem);
   const int Hc = ceil_div(g.H, g.stride), Wc = ceil_div(g.W, g.stride);
   dim3 grid((unsigned)(g.B * ceil_div(Hc, CV_TH) * ceil_div(Wc, CV_TW)), g.Cout / BN);
   tc_conv3x3_kernel<BN, KS, RES><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, g);
@@ -572,18 +568,9 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, C64_TW, C64_TH + 2)) return e;
     if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, 64)) return e;
     ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
-    static bool attr_set = false;
-    if (!attr_set) {
-      IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
-      attr_set = true;
-    }
+    IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<false>, C64_SMEM);
     const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
-    static int num_sms = 0;
-    if (!num_sms) {
-      int dev = 0;
-      IMW_CHECK_CUDA(cudaGetDevice(&dev));
-      IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = imw_num_sms();
     dim3 grid((unsigned)(total < num_sms ? total : num_sms), 1);
     tc_conv3x3_c64_kernel<false><<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
     IMW_CHECK_LAUNCH();
@@ -603,15 +590,8 @@ int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const
   if (int e = make_map_wgt(&tmW, w1b_planes, 3 * 9 * 64, 64, 64)) return e;
   ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (__nv_bfloat16*)out, (float*)out};
   g.img = img; g.w1a = w1a; g.b1a = b1a;
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
-    int dev = 0;
-    IMW_CHECK_CUDA(cudaGetDevice(&dev));
-    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<true>, C64_SMEM);
+  const int num_sms = imw_num_sms();
   const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
   tc_conv3x3_c64_kernel<true><<<dim3((unsigned)(total < num_sms ? total : num_sms)), C64_FUSE_THREADS, C64_SMEM, st>>>(tmW, tmW, g, total);
   IMW_CHECK_LAUNCH();

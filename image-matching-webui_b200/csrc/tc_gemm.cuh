@@ -243,15 +243,8 @@ static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, 
   if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, TC_BK, TC_BM)) return e;
   if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)w_rows, (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
   constexpr size_t smem = tc_gemm_smem_bytes<BN, SPLIT>();
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_tf32_kernel<BN, SPLIT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IMW_CHECK_CUDA(cudaGetDevice(&dev));
-    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE((tc_gemm_tf32_kernel<BN, SPLIT, Epi>), smem);
+  const int num_sms = imw_num_sms();
   const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
   dim3 grid((unsigned)(total < num_sms ? total : num_sms));
   tc_gemm_tf32_kernel<BN, SPLIT, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);

@@ -210,15 +210,8 @@ static inline int launch_tc_simreduce(const SimArgs& a, int slots, Op op, cudaSt
   CUtensorMap tmX;
   if (int e = tc_make_map_2d_f32(&tmX, a.X, (uint64_t)slots * a.cap, (uint64_t)a.K, (uint64_t)a.ld, TC_BK, TC_BM)) return e;
   constexpr size_t smem = (size_t)TC_STAGES * 2 * (TC_BM * 128 + 128 * 128) + 1024 + 256 + 128 * sizeof(typename Op::State);
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    IMW_CHECK_CUDA(cudaFuncSetAttribute(tc_simreduce_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IMW_CHECK_CUDA(cudaGetDevice(&dev));
-    IMW_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
-  }
+  IMW_SMEM_ATTR_ONCE(tc_simreduce_kernel<Op>, smem);
+  const int num_sms = imw_num_sms();
   const int m_tiles = slots * (a.cap / TC_BM);
   if (m_tiles == 0) return IMW_OK;
   tc_simreduce_kernel<Op><<<dim3((unsigned)(m_tiles < num_sms ? m_tiles : num_sms)), TCS_THREADS, smem, st>>>(tmX, a, op, m_tiles);

@@ -8,6 +8,69 @@ from . import _lib as L
 
 
 # ---------------------------------------------------------------------------------------------------
+# pre- / post-processing of the hloc drivers
+# ---------------------------------------------------------------------------------------------------
+PRE_DEFAULT = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "force_resize": False, "width": 320, "height": 240}
+
+
+def pre_conf_struct(conf):
+    c = {**PRE_DEFAULT, **{k: v for k, v in (conf or {}).items() if k in PRE_DEFAULT}}
+    return L.PreConf(int(bool(c["grayscale"])), int(c["resize_max"] or 0), int(bool(c["force_resize"])), int(c["width"]), int(c["height"]),
+                     int(c["dfactor"] or 1))
+
+
+def preprocess_plan(conf, height, width, channels):
+    """(out_channels, out_height, out_width) of ops.preprocess for frames of this size (host arithmetic only)."""
+    oc, oh, ow, wsb = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    pc = pre_conf_struct(conf)
+    L.check(L.lib().imw_preprocess_plan(C.byref(pc), int(height), int(width), int(channels), C.byref(oc), C.byref(oh), C.byref(ow), C.byref(wsb)))
+    return oc.value, oh.value, ow.value
+
+
+def preprocess(images_u8, conf, out=None):
+    """images_u8 [B,H,W] or [B,H,W,3] uint8 CUDA (decoded frames) -> fp32 [B,C,H',W'] in [0,1], exactly the tensor the
+    reference's extract() feeds the extractor (extract_features.py:120-162)."""
+    L.require_cuda(images_u8, "preprocess(images)")
+    assert images_u8.dtype == torch.uint8 and images_u8.dim() in (3, 4)
+    x = images_u8.contiguous()
+    B, H, W = x.shape[:3]
+    Cc = x.shape[3] if x.dim() == 4 else 1
+    oc, oh, ow = preprocess_plan(conf, H, W, Cc)
+    dev = x.device
+    if out is None:
+        out = torch.empty(B, oc, oh, ow, device=dev)
+    assert out.shape == (B, oc, oh, ow) and out.is_contiguous()
+    pc = pre_conf_struct(conf)
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_preprocess_workspace_bytes(C.byref(pc), B, H, W, Cc), "pre")
+    with torch.cuda.device(dev):
+        L.check(lib.imw_preprocess(C.byref(pc), B, H, W, Cc, L.ptr(x), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    return out
+
+
+def gather_matches(keypoints, matches, counts, scores=None, scales=None, out=None):
+    """Device-side match_features.py:244-257 for a batch: keypoints [2P,cap,2], matches [2P,cap] int32 (matches0 in even
+    slots), counts [2P], scores [2P,cap] (optional), scales [2P,2] fp32 = original_size / size (optional).
+    Returns (mkpts0 [P,cap,2], mkpts1 [P,cap,2], mcount [P]) or, with `out` (dict of preallocated buffers incl. the
+    *_orig / mconf ones), fills and returns it."""
+    L.require_cuda(keypoints, "gather_matches(keypoints)")
+    S, cap, _ = keypoints.shape
+    P, dev = S // 2, keypoints.device
+    assert matches.shape == (S, cap) and matches.dtype == torch.int32 and counts.dtype == torch.int32 and counts.numel() == S
+    simple = out is None
+    if out is None:
+        out = {"mkpts0": torch.empty(P, cap, 2, device=dev), "mkpts1": torch.empty(P, cap, 2, device=dev),
+               "mcount": torch.empty(P, dtype=torch.int32, device=dev)}
+    with torch.cuda.device(dev):
+        L.check(L.lib().imw_gather_matches(P, cap, L.ptr(keypoints.contiguous()), L.ptr(matches.contiguous()),
+                                           L.ptr(scores.contiguous() if scores is not None else None), L.ptr(counts.contiguous()),
+                                           L.ptr(scales.contiguous() if scales is not None else None), L.ptr(out["mkpts0"]), L.ptr(out["mkpts1"]),
+                                           L.ptr(out.get("mkpts0_orig")), L.ptr(out.get("mkpts1_orig")), L.ptr(out.get("mconf")),
+                                           L.ptr(out["mcount"]), L.stream_ptr(dev)))
+    return (out["mkpts0"], out["mkpts1"], out["mcount"]) if simple else out
+
+
+# ---------------------------------------------------------------------------------------------------
 # SuperPoint
 # ---------------------------------------------------------------------------------------------------
 SP_LAYERS = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",

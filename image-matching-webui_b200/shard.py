@@ -24,3 +24,16 @@ def gather_match_counts(local_counts: torch.Tensor, n_pairs: int, group=None):
     dist.all_gather_into_tensor(out, buf, group=group)
     parts = [out[r * cap: r * cap + (shard_range(n_pairs, r, world)[1] - shard_range(n_pairs, r, world)[0])] for r in range(world)]
     return torch.cat(parts)
+
+
+def gather_stream_counts(local_counts: torch.Tensor, group=None):
+    """The stream's single collective: every rank contributes the int32 match counts of all pairs it processed
+    (equal-sized shards: steps x pairs_per_step), every rank receives the [world * n] vector.  No-op without a process
+    group (single GPU)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_counts
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local_counts.numel(), dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(out, local_counts.contiguous(), group=group)
+    return out

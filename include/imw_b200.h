@@ -30,6 +30,51 @@ const char* imw_last_error(void);
 int imw_version(void);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 unsigned long long imw_launch_count(void);
+/* Launch-site profiler (measurement aid, bench.py): between imw_prof_begin(stream) and imw_prof_end() every kernel launch
+ * of the library records a CUDA event behind itself on the launching stream; imw_prof_end synchronises them and writes
+ * "launcher signature:line<TAB>launches<TAB>total_ms" lines (one per launch site) into buf.  Returns the number of
+ * launches seen (<0 = error).  Off by default: no events, no synchronisation. */
+int imw_prof_begin(imw_stream_t stream);
+long long imw_prof_end(char* buf, size_t buf_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image pre-processing of the extraction drivers.
+ * Replaces: hloc/extract_features.py:120-162 (preprocess + the RGB2GRAY of extract) and hloc/match_dense.py:588-640:
+ * cv2.cvtColor(RGB2GRAY) on uint8, astype(float32), cv2.resize(INTER_AREA) for resize_max and force_resize
+ * (INTER_LINEAR when up-sampling, :30-31), / 255, torchvision antialias resize down to a multiple of dfactor.
+ * Bit-identical to the libraries the reference calls for gray / INTER_AREA / /255 / antialias (oracle/preprocess.py);
+ * the INTER_LINEAR up-sampling branch follows OpenCV's own arithmetic (pip builds route it through IPP: ~4e-6 relative).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int grayscale;    /* conf["grayscale"]: RGB frames are converted to gray first */
+  int resize_max;   /* conf["resize_max"]; <= 0: none.  Only ever down-scales (extract_features.py:124-129) */
+  int force_resize; /* conf["force_resize"]: resize to (width, height) */
+  int width, height;
+  int dfactor;      /* output size is floored to a multiple of dfactor (antialias resize when it changes) */
+} imw_pre_conf;
+
+/* output geometry of one frame size (host-only arithmetic, no GPU work): channels / height / width of the tensor
+ * imw_preprocess writes, and the per-image workspace */
+int imw_preprocess_plan(const imw_pre_conf* conf, int height, int width, int channels, int* out_channels, int* out_height,
+                        int* out_width, size_t* workspace_bytes);
+size_t imw_preprocess_workspace_bytes(const imw_pre_conf* conf, int batch, int height, int width, int channels);
+/* images [B][H][W][channels] uint8 on the DEVICE (channels 1 = gray, 3 = RGB interleaved, as decoded), same size for the
+ * batch -> out [B][out_channels][out_height][out_width] fp32 in [0,1]. */
+int imw_preprocess(const imw_pre_conf* conf, int batch, int height, int width, int channels, const unsigned char* images,
+                   float* out, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Match post-processing.
+ * Replaces: hloc/match_features.py:236-257 (valid = matches0 > -1, gather of the matched keypoints, rescale to the
+ * original image with (k + 0.5) * s - 0.5) for a batch of pairs, on the device, in ascending keypoint order.
+ * keypoints [2P][cap][2], matches [2P][cap] (matches0 in even slots), matching_scores [2P][cap] (nullable),
+ * counts [2P], scales [2P][2] = original_size / size per image as fp32 (nullable: 1).
+ * Outputs: mkpts0/1 [P][cap][2] (resized-image coordinates), mkpts0/1_orig [P][cap][2] (nullable pair), mconf [P][cap]
+ * (nullable), mcount [P].
+ * ---------------------------------------------------------------------------------------------- */
+int imw_gather_matches(int n_pairs, int cap, const float* keypoints, const int* matches, const float* matching_scores,
+                       const int* counts, const float* scales, float* mkpts0, float* mkpts1, float* mkpts0_orig,
+                       float* mkpts1_orig, float* mconf, int* mcount, imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SuperPoint extractor.

@@ -175,6 +175,8 @@ def lib():
         L.imw_preprocess.argtypes = [C.POINTER(PreConf), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]
         L.imw_gather_matches.restype = C.c_int
         L.imw_gather_matches.argtypes = [C.c_int, C.c_int] + [vp] * 12
+        L.imw_rescale_keypoints.restype = C.c_int
+        L.imw_rescale_keypoints.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp]
         L.imw_prof_begin.restype = C.c_int
         L.imw_prof_begin.argtypes = [vp]
         L.imw_prof_end.restype = C.c_longlong

@@ -225,6 +225,16 @@ __global__ void __launch_bounds__(1024) pp_gather_matches_kernel(const float* __
   if (tid == 0) mcount[p] = s_base;
 }
 
+// keypoints_orig = (k + 0.5) * scale - 0.5 for every keypoint of every image (match_features.py:251-254, match_dense.py:655-656)
+__global__ void pp_rescale_kernel(const float* __restrict__ kpts, const int* __restrict__ counts, const float* __restrict__ scales,
+                                  float* __restrict__ out, int cap) {
+  const int z = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (counts ? counts[z] : cap)) return;
+  const long long o = ((long long)z * cap + i) * 2;
+  out[o] = __fsub_rn(__fmul_rn(__fadd_rn(kpts[o], 0.5f), scales[2 * z]), 0.5f);
+  out[o + 1] = __fsub_rn(__fmul_rn(__fadd_rn(kpts[o + 1], 0.5f), scales[2 * z + 1]), 0.5f);
+}
+
 struct Plan { int Co, h1, w1, lin1, h2, w2, lin2, hf, wf, n_resize; };
 
 // size logic of extract_features.py:120-156
@@ -364,6 +374,14 @@ extern "C" int imw_gather_matches(int n_pairs, int cap, const float* keypoints, 
   IMW_REQUIRE((mkpts0_orig == nullptr) == (mkpts1_orig == nullptr), "imw_gather_matches: both *_orig outputs or none");
   pp_gather_matches_kernel<<<n_pairs, 1024, 0, st>>>(keypoints, matches, matching_scores, counts, scales, mkpts0, mkpts1, mkpts0_orig,
                                                      mkpts1_orig, mconf, mcount, cap);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
+extern "C" int imw_rescale_keypoints(int n_sets, int cap, const float* keypoints, const int* counts, const float* scales, float* out,
+                                     cudaStream_t st) {
+  IMW_REQUIRE(n_sets > 0 && cap > 0 && keypoints && scales && out, "imw_rescale_keypoints: bad arguments");
+  pp_rescale_kernel<<<dim3(ceil_div(cap, 256), n_sets), 256, 0, st>>>(keypoints, counts, scales, out, cap);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -1,66 +1,59 @@
-"""In-memory extraction driver -- mirror of the reference's imcui/hloc/extract_features.py:27-41 (resize_image)
-and :106-170 (extract): RGB->gray with cv2 on uint8, INTER_AREA resizes, /255, torchvision antialias resize to a
-multiple of dfactor, H2D, call the extractor, merge dicts.  Pre-processing stays on the host with the very same
-cv2 / torchvision calls so that the model input is bit-identical to the reference's (SURVEY.md 8(f) rank 1 lists
-a GPU version as the next row)."""
-from types import SimpleNamespace
+"""Extraction driver -- drop-in for `extract` of imcui/hloc/extract_features.py:106-170, with the image preparation on
+the GPU.
 
-import cv2
-import numpy as np
+The reference converts, resizes and normalises every image with cv2 / torchvision on the host and then uploads a float
+tensor; here the decoded uint8 frame is uploaded as it is and `imw_preprocess` (csrc/prepost.cu) produces the model input
+on the device -- bit-identical to the reference's tensor for gray conversion, INTER_AREA resizes, /255 and the dfactor
+alignment (tests/test_gpu_prepost.py).  `extract_batch` is the same call for many frames at once: frames of equal size
+share one upload, one pre-processing pass and one extractor forward."""
 import torch
-import torchvision.transforms.functional as F
 
 from .configs import confs_dict
+from .pipeline import FramePrep
 
 confs = confs_dict["extractors"]
 
 
-def resize_image(image, size, interp):
-    """extract_features.py:27-41 (cv2 branch; the PIL branch is not used by extract())."""
-    if not interp.startswith("cv2_"):
-        raise ValueError(f"Unknown interpolation {interp}.")
-    interp = getattr(cv2, "INTER_" + interp[len("cv2_"):].upper())
-    h, w = image.shape[:2]
-    if interp == cv2.INTER_AREA and (w < size[0] or h < size[1]):
-        interp = cv2.INTER_LINEAR
-    return cv2.resize(image, size, interpolation=interp)
+def _model_device(model):
+    for t in model.buffers():
+        return t.device
+    for t in model.parameters():
+        return t.device
+    return torch.device("cuda")
 
 
-def preprocess(image: np.ndarray, conf: SimpleNamespace, device):
-    """extract_features.py:120-156."""
-    image = image.astype(np.float32, copy=False)
-    size = image.shape[:2][::-1]
-    if conf.resize_max:
-        scale = conf.resize_max / max(size)
-        if scale < 1.0:
-            size_new = tuple(int(round(x * scale)) for x in size)
-            image = resize_image(image, size_new, "cv2_area")
-    if conf.force_resize:
-        image = resize_image(image, (conf.width, conf.height), "cv2_area")
-    if conf.grayscale:
-        assert image.ndim == 2, image.shape
-        image = image[None]
-    else:
-        image = image.transpose((2, 0, 1))
-    image = torch.from_numpy(image / 255.0).float()
-    size_new = tuple(map(lambda x: int(x // conf.dfactor * conf.dfactor), image.shape[-2:]))
-    image = F.resize(image, size=size_new, antialias=True)
-    input_ = image.to(device, non_blocking=True)[None]
-    return {"image": input_, "original_size": np.array(size), "size": np.array(image.shape[1:][::-1])}
+def _feature_dict(pred, b, image, frame, original_size, size):
+    """One image's entry of a (possibly batched) extractor output, in the reference's container types (:164-170)."""
+    one = {}
+    for k, v in pred.items():
+        if isinstance(v, (list, tuple)):
+            one[k] = type(v)([v[b]])
+        elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] > b:
+            one[k] = v[b:b + 1]
+        else:
+            one[k] = v
+    one["image_size"] = original_size
+    return {**one, "image": image, "original_size": original_size, "size": size, "image_orig": frame}
+
+
+@torch.no_grad()
+def extract_batch(model, frames, conf):
+    """frames: list of uint8 RGB [H,W,3] / gray [H,W] arrays (any sizes).  Returns one feature dict per frame with the keys
+    `extract` returns.  Same-size frames are pre-processed and extracted together."""
+    prepped = FramePrep(conf, _model_device(model))(frames)
+    groups = {}
+    for i, (img, _, _) in enumerate(prepped):
+        groups.setdefault(tuple(img.shape), []).append(i)
+    out = [None] * len(frames)
+    for _, idx in groups.items():
+        batch = torch.cat([prepped[i][0] for i in idx]) if len(idx) > 1 else prepped[idx[0]][0]
+        pred = model({"image": batch})
+        for b, i in enumerate(idx):
+            out[i] = _feature_dict(pred, b, prepped[i][0], frames[i], prepped[i][1], prepped[i][2])
+    return out
 
 
 def extract(model, image_0, conf):
-    """extract_features.py:106-170.  image_0: uint8 RGB [H,W,3] (or gray [H,W])."""
-    default_conf = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "cache_images": False, "force_resize": False,
-                    "width": 320, "height": 240, "interpolation": "cv2_area"}
-    conf = SimpleNamespace(**{**default_conf, **conf})
-    device = next(model.buffers()).device if any(True for _ in model.buffers()) else ("cuda" if torch.cuda.is_available() else "cpu")
-    if len(image_0.shape) == 3 and conf.grayscale:
-        image0 = cv2.cvtColor(image_0, cv2.COLOR_RGB2GRAY)
-    else:
-        image0 = image_0
-    data = preprocess(image0, conf, device)
-    data["image_orig"] = image_0
-    pred = model({"image": data["image"]})
-    pred["image_size"] = data["original_size"]
-    return {**pred, **data}
+    """extract_features.py:106-170: image_0 uint8 RGB [H,W,3] (or gray [H,W]) -> {keypoints, scores, descriptors, image,
+    original_size, size, image_orig, image_size}."""
+    return extract_batch(model, [image_0], conf)[0]

@@ -70,6 +70,19 @@ def gather_matches(keypoints, matches, counts, scores=None, scales=None, out=Non
     return (out["mkpts0"], out["mkpts1"], out["mcount"]) if simple else out
 
 
+def rescale_keypoints(keypoints, scales, counts=None, out=None):
+    """keypoints [S,cap,2] fp32, scales [S,2] fp32 -> (k + 0.5) * s - 0.5 (match_features.py:251-254)."""
+    L.require_cuda(keypoints, "rescale_keypoints(keypoints)")
+    S, cap, _ = keypoints.shape
+    dev = keypoints.device
+    if out is None:
+        out = torch.empty_like(keypoints)
+    with torch.cuda.device(dev):
+        L.check(L.lib().imw_rescale_keypoints(S, cap, L.ptr(keypoints.contiguous()), L.ptr(counts), L.ptr(scales.contiguous()), L.ptr(out),
+                                              L.stream_ptr(dev)))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # SuperPoint
 # ---------------------------------------------------------------------------------------------------

@@ -76,6 +76,11 @@ int imw_gather_matches(int n_pairs, int cap, const float* keypoints, const int* 
                        const int* counts, const float* scales, float* mkpts0, float* mkpts1, float* mkpts0_orig,
                        float* mkpts1_orig, float* mconf, int* mcount, imw_stream_t stream);
 
+/* keypoints [n_sets][cap][2], counts [n_sets] (nullable: all cap rows), scales [n_sets][2] -> out = (k + 0.5) * s - 0.5
+ * (hloc/match_features.py:251-254, hloc/match_dense.py:655-659) */
+int imw_rescale_keypoints(int n_sets, int cap, const float* keypoints, const int* counts, const float* scales, float* out,
+                          imw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * SuperPoint extractor.
  * Replaces: hloc/extractors/superpoint.py:56-57 (SuperPoint._forward) ->

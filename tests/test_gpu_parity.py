@@ -388,20 +388,31 @@ def test_dual_softmax_large_property(dev, tc):
     assert (m0[0] > -1).sum() > 1500
 
 
-def test_api_pipeline_end_to_end(golden, dev):
-    """ImageMatchingAPI mirror (api/core.py): uint8 RGB pair -> extract x2 -> LightGlue -> MAGSAC++ on the GPU; the raw
-    match count equals the reference LightGlue result on the same pair (golden lg_real, CUDA semantics)."""
-    from imcui_b200.api import ImageMatchingAPI
-    from imcui_b200.ui.utils import get_matcher_zoo
-    conf = get_matcher_zoo({"superpoint+lightglue": {"matcher": "superpoint-lightglue", "feature": "superpoint_max", "dense": False,
-                                                     "standalone": False}})["superpoint+lightglue"]
-    api = ImageMatchingAPI(conf={**conf, "ransac": {"enable": True, "method": "B200_MAGSAC", "reproj_threshold": 8, "confidence": 0.9999,
-                                                    "max_iter": 10000}}, device="cuda:0")
+def test_registry_pipeline_end_to_end(golden, dev):
+    """The registry path a Gradio / API caller drives: zoo entry -> get_feature_model / get_model -> extract x2 (GPU
+    pre-processing from the decoded RGB frames) -> match_images (GPU post-processing) -> filter_matches (GPU MAGSAC++);
+    the raw match count equals the reference LightGlue result on the same pair (golden lg_real, CUDA semantics)."""
+    from imcui_b200.hloc import extract_features, match_features
+    from imcui_b200.ui import utils as U
+    conf = U.get_matcher_zoo({"superpoint+lightglue": {"matcher": "superpoint-lightglue", "feature": "superpoint_max", "dense": False,
+                                                       "standalone": False}})["superpoint+lightglue"]
+    extractor, matcher = U.get_feature_model(conf["feature"], dev), U.get_model(conf["matcher"], dev)
+    extractor.conf["max_keypoints"], extractor.conf["keypoint_threshold"] = 1024, 0.015          # api/core.py:78-96 overrides
+    pre = {**conf["feature"]["preprocessing"], "force_resize": True, "width": 640, "height": 480}
     rgb0 = np.load(GOLDEN / "data" / "02928139_3448003521.npz")["rgb"]
     rgb1 = np.load(GOLDEN / "data" / "17295357_9106075285.npz")["rgb"]
-    pred = api(rgb0, rgb1)
+    f0, f1 = extract_features.extract(extractor, rgb0, pre), extract_features.extract(extractor, rgb1, pre)
+    g = golden("sp_real")
+    assert torch.equal(f0["image"].cpu(), torch.from_numpy(g["images"][0])[None]) and tuple(f0["size"]) == (640, 480)
+    pred = match_features.match_images(matcher, f0, f1)
+    pred = U.filter_matches(pred, "B200_MAGSAC", 8, 0.9999, 10000)
     n_ref = int((golden("lg_real")["cuda/0/matches0"] > -1).sum())
     n = len(pred["mkeypoints0_orig"])
-    print(f"[api] raw matches {n} (reference {n_ref}), verified {len(pred['mmkeypoints0_orig'])}")
-    assert abs(n - n_ref) <= 2 and pred["mconf"].shape == (n,)
+    print(f"[registry] raw matches {n} (reference {n_ref}), verified {len(pred['mmkeypoints0_orig'])}")
+    assert abs(n - n_ref) <= 2 and pred["mconf"].shape == (n,) and pred["keypoints0"].shape[1] == 2
+    s0 = f0["original_size"] / f0["size"]
+    assert np.allclose(pred["mkeypoints0_orig"], (pred["mkeypoints0"] + 0.5) * s0 - 0.5, atol=1e-3)
     assert 8 <= len(pred["mmkeypoints0_orig"]) <= n and "geom_info" in pred and "Fundamental" in pred["geom_info"]
+    # the batch sibling gives the same features
+    fb = extract_features.extract_batch(extractor, [rgb0, rgb1, rgb0], pre)
+    assert torch.equal(fb[2]["keypoints"][0], f0["keypoints"][0]) and torch.equal(fb[1]["descriptors"][0], f1["descriptors"][0])

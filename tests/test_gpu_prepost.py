@@ -142,3 +142,89 @@ def test_gather_matches_equals_numpy(dev):
             ref = torch.from_numpy(mk + 0.5)
             ref[:, 0] *= s[0]; ref[:, 1] *= s[1]          # scale_keypoints: fp32 tensor times a scalar
             assert np.array_equal(out[key][p, :n].cpu().numpy(), (ref - 0.5).numpy()), (p, key)
+
+
+def test_match_images_postprocessing_with_a_fake_matcher(dev):
+    """match_images: valid mask, gather and the (k + 0.5) * s - 0.5 rescale (match_features.py:244-257), all container types."""
+    from imcui_b200.hloc import match_features as mf
+
+    class Fake(torch.nn.Module):
+        def forward(self, data):
+            n = data["keypoints0"].shape[1]
+            m = torch.full((1, n), -1, dtype=torch.long, device=dev)
+            m[0, 0], m[0, 2] = 1, 0
+            return {"matches0": m, "matching_scores0": torch.linspace(0, 1, n, device=dev)[None], "stop": 3}
+
+    def feat(n, orig, size):
+        return {"keypoints": [torch.arange(2 * n, dtype=torch.float32, device=dev).view(n, 2)], "scores": (torch.ones(n, device=dev),),
+                "descriptors": [torch.zeros(4, n, device=dev)], "image": torch.zeros(1, 1, 8, 8, device=dev), "image_orig": np.zeros((2, 2, 3)),
+                "original_size": np.array(orig), "size": np.array(size)}
+    out = mf.match_images(Fake(), feat(3, (1280, 960), (640, 480)), feat(2, (640, 480), (640, 480)))
+    assert out["mkeypoints0"].tolist() == [[0, 1], [4, 5]] and out["mkeypoints1"].tolist() == [[2, 3], [0, 1]]
+    assert np.array_equal(out["mkeypoints0_orig"], ((np.array([[0, 1], [4, 5]], np.float32) + 0.5) * 2 - 0.5).astype(np.float32))
+    assert out["mkeypoints1_orig"].tolist() == [[2, 3], [0, 1]]
+    assert out["keypoints0"].shape == (3, 2) and out["keypoints1_orig"].tolist() == [[0, 1], [2, 3]]
+    assert out["mconf"].tolist() == [0.0, 1.0] and out["image0_orig"].shape == (2, 2, 3)
+    # no matches at all: empty arrays, not an error
+    class Nope(torch.nn.Module):
+        def forward(self, data):
+            n = data["keypoints0"].shape[1]
+            return {"matches0": torch.full((1, n), -1, dtype=torch.long, device=dev), "matching_scores0": torch.zeros(1, n, device=dev)}
+    out = mf.match_images(Nope(), feat(3, (640, 480), (640, 480)), feat(2, (640, 480), (640, 480)))
+    assert out["mkeypoints0"].shape == (0, 2) and out["mconf"].shape == (0,)
+
+
+def test_match_dense_postprocessing_with_a_fake_matcher(dev):
+    """match_dense.match_images (reference :577-686): force-resize to 640x480 on the GPU, 'scores' adopted as mconf and the
+    (k + 0.5) * s - 0.5 rescale with s = original / network size."""
+    from imcui_b200.hloc import match_dense as md
+    from imcui_b200.hloc.configs import confs_dict
+    seen = {}
+
+    class Fake(torch.nn.Module):
+        def forward(self, data):
+            seen["shape"] = (tuple(data["image0"].shape), tuple(data["image1"].shape))
+            return {"keypoints0": torch.tensor([[0.0, 0.0], [8.0, 16.0]], device=dev), "keypoints1": torch.tensor([[1.0, 2.0], [9.5, 18.25]], device=dev),
+                    "scores": torch.tensor([0.9, 0.4], device=dev)}
+    rgb0 = np.random.RandomState(0).randint(0, 255, (960, 1280, 3), dtype=np.uint8)
+    rgb1 = np.random.RandomState(1).randint(0, 255, (480, 640, 3), dtype=np.uint8)
+    out = md.match_images(Fake(), rgb0, rgb1, confs_dict["matchers"]["loftr"]["preprocessing"], device=dev)
+    assert seen["shape"] == ((1, 1, 480, 640), (1, 1, 480, 640))
+    assert out["scale0"].tolist() == [2.0, 2.0] and out["scale1"].tolist() == [1.0, 1.0]
+    np.testing.assert_allclose(out["mkeypoints0_orig"], (np.array([[0, 0], [8, 16]]) + 0.5) * 2 - 0.5)
+    np.testing.assert_allclose(out["mkeypoints1_orig"], [[1, 2], [9.5, 18.25]])
+    assert np.array_equal(out["keypoints0"], out["mkeypoints0"]) and out["mconf"].tolist() == pytest.approx([0.9, 0.4])
+    assert out["new_size0"].tolist() == [640, 480] and out["original_size0"].tolist() == [1280, 960]
+    # gray conversion + /255 of image 1 (no resize needed) and the 2x2 area resize of image 0 are the plain cv2 results
+    assert np.array_equal(out["image1"], (cv2.cvtColor(rgb1, cv2.COLOR_RGB2GRAY).astype(np.float32) / 255.0))
+    g0 = cv2.resize(cv2.cvtColor(rgb0, cv2.COLOR_RGB2GRAY).astype(np.float32), (640, 480), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(out["image0"], (g0 / 255.0).astype(np.float32))
+
+
+def test_verify_pairs_batched_and_oversized(dev):
+    """verify_pairs: many pairs through two estimator launches == one pair at a time; a set beyond one CTA's capacity
+    (LoFTR without a cap can return 16 k matches) still gets a model and a full-length mask."""
+    from imcui_b200.ui import utils as U
+    rng = np.random.default_rng(9)
+    Hm = np.array([[1.02, 0.03, 5.0], [-0.02, 0.98, -3.0], [1e-5, 2e-5, 1.0]])
+
+    def pair(n, outl=0.3):
+        x = rng.uniform([0, 0], [640, 480], (n, 2)).astype(np.float32)
+        q = np.c_[x, np.ones(n)] @ Hm.T
+        y = (q[:, :2] / q[:, 2:]).astype(np.float32) + rng.normal(0, 0.5, (n, 2)).astype(np.float32)
+        bad = rng.uniform(size=n) < outl
+        y[bad] = rng.uniform([0, 0], [640, 480], (int(bad.sum()), 2)).astype(np.float32)
+        return {"mkeypoints0_orig": x, "mkeypoints1_orig": y, "mconf": rng.uniform(size=n).astype(np.float32),
+                "image0_orig": np.zeros((480, 640, 3), np.uint8), "image1_orig": np.zeros((480, 640, 3), np.uint8)}, ~bad
+    preds, gts = zip(*[pair(n) for n in (300, 900, 5, 2, 14000)])
+    out = U.verify_pairs([dict(p) for p in preds], "B200_MAGSAC", 3.0, 0.9999, 10000)
+    for p, gt, n in zip(out, gts, (300, 900, 5, 2, 14000)):
+        if n < 8:
+            assert p["H"] is None and p["geom_info"] == {}
+            continue
+        assert p["H"].shape == (3, 3) and "Fundamental" in p["geom_info"] and "Homography" in p["geom_info"]
+        k = len(p["mmkeypoints0_orig"])
+        assert abs(k - int(gt.sum())) <= 0.06 * gt.sum(), (n, k, int(gt.sum()))
+        assert p["mmconf"].shape == (k,)
+    single = U.filter_matches(dict(preds[1]), "B200_MAGSAC", 3.0, 0.9999, 10000)
+    assert abs(len(single["mmkeypoints0_orig"]) - len(out[1]["mmkeypoints0_orig"])) <= 0.03 * 900

@@ -9,73 +9,70 @@ import torch
 from conftest import GOLDEN
 
 
-def test_preprocess_is_bit_identical_to_reference(golden):
-    """extract() pre-processing (gray, INTER_AREA force-resize, /255, dfactor alignment) == the tensors the
-    reference's own calls produced (stored as the golden SuperPoint inputs)."""
-    from imcui_b200.hloc import extract_features as ef
-    from imcui_b200.hloc.configs import confs_dict
-    g = golden("sp_real")
-    pre = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "force_resize": False, "width": 320, "height": 240,
-           **confs_dict["extractors"]["superpoint_max"]["preprocessing"]}
-    for i, name in enumerate(["02928139_3448003521", "17295357_9106075285"]):
-        rgb = np.load(GOLDEN / "data" / f"{name}.npz")["rgb"]
-        d = ef.preprocess(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY), SimpleNamespace(**pre), "cpu")
-        assert torch.equal(d["image"][0], torch.from_numpy(g["images"][i]))
-        assert tuple(d["size"]) == (640, 480) and tuple(d["original_size"]) == rgb.shape[:2][::-1]
+def test_preprocess_plan_equals_the_reference_size_logic():
+    """Output geometry of imw_preprocess (host arithmetic of the C ABI, no GPU needed) == the size logic of
+    extract_features.py:120-156 as restated by the oracle, incl. Python's round-half-even and the dfactor floor."""
+    from oracle import preprocess as op
+    from imcui_b200 import ops
+    for (h, w, c) in ((1063, 780, 3), (673, 1013, 3), (480, 640, 1), (1001, 1500, 3), (250, 1000, 1)):
+        for conf in ({"grayscale": True, "resize_max": 1024, "dfactor": 8}, {"grayscale": False, "resize_max": 500, "dfactor": 16},
+                     {"grayscale": True, "resize_max": 1600, "force_resize": True, "width": 640, "height": 480, "dfactor": 8},
+                     {"grayscale": True, "resize_max": 375, "dfactor": 1}):
+            frame = np.zeros((h, w, 3) if c == 3 else (h, w), np.uint8)
+            if c == 1 and not conf["grayscale"]:
+                continue
+            x, orig, size = op.preprocess(frame[:8, :8] if False else frame, conf) if h * w < 400000 else (None, None, None)
+            oc, oh, ow = ops.preprocess_plan(conf, h, w, c)
+            assert oc == (1 if (conf["grayscale"] or c == 1) else 3)
+            if x is not None:
+                assert (oc, oh, ow) == x.shape, (h, w, conf)
+            sc = conf["resize_max"] / max(h, w)
+            hh, ww = (int(round(h * sc)), int(round(w * sc))) if sc < 1.0 else (h, w)
+            if conf.get("force_resize"):
+                hh, ww = conf["height"], conf["width"]
+            assert (oh, ow) == (hh // conf["dfactor"] * conf["dfactor"], ww // conf["dfactor"] * conf["dfactor"])
 
 
-def test_resize_image_switches_to_linear_when_upsampling():
-    from imcui_b200.hloc.extract_features import resize_image
-    img = np.random.RandomState(0).rand(10, 12).astype(np.float32)
-    up = resize_image(img, (24, 20), "cv2_area")
-    assert np.array_equal(up, cv2.resize(img, (24, 20), interpolation=cv2.INTER_LINEAR))
+def test_drivers_refuse_cpu():
+    """extract / match_dense.match_images prepare images on the GPU: a CPU device raises instead of computing elsewhere."""
+    from imcui_b200.hloc import extract_features as ef, match_dense as md
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("anchor", torch.zeros(1))
+    rgb = np.zeros((48, 64, 3), np.uint8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ef.extract(Fake(), rgb, {"grayscale": True})
+    with pytest.raises(RuntimeError, match="CUDA"):
+        md.match_images(Fake(), rgb, rgb, {"grayscale": True}, device="cpu")
 
 
-def test_match_images_postprocessing_with_a_fake_matcher():
-    """match_images: valid mask, gather and the (k + 0.5) * s - 0.5 rescale (match_features.py:244-257)."""
+def test_pair_inputs_containers():
+    """match_features.pair_inputs: list / tuple / batched-tensor feature containers -> [1,N,2], [1,N], [1,D,N] (:207-234)."""
     from imcui_b200.hloc import match_features as mf
 
-    class Fake(torch.nn.Module):
-        def forward(self, data):
-            n = data["keypoints0"].shape[1]
-            m = torch.full((1, n), -1, dtype=torch.long)
-            m[0, 0], m[0, 2] = 1, 0
-            return {"matches0": m, "matching_scores0": torch.linspace(0, 1, n)[None], "stop": 3}
-
-    def feat(n, orig, size):
-        return {"keypoints": [torch.arange(2 * n, dtype=torch.float32).view(n, 2)], "scores": (torch.ones(n),),
-                "descriptors": [torch.zeros(4, n)], "image": torch.zeros(1, 1, 8, 8), "image_orig": np.zeros((2, 2, 3)),
-                "original_size": np.array(orig), "size": np.array(size)}
-    out = mf.match_images(Fake(), feat(3, (1280, 960), (640, 480)), feat(2, (640, 480), (640, 480)))
-    assert out["mkeypoints0"].tolist() == [[0, 1], [4, 5]] and out["mkeypoints1"].tolist() == [[2, 3], [0, 1]]
-    np.testing.assert_allclose(out["mkeypoints0_orig"], (np.array([[0, 1], [4, 5]]) + 0.5) * 2 - 0.5)
-    np.testing.assert_allclose(out["mkeypoints1_orig"], [[2, 3], [0, 1]])
-    assert out["mconf"].shape == (2,)
+    def feat(n, as_list):
+        k = torch.arange(2 * n, dtype=torch.float32).view(n, 2)
+        return {"keypoints": [k] if as_list else k[None], "scores": (torch.ones(n),), "descriptors": [torch.zeros(4, n)],
+                "image": torch.zeros(1, 1, 8, 8), "scales": torch.ones(1, n)}
+    d = mf.pair_inputs(feat(3, True), feat(2, False))
+    assert d["keypoints0"].shape == (1, 3, 2) and d["keypoints1"].shape == (1, 2, 2)
+    assert d["scores0"].shape == (1, 3) and d["descriptors1"].shape == (1, 4, 2) and "scales0" in d and "oris0" not in d
 
 
-def test_match_dense_postprocessing_with_a_fake_matcher():
-    """match_dense.match_images (reference :577-686): force-resize to 640x480, dfactor alignment, the swap-free output
-    keys, 'scores' adopted as mconf and the (k + 0.5) * s - 0.5 rescale with s = original / network size."""
-    from imcui_b200.hloc import match_dense as md
-    from imcui_b200.hloc.configs import confs_dict
-    seen = {}
-
-    class Fake(torch.nn.Module):
-        def forward(self, data):
-            seen["shape"] = (tuple(data["image0"].shape), tuple(data["image1"].shape))
-            return {"keypoints0": torch.tensor([[0.0, 0.0], [8.0, 16.0]]), "keypoints1": torch.tensor([[1.0, 2.0], [9.5, 18.25]]),
-                    "scores": torch.tensor([0.9, 0.4])}
-    rgb0 = np.random.RandomState(0).randint(0, 255, (960, 1280, 3), dtype=np.uint8)
-    rgb1 = np.random.RandomState(1).randint(0, 255, (480, 640, 3), dtype=np.uint8)
-    out = md.match_images(Fake(), rgb0, rgb1, confs_dict["matchers"]["loftr"]["preprocessing"], device="cpu")
-    assert seen["shape"] == ((1, 1, 480, 640), (1, 1, 480, 640))
-    assert out["scale0"].tolist() == [2.0, 2.0] and out["scale1"].tolist() == [1.0, 1.0]
-    np.testing.assert_allclose(out["mkeypoints0_orig"], (np.array([[0, 0], [8, 16]]) + 0.5) * 2 - 0.5)
-    np.testing.assert_allclose(out["mkeypoints1_orig"], [[1, 2], [9.5, 18.25]])
-    assert np.array_equal(out["keypoints0"], out["mkeypoints0"]) and out["mconf"].tolist() == pytest.approx([0.9, 0.4])
-    assert out["new_size0"].tolist() == [640, 480] and out["original_size0"].tolist() == [1280, 960]
-    # gray conversion + area resize + /255 of image 1 (no resize needed) is the plain cv2 result
-    assert np.array_equal(out["image1"], (cv2.cvtColor(rgb1, cv2.COLOR_RGB2GRAY).astype(np.float32) / 255.0))
+def test_set_null_pred_and_registry_parsing():
+    from imcui_b200.ui import utils as U
+    p = U.set_null_pred("KEYPOINT", {})
+    assert p["H"] is None and p["geom_info"] == {} and p["mmkeypoints0_orig"].size == 0      # reference ui/utils.py:382-398
+    out = U.filter_matches({"mkeypoints0_orig": np.zeros((3, 2)), "mkeypoints1_orig": np.zeros((3, 2)), "mconf": np.ones(3)})
+    assert out["H"] is None and out["geom_info"] == {}                                       # < 4 matches (:502-503)
+    zoo = U.get_matcher_zoo({"superpoint+mnn": {"matcher": "NN-mutual", "feature": "superpoint_max", "dense": False, "standalone": False},
+                             "loftr": {"matcher": "loftr", "dense": True, "standalone": True}})
+    assert zoo["superpoint+mnn"]["feature"]["model"]["name"] == "superpoint" and zoo["superpoint+mnn"]["matcher"]["model"]["name"] == "nearest_neighbor"
+    assert zoo["loftr"]["standalone"] and "feature" not in zoo["loftr"] and zoo["loftr"]["matcher"]["model"]["name"] == "loftr"
+    with pytest.raises(NotImplementedError):
+        U.proc_ransac_matches(np.zeros((9, 2)), np.zeros((9, 2)), "POSELIB")
 
 
 def test_loftr_weight_packing_layout():
@@ -125,20 +122,3 @@ def test_plugin_classes_keep_the_reference_contract():
         for k, v in r["default_conf"].items():
             assert cls.default_conf[k] == v, (key, k, cls.default_conf.get(k), v)
         assert set(cls.default_conf) - set(r["default_conf"]) <= engine_keys, (key, set(cls.default_conf) - set(r["default_conf"]))
-
-
-def test_api_pipeline_builds_from_the_registry_and_refuses_cpu():
-    """ImageMatchingAPI mirror: zoo entry -> conf dicts -> plugins through dynamic_load; the product path has no CPU
-    fallback, so a forward on a machine without CUDA raises instead of silently computing elsewhere."""
-    from imcui_b200.api import ImageMatchingAPI
-    from imcui_b200.ui.utils import get_matcher_zoo
-    zoo = get_matcher_zoo({"superpoint+mnn": {"matcher": "NN-mutual", "feature": "superpoint_max", "dense": False, "standalone": False}})
-    conf = zoo["superpoint+mnn"]
-    assert conf["feature"]["model"]["name"] == "superpoint" and conf["matcher"]["model"]["name"] == "nearest_neighbor"
-    api = ImageMatchingAPI(conf={**conf, "ransac": {"enable": False}}, device="cpu", max_keypoints=512)
-    assert type(api.extractor).__name__ == "SuperPoint" and type(api.matcher).__name__ == "NearestNeighbor"
-    assert api.extractor.conf["max_keypoints"] == 512 and api.extractor.conf["keypoint_threshold"] == 0.015   # core.py:78-96
-    rgb = np.load(GOLDEN / "data" / "02928139_3448003521.npz")["rgb"]
-    if not torch.cuda.is_available():
-        with pytest.raises(Exception, match="CUDA|cuda"):
-            api(rgb, rgb)

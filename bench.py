@@ -177,49 +177,58 @@ class Config2:
         self.dev, self.args, self.P = dev, args, args.pairs or self.default_pairs
         P = self.P
         host_only = dev is None                       # reference arm: no engine, only the few pairs the CPU leg needs
-        # the stream: NB batches of P pairs, seeds b*P .. b*P+P-1 (identical on every rank, dealt round-robin)
+        # the stream: NB batches of P pairs, seeds b*P .. b*P+P-1 (identical on every rank, dealt round-robin); decoded RGB
+        # frames [2P,480,640,3] uint8, slot 2p+side -- what the reference's extract() is handed (extract_features.py:106)
         self.h_batches = []
         for b in range(1 if host_only else NB):
             n = self.ref_pairs_per_step if host_only else P
             a, c = synth.make_pair_batch(range(b * P, b * P + n), H, W)
-            u8 = np.empty((2 * n, H, W), np.uint8)
-            u8[0::2], u8[1::2] = a, c
-            self.h_batches.append(torch.from_numpy(u8) if host_only else torch.from_numpy(u8).pin_memory())
+            g = np.empty((2 * n, H, W), np.uint8)
+            g[0::2], g[1::2] = a, c
+            rgb = synth.to_rgb(g)
+            self.h_batches.append(torch.from_numpy(rgb) if host_only else torch.from_numpy(rgb).pin_memory())
         if host_only:
             return
-        from imcui_b200.engine import PairEngine
+        from imcui_b200.engine import PairEngine, PairStream
+        from imcui_b200.hloc.configs import confs_dict
         lg_mode = 0 if args.fp32 else (2 if args.tf32 else 1)
+        self.pre = dict(confs_dict["extractors"]["superpoint_max"]["preprocessing"])     # grayscale, resize_max 1600, dfactor 8
         self.eng = PairEngine(dev, P, H, W, sp_conf={**SP_CONF, "tensor_cores": not (args.fp32 or args.sp_simt)},
-                              lg_conf={"use_tensor_cores": lg_mode})
-        self.d_batches = [hb.to(dev) for hb in self.h_batches]       # uint8, resident in HBM
+                              lg_conf={"use_tensor_cores": lg_mode}, frame_shape=(H, W, 3), pre_conf=self.pre)
+        self.stream = PairStream(self.eng)
+        self.record = self.eng.new_record()
+        self.d_batches = [hb.to(dev) for hb in self.h_batches]       # decoded uint8 frames, resident in HBM
         self.dtype = "f32" if args.fp32 else ("f32-equivalent: bf16x3 split tcgen05 convs (SuperPoint), " + ("single-TF32" if args.tf32 else "3xTF32 split") +
                                               " tcgen05 linears / attention / assignment (LightGlue), f32 detector post-processing")
-        self.last = None
 
     def step_device(self, b):
-        """inputs resident in HBM (uint8 frames) -> matches resident in HBM.  Returns per-pair match counts [P] int32."""
-        sp, lg = self.eng.match_device(self.eng.to_float(self.d_batches[b]))
-        self.last = (sp, lg)
-        return (lg["matches"][0::2] > -1).sum(1, dtype=torch.int32)
+        """decoded frames resident in HBM -> match records resident in HBM (pre-processing, SuperPoint, LightGlue, match gather).
+        Returns per-pair match counts [P] int32."""
+        return self.eng.match_frames_device(self.d_batches[b], self.record)["mcount"]
 
-    def step_host(self, b):
-        return self.eng.match_host(self.h_batches[b])
+    def e2e(self, batch_ids):
+        """the stream driver a match_from_paths-style caller uses: pinned host frames in, pinned host match records out,
+        H2D / compute / D2H double-buffered (engine.PairStream).  Returns the number of matches seen (forces the host read)."""
+        total = 0
+        for rec in self.stream.run(self.h_batches[b] for b in batch_ids):
+            total += int(rec["mcount"].sum())
+        return total
 
     @property
     def h2d_bytes(self):
-        return self.eng.h2d_bytes
+        return self.stream.h2d_bytes
 
     @property
     def d2h_bytes(self):
-        return self.eng.d2h_bytes
+        return self.stream.d2h_bytes
 
     def stats(self):
-        sp, lg = self.last
-        return {"mean_keypoints": float(sp["counts"][0].float().mean()), "mean_stop_layer": float(lg["stop"].float().mean())}
+        return {"mean_keypoints": float(self.record["n_kpts"].float().mean()), "mean_stop_layer": float(self.record["stop"].float().mean())}
 
     def workload(self, world):
         st = self.stats()
-        return {"workload": "SuperPoint+LightGlue, batch=64 synthetic 640x480 pairs per GPU (BASELINE configs[1])",
+        return {"workload": "SuperPoint+LightGlue, batch=64 synthetic 640x480 pairs per GPU (BASELINE configs[1]); each step starts from the decoded RGB frames "
+                            "(GPU gray conversion / normalisation = extract()'s pre-processing) and ends with the matched keypoints in original-frame coordinates",
                 "pairs_per_gpu": self.P, "max_keypoints": 1024, "weights": "superpoint_v1 + GIM SP-LightGlue (real)",
                 "lightglue": "depth_confidence 0.95, width_confidence 0.99, CUDA pruning threshold 1536 (reference CUDA semantics)",
                 **st, "stream": f"cycle of {NB} distinct batches dealt round-robin over ranks (seeds 0..{NB * self.P - 1})",
@@ -250,16 +259,21 @@ class Config2:
         from oracle import superpoint as osp
         from oracle.check import to_float
         ws = oracle.load_weights("superpoint_v1.pt")
-        img = to_float(self.h_batches[0][:1].numpy())
+        img = to_float(self._gray(0, 1)[:1])
         return lambda: osp.forward(ws, img, SP_CONF)
+
+    def _gray(self, first_pair, n_pairs):
+        """the reference's own first step on the host: cv2.cvtColor(RGB2GRAY) of the decoded frames (extract_features.py:159-162)"""
+        import cv2
+        rgb = self.h_batches[0][2 * first_pair: 2 * (first_pair + n_pairs)].numpy()
+        return np.stack([cv2.cvtColor(f, cv2.COLOR_RGB2GRAY) for f in rgb])
 
     def cpu_pairs(self, n_pairs, first=0):
         """The reference's CPU path (oracle port: same PyTorch fp32 graph as the reference modules, CPU semantics =
         pruning at every layer) on pairs [first, first + n_pairs) of stream batch 0.  Returns seconds."""
         from oracle import check
-        imgs = self.h_batches[0][2 * first: 2 * (first + n_pairs)].numpy()
         t0 = time.perf_counter()
-        check.oracle_pairs(imgs, SP_CONF, {"pruning_min_kpts": -1})
+        check.oracle_pairs(self._gray(first, n_pairs), SP_CONF, {"pruning_min_kpts": -1})
         return time.perf_counter() - t0
 
     cpu_sample_desc = "SuperPoint x2 + LightGlue per pair, torch CPU fp32, reference CPU semantics (early stop + pruning every layer)"
@@ -268,9 +282,10 @@ class Config2:
         """match-F1 of the engine (the timed defaults) vs the oracle with the same (CUDA) LightGlue semantics on the first
         n_pairs pairs of stream batch 0 -- BASELINE metric 'match-F1 vs ref' (SURVEY.md 8(d))."""
         from oracle import check
-        hm, _, hk, hc, hstop = self.eng.match_host(self.h_batches[0])
-        got = check.engine_pairs(hm.numpy(), hk.numpy(), hc.numpy(), hstop.numpy(), n_pairs)
-        ref = check.oracle_pairs(self.h_batches[0][: 2 * n_pairs].numpy(), SP_CONF)
+        self.eng.match_frames_device(self.d_batches[0], self.record)
+        sp, lg = self.eng.sp_out, self.eng.lg_out
+        got = check.engine_pairs(lg["matches"].cpu().numpy(), sp["keypoints"].cpu().numpy(), sp["counts"].cpu().numpy(), lg["stop"].cpu().numpy(), n_pairs)
+        ref = check.oracle_pairs(self._gray(0, n_pairs), SP_CONF)
         return check.summarize([check.compare_pair(g, r) for g, r in zip(got, ref)])
 
 
@@ -371,12 +386,11 @@ def main():
     stats = cfg.workload(world)
 
     # ---- end to end through the public host API (pinned host buffers in, host results out) --------
-    for g in range(2):
-        cfg.step_host(batch_of(g))
+    run_host = cfg.e2e if hasattr(cfg, "e2e") else (lambda ids: [cfg.step_host(b) for b in ids])
+    run_host([batch_of(g) for g in range(2)])
     barrier()
     t0 = time.perf_counter()
-    for k in range(K):
-        cfg.step_host(batch_of(2 + k))
+    run_host([batch_of(2 + k) for k in range(K)])
     barrier()
     e2e_rank = rank_times((time.perf_counter() - t0) * 1e3)
     e2e_value = world * P * K / (max(e2e_rank) / 1e3)

@@ -282,7 +282,7 @@ class Config4(_Base):
         # score_head.0, which writes the 128-channel full-resolution map once: 128 x H x W x 4 B out + the four pyramid levels in
         n_img = 2 * self.P
         by = (128 * 480 * 640 * 4 + (16 * 480 * 640 + 32 * 240 * 320 + 64 * 60 * 80 + 128 * 15 * 20) * 4 + 8 * 480 * 640 * 4) / 1e9
-        return roofline_from_sites(prof, ["ak_fuse"], by * n_img, "GB/s", "hbm",
+        return roofline_from_sites(prof, ["ak_fuse_kernel"], by * n_img, "GB/s", "hbm",
                                    "ak_fuse_kernel (ALIKED: four 1x1 heads + x2/x8/x32 bilinear upsampling + concat + L2 norm + score_head.0; the 128-channel map is written once)",
                                    note="algorithmic bytes = 128-ch fp32 feature map written + 8-ch score features written + pyramid levels read")
 

@@ -601,14 +601,14 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     const int SB = (n_images - i0) < AK_SUB_BATCH ? (n_images - i0) : AK_SUB_BATCH;
     const long long P = (long long)SB * Hp * Wp;
     ak_pad_image_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(images + (long long)i0 * channels * H * W, b.img4, SB, channels, H, W, Hp, Wp, pt, pl);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_pad_image_kernel");
     // block1 (ConvBlock 3 -> 16 -> 16)
     RUN((ak_conv<16, 4>(ak_args(b.img4, SB, Hp, Wp, 4, w.b1c1_w, w.b1c1_b, b.mid, 16, 16, 1), st)));
     RUN((ak_conv<16, 16>(ak_args(b.mid, SB, Hp, Wp, 16, w.b1c2_w, w.b1c2_b, b.x1, 16, 16, 1), st)));
     // block2 (ResBlock 16 -> 32 at 1/2)
     const int H2 = Hp / 2, W2 = Wp / 2, H8 = Hp / 8, W8 = Wp / 8, H32 = Hp / 32, W32 = Wp / 32;
     ak_avgpool_kernel<2><<<(unsigned)((P / 4 * 16 + 255) / 256), 256, 0, st>>>(b.x1, b.p1, SB, H2, W2, 16);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_avgpool_kernel<2>");
     RUN((ak_conv<32, 16>(ak_args(b.p1, SB, H2, W2, 16, w.b2c1_w, w.b2c1_b, b.t2, 32, 32, 1), st)));
     {
       AkConvArgs a = ak_args(b.t2, SB, H2, W2, 32, w.b2c2_w, w.b2c2_b, b.x2, 32, 32, 1);
@@ -617,7 +617,7 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     }
     // block3 (deformable ResBlock 32 -> 64 at 1/8)
     ak_avgpool_kernel<4><<<(unsigned)((P / 64 * 32 + 255) / 256), 256, 0, st>>>(b.x2, b.p2, SB, H8, W8, 32);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_avgpool_kernel<4>");
     {
       AkConvArgs o = ak_args(b.p2, SB, H8, W8, 32, w.b3o1_w, w.b3o1_b, b.off, 24, 18, 2);
       o.maxoff = (float)(H8 > W8 ? H8 : W8) / 4.0f;
@@ -632,7 +632,7 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     }
     // block4 (deformable ResBlock 64 -> 128 at 1/32)
     ak_avgpool_kernel<4><<<(unsigned)((P / 1024 * 64 + 255) / 256), 256, 0, st>>>(b.x3, b.p3, SB, H32, W32, 64);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_avgpool_kernel<4>");
     {
       AkConvArgs o = ak_args(b.p3, SB, H32, W32, 64, w.b4o1_w, w.b4o1_b, b.off, 24, 18, 2);
       o.maxoff = (float)(H32 > W32 ? H32 : W32) / 4.0f;
@@ -647,13 +647,13 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     }
     // aggregation heads + fused upsample / concat / normalise / score_head.0
     ak_conv1x1_selu_kernel<<<(unsigned)((P / 4 * 32 + 255) / 256), 256, 0, st>>>(b.x2, w.conv2_w, b.a2, P / 4, 32);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_conv1x1_selu_kernel");
     ak_conv1x1_selu_kernel<<<(unsigned)((P / 64 * 32 + 255) / 256), 256, 0, st>>>(b.x3, w.conv3_w, b.a3, P / 64, 64);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_conv1x1_selu_kernel");
     ak_conv1x1_selu_kernel<<<(unsigned)((P / 1024 * 32 + 255) / 256), 256, 0, st>>>(b.x4, w.conv4_w, b.a4, P / 1024, 128);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_conv1x1_selu_kernel");
     ak_fuse_kernel<<<148 * 16, 256, 0, st>>>(b.x1, w.conv1_w, b.a2, b.a3, b.a4, w.s0_w, b.feat, b.s0, SB, Hp, Wp, H, W, pt, pl);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_fuse_kernel");
     // score head tail (3x3 8 -> 4, 4 -> 4, 4 -> 1 + sigmoid, cropped to the unpadded window)
     RUN((ak_conv<4, 8>(ak_args(b.s0, SB, Hp, Wp, 8, w.s2_w, nullptr, b.s1, 4, 4, 1), st)));
     RUN((ak_conv<4, 4>(ak_args(b.s1, SB, Hp, Wp, 4, w.s4_w, nullptr, b.s2, 4, 4, 1), st)));
@@ -669,7 +669,7 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     const float thr = topk_mode ? 0.f : conf->detection_threshold;
     if (!topk_mode) {
       ak_threshold_kernel<<<SB, 1024, 0, st>>>(b.score, b.nms, b.thr, H, W, conf->nms_radius, thr, mean_mode ? 1 : 0);
-      IMW_CHECK_LAUNCH();
+      IMW_CHECK_LAUNCH_T("ak_threshold_kernel");
     }
     RUN(sp_select(b.nms, b.keys, (int)sp_select_key_cap(H, W), b.kint, scores + (long long)i0 * cap, b.sel_counts, SB, H, W, thr,
                   conf->nms_radius, topk_mode ? conf->max_num_keypoints : n_limit, cap, st, topk_mode ? nullptr : b.thr));
@@ -677,12 +677,12 @@ extern "C" int imw_aliked_forward(const imw_aliked_weights* Wt, const imw_aliked
     IMW_CHECK_CUDA(cudaMemcpyAsync(counts + n_images + i0, b.sel_counts + SB, sizeof(int) * SB, cudaMemcpyDeviceToDevice, st));
     ak_dkd_refine_kernel<<<dim3(ceil_div(cap, 256), SB), 256, 0, st>>>(b.score, b.kint, b.sel_counts, b.kp_norm, keypoints + (long long)i0 * cap * 2,
                                                                        scores + (long long)i0 * cap, H, W, cap, conf->nms_radius);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_dkd_refine_kernel");
     // SDDH
     AkSddhArgs sa{b.feat, H, W, b.kp_norm, b.sel_counts, cap, w.sd_off0_w, w.sd_off0_b, w.sd_off2_w, w.sd_off2_b, w.sd_sf_w, w.sd_agg,
                   descriptors + (long long)i0 * cap * 128};
     ak_sddh_kernel<<<dim3(ceil_div(cap, SD_TK), SB), 256, (SD_TK * SD_M * SD_C + SD_TK * SD_C + 3 * SD_TK * 32) * sizeof(float), st>>>(sa);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ak_sddh_kernel");
   }
   return IMW_OK;
 }

@@ -379,7 +379,7 @@ extern "C" int imw_nearest_neighbor(int P, int cap, int dim, const float* desc, 
   if (use_tensor_cores && tc_simreduce_ok(sa)) { if (int e = launch_tc_simreduce(sa, 2 * P, op, st)) return e; }
   else IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, op, st));
   nn_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.m, b.f0, counts, matches0, scores0, cap, do_mutual_check);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("nn_finish_kernel");
   return IMW_OK;
 }
 
@@ -392,7 +392,7 @@ extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, cons
   matcher_carve(ws, b, P, cap);
   if (ws.overflow) { imw_set_error("imw_dual_softmax: workspace too small"); return IMW_ERR_WORKSPACE; }
   normalize_rows_kernel<<<dim3(ceil_div(cap, 8), 2 * P), 256, 0, st>>>(desc, b.norm, counts, cap, dim);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("normalize_rows_kernel");
   SimArgs sa{b.norm, cap, dim, dim, counts, nullptr};
   if (use_tensor_cores && tc_simreduce_ok(sa)) {
     if (int e = launch_tc_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st)) return e;
@@ -402,6 +402,6 @@ extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, cons
     IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st));
   }
   dsm_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.bv, b.bj, counts, matches0, scores0, cap, match_threshold);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("dsm_finish_kernel");
   return IMW_OK;
 }

@@ -38,6 +38,13 @@ void imw_prof_mark(const char* site, int line, cudaStream_t st);
     IMW_COUNT_LAUNCH(st);                \
     IMW_CHECK_CUDA(cudaGetLastError());  \
   } while (0)
+// same, with the kernel's name as the profile key (for launches written inline in a long forward function)
+#define IMW_CHECK_LAUNCH_T(tag)                                 \
+  do {                                                          \
+    ++g_imw_launches;                                           \
+    if (g_imw_prof_on) imw_prof_mark(tag, __LINE__, st);        \
+    IMW_CHECK_CUDA(cudaGetLastError());                         \
+  } while (0)
 
 #define IMW_REQUIRE(cond, ...)                                                            \
   do {                                                                                    \

@@ -401,7 +401,7 @@ int imw_attention_simt(const float* q, const float* k, const float* v, float* ct
   const size_t at_smem = (size_t)4 * 64 * ATP * sizeof(float);
   IMW_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem));
   attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, slots), 256, at_smem, st>>>(q, k, v, ctx, counts, skip, cap, scale, cross);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("attn_kernel");
   return IMW_OK;
 }
 
@@ -456,13 +456,13 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   int cur = 0;
 
   init_state_kernel<<<ceil_div(P, 128), 128, 0, st>>>(counts_in, b.counts, b.counts0, b.done, b.empty, stop, b.cnt, P, L);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("init_state_kernel");
   // prune output: 1 (+1 per surviving pruning step) when pruning is enabled, n_layers otherwise (:617-619)
   init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(W->input_dim == D ? desc : nullptr, b.xm[0], b.ind[0], matches, mscores, prune, b.counts, cap,
                                                                 prune_semantics ? 1 : L);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("init_tokens_kernel");
   posenc_kernel<<<S, 256, 0, st>>>(kpts, b.counts, W->posenc_wr, b.enc[0], cap);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("posenc_kernel");
 
   const size_t at_smem = (size_t)4 * 64 * ATP * sizeof(float);
   IMW_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem));
@@ -496,7 +496,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
       return launch_tc_attn(q, k, v, a, st);
     }
     attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, S), 256, at_smem, st>>>(q, k, v, b.ctx, b.counts, b.done, cap, scale, cross);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("attn_kernel");
     return IMW_OK;
   };
   auto gemm = [&](const float* A, long long sA, int lda, const float* Wt, int N, int K) {
@@ -509,7 +509,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     float* xm = b.xm[cur];
     if (int e = linear(xm, 512, blk.ffn0_w, 512, 512, 512, EpiStore{b.h, 512, sXM, blk.ffn0_b, 0}, b.done, nullptr)) return e;
     ln_gelu_kernel<<<rows8, 256, 0, st>>>(b.h, b.counts, b.done, blk.ln_g, blk.ln_b, cap);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("ln_gelu_kernel");
     if (int e = linear(b.h, 512, blk.ffn3_w, D, D, 512, EpiStore{xm, 512, sXM, blk.ffn3_b, 1}, b.done, nullptr)) return e;
     return IMW_OK;
   };
@@ -536,17 +536,17 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     const float thr = lg_conf_threshold(i, L);
     if (do_stop) {
       token_logit_kernel<<<rows8, 256, 0, st>>>(xm, 512, b.counts, b.done, W->token_w, W->token_b, nullptr, i, b.conf, 1, thr, b.cnt, cap);
-      IMW_CHECK_LAUNCH();
+      IMW_CHECK_LAUNCH_T("token_logit_kernel");
       exit_kernel<<<ceil_div(P, 128), 128, 0, st>>>(b.cnt, b.done, stop, b.counts0, P, conf->depth_confidence, i);
-      IMW_CHECK_LAUNCH();
+      IMW_CHECK_LAUNCH_T("exit_kernel");
     }
     if (do_prune) {
       token_logit_kernel<<<rows8, 256, 0, st>>>(xm, 512, b.counts, b.done, W->match_w, W->match_b, nullptr, i, b.mscore, 1, 0.f, nullptr, cap);
-      IMW_CHECK_LAUNCH();
+      IMW_CHECK_LAUNCH_T("token_logit_kernel");
       prune_kernel<<<S, 1024, 0, st>>>(b.xm[cur], b.xm[cur ^ 1], b.enc[cur], b.enc[cur ^ 1], b.ind[cur], b.ind[cur ^ 1], b.conf,
                                        b.mscore, b.counts, b.done, prune, cap, conf->pruning_min_kpts, conf->width_confidence, thr,
                                        do_stop ? 1 : 0);
-      IMW_CHECK_LAUNCH();
+      IMW_CHECK_LAUNCH_T("prune_kernel");
       cur ^= 1;
     }
   }
@@ -558,9 +558,9 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     g.skip = b.empty; g.wsel_minus1 = stop; g.wsel_shift = 1; g.strideWsel = (long long)D * D;
     IMW_CHECK_CUDA(launch_gemm(g, S, EpiFinalProj{b.md, cap, W->final_b, stop}, st));
     token_logit_kernel<<<rows8, 256, 0, st>>>(xm, 512, b.counts, b.empty, W->match_w, W->match_b, stop, 0, b.zl, 0, 0.f, nullptr, cap);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("token_logit_kernel");
     logsigmoid_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.zl, b.counts, b.empty, cap);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("logsigmoid_kernel");
     SimArgs sa{b.md, cap, D, D, b.counts, b.empty};
     if (use_tc && tc_simreduce_ok(sa)) {  // 3xTF32 similarity tiles in TMEM, same reduction functors
       if (int e = launch_tc_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st)) return e;
@@ -571,7 +571,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
     }
     match_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.best_v, b.best_j, b.counts, b.ind[cur], b.empty, matches, mscores,
                                                               cap, conf->filter_threshold);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("match_kernel");
   }
   return IMW_OK;
 }
@@ -610,11 +610,11 @@ extern "C" int imw_debug_attention(const float* q, const float* k, const float* 
     const size_t at_smem = (size_t)4 * 64 * ATP * sizeof(float);
     IMW_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem));
     attn_kernel<<<dim3(ceil_div(cap, AT), HEADS, slots), 256, at_smem, st>>>(q, k, v, ctx, counts, skip, cap, scale, cross);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("attn_kernel");
     return IMW_OK;
   }
   attn_prep_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, k, v, qp, kp, vtp, n, cap);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("attn_prep_planes_kernel");
   TcAttnArgs a{ctx, counts, skip, cap, slots, scale, cross, (long long)slots * HEADS * cap, (long long)slots * HEADS * HD};
   return launch_tc_attn(qp, kp, vtp, a, st);
 }

@@ -499,7 +499,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   {
     dim3 grid(ceil_div(w2, 16) * ceil_div(h2, 16), 1, S);
     lf_conv1_kernel<<<grid, 256, 0, st>>>(images, bb.conv1_w, bb.conv1_b, (__nv_bfloat16*)b.pa, S, H, Wd);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_conv1_kernel");
   }
   auto conv = [&](const void* in, const imw_loftr_conv& c, const void* res, void* out, int Hin, int Win, int act, int f32) {
     return tc_conv_general(in, c.w, c.b, res, out, S, Hin, Win, c.cin, c.cout, c.ksize, c.stride, act, f32, st);
@@ -530,7 +530,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     const size_t n = (size_t)S * h4 * w4 * 256;
     lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pe2, (const __nv_bfloat16*)x3_out,
                                                                        (__nv_bfloat16*)b.pb, S, h4, w4, 256);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
   }
   RUN(conv(b.pb, bb.l2_out2[0], nullptr, b.pe2, h4, w4, 2, 0));  RUN(conv(b.pe2, bb.l2_out2[1], nullptr, x2a, h4, w4, 0, 0));  // x2_out -> pd
   RUN(conv(b.pa, bb.l1_out, nullptr, b.pb, h2, w2, 0, 0));                // layer1_outconv(x1) -> pb (256 padded)
@@ -538,19 +538,19 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     const size_t n = (size_t)S * h2 * w2 * 256;
     lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pb, (const __nv_bfloat16*)x2a,
                                                                        (__nv_bfloat16*)b.pc, S, h2, w2, 256);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
   }
   RUN(conv(b.pc, bb.l1_out2[0], nullptr, b.pb, h2, w2, 2, 0));   RUN(conv(b.pb, bb.l1_out2[1], nullptr, b.ff, h2, w2, 0, 1));  // fine map fp32
   if (dbg_backbone_c) IMW_CHECK_CUDA(cudaMemcpyAsync(dbg_backbone_c, b.fc, sizeof(float) * (size_t)S * L * CD, cudaMemcpyDeviceToDevice, st));
 
   // ---------------- coarse transformer -----------------------------------------------------------------------------------
   lf_tokens_kernel<<<dim3((unsigned)(((size_t)L * CD + 255) / 256), S), 256, 0, st>>>(b.fc, W->pos_enc, b.xm, L, cap);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("lf_tokens_kernel");
   lf_fill_int_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.cntL, S, L);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("lf_fill_int_kernel");
   // per-slot skip masks for the sequential cross layers: skip_even[z] = (z even), skip_odd[z] = (z odd)
   lf_parity_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.skip_even, b.skip_odd, S);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("lf_parity_kernel");
   const int use_tc = conf->use_tensor_cores;
   const int kv_split = LF_KV_SPLIT;
   auto tok_linear = [&](const float* A, int lda, const float* Wt, int N, int K, auto epi, const int* skip) -> int {
@@ -571,14 +571,14 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     // projections for every slot (q of the updated slots, k/v of their sources)
     if (int e = tok_linear(b.xm, 512, ly.qkv_w, 3 * CD, CD, EpiLinAttnQKV{b.q, b.k, b.v, CD, (long long)cap * CD, (float)L}, nullptr)) return e;
     la_kv_kernel<32><<<dim3(S, NH, kv_split), 1024, 0, st>>>(b.k, b.v, b.kv_part, b.ksum_part, nullptr, L, (long long)cap * CD, CD, skip_q, kv_xor);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("la_kv_kernel<32>");
     la_kv_reduce_kernel<<<ceil_div(S * NH * 32 * 32, 256), 256, 0, st>>>(b.kv_part, b.kv, (long long)S * NH, 32 * 32, kv_split, skip_q, NH);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("la_kv_reduce_kernel");
     la_kv_reduce_kernel<<<ceil_div(S * NH * 32, 256), 256, 0, st>>>(b.ksum_part, b.ksum, (long long)S * NH, 32, kv_split, skip_q, NH);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("la_kv_reduce_kernel");
     la_apply_kernel<32><<<dim3(ceil_div(L, 8 * 16), S), 256, 0, st>>>(b.q, b.kv, b.ksum, b.msg, nullptr, L, (long long)cap * CD, CD, CD,
                                                                     (long long)cap * CD, skip_q, kv_xor);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("la_apply_kernel<32>");
     if (int e = tok_linear(b.msg, CD, ly.merge_w, CD, CD, EpiPlain{b.tmp, CD, (long long)cap * CD, 0, nullptr}, skip_q)) return e;
     lf_layernorm_kernel<CD><<<dim3(ceil_div(L, 8), S), 256, 0, st>>>(b.tmp, CD, (long long)cap * CD, b.xm + CD, 512, (long long)cap * 512,
                                                                    ly.norm1_g, ly.norm1_b, nullptr, L, skip_q, 0);
@@ -614,15 +614,15 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     int* j_ids = b.fcnt + (size_t)P * mcap;
     lf_coarse_select_kernel<<<P, 1024, 0, st>>>(b.best_v, b.best_j, L, cap, hc, wc, conf->match_threshold, conf->border_rm, i_ids, j_ids,
                                                 confidence, counts, mcap);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_coarse_select_kernel");
     // ---------------- fine level ---------------------------------------------------------------------------------------
     const int stride_f = h2 / hc;
     lf_gather_windows_kernel<<<dim3(mcap, 2, P), FD, 0, st>>>(b.ff, i_ids, j_ids, counts, b.U, h2, w2, wc, stride_f, mcap, P);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_gather_windows_kernel");
     lf_gather_coarse_kernel<<<dim3(mcap, 2, P), CD, 0, st>>>(b.xm, i_ids, j_ids, counts, b.G, cap, mcap, P);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_gather_coarse_kernel");
     lf_scale_counts_kernel<<<ceil_div(2 * P, 128), 128, 0, st>>>(counts, b.rows25, P);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_scale_counts_kernel");
     const int G2 = 2 * P;  // (side, pair) groups of the fine stage: g = side * P + p
     // ctx = down_proj(coarse feats) (fine_preprocess.py:51-53), then its share of merge_feat: Wm[:, 128:] ctx + b.
     // All mcap rows are computed (rows beyond the match count are never read back).
@@ -658,11 +658,11 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
         la_kv_kernel<16><<<dim3((unsigned)(P * mcap), NH), 256, 0, st>>>(b.fk + (long long)src * P * fgs * FD, b.fv + (long long)src * P * fgs * FD,
                                                                        b.fkv + (long long)side * P * mcap * NH * 256, b.fksum + (long long)side * P * mcap * NH * 16,
                                                                        nullptr, 25, 25LL * FD, FD, nullptr, 0);
-        IMW_CHECK_LAUNCH();
+        IMW_CHECK_LAUNCH_T("la_kv_kernel<16>");
         la_apply_kernel<16><<<dim3(2, (unsigned)(P * mcap)), 256, 0, st>>>(b.fq + (long long)side * P * fgs * FD, b.fkv + (long long)side * P * mcap * NH * 256,
                                                                         b.fksum + (long long)side * P * mcap * NH * 16, b.fmsg + (long long)side * P * fgs * FD,
                                                                         nullptr, 25, 25LL * FD, FD, FD, 25LL * FD, nullptr, 0);
-        IMW_CHECK_LAUNCH();
+        IMW_CHECK_LAUNCH_T("la_apply_kernel<16>");
       }
       if (int e = fine_linear(b.fmsg, FD, ly.merge_w, FD, FD, EpiPlain{b.ftmp + (long long)q_lo * P * fgs * FD, FD, fgs * FD, 0, nullptr}, q_lo, q_hi)) return e;
       lf_layernorm_kernel<FD><<<dim3(ceil_div(mcap * 25, 8), (q_hi - q_lo) * P), 256, 0, st>>>(
@@ -684,7 +684,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     }
     lf_fine_match_kernel<<<dim3(ceil_div(mcap, 8), P), 256, 0, st>>>(b.fx, i_ids, j_ids, counts, keypoints0, keypoints1, wc, (float)H / hc,
                                                                     (float)H / h2, mcap, P);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("lf_fine_match_kernel");
   }
 #undef RUN
   return IMW_OK;

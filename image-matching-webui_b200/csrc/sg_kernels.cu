@@ -217,12 +217,12 @@ extern "C" int imw_superglue_forward(const imw_sg_weights* W, const imw_sg_conf*
   const long long sXM = (long long)cap * 512;
 
   sg_state_kernel<<<ceil_div(P, 128), 128, 0, st>>>(counts, b.empty, b.mcnt, b.ncnt, P);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sg_state_kernel");
   sg_init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(desc, b.xm, matches, mscores, counts, cap);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sg_init_tokens_kernel");
   // ---- keypoint encoder (superglue.py:75-84): 3 -> 32 -> 64 -> 128 -> 256 -> 256, fp32 CUDA cores (tiny)
   sg_kenc_input_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(kpts, scores, counts, image_wh, b.kin, cap);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sg_kenc_input_kernel");
   {
     const int dims[6] = {16, 32, 64, 128, 256, 256};
     const float* in = b.kin;
@@ -295,17 +295,17 @@ extern "C" int imw_superglue_forward(const imw_sg_weights* W, const imw_sg_conf*
   IMW_CHECK_CUDA(cudaMemsetAsync(b.vv, 0, sizeof(float) * (size_t)P * (cap + 1), st));
   for (int it = 0; it < conf->sinkhorn_iterations; it++) {
     sk_row_kernel<<<dim3(ceil_div(cap + 1, 8), P), 256, 0, st>>>(sk);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("sk_row_kernel");
     sk_col_kernel<<<dim3(ceil_div(cap + 1, 32), P), 256, 0, st>>>(sk);
-    IMW_CHECK_LAUNCH();
+    IMW_CHECK_LAUNCH_T("sk_col_kernel");
   }
   if (conf->sinkhorn_iterations == 0) IMW_CHECK_CUDA(cudaMemsetAsync(b.u, 0, sizeof(float) * (size_t)P * (cap + 1), st));
   sk_rowmax_kernel<<<dim3(ceil_div(cap, 8), P), 256, 0, st>>>(sk, b.best_v, b.best_j);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sk_rowmax_kernel");
   sk_colmax_kernel<<<dim3(ceil_div(cap, 32), P), 256, 0, st>>>(sk, b.best_v, b.best_j);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sk_colmax_kernel");
   sg_match_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.best_v, b.best_j, counts, b.empty, matches, mscores, cap,
                                                                conf->match_threshold);
-  IMW_CHECK_LAUNCH();
+  IMW_CHECK_LAUNCH_T("sg_match_kernel");
   return IMW_OK;
 }

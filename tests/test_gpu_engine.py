@@ -103,3 +103,38 @@ def test_engine_device_path_equals_host_path(dev, stream):
     torch.cuda.synchronize()
     assert torch.equal(lg["matches"].cpu(), hm) and torch.equal(lg["stop"].cpu(), hstop)
     assert torch.equal(sp["keypoints"].cpu(), hk) and torch.equal(sp["counts"].cpu(), hc)
+
+
+def test_pair_stream_from_rgb_frames_equals_the_registry_path(dev, stream):
+    """PairStream (double-buffered H2D / compute / D2H over three streams, buffers reused every other batch) on decoded RGB
+    frames == the plugin path one pair at a time (extract -> match_images) on the same frames: identical matched keypoints
+    in original-frame coordinates; and batch i's record is not disturbed by batches i+1, i+2 in flight."""
+    from imcui_b200.engine import PairEngine, PairStream
+    from imcui_b200.hloc import extract_features, match_features
+    from imcui_b200.ui import utils as U
+    from imcui_b200.utils import synth
+    imgs, _ = stream
+    P, NBATCH = 2, 5
+    rgb = synth.to_rgb(imgs[: 2 * P * NBATCH])                                     # [20,480,640,3]
+    pre = {"grayscale": True, "resize_max": 1600, "dfactor": 8}
+    eng = PairEngine(dev, P, 480, 640, frame_shape=(480, 640, 3), pre_conf=pre)
+    batches = [torch.from_numpy(rgb[2 * P * b: 2 * P * (b + 1)]).pin_memory() for b in range(NBATCH)]
+    recs = []
+    for rec in PairStream(eng).run(iter(batches)):
+        recs.append({k: v.clone() for k, v in rec.items()})
+    assert len(recs) == NBATCH
+    conf = U.get_matcher_zoo({"x": {"matcher": "superpoint-lightglue", "feature": "superpoint_max", "dense": False, "standalone": False}})["x"]
+    ext, mat = U.get_feature_model(conf["feature"], dev), U.get_model(conf["matcher"], dev)
+    ext.conf.update(SP_CONF)
+    for b in (0, 3, 4):
+        for p in range(P):
+            f0 = extract_features.extract(ext, rgb[2 * (P * b + p)], pre)
+            f1 = extract_features.extract(ext, rgb[2 * (P * b + p) + 1], pre)
+            ref = match_features.match_images(mat, f0, f1)
+            n = int(recs[b]["mcount"][p])
+            a = {tuple(r) for r in np.concatenate([recs[b]["mkpts0_orig"][p, :n].numpy(), recs[b]["mkpts1_orig"][p, :n].numpy()], 1).tolist()}
+            r = {tuple(r) for r in np.concatenate([ref["mkeypoints0_orig"], ref["mkeypoints1_orig"]], 1).tolist()}
+            f1s = 2 * len(a & r) / max(len(a) + len(r), 1)
+            print(f"[stream] batch {b} pair {p}: {n} matches, F1 vs plugin path {f1s:.4f}")
+            assert f1s >= 0.995, (b, p, f1s)      # single-pair plugin call vs batch-of-2 engine: same kernels, same decisions
+            assert int(recs[b]["n_kpts"][2 * p]) == len(ref["keypoints0"])

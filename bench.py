@@ -198,7 +198,7 @@ class Config2:
         self.stream = PairStream(self.eng)
         self.record = self.eng.new_record()
         self.d_batches = [hb.to(dev) for hb in self.h_batches]       # decoded uint8 frames, resident in HBM
-        self.dtype = "f32" if args.fp32 else ("f32-equivalent: bf16x3 split tcgen05 convs (SuperPoint), " + ("single-TF32" if args.tf32 else "3xTF32 split") +
+        self.dtype = "f32" if args.fp32 else ("f32-equivalent: split-fp16 (2 planes, 3 products) tcgen05 convs (SuperPoint), " + ("single-TF32" if args.tf32 else "3xTF32 split") +
                                               " tcgen05 linears / attention / assignment (LightGlue), f32 detector post-processing")
 
     def step_device(self, b):
@@ -248,8 +248,8 @@ class Config2:
             except Exception:
                 pass
             return roofline_from_sites(prof, ["tc_conv1ab_fused"], (SP_LAYER_GFLOP["conv1a"] + SP_LAYER_GFLOP["conv1b"]) * n_img, "TFLOP/s", "tensor",
-                                       "tc_conv3x3_c64_kernel<fused conv1a> (SuperPoint conv1a 1->64 + conv1b 64->64 @480x640, tcgen05 bf16x3 split = fp32-equivalent)",
-                                       note="split precision: six bf16 partial products per fp32-equivalent product (issued as four MMAs over N-concatenated weight planes): tensor-pipe FLOP/s = 6 x achieved",
+                                       "tc_conv3x3_c64_kernel<fused conv1a> (SuperPoint conv1a 1->64 + conv1b 64->64 @480x640, tcgen05 split-fp16 = fp32-equivalent)",
+                                       note="split precision: three fp16 partial products per fp32-equivalent product (issued as two MMAs over N-concatenated weight planes): tensor-pipe FLOP/s = 3 x achieved",
                                        traffic=traffic)
         return roofline_from_sites(prof, ["sp_conv3x3"], 0.0, "TFLOP/s", "tensor", "conv3x3_nhwc_kernel (fp32 CUDA cores)")
 

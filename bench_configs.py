@@ -128,7 +128,7 @@ class Config3(_Base):
     workload_desc = ("LoFTR (ResNet-FPN 8/2, 4x(self,cross) linear-attention coarse transformer, dual-softmax coarse matching, fine refinement), "
                      "batch=32 synthetic 1024x1024 grayscale pairs per GPU (BASELINE configs[2]); seeded random weights (no LoFTR checkpoint "
                      "offline), coarse threshold lowered so that the fine stage is loaded")
-    dtype = "f32-equivalent: bf16x3 split tcgen05 convs (backbone), 3xTF32 tcgen05 linears / coarse similarity, f32 linear attention"
+    dtype = "f32-equivalent: split-fp16 tcgen05 convs (backbone), 3xTF32 tcgen05 linears / coarse similarity, f32 linear attention"
     HW = 1024
     THR = 1e-9
     cpu_sample_desc = "SE2LoFTR module restated (oracle/loftr.py), torch CPU fp32, one 1024x1024 pair (materialises the 1.07 GB confidence matrix)"
@@ -180,8 +180,8 @@ class Config3(_Base):
     def roofline(self, prof):
         # all tcgen05 implicit-GEMM conv launches of the ResNet-FPN backbone: 1.014 TFLOP / image minus the 7x7 stem (3.3 GFLOP, CUDA cores)
         return roofline_from_sites(prof, ["launch_conv_t"], (1014.0 - 3.3) * 2 * self.P, "TFLOP/s", "tensor",
-                                   "tc_conv3x3_kernel<BN,KS,RES> (LoFTR ResNet-FPN backbone @1024x1024: every 3x3 / 1x1 conv, tcgen05 bf16x3 split = fp32-equivalent)",
-                                   note="split precision: six bf16 partial products per fp32-equivalent product; 196-channel layers zero-padded to 256 (padding FLOPs not counted)")
+                                   "tc_conv3x3_kernel<BN,KS,RES> (LoFTR ResNet-FPN backbone @1024x1024: every 3x3 / 1x1 conv, tcgen05 split-fp16 = fp32-equivalent)",
+                                   note="split precision: three fp16 partial products per fp32-equivalent product; 196-channel layers zero-padded to 256 (padding FLOPs not counted)")
 
     def cpu_unit(self):
         from oracle import loftr as ol
@@ -319,7 +319,7 @@ class Config1(_Base):
     workload_desc = ("the reference's CPU-runnable case (tests/test_basic.py `test_one`, BASELINE configs[0]): tests/data pair (780x1063 and "
                      "1013x673 RGB JPEGs) -> RGB2GRAY, INTER_AREA force-resize to 640x480 -> SuperPoint (nms 3, thr 0.015, max 1024) -> mutual NN "
                      "-> MAGSAC F + H 3 px / 0.9999 / 10000; ONE pair per step (latency-bound by construction)")
-    dtype = "f32-equivalent: bf16x3 split tcgen05 convs, 3xTF32 tcgen05 similarity, f64 MAGSAC++ solvers"
+    dtype = "f32-equivalent: split-fp16 tcgen05 convs, 3xTF32 tcgen05 similarity, f64 MAGSAC++ solvers"
     cpu_sample_desc = "cv2 pre-processing + SuperPoint x2 + NearestNeighbor (oracle ports, torch CPU fp32) + cv2 USAC_MAGSAC F and H"
     SP = {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4}
     PRE = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "force_resize": True, "width": 640, "height": 480}

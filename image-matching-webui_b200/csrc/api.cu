@@ -96,18 +96,18 @@ struct SPBuffers {
 size_t sp_carve(Workspace& ws, SPBuffers& b, int B, int H, int W) {
   const size_t sb = (size_t)(B < SP_SUB ? B : SP_SUB);
   const size_t h = H / 8, w = W / 8;
-  // x3/2: the same buffers hold either fp32 or three bf16 planes (6 bytes per element)
-  b.a1 = ws.take<float>(sb * H * W * 64 * 3 / 2);
-  b.a2 = ws.take<float>(sb * (H / 2) * (W / 2) * 64 * 3 / 2);
-  b.a3 = ws.take<float>(sb * (H / 2) * (W / 2) * 64 * 3 / 2);
-  b.a4 = ws.take<float>(sb * (H / 4) * (W / 4) * 64 * 3 / 2);
-  b.a5 = ws.take<float>(sb * (H / 4) * (W / 4) * 128 * 3 / 2);
-  b.a6 = ws.take<float>(sb * h * w * 128 * 3 / 2);
-  b.a7 = ws.take<float>(sb * h * w * 128 * 3 / 2);
-  b.a8 = ws.take<float>(sb * h * w * 128 * 3 / 2);
-  b.pa = ws.take<float>(sb * h * w * 256 * 3 / 2);
+  // the same buffers hold either fp32 or two fp16 planes (4 bytes per element either way)
+  b.a1 = ws.take<float>(sb * H * W * 64);
+  b.a2 = ws.take<float>(sb * (H / 2) * (W / 2) * 64);
+  b.a3 = ws.take<float>(sb * (H / 2) * (W / 2) * 64);
+  b.a4 = ws.take<float>(sb * (H / 4) * (W / 4) * 64);
+  b.a5 = ws.take<float>(sb * (H / 4) * (W / 4) * 128);
+  b.a6 = ws.take<float>(sb * h * w * 128);
+  b.a7 = ws.take<float>(sb * h * w * 128);
+  b.a8 = ws.take<float>(sb * h * w * 128);
+  b.pa = ws.take<float>(sb * h * w * 256);
   b.logits = ws.take<float>(sb * h * w * 128);
-  b.da = ws.take<float>(sb * h * w * 256 * 3 / 2);
+  b.da = ws.take<float>(sb * h * w * 256);
   b.dense = ws.take<float>((size_t)B * H * W);
   b.nms = ws.take<float>((size_t)B * H * W);
   b.dd = ws.take<float>((size_t)B * h * w * 256);
@@ -145,7 +145,7 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
   const bool use_tc = conf->use_tensor_cores != 0;
   if (use_tc) {
     IMW_REQUIRE(W % 16 == 0, "imw_superpoint_forward: the tensor-core path needs W %% 16 == 0 (got %d)", W);
-    for (int l : {1, 2, 3, 4, 5, 6, 7, 8, 10}) IMW_REQUIRE(wt->wp[l] != nullptr, "imw_superpoint_forward: bf16-plane weights missing for layer %d", l);
+    for (int l : {1, 2, 3, 4, 5, 6, 7, 8, 10}) IMW_REQUIRE(wt->wp[l] != nullptr, "imw_superpoint_forward: fp16-plane weights missing for layer %d", l);
   }
   const bool tc_heads = use_tc && wt->wp[9] && wt->wp[11];
   int rc;
@@ -154,7 +154,7 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
     const int nb = (B - b0 < SP_SUB) ? (B - b0) : SP_SUB;
     const float* img = image + (size_t)b0 * H * W;
     if (use_tc) {
-      // encoder + both 3x3 head convs on tcgen05, activations carried as three bf16 planes
+      // encoder + both 3x3 head convs on tcgen05, activations carried as two fp16 planes (split_planes.cuh)
       if (conf->use_tensor_cores == 1) {   // conv1a evaluated inside the conv1b kernel (no plane traffic for the first layer)
         RUN(tc_conv1ab_fused(img, wt->w[0], wt->b[0], wt->wp[1], wt->b[1], b.a2, nb, H, W, 1, st));
       } else {                             // 2: unfused pair (kept for A/B measurements)

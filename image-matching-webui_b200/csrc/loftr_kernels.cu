@@ -7,7 +7,7 @@
 //   utils/coarse_matching.py:108-250   dual-softmax confidence, threshold, border, mutual max -- streamed, the
 //                                      L x S confidence matrix (1.07 GB per pair at 1024^2) is never materialised
 //   loftr_module/fine_preprocess.py:29-59, utils/fine_matching.py:18-77  5x5 windows gathered on demand (no F.unfold)
-#include <cuda_bf16.h>
+#include "split_planes.cuh"
 #include <math_constants.h>
 
 #include "../../include/imw_b200.h"
@@ -22,19 +22,11 @@ namespace {
 
 constexpr int CD = 256, FD = 128, NH = 8;
 
-__device__ __forceinline__ void lf_split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
-  a = __float2bfloat16_rn(x);
-  float r = x - __bfloat162float(a);
-  b = __float2bfloat16_rn(r);
-  c = __float2bfloat16_rn(r - __bfloat162float(b));
-}
-__device__ __forceinline__ float lf_merge3(const __nv_bfloat16* p, size_t plane, size_t i) {
-  return (__bfloat162float(p[i]) + __bfloat162float(p[plane + i])) + __bfloat162float(p[2 * plane + i]);
-}
+__device__ __forceinline__ float lf_merge(const plane_t* p, size_t plane, size_t i) { return merge2(p[i], p[plane + i]); }
 
 // ---- conv1: 7x7 stride 2 pad 3, 1 -> 128 channels, BN folded, ReLU (resnet_fpn.py:60-62,102) -> bf16 planes ----------
 __global__ void __launch_bounds__(256) lf_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[49][128]*/,
-                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
+                                                       const float* __restrict__ bias, plane_t* __restrict__ out, int B,
                                                        int H, int W) {
   __shared__ __align__(16) float s_in[37][38];
   __shared__ __align__(16) float s_w[49][128];
@@ -63,17 +55,17 @@ __global__ void __launch_bounds__(256) lf_conv1_kernel(const float* __restrict__
         a[0] = fmaf(v, w4.x, a[0]); a[1] = fmaf(v, w4.y, a[1]); a[2] = fmaf(v, w4.z, a[2]); a[3] = fmaf(v, w4.w, a[3]);
       }
     const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * 128 + cq * 4;
-    __align__(8) __nv_bfloat16 q[3][4];
+    __align__(8) plane_t q[NP][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) lf_split3(fmaxf(a[k] + bias[cq * 4 + k], 0.f), q[0][k], q[1][k], q[2][k]);
+    for (int k = 0; k < 4; k++) split2(fmaxf(a[k] + bias[cq * 4 + k], 0.f), q[0][k], q[1][k]);
 #pragma unroll
-    for (int s = 0; s < 3; s++) *reinterpret_cast<uint2*>(out + s * plane + off) = *reinterpret_cast<const uint2*>(q[s]);
+    for (int s = 0; s < NP; s++) *reinterpret_cast<uint2*>(out + s * plane + off) = *reinterpret_cast<const uint2*>(q[s]);
   }
 }
 
 // ---- FPN: out = a + bilinear_2x(b) (align_corners=True), resnet_fpn.py:110-115 -- bf16 planes in / out -------------------
-__global__ void __launch_bounds__(256) lf_upsample_add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ bsrc,
-                                                              __nv_bfloat16* __restrict__ out, int B, int Ho, int Wo, int C) {
+__global__ void __launch_bounds__(256) lf_upsample_add_kernel(const plane_t* __restrict__ a, const plane_t* __restrict__ bsrc,
+                                                              plane_t* __restrict__ out, int B, int Ho, int Wo, int C) {
   // one thread = 8 consecutive channels of one output pixel (16-byte loads / stores per plane)
   const size_t n = (size_t)B * Ho * Wo * C, i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
@@ -88,13 +80,11 @@ __global__ void __launch_bounds__(256) lf_upsample_add_kernel(const __nv_bfloat1
   const int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
   const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
   const size_t ps = (size_t)B * hs * ws * C;
-  auto load8 = [](const __nv_bfloat16* base, size_t plane, size_t off, float (&v)[8]) {   // p0 + p1 + p2 of 8 channels
-    const uint4 q0 = *reinterpret_cast<const uint4*>(base + off), q1 = *reinterpret_cast<const uint4*>(base + plane + off),
-                q2 = *reinterpret_cast<const uint4*>(base + 2 * plane + off);
-    const __nv_bfloat16 *e0 = reinterpret_cast<const __nv_bfloat16*>(&q0), *e1 = reinterpret_cast<const __nv_bfloat16*>(&q1),
-                        *e2 = reinterpret_cast<const __nv_bfloat16*>(&q2);
+  auto load8 = [](const plane_t* base, size_t plane, size_t off, float (&v)[8]) {   // hi + lo * 2^-11 of 8 channels
+    const uint4 q0 = *reinterpret_cast<const uint4*>(base + off), q1 = *reinterpret_cast<const uint4*>(base + plane + off);
+    const plane_t *e0 = reinterpret_cast<const plane_t*>(&q0), *e1 = reinterpret_cast<const plane_t*>(&q1);
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (__bfloat162float(e0[k]) + __bfloat162float(e1[k])) + __bfloat162float(e2[k]);
+    for (int k = 0; k < 8; k++) v[k] = merge2(e0[k], e1[k]);
   };
   float s00[8], s01[8], s10[8], s11[8], av[8];
   load8(bsrc, ps, (((size_t)b * hs + y0) * ws + x0) * C + c, s00);
@@ -102,21 +92,20 @@ __global__ void __launch_bounds__(256) lf_upsample_add_kernel(const __nv_bfloat1
   load8(bsrc, ps, (((size_t)b * hs + y1) * ws + x0) * C + c, s10);
   load8(bsrc, ps, (((size_t)b * hs + y1) * ws + x1) * C + c, s11);
   load8(a, n, i, av);
-  __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
+  __align__(16) plane_t o0[8], o1[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const float up = hy * (hx * s00[k] + lx * s01[k]) + ly * (hx * s10[k] + lx * s11[k]);
-    lf_split3(av[k] + up, o0[k], o1[k], o2[k]);
+    split2(av[k] + up, o0[k], o1[k]);
   }
   *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(o0);
   *reinterpret_cast<uint4*>(out + n + i) = *reinterpret_cast<const uint4*>(o1);
-  *reinterpret_cast<uint4*>(out + 2 * n + i) = *reinterpret_cast<const uint4*>(o2);
 }
 
 // bf16 planes -> fp32 (fine feature map used by the window gather)
-__global__ void lf_planes_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+__global__ void lf_planes_to_f32_kernel(const plane_t* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = lf_merge3(in, n, i);
+  if (i < n) out[i] = lf_merge(in, n, i);
 }
 
 // tokens: xm[z][l][0:256] = coarse_feat[z][l][:] + pe[l][:]   (loftr.py:58-59)
@@ -449,9 +438,9 @@ struct LFBuffers {
 
 size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H, int W, int cap, int mcap) {
   const size_t S = 2 * (size_t)P, h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2, h8 = (h4 + 1) / 2, w8 = (w4 + 1) / 2;
-  const size_t big = S * h2 * w2 * 256 * 3;  // bf16 elements of the largest plane set (1/2 res, 256 padded channels)
-  b.pa = ws.take<__nv_bfloat16>(big); b.pb = ws.take<__nv_bfloat16>(big); b.pc = ws.take<__nv_bfloat16>(big);
-  b.pd = ws.take<__nv_bfloat16>(S * h4 * w4 * 256 * 3); b.pe2 = ws.take<__nv_bfloat16>(S * h4 * w4 * 256 * 3);
+  const size_t big = S * h2 * w2 * 256 * NP;  // fp16 elements of the largest plane set (1/2 res, 256 padded channels)
+  b.pa = ws.take<plane_t>(big); b.pb = ws.take<plane_t>(big); b.pc = ws.take<plane_t>(big);
+  b.pd = ws.take<plane_t>(S * h4 * w4 * 256 * NP); b.pe2 = ws.take<plane_t>(S * h4 * w4 * 256 * NP);
   b.fc = ws.take<float>(S * h8 * w8 * CD); b.ff = ws.take<float>(S * h2 * w2 * FD);
   const size_t T = S * cap;
   b.xm = ws.take<float>(T * 512); b.q = ws.take<float>(T * CD); b.k = ws.take<float>(T * CD); b.v = ws.take<float>(T * CD);
@@ -498,7 +487,7 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   const imw_loftr_backbone& bb = W->backbone;
   {
     dim3 grid(ceil_div(w2, 16) * ceil_div(h2, 16), 1, S);
-    lf_conv1_kernel<<<grid, 256, 0, st>>>(images, bb.conv1_w, bb.conv1_b, (__nv_bfloat16*)b.pa, S, H, Wd);
+    lf_conv1_kernel<<<grid, 256, 0, st>>>(images, bb.conv1_w, bb.conv1_b, (plane_t*)b.pa, S, H, Wd);
     IMW_CHECK_LAUNCH_T("lf_conv1_kernel");
   }
   auto conv = [&](const void* in, const imw_loftr_conv& c, const void* res, void* out, int Hin, int Win, int act, int f32) {
@@ -528,16 +517,16 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   RUN(conv(x2a, bb.l2_out, nullptr, b.pe2, h4, w4, 0, 0));                // layer2_outconv(x2) -> pe2
   {
     const size_t n = (size_t)S * h4 * w4 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pe2, (const __nv_bfloat16*)x3_out,
-                                                                       (__nv_bfloat16*)b.pb, S, h4, w4, 256);
+    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pe2, (const plane_t*)x3_out,
+                                                                       (plane_t*)b.pb, S, h4, w4, 256);
     IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
   }
   RUN(conv(b.pb, bb.l2_out2[0], nullptr, b.pe2, h4, w4, 2, 0));  RUN(conv(b.pe2, bb.l2_out2[1], nullptr, x2a, h4, w4, 0, 0));  // x2_out -> pd
   RUN(conv(b.pa, bb.l1_out, nullptr, b.pb, h2, w2, 0, 0));                // layer1_outconv(x1) -> pb (256 padded)
   {
     const size_t n = (size_t)S * h2 * w2 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)b.pb, (const __nv_bfloat16*)x2a,
-                                                                       (__nv_bfloat16*)b.pc, S, h2, w2, 256);
+    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pb, (const plane_t*)x2a,
+                                                                       (plane_t*)b.pc, S, h2, w2, 256);
     IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
   }
   RUN(conv(b.pc, bb.l1_out2[0], nullptr, b.pb, h2, w2, 2, 0));   RUN(conv(b.pb, bb.l1_out2[1], nullptr, b.ff, h2, w2, 0, 1));  // fine map fp32

@@ -4,7 +4,7 @@
 //
 // Layout: activations NHWC fp32 ([B][H][W][C]); weights re-laid out by the host to
 // [tap = ky*3+kx][Cin][Cout] so the Cout slice of one (tap, cin) is contiguous.
-#include <cuda_bf16.h>
+#include "split_planes.cuh"
 
 #include "common.cuh"
 #include "sp_kernels.h"
@@ -138,7 +138,7 @@ conv3x3_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
 // thread -> 4 output channels (t%16) of pixel (t/16); a warp writes 2 pixels x 256 B contiguous.
 __global__ void __launch_bounds__(256)
 conv3x3_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[9][1][64]*/,
-                  const float* __restrict__ bias, float* __restrict__ out, __nv_bfloat16* __restrict__ out_planes,
+                  const float* __restrict__ bias, float* __restrict__ out, plane_t* __restrict__ out_planes,
                   size_t plane_stride, int H, int W) {
   __shared__ float s_in[18][19];
   const int tiles_x = (W + TILE - 1) / TILE;
@@ -172,18 +172,13 @@ conv3x3_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /
       }
     float4 o = make_float4(fmaxf(a[0] + bv[0], 0.f), fmaxf(a[1] + bv[1], 0.f), fmaxf(a[2] + bv[2], 0.f), fmaxf(a[3] + bv[3], 0.f));
     const size_t off = (((size_t)b * H + gy) * W + gx) * 64 + cq * 4;
-    if (out_planes) {  // three bf16 planes x = p0 + p1 + p2 for the tcgen05 split-precision convs
+    if (out_planes) {  // two fp16 planes x = hi + lo * 2^-11 for the tcgen05 split-precision convs (split_planes.cuh)
       float ov[4] = {o.x, o.y, o.z, o.w};
-      __align__(8) __nv_bfloat16 p[3][4];
+      __align__(8) plane_t p[NP][4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        p[0][k] = __float2bfloat16_rn(ov[k]);
-        float r = ov[k] - __bfloat162float(p[0][k]);
-        p[1][k] = __float2bfloat16_rn(r);
-        p[2][k] = __float2bfloat16_rn(r - __bfloat162float(p[1][k]));
-      }
+      for (int k = 0; k < 4; k++) split2(ov[k], p[0][k], p[1][k]);
 #pragma unroll
-      for (int q = 0; q < 3; q++) *reinterpret_cast<uint2*>(out_planes + q * plane_stride + off) = *reinterpret_cast<const uint2*>(p[q]);
+      for (int q = 0; q < NP; q++) *reinterpret_cast<uint2*>(out_planes + q * plane_stride + off) = *reinterpret_cast<const uint2*>(p[q]);
     } else {
       *reinterpret_cast<float4*>(out + off) = o;
     }
@@ -207,7 +202,7 @@ int sp_conv3x3(const float* in, const float* w, const float* bias, float* out, i
 int sp_conv3x3_c1(const float* img, const float* w, const float* bias, float* out, void* out_planes, int B, int H, int W,
                   cudaStream_t st) {
   dim3 grid(ceil_div(W, TILE) * ceil_div(H, TILE), 1, B);
-  conv3x3_c1_kernel<<<grid, 256, 0, st>>>(img, w, bias, out, (__nv_bfloat16*)out_planes, (size_t)B * H * W * 64, H, W);
+  conv3x3_c1_kernel<<<grid, 256, 0, st>>>(img, w, bias, out, (plane_t*)out_planes, (size_t)B * H * W * 64, H, W);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -1,30 +1,28 @@
-// tcgen05 implicit-GEMM 3x3 convolution with fp32-equivalent precision (bf16 x 3 split operands).
+// tcgen05 implicit-GEMM 3x3 convolution with fp32-equivalent precision (two fp16 planes per operand, three products).
 //
 // Why split precision: SuperPoint's detector branch feeds exact-equality NMS, a hard threshold and a top-k
 // cut; single TF32/BF16 operands flip 1.5 % / 8.7 % of the keypoints.  Every fp32
-// value is carried as three bf16 planes x = x1 + x2 + x3 (8 + 8 + 8 mantissa bits, exact to 2^-24 relative)
-// and the product is assembled from the six leading partial products
-//     a1b1 + a1b2 + a2b1 + a1b3 + a2b2 + a3b1        (dropped terms <= 2^-24 |a||b|)
-// accumulated in fp32 in TMEM = 1/6 of the bf16 tensor peak.  The three weight planes of a stage are contiguous in N
-// ([b1 | b2 | b3] rows), so the six products are issued as FOUR kind::f16 MMAs per k-step
-//     a1 x b1 -> main          a1 x [b2|b3] -> [c1|c2]          a2 x [b1|b2] -> [c1|c2]          a3 x b1 -> c2
-// which reads the activation tile four times instead of six (shared-memory operand reads bound these kernels).
+// value is carried as two fp16 planes x = hi + lo * 2^-11 (split_planes.cuh) and a product is assembled from
+//     a_hi b_hi + (a_hi b_lo + a_lo b_hi) * 2^-11        (dropped term <= 2^-22 |a||b|)
+// accumulated in fp32 in TMEM = 1/3 of the fp16 tensor peak.  The two weight planes of a stage are contiguous in N
+// ([b_hi | b_lo] rows), so the three products are issued as TWO kind::f16 MMAs per k-step
+//     a_hi x [b_hi | b_lo] -> [main | cross]          a_lo x b_hi -> cross
+// (round 1 carried three bf16 planes and six products in four MMAs: twice the tensor work and operand traffic).
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
 // accumulating MMAs (measured: ~1e-5 relative after 216 MMAs into one accumulator).  The accumulation is therefore
-// spread over FOUR TMEM accumulators -- the leading a1*b1 term alternates between two of them k-step by k-step, the
-// first-order (2^-8) and second-order (2^-16) cross terms have their own -- summed in fp32 in the epilogue.
+// spread over two [main | cross] accumulator sets that alternate k-step by k-step, summed in fp32 in the epilogue.
 //
 // Generic kernel (tc_conv3x3_kernel<BN, KS, RES>): GEMM view M = 128 output pixels (8 rows x 16 cols of one image),
 // N = Cout tile (64 / 128), K = taps x Cin; 3x3 (pad 1) or 1x1, stride 1 or 2.  The taps are shifted TMA box loads of
 // the NHWC activation planes (4-D tensor map, element strides for stride 2, out-of-bounds coordinates zero-filled =
 // the conv's zero padding), 64 channels = one 128-byte swizzled row per pixel.
-//   warp 0: TMA producer (3 activation planes + 3 weight planes per (tap, 64-channel chunk) stage)
-//   warp 1: TMEM alloc + tcgen05.mma issue (16 MMAs per stage)
+//   warp 0: TMA producer (2 activation planes + 2 weight planes per (tap, 64-channel chunk) stage)
+//   warp 1: TMEM alloc + tcgen05.mma issue (8 MMAs per stage)
 //   warps 2-5: epilogue: tcgen05.ld, bias, optional residual planes, ReLU / LeakyReLU, optional fused 2x2 max-pool
-//              (lane shuffles: the 2x2 window lives in one warp), re-split into bf16 planes (or fp32) and store NHWC.
+//              (lane shuffles: the 2x2 window lives in one warp), re-split into fp16 planes (or fp32) and store NHWC.
 // Cin = Cout = 64 specialisation (tc_conv3x3_c64_kernel<FUSE>): persistent, halo tile as three dx-shifted copies,
 // double-buffered TMEM; FUSE evaluates SuperPoint's conv1a inside the CTA (see below).
-#include <cuda_bf16.h>
+#include "split_planes.cuh"
 
 #include "../../include/imw_b200.h"
 #include "common.cuh"
@@ -41,10 +39,10 @@ struct ConvArgs {
   int H, W, Cin, Cout, B;     // H, W: INPUT size; output = ceil(H/stride) x ceil(W/stride) (then /2 if pooled)
   int relu, pool, out_fp32;   // relu: 0 none, 1 ReLU, 2 LeakyReLU(0.01)
   const float* bias;
-  __nv_bfloat16* out_planes;  // [3][B][Ho][Wo][Cout]
+  plane_t* out_planes;        // [NP][B][Ho][Wo][Cout]
   float* out_f32;             // [B][Ho][Wo][Cout]
   int ksize = 3, stride = 1;  // 3x3 (pad 1) or 1x1 (pad 0); stride 1 or 2 (TMA element strides)
-  const __nv_bfloat16* res_planes = nullptr;  // optional residual [3][B][Ho][Wo][Cout], added before the activation
+  const plane_t* res_planes = nullptr;  // optional residual [NP][B][Ho][Wo][Cout], added before the activation
   // fused first layer (tc_conv3x3_c64_kernel<true>): the activation operand is conv1a(image) computed in the CTA
   const float* img = nullptr;   // [B][H][W] fp32
   const float* w1a = nullptr;   // [9][64]
@@ -52,18 +50,11 @@ struct ConvArgs {
 };
 
 template <int BN>
-constexpr int conv_stage_bytes() { return 3 * CV_A_BYTES + 3 * BN * 128; }
+constexpr int conv_stage_bytes() { return NP * CV_A_BYTES + NP * BN * 128; }
 template <int BN>
-constexpr int conv_stages() { return BN == 64 ? 3 : 2; }
+constexpr int conv_stages() { return BN == 64 ? 4 : 3; }
 template <int BN>
 constexpr size_t conv_smem_bytes() { return (size_t)conv_stages<BN>() * conv_stage_bytes<BN>() + 1024 + 256; }
-
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
-  a = __float2bfloat16_rn(x);
-  float r = x - __bfloat162float(a);
-  b = __float2bfloat16_rn(r);
-  c = __float2bfloat16_rn(r - __bfloat162float(b));
-}
 
 // KS: kernel size (3 or 1) and RES: residual input are compile-time so that the SuperPoint instantiation <BN, 3, false>
 // keeps constant tap arithmetic in the single-thread producer / MMA loops and a lean epilogue.
@@ -114,42 +105,35 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc::mbar_expect_tx(full + s, STAGE);
         uint8_t* st = smem + s * STAGE;
 #pragma unroll
-        for (int p = 0; p < 3; p++)  // activation planes: tensor dims (C, W, H, plane*B + b); stride-2 via element strides
+        for (int p = 0; p < NP; p++)  // activation planes: tensor dims (C, W, H, plane*B + b); stride-2 via element strides
           tc::tma_load_4d(st + p * CV_A_BYTES, &tmA, full + s, ck * CV_CK, x0 * g.stride + dx, y0 * g.stride + dy, p * g.B + b);
 #pragma unroll
-        for (int p = 0; p < 3; p++)  // weight planes: rows (plane*9 + tap)*Cout + n, cols Cin
-          tc::tma_load_2d(st + 3 * CV_A_BYTES + p * B_BYTES, &tmW, full + s, ck * CV_CK, (p * ntaps + tap) * g.Cout + n0);
+        for (int p = 0; p < NP; p++)  // weight planes: rows (plane*9 + tap)*Cout + n, cols Cin
+          tc::tma_load_2d(st + NP * CV_A_BYTES + p * B_BYTES, &tmW, full + s, ck * CV_CK, (p * ntaps + tap) * g.Cout + n0);
       }
     }
   } else if (warp == 1) {
     {
       const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_BF16, 128, 2 * BN);
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_F16, 128, 2 * BN);
       int tap = 0, ck = 0;
       for (int it = 0; it < steps; it++, ck++) {
         if (ck == chunks) { ck = 0; tap++; }
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         tc::mbar_wait(full + s, ph);
         tc::fence_after_sync();
-        const uint32_t a0 = tc::smem_u32(smem + s * STAGE), b0 = a0 + 3 * CV_A_BYTES;
+        const uint32_t a0 = tc::smem_u32(smem + s * STAGE), b0 = a0 + NP * CV_A_BYTES;
+        // The two weight planes are contiguous in N ([b_hi | b_lo] rows): a_hi x [b_hi | b_lo] -> [main | cross] is ONE MMA of
+        // N = 2 BN, a_lo x b_hi -> cross the second.  The [main | cross] accumulator set alternates step by step: shorter
+        // truncating-add chains.
+        const uint32_t d_set = tmem_base + (it & 1) * 2 * BN;
 #pragma unroll
         for (int k = 0; k < CV_CK / 16; k++) {
-          uint64_t ad[3], bd[3];
-#pragma unroll
-          for (int p = 0; p < 3; p++) {
-            ad[p] = tc::make_smem_desc_sw128(a0 + p * CV_A_BYTES + k * 32);
-            bd[p] = tc::make_smem_desc_sw128(b0 + p * B_BYTES + k * 32);
-          }
-          // The three weight planes are contiguous in N ([b0 | b1 | b2] rows), so the six partial products of the
-          // split are issued as four MMAs that read each operand tile less often (shared-memory operand bandwidth is
-          // what bounds this kernel): a0 x b0 -> main, a0 x [b1|b2] and a1 x [b0|b1] -> [c1|c2], a2 x b0 -> c2.
-          // main alternates between two accumulators step by step: shorter truncating-add chains.
-          const uint32_t d_main = tmem_base + (it & 1) * BN, d_c1 = tmem_base + 2 * BN, d_c2 = tmem_base + 3 * BN;
+          const uint64_t a_hi = tc::make_smem_desc_sw128(a0 + k * 32), a_lo = tc::make_smem_desc_sw128(a0 + CV_A_BYTES + k * 32);
+          const uint64_t b_hi = tc::make_smem_desc_sw128(b0 + k * 32);
           if (leader) {
-            tc::mma_f16(d_main, ad[0], bd[0], idesc, (it >= 2 || k) ? 1u : 0u);
-            tc::mma_f16(d_c1, ad[0], bd[1], idesc2, (it | k) ? 1u : 0u);
-            tc::mma_f16(d_c1, ad[1], bd[0], idesc2, 1u);
-            tc::mma_f16(d_c2, ad[2], bd[0], idesc, 1u);
+            tc::mma_f16(d_set, a_hi, b_hi, idesc2, (it >= 2 || k) ? 1u : 0u);
+            tc::mma_f16(d_set + BN, a_lo, b_hi, idesc, 1u);
           }
         }
         if (leader) tc::mma_commit(empty + s);
@@ -174,28 +158,27 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32], t[32];
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-      tc::tmem_ld32(lane_base, v);
-      if (steps >= 2) {   // second main accumulator (odd k-steps)
-        tc::tmem_ld32(lane_base + BN, t);
+      float u[32];
+      tc::tmem_ld32(lane_base, v);          // set 0: [main | cross]
+      tc::tmem_ld32(lane_base + BN, u);
+      if (steps >= 2) {   // set 1 (odd k-steps)
+        tc::tmem_ld32(lane_base + 2 * BN, t);
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += t[j];
+        tc::tmem_ld32(lane_base + 3 * BN, t);
+#pragma unroll
+        for (int j = 0; j < 32; j++) u[j] += t[j];
       }
-      tc::tmem_ld32(lane_base + 2 * BN, t);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += t[j];
-      tc::tmem_ld32(lane_base + 3 * BN, t);
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += t[j];
+      for (int j = 0; j < 32; j++) v[j] = fmaf(u[j], PLANE_LO_INV, v[j]);
       if (RES && in_img) {  // residual branch of a BasicBlock (added before the activation)
-        const __nv_bfloat16* r0 = g.res_planes + opix + c0;
+        const plane_t* r0 = g.res_planes + opix + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          uint4 a = *reinterpret_cast<const uint4*>(r0 + j), bq = *reinterpret_cast<const uint4*>(r0 + plane_stride + j),
-                cq = *reinterpret_cast<const uint4*>(r0 + 2 * plane_stride + j);
-          const __nv_bfloat16 *pa = reinterpret_cast<const __nv_bfloat16*>(&a), *pb = reinterpret_cast<const __nv_bfloat16*>(&bq),
-                              *pc = reinterpret_cast<const __nv_bfloat16*>(&cq);
+          uint4 a = *reinterpret_cast<const uint4*>(r0 + j), bq = *reinterpret_cast<const uint4*>(r0 + plane_stride + j);
+          const plane_t *pa = reinterpret_cast<const plane_t*>(&a), *pb = reinterpret_cast<const plane_t*>(&bq);
 #pragma unroll
-          for (int e = 0; e < 8; e++) t[j + e] = (__bfloat162float(pa[e]) + __bfloat162float(pb[e])) + __bfloat162float(pc[e]);
+          for (int e = 0; e < 8; e++) t[j + e] = merge2(pa[e], pb[e]);
         }
       } else if (RES) {
 #pragma unroll
@@ -219,17 +202,15 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-          __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
+          __align__(16) plane_t p0[32], p1[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
+          for (int j = 0; j < 32; j++) split2(v[j], p0[j], p1[j]);
           uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
           uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
-          uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             o0[j] = reinterpret_cast<const uint4*>(p0)[j];
             o1[j] = reinterpret_cast<const uint4*>(p1)[j];
-            o2[j] = reinterpret_cast<const uint4*>(p2)[j];
           }
         }
       }
@@ -249,9 +230,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // through a 2-stage ring (24 KB per tap).
 constexpr int C64_TH = 16, C64_TW = 8;
 constexpr int C64_COPY = 18 * 8 * 128;            // one (plane, dx) halo copy: 18 rows x 8 px x 128 B
-constexpr int C64_A_BYTES = 9 * C64_COPY;         // 3 planes x 3 dx
-constexpr int C64_B_STAGE = 3 * 64 * 128;         // 3 weight planes of one tap
-constexpr int C64_B_STAGES = 2;
+constexpr int C64_A_BYTES = NP * 3 * C64_COPY;    // NP planes x 3 dx
+constexpr int C64_B_STAGE = NP * 64 * 128;        // NP weight planes of one tap
+constexpr int C64_B_STAGES = 4;
 constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256 + 2 * 240 * sizeof(float) /*fused: image patches*/;
 constexpr int C64_FUSE_PROD = 256;   // conv1a producer threads (8 warps)
 constexpr int C64_FUSE_THREADS = CV_THREADS + C64_FUSE_PROD;
@@ -268,7 +249,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   constexpr int BN = 64;
   extern __shared__ uint8_t cv_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                       // [dx][plane][18*8 rows][128 B]
+  uint8_t* sA = smem;                       // [dx][plane][18*8 rows][128 B]   (plane: hi, lo)
   uint8_t* sB = smem + C64_A_BYTES;         // [stage][plane][64 rows][128 B]
   uint64_t* a_full = (uint64_t*)(sB + C64_B_STAGES * C64_B_STAGE);  // [3] one per dx slot
   uint64_t* a_empty = a_full + 3;
@@ -305,16 +286,16 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
           if (!FUSE && dyi == 0) {
             tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);
-            tc::mbar_expect_tx(a_full + dxi, 3 * C64_COPY);
+            tc::mbar_expect_tx(a_full + dxi, NP * C64_COPY);
 #pragma unroll
-            for (int p = 0; p < 3; p++)
-              tc::tma_load_4d(sA + (dxi * 3 + p) * C64_COPY, &tmA, a_full + dxi, 0, x0 + dxi - 1, y0 - 1, p * g.B + b);
+            for (int p = 0; p < NP; p++)
+              tc::tma_load_4d(sA + (dxi * NP + p) * C64_COPY, &tmA, a_full + dxi, 0, x0 + dxi - 1, y0 - 1, p * g.B + b);
           }
           const int c = i * 9 + it, s = c % C64_B_STAGES, ph = (c / C64_B_STAGES) & 1;
           tc::mbar_wait(b_empty + s, ph ^ 1);
           tc::mbar_expect_tx(b_full + s, C64_B_STAGE);
 #pragma unroll
-          for (int p = 0; p < 3; p++)
+          for (int p = 0; p < NP; p++)
             tc::tma_load_2d(sB + s * C64_B_STAGE + p * 64 * 128, &tmW, b_full + s, 0, (p * 9 + tap) * g.Cout);
         }
       }
@@ -322,7 +303,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     {
       const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_BF16, 128, 2 * BN);
+      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_F16, 128, 2 * BN);
       int i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
         const int acc = i & 1;
@@ -335,21 +316,15 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (dyi == 0) tc::mbar_wait(a_full + dxi, i & 1);
           tc::mbar_wait(b_full + s, ph);
           tc::fence_after_sync();
-          const uint32_t a0 = tc::smem_u32(sA + dxi * 3 * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
-          const uint32_t d_main = d_base + (it & 1) * BN, d_c1 = d_base + 2 * BN, d_c2 = d_base + 3 * BN;
+          const uint32_t a0 = tc::smem_u32(sA + dxi * NP * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * C64_B_STAGE);
+          const uint32_t d_set = d_base + (it & 1) * 2 * BN;     // [main | cross] sets alternate tap by tap
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            uint64_t ad[3], bd[3];
-#pragma unroll
-            for (int p = 0; p < 3; p++) {
-              ad[p] = tc::make_smem_desc_sw128(a0 + p * C64_COPY + k * 32);
-              bd[p] = tc::make_smem_desc_sw128(b0 + p * 64 * 128 + k * 32);
-            }
-            if (leader) {  // four MMAs for the six partial products ([b0|b1|b2] contiguous in N), see tc_conv3x3_kernel
-              tc::mma_f16(d_main, ad[0], bd[0], idesc, (it >= 2 || k) ? 1u : 0u);
-              tc::mma_f16(d_c1, ad[0], bd[1], idesc2, (it | k) ? 1u : 0u);
-              tc::mma_f16(d_c1, ad[1], bd[0], idesc2, 1u);
-              tc::mma_f16(d_c2, ad[2], bd[0], idesc, 1u);
+            const uint64_t a_hi = tc::make_smem_desc_sw128(a0 + k * 32), a_lo = tc::make_smem_desc_sw128(a0 + C64_COPY + k * 32);
+            const uint64_t b_hi = tc::make_smem_desc_sw128(b0 + k * 32);
+            if (leader) {  // two MMAs for the three partial products ([b_hi | b_lo] contiguous in N), see tc_conv3x3_kernel
+              tc::mma_f16(d_set, a_hi, b_hi, idesc2, (it >= 2 || k) ? 1u : 0u);
+              tc::mma_f16(d_set + BN, a_lo, b_hi, idesc, 1u);
             }
           }
           if (leader) {
@@ -386,7 +361,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");
       for (int dxi = 0; dxi < 3; dxi++) {
         tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);   // the MMAs of the previous tile have read this dx slot
-        uint8_t* copy = sA + dxi * 3 * C64_COPY;
+        uint8_t* copy = sA + dxi * NP * C64_COPY;
 #pragma unroll 1
         for (int k = 0; k < (144 + C64_FUSE_PROD / 8 - 1) / (C64_FUSE_PROD / 8); k++) {
           const int pidx = t / 8 + (C64_FUSE_PROD / 8) * k;   // pixel of the copy: halo row pidx / 8, column pidx % 8
@@ -409,13 +384,12 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int c = 0; c < 8; c++) a[c] = fmaxf(a[c] + bv[c], 0.f);
           }
-          __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
+          __align__(16) plane_t p0[8], p1[8];
 #pragma unroll
-          for (int c = 0; c < 8; c++) split3(a[c], p0[c], p1[c], p2[c]);
+          for (int c = 0; c < 8; c++) split2(a[c], p0[c], p1[c]);
           const int off = pidx * 128 + ((chunk ^ (pidx & 7)) * 16);   // SWIZZLE_128B: 16-byte unit c of row r sits at c ^ (r & 7)
           *reinterpret_cast<uint4*>(copy + off) = *reinterpret_cast<const uint4*>(p0);
           *reinterpret_cast<uint4*>(copy + C64_COPY + off) = *reinterpret_cast<const uint4*>(p1);
-          *reinterpret_cast<uint4*>(copy + 2 * C64_COPY + off) = *reinterpret_cast<const uint4*>(p2);
         }
         tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
         tc::mbar_arrive(a_full + dxi);
@@ -442,16 +416,15 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32], tt[32];
         const uint32_t lane_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + c0;
-        tc::tmem_ld32(lane_base, v);
-        tc::tmem_ld32(lane_base + BN, tt);
+        float u[32];
+        tc::tmem_ld32(lane_base, v);              // set 0 main
+        tc::tmem_ld32(lane_base + 2 * BN, tt);    // set 1 main
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += tt[j];
-        tc::tmem_ld32(lane_base + 2 * BN, tt);
+        tc::tmem_ld32(lane_base + BN, u);         // set 0 cross (scaled by 2^11)
+        tc::tmem_ld32(lane_base + 3 * BN, tt);    // set 1 cross
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += tt[j];
-        tc::tmem_ld32(lane_base + 3 * BN, tt);
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += tt[j];
+        for (int j = 0; j < 32; j++) v[j] = fmaf(u[j] + tt[j], PLANE_LO_INV, v[j]);
         if (c0 + 32 >= BN) {  // last TMEM read of this accumulator set: hand it back to the MMA warp
           tc::fence_before_sync();
           tc::mbar_arrive(tmem_empty + acc);
@@ -472,17 +445,15 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            __align__(16) __nv_bfloat16 p0[32], p1[32], p2[32];
+            __align__(16) plane_t p0[32], p1[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) split3(v[j], p0[j], p1[j], p2[j]);
+            for (int j = 0; j < 32; j++) split2(v[j], p0[j], p1[j]);
             uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
             uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
-            uint4* o2 = reinterpret_cast<uint4*>(g.out_planes + 2 * plane_stride + opix + c0);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               o0[j] = reinterpret_cast<const uint4*>(p0)[j];
               o1[j] = reinterpret_cast<const uint4*>(p1)[j];
-              o2[j] = reinterpret_cast<const uint4*>(p2)[j];
             }
           }
         }
@@ -494,29 +465,29 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// fp32 NHWC -> three bf16 planes (and back): interop with the CUDA-core path and the unit tests
-__global__ void split_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+// fp32 NHWC -> two fp16 planes (and back): interop with the CUDA-core path and the unit tests
+__global__ void split_planes_kernel(const float* __restrict__ in, plane_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  __nv_bfloat16 a, b, c;
-  split3(in[i], a, b, c);
-  out[i] = a; out[n + i] = b; out[2 * n + i] = c;
+  plane_t a, b;
+  split2(in[i], a, b);
+  out[i] = a; out[n + i] = b;
 }
-__global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+__global__ void merge_planes_kernel(const plane_t* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = (__bfloat162float(in[i]) + __bfloat162float(in[n + i])) + __bfloat162float(in[2 * n + i]);
+  out[i] = merge2(in[i], in[n + i]);
 }
 
-int make_map_act(CUtensorMap* map, const void* base, int B3, int H, int W, int C, int box_w = CV_TW, int box_h = CV_TH, int stride = 1) {
+int make_map_act(CUtensorMap* map, const void* base, int BP, int H, int W, int C, int box_w = CV_TW, int box_h = CV_TH, int stride = 1) {
   PFN_encodeTiled fn = tc_get_encode_fn();
   if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B3};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BP};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   // with element strides the box extent is given in INPUT elements: N loaded elements <=> boxDim = N * stride
   cuuint32_t box[4] = {CV_CK, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { imw_set_error("cuTensorMapEncodeTiled(act) failed: %d", (int)r); return IMW_ERR_CUDA; }
@@ -529,7 +500,7 @@ int make_map_wgt(CUtensorMap* map, const void* base, int rows, int Cin, int BN) 
   cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
   cuuint32_t box[2] = {CV_CK, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { imw_set_error("cuTensorMapEncodeTiled(wgt) failed: %d", (int)r); return IMW_ERR_CUDA; }
@@ -555,8 +526,8 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& 
 
 }  // namespace
 
-// in_planes [3][B][H][W][Cin] bf16, w_planes [3][9][Cout][Cin] bf16, bias [Cout] fp32.
-// out: planes [3][B][Ho][Wo][Cout] bf16 or fp32 [B][Ho][Wo][Cout].
+// in_planes [NP][B][H][W][Cin] fp16, w_planes [NP][9][Cout][Cin] fp16 (split_planes.cuh), bias [Cout] fp32.
+// out: planes [NP][B][Ho][Wo][Cout] fp16 or fp32 [B][Ho][Wo][Cout].
 int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,
                int Cout, int relu, int pool, int out_fp32, cudaStream_t st) {
   IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0, "tc_conv3x3: Cin %% 64, Cout %% 64 (got %d,%d)", Cin, Cout);
@@ -565,9 +536,9 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   if (Cin == 64 && Cout == 64 && W % C64_TW == 0) {  // halo-copy specialisation
-    if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, C64_TW, C64_TH + 2)) return e;
-    if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, 64)) return e;
-    ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+    if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin, C64_TW, C64_TH + 2)) return e;
+    if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, 64)) return e;
+    ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
     IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<false>, C64_SMEM);
     const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
     const int num_sms = imw_num_sms();
@@ -576,9 +547,9 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   }
-  if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin)) return e;
-  if (int e = make_map_wgt(&tmW, w_planes, 3 * 9 * Cout, Cin, BN)) return e;
-  ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
+  if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, BN)) return e;
+  ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 
@@ -587,8 +558,8 @@ int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const
                      int H, int W, int pool, cudaStream_t st) {
   IMW_REQUIRE(W % C64_TW == 0 && (!pool || (H % 2 == 0)), "tc_conv1ab_fused: W %% 8 == 0 (even H when pooled)");
   CUtensorMap tmW;
-  if (int e = make_map_wgt(&tmW, w1b_planes, 3 * 9 * 64, 64, 64)) return e;
-  ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (__nv_bfloat16*)out, (float*)out};
+  if (int e = make_map_wgt(&tmW, w1b_planes, NP * 9 * 64, 64, 64)) return e;
+  ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (plane_t*)out, (float*)out};
   g.img = img; g.w1a = w1a; g.b1a = b1a;
   IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<true>, C64_SMEM);
   const int num_sms = imw_num_sms();
@@ -599,7 +570,7 @@ int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const
 }
 
 // General form used by the LoFTR backbone: 3x3 / 1x1, stride 1 / 2, optional residual, act 0 none / 1 ReLU / 2 LeakyReLU(0.01).
-// w_planes [3][k*k][Cout][Cin] bf16; bias may be NULL (bias-free convs without BatchNorm).
+// w_planes [NP][k*k][Cout][Cin] fp16; bias may be NULL (bias-free convs without BatchNorm).
 int tc_conv_general(const void* in_planes, const void* w_planes, const float* bias, const void* res_planes, void* out, int B,
                     int H, int W, int Cin, int Cout, int ksize, int stride, int act, int out_fp32, cudaStream_t st) {
   IMW_REQUIRE(Cin % CV_CK == 0 && Cout % 64 == 0, "tc_conv_general: Cin %% 64, Cout %% 64 (got %d,%d)", Cin, Cout);
@@ -607,20 +578,20 @@ int tc_conv_general(const void* in_planes, const void* w_planes, const float* bi
   IMW_REQUIRE(!(ksize == 1 && res_planes), "tc_conv_general: residual input is only built for 3x3 convs");
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
-  if (int e = make_map_act(&tmA, in_planes, 3 * B, H, W, Cin, CV_TW, CV_TH, stride)) return e;
-  if (int e = make_map_wgt(&tmW, w_planes, 3 * ksize * ksize * Cout, Cin, BN)) return e;
-  ConvArgs g{H, W, Cin, Cout, B, act, 0, out_fp32, bias, (__nv_bfloat16*)out, (float*)out};
-  g.ksize = ksize; g.stride = stride; g.res_planes = (const __nv_bfloat16*)res_planes;
+  if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin, CV_TW, CV_TH, stride)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, NP * ksize * ksize * Cout, Cin, BN)) return e;
+  ConvArgs g{H, W, Cin, Cout, B, act, 0, out_fp32, bias, (plane_t*)out, (float*)out};
+  g.ksize = ksize; g.stride = stride; g.res_planes = (const plane_t*)res_planes;
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 
 int tc_split_planes(const float* in, void* out_planes, size_t n, cudaStream_t st) {
-  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat16*)out_planes, n);
+  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (plane_t*)out_planes, n);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }
 int tc_merge_planes(const void* in_planes, float* out, size_t n, cudaStream_t st) {
-  merge_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)in_planes, out, n);
+  merge_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const plane_t*)in_planes, out, n);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }
@@ -639,9 +610,9 @@ extern "C" int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout
                                     cudaStream_t st) {
   const size_t n_in = (size_t)B * H * W * Cin, n_w = (size_t)9 * Cout * Cin;
   Workspace ws(scratch, scratch_bytes);
-  __nv_bfloat16* in_p = ws.take<__nv_bfloat16>(3 * n_in);
+  plane_t* in_p = ws.take<plane_t>(NP * n_in);
   float* w_t = ws.take<float>(n_w);
-  __nv_bfloat16* w_p = ws.take<__nv_bfloat16>(3 * n_w);
+  plane_t* w_p = ws.take<plane_t>(NP * n_w);
   if (ws.overflow) { imw_set_error("imw_debug_conv3x3_tc: scratch too small (%zu needed)", ws.off); return IMW_ERR_WORKSPACE; }
   if (int e = tc_split_planes(in, in_p, n_in, st)) return e;
   transpose_taps_kernel<<<(unsigned)((n_w + 255) / 256), 256, 0, st>>>(w_tap_cin_cout, w_t, Cin, Cout);  // -> [tap][Cout][Cin]

@@ -16,7 +16,7 @@ class SuperPoint(BaseModel):
         "max_keypoints": -1,
         "remove_borders": 4,
         "fix_sampling": False,
-        # B200 engine switch (not in the reference): encoder convs on tcgen05 with bf16 x 3 split operands
+        # B200 engine switch (not in the reference): encoder convs on tcgen05 with split-fp16 operands (2 planes, 3 products)
         # (fp32-equivalent products, needs W % 128 == 0); False = fp32 CUDA-core convs
         "tensor_cores": True,
     }

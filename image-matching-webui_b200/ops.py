@@ -102,14 +102,14 @@ def sp_pack_weights(state_dict):
             w = w.reshape(w.shape[0], w.shape[1])
         out[name + "_w"] = w.contiguous()
         out[name + "_b"] = state_dict[name + ".bias"].float().contiguous()
-        if name in SP_TC_LAYERS:  # [3 planes][tap][Cout][Cin] bf16, w = p0 + p1 + p2 (tcgen05 split-precision path)
+        if name in SP_TC_LAYERS:  # [2 planes][tap][Cout][Cin] fp16, w = hi + lo * 2^-11 (tcgen05 split-precision path)
             wt = state_dict[name + ".weight"].float().permute(2, 3, 0, 1).reshape(9, w.shape[2], w.shape[1]).contiguous()
-            out[name + "_wp"] = split_bf16_planes(wt)
-        elif name in ("convPb", "convDb"):  # 1x1 heads on the same path: [3][1][Cout_p][Cin], the 65 detector outputs padded to 128
+            out[name + "_wp"] = split_f16_planes(wt)
+        elif name in ("convPb", "convDb"):  # 1x1 heads on the same path: [2][1][Cout_p][Cin], the 65 detector outputs padded to 128
             co, ci = w.shape
             cop = (co + 127) // 128 * 128
             wt = torch.zeros(1, cop, ci); wt[0, :co] = w
-            out[name + "_wp"] = split_bf16_planes(wt)
+            out[name + "_wp"] = split_f16_planes(wt)
             bp = torch.zeros(cop); bp[:co] = out[name + "_b"]
             out[name + "_b"] = bp
     return out
@@ -118,13 +118,15 @@ def sp_pack_weights(state_dict):
 SP_TC_LAYERS = ["conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convDa"]
 
 
-def split_bf16_planes(x):
-    """fp32 -> [3, ...] bf16 with x == p0 + p1 + p2 to 2^-24 relative (round-to-nearest at each step)."""
-    p0 = x.bfloat16()
-    r = x - p0.float()
-    p1 = r.bfloat16()
-    p2 = (r - p1.float()).bfloat16()
-    return torch.stack([p0, p1, p2]).contiguous()
+PLANE_LO_SCALE = 2048.0   # csrc/split_planes.cuh
+
+
+def split_f16_planes(x):
+    """fp32 -> [2, ...] fp16 planes (hi, lo * 2^11) with x == hi + lo * 2^-11 to 2^-22 relative (csrc/split_planes.cuh)."""
+    x = x.float().clamp(-65504.0, 65504.0)
+    hi = x.half()
+    lo = ((x - hi.float()) * PLANE_LO_SCALE).half()
+    return torch.stack([hi, lo]).contiguous()
 
 
 def sp_weights_struct(bufs):
@@ -405,7 +407,7 @@ def _pad_to(n, m=64):
 
 
 def _loftr_conv(sd, conv_key, bn_prefix, stride):
-    """Conv2d (bias-free) [+ BatchNorm2d eval] -> three bf16 planes [3][k*k][Cout_p][Cin_p] + fp32 bias [Cout_p];
+    """Conv2d (bias-free) [+ BatchNorm2d eval] -> two fp16 planes [2][k*k][Cout_p][Cin_p] + fp32 bias [Cout_p];
     channel counts zero-padded to multiples of 64 (196 -> 256)."""
     w = sd[conv_key].float()
     co, ci, k, _ = w.shape
@@ -420,7 +422,7 @@ def _loftr_conv(sd, conv_key, bn_prefix, stride):
     bias = torch.zeros(cop)
     if b is not None:
         bias[:co] = b
-    return {"w": split_bf16_planes(wt), "b": bias if b is not None else None, "cin": cip, "cout": cop, "ksize": k, "stride": stride}
+    return {"w": split_f16_planes(wt), "b": bias if b is not None else None, "cin": cip, "cout": cop, "ksize": k, "stride": stride}
 
 
 def loftr_pack_weights(sd):
@@ -618,7 +620,7 @@ def debug_gemm(A, W, bias, mode="3xtf32"):
 
 
 def debug_conv3x3(x, w, bias, relu=True, pool=False, tensor_cores=True):
-    """One 3x3 conv layer, NHWC fp32 in/out; w [9][Cin][Cout] fp32.  tensor_cores: tcgen05 bf16x3 path."""
+    """One 3x3 conv layer, NHWC fp32 in/out; w [9][Cin][Cout] fp32.  tensor_cores: tcgen05 split-fp16 path."""
     L.require_cuda(x, "debug_conv3x3(x)")
     B, H, W_, Cin = x.shape
     Cout = w.shape[2]

@@ -90,9 +90,9 @@ int imw_rescale_keypoints(int n_sets, int cap, const float* keypoints, const int
 typedef struct {
   const float* w[12]; /* conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db */
   const float* b[12];
-  /* optional: 3x3 kernels of conv1b..conv4b, convPa, convDa as three bf16 planes [3][9][Cout][Cin]
-     (w = p0 + p1 + p2) for the tcgen05 split-precision path; NULL entries -> CUDA-core path only.
-     wp[9] / wp[11] (optional): the 1x1 heads as planes [3][1][Cout_p][256], convPb's 65 outputs zero-padded to
+  /* optional: 3x3 kernels of conv1b..conv4b, convPa, convDa as two fp16 planes [2][9][Cout][Cin]
+     (w = hi + lo * 2^-11, lo stored pre-scaled by 2^11: csrc/split_planes.cuh) for the tcgen05 split-precision path; NULL entries -> CUDA-core path only.
+     wp[9] / wp[11] (optional): the 1x1 heads as planes [2][1][Cout_p][256], convPb's 65 outputs zero-padded to
      Cout_p = 128 -- then b[9] must hold 128 values (65 + zeros) */
   const void* wp[12];
 } imw_sp_weights;
@@ -102,7 +102,7 @@ typedef struct {
   float keypoint_threshold; /* conf["keypoint_threshold"] */
   int max_keypoints;        /* conf["max_keypoints"]; -1 = no cap; 0 or < -1 -> error (superpoint.py:139-141) */
   int remove_borders;       /* conf["remove_borders"] */
-  int use_tensor_cores;     /* 1: encoder convs on tcgen05 (bf16 x 3 split operands = fp32-equivalent), 0: fp32 CUDA cores */
+  int use_tensor_cores;     /* 1: encoder convs on tcgen05 (two fp16 planes per operand, three products = fp32-equivalent), 0: fp32 CUDA cores */
 } imw_sp_conf;
 
 size_t imw_superpoint_workspace_bytes(int batch, int height, int width);
@@ -263,7 +263,7 @@ int imw_aliked_forward(const imw_aliked_weights* weights, const imw_aliked_conf*
  * LoFTR dense matcher.
  * Replaces: hloc/matchers/loftr.py:41-71 -> kornia.feature.LoFTR == third_party/SE2LoFTR/src/loftr/loftr.py:29-75
  * (ResNet-FPN backbone, coarse linear-attention transformer, dual-softmax coarse matching, fine refinement).
- * Weights prepared by the host: BatchNorm folded, conv kernels as three bf16 planes [3][k*k][Cout][Cin] with the
+ * Weights prepared by the host: BatchNorm folded, conv kernels as two fp16 planes [2][k*k][Cout][Cin] with the
  * 196-channel tensors zero-padded to 256, encoder q/k/v stacked to [3*d][d].
  * ---------------------------------------------------------------------------------------------- */
 typedef struct { const void* w; const float* b; int cin, cout, ksize, stride; } imw_loftr_conv;
@@ -287,7 +287,7 @@ typedef struct {
   float match_threshold; /* match_coarse.thr */
   float temperature;     /* match_coarse.dsmax_temperature (0.1) */
   int border_rm;         /* match_coarse.border_rm (2) */
-  int use_tensor_cores;  /* encoder linears: 1 = 3xTF32, 2 = TF32, 0 = fp32 CUDA cores (convs are always tcgen05 bf16x3) */
+  int use_tensor_cores;  /* encoder linears: 1 = 3xTF32, 2 = TF32, 0 = fp32 CUDA cores (convs are always tcgen05 split-fp16) */
 } imw_loftr_conf;
 
 size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_matches);
@@ -327,11 +327,11 @@ int imw_debug_attention(const float* q, const float* k, const float* v, const in
 int imw_debug_conv3x3_tc(const float* in, const float* w_tap_cin_cout, const float* bias, float* out, int batch, int height,
                          int width, int cin, int cout, int relu, int pool, void* scratch, size_t scratch_bytes,
                          imw_stream_t stream);
-/* the tcgen05 conv alone on pre-split operands: in [3][B][H][W][Cin] bf16, w [3][9][Cout][Cin] bf16, out planes */
+/* the tcgen05 conv alone on pre-split operands: in [2][B][H][W][Cin] fp16, w [2][9][Cout][Cin] fp16, out planes */
 int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, const float* bias, void* out_planes, int batch,
                                 int height, int width, int cin, int cout, int relu, int pool, imw_stream_t stream);
 /* SuperPoint conv1a (1 -> 64) evaluated inside the conv1b (64 -> 64) tcgen05 kernel: image [B][H][W] fp32, w1a [9][64],
- * w1b_planes [3][9][64][64] bf16 -> conv1b output planes [3][B][H/2][W/2][64] (pool = 1) */
+ * w1b_planes [2][9][64][64] fp16 -> conv1b output planes [2][B][H/2][W/2][64] (pool = 1) */
 /* tuning hook: images per pass of the SuperPoint conv stack (default 8); returns the value in effect */
 int imw_debug_set_sp_sub(int n);
 int imw_debug_conv1ab_fused(const float* image, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,

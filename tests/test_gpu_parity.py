@@ -29,7 +29,7 @@ def _load(root, name, conf, dev):
     return dynamic_load(root, name)(conf).eval().to(dev)
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-bf16x3"])
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-fp16x2"])
 @pytest.mark.parametrize("case,confs", [("sp_real", ["api", "max1024", "nocap"]), ("sp_synth", ["max1024", "max2048"])])
 def test_superpoint_matches_reference(golden, dev, case, confs, tc):
     from imcui_b200.hloc import extractors
@@ -68,7 +68,7 @@ def test_superpoint_ragged_sizes_vs_oracle(dev, hw):
     assert (out["descriptors"][0].cpu() - ref["descriptors"][0]).abs().max() < 1e-3
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-bf16x3"])
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-fp32", "tcgen05-fp16x2"])
 def test_superpoint_dense_scores(golden, dev, tc):
     from imcui_b200 import ops
     from imcui_b200.hloc import extractors
@@ -223,7 +223,7 @@ def test_tcgen05_gemm_unit(dev):
 
 
 def test_tcgen05_conv_unit(dev):
-    """tcgen05 bf16x3 implicit-GEMM conv == fp32 CUDA-core conv to fp32 rounding noise, incl. zero padding,
+    """tcgen05 split-fp16 implicit-GEMM conv == fp32 CUDA-core conv to fp32 rounding noise, incl. zero padding,
     fused ReLU / 2x2 max-pool, partial tiles (H % 8 != 0) and both Cout tile widths."""
     from imcui_b200 import ops
     torch.manual_seed(1)

@@ -195,9 +195,11 @@ def test_match_dense_postprocessing_with_a_fake_matcher(dev):
     np.testing.assert_allclose(out["mkeypoints1_orig"], [[1, 2], [9.5, 18.25]])
     assert np.array_equal(out["keypoints0"], out["mkeypoints0"]) and out["mconf"].tolist() == pytest.approx([0.9, 0.4])
     assert out["new_size0"].tolist() == [640, 480] and out["original_size0"].tolist() == [1280, 960]
-    # gray conversion + /255 of image 1 (no resize needed) and the 2x2 area resize of image 0 are the plain cv2 results
+    # gray conversion + /255 of image 1 (no resize needed) and the two area resizes of image 0 (resize_max 1024: 1280x960 ->
+    # 1024x768, then force_resize -> 640x480) are the plain cv2 results
     assert np.array_equal(out["image1"], (cv2.cvtColor(rgb1, cv2.COLOR_RGB2GRAY).astype(np.float32) / 255.0))
-    g0 = cv2.resize(cv2.cvtColor(rgb0, cv2.COLOR_RGB2GRAY).astype(np.float32), (640, 480), interpolation=cv2.INTER_AREA)
+    g0 = cv2.resize(cv2.cvtColor(rgb0, cv2.COLOR_RGB2GRAY).astype(np.float32), (1024, 768), interpolation=cv2.INTER_AREA)
+    g0 = cv2.resize(g0, (640, 480), interpolation=cv2.INTER_AREA)
     assert np.array_equal(out["image0"], (g0 / 255.0).astype(np.float32))
 
 

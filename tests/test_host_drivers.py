@@ -76,16 +76,16 @@ def test_set_null_pred_and_registry_parsing():
 
 
 def test_loftr_weight_packing_layout():
-    """BN folding, 196 -> 256 zero padding and the three-plane bf16 split of the LoFTR backbone convolutions."""
+    """BN folding, 196 -> 256 zero padding and the two-plane fp16 split of the LoFTR backbone convolutions."""
     from imcui_b200 import ops
     from oracle import loftr as ol
     sd = ol.random_weights(0)
     pk = ops.loftr_pack_weights(sd)
     c = pk["convs"]["l2.0"]
-    assert (c["cin"], c["cout"], c["ksize"], c["stride"]) == (128, 256, 3, 2) and tuple(c["w"].shape) == (3, 9, 256, 128)
+    assert (c["cin"], c["cout"], c["ksize"], c["stride"]) == (128, 256, 3, 2) and tuple(c["w"].shape) == (2, 9, 256, 128)
     g = sd["backbone.layer2.0.bn1.weight"] / torch.sqrt(sd["backbone.layer2.0.bn1.running_var"] + 1e-5)
     w = (sd["backbone.layer2.0.conv1.weight"] * g[:, None, None, None]).permute(2, 3, 0, 1).reshape(9, 196, 128)
-    rec = c["w"].float().sum(0)
+    rec = c["w"][0].float() + c["w"][1].float() / 2048.0
     assert float((rec[:, :196] - w).abs().max()) < 1e-6 * float(w.abs().max()) + 1e-7 and float(rec[:, 196:].abs().max()) == 0.0
     assert float(c["b"][196:].abs().max()) == 0.0 and pk["convs"]["l3_out"]["b"] is None
     assert tuple(pk["conv1_w"].shape) == (49, 128) and tuple(pk["c0.qkv_w"].shape) == (768, 256) and tuple(pk["f1.mlp0_w"].shape) == (256, 256)

@@ -28,3 +28,8 @@ class DualSoftMax(BaseModel):
         m0, s0 = ops.dual_softmax(ds, counts, self.conf["match_threshold"], self.conf["inv_temperature"], self.conf["tensor_cores"])
         # reference dtypes: int64 matches, float64 scores (NumPy round trip, dual_softmax.py:29-35)
         return {"matches0": m0[:, :n].long(), "matching_scores0": s0[:, :n].double()}
+
+    def match_batch(self, batch):
+        """see LightGlue.match_batch"""
+        return ops.dual_softmax(batch["descriptors"], batch["counts"], self.conf["match_threshold"], self.conf["inv_temperature"],
+                                self.conf["tensor_cores"])

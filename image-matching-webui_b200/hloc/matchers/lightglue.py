@@ -95,3 +95,11 @@ class LightGlue(BaseModel):
             "scores": [ms0[0][valid]],
             "prune0": prune0, "prune1": prune1,
         }
+
+    def match_batch(self, batch):
+        """Many pairs in one library call (hloc/pairs_stream.py): batch = {keypoints [2P,cap,2], descriptors [2P,cap,D] token-major,
+        scores [2P,cap], counts [2P] int32, image_wh [2P,2]} (slot 2p+side, cap % 128 == 0) -> (matches0 [P,cap] int32,
+        matching_scores0 [P,cap]).  Every pair keeps the reference's B = 1 semantics (own early exit, own pruning)."""
+        out = ops.lightglue_forward(self._bufs(), self.conf["n_layers"], batch["keypoints"], batch["descriptors"], batch["counts"],
+                                    self._kernel_conf())
+        return out["matches"][0::2], out["scores"][0::2]

@@ -38,3 +38,8 @@ class NearestNeighbor(BaseModel):
         m0, s0 = ops.nearest_neighbor(ds, counts, self.conf["ratio_threshold"], self.conf["distance_threshold"],
                                       self.conf["do_mutual_check"], self.conf["tensor_cores"])
         return {"matches0": m0[:, :n].long(), "matching_scores0": s0[:, :n]}
+
+    def match_batch(self, batch):
+        """see LightGlue.match_batch: descriptors [2P,cap,D] token-major, counts [2P] -> (matches0 [P,cap], scores0 [P,cap])"""
+        return ops.nearest_neighbor(batch["descriptors"], batch["counts"], self.conf["ratio_threshold"], self.conf["distance_threshold"],
+                                    self.conf["do_mutual_check"], self.conf["tensor_cores"])

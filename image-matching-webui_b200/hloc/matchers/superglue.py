@@ -53,3 +53,12 @@ class SuperGlue(BaseModel):
                                              "match_threshold": self.conf["match_threshold"], "use_tensor_cores": tc})
         return {"matches0": matches[0, :m].long()[None], "matches1": matches[1, :n].long()[None],
                 "matching_scores0": ms[0, :m][None], "matching_scores1": ms[1, :n][None]}
+
+    def match_batch(self, batch):
+        """see LightGlue.match_batch (image_wh [2P,2] int32 feeds the keypoint normalisation, superglue.py:65-72)"""
+        tc = {False: 0, True: 1, "3xtf32": 1, "tf32": 2}[self.conf["tensor_cores"]]
+        matches, ms = ops.superglue_forward(self._bufs(), self.bin_score, batch["keypoints"], batch["scores"], batch["descriptors"],
+                                            batch["counts"], batch["image_wh"],
+                                            {"sinkhorn_iterations": self.conf["sinkhorn_iterations"],
+                                             "match_threshold": self.conf["match_threshold"], "use_tensor_cores": tc})
+        return matches[0::2], ms[0::2]

@@ -177,6 +177,14 @@ def lib():
         L.imw_gather_matches.argtypes = [C.c_int, C.c_int] + [vp] * 12
         L.imw_rescale_keypoints.restype = C.c_int
         L.imw_rescale_keypoints.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        L.imw_quantize_keypoints.restype = C.c_int
+        L.imw_quantize_keypoints.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, vp, vp, vp]
+        L.imw_nearest_point.restype = C.c_int
+        L.imw_nearest_point.argtypes = [C.c_int, vp, C.c_int, vp, C.c_float, vp, vp]
+        L.imw_unique_matches_workspace_bytes.restype = C.c_size_t
+        L.imw_unique_matches_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        L.imw_unique_matches.restype = C.c_int
+        L.imw_unique_matches.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
         L.imw_prof_begin.restype = C.c_int
         L.imw_prof_begin.argtypes = [vp]
         L.imw_prof_end.restype = C.c_longlong

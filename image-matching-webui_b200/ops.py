@@ -70,6 +70,49 @@ def gather_matches(keypoints, matches, counts, scores=None, scales=None, out=Non
     return (out["mkpts0"], out["mkpts1"], out["mcount"]) if simple else out
 
 
+def quantize_keypoints(keypoints, cell_size, counts=None):
+    """`to_cpts` (match_dense.py:37-40): keypoints [S,cap,2] fp32 -> (cells [S,cap,2] int32, coords [S,cap,2] fp32)."""
+    L.require_cuda(keypoints, "quantize_keypoints(keypoints)")
+    S, cap, _ = keypoints.shape
+    dev = keypoints.device
+    cells = torch.zeros(S, cap, 2, dtype=torch.int32, device=dev)
+    coords = torch.zeros(S, cap, 2, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().imw_quantize_keypoints(S, cap, L.ptr(keypoints.contiguous()), L.ptr(counts), float(cell_size), L.ptr(cells), L.ptr(coords),
+                                               L.stream_ptr(dev)))
+    return cells, coords
+
+
+def nearest_point(query, points, max_error):
+    """`assign_keypoints(update=False)` (match_dense.py:52-59): query [K,2], points [M,2] fp32 -> ids [K] int32 (-1 beyond max_error)."""
+    L.require_cuda(query, "nearest_point(query)")
+    K, M = query.shape[0], points.shape[0]
+    ids = torch.full((K,), -1, dtype=torch.int32, device=query.device)
+    if K == 0 or M == 0:
+        return ids
+    with torch.cuda.device(query.device):
+        L.check(L.lib().imw_nearest_point(K, L.ptr(query.float().contiguous()), M, L.ptr(points.float().contiguous()), float(max_error), L.ptr(ids),
+                                          L.stream_ptr(query.device)))
+    return ids
+
+
+def unique_matches(ids0, ids1, scores, counts, id_cap):
+    """`kpids_to_matches0` (match_dense.py:99-121) for a batch: ids0/ids1 [P,cap] int32, scores [P,cap] fp32, counts [P] ->
+    (matches0 [P,id_cap] int32, scores0 [P,id_cap] fp16, n_kps0 [P] int32)."""
+    L.require_cuda(ids0, "unique_matches(ids0)")
+    P, cap = ids0.shape
+    dev = ids0.device
+    m0 = torch.empty(P, id_cap, dtype=torch.int32, device=dev)
+    s0 = torch.empty(P, id_cap, dtype=torch.float16, device=dev)
+    nk = torch.empty(P, dtype=torch.int32, device=dev)
+    lib = L.lib()
+    ws = L.workspaces.get(dev, lib.imw_unique_matches_workspace_bytes(P, id_cap), "dense_agg")
+    with torch.cuda.device(dev):
+        L.check(lib.imw_unique_matches(P, cap, int(id_cap), L.ptr(ids0.contiguous()), L.ptr(ids1.contiguous()), L.ptr(scores.float().contiguous()),
+                                       L.ptr(counts.contiguous()), L.ptr(m0), L.ptr(s0), L.ptr(nk), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    return m0, s0, nk
+
+
 def rescale_keypoints(keypoints, scales, counts=None, out=None):
     """keypoints [S,cap,2] fp32, scales [S,2] fp32 -> (k + 0.5) * s - 0.5 (match_features.py:251-254)."""
     L.require_cuda(keypoints, "rescale_keypoints(keypoints)")

@@ -76,6 +76,24 @@ int imw_gather_matches(int n_pairs, int cap, const float* keypoints, const int* 
                        const int* counts, const float* scales, float* mkpts0, float* mkpts1, float* mkpts0_orig,
                        float* mkpts1_orig, float* mconf, int* mcount, imw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense-match aggregation (per-pair array work of hloc/match_dense.py:37-121).
+ * imw_quantize_keypoints: `to_cpts` (:37-40): cells [n][cap][2] = rint((k + 0.5) / cell_size) and coords [n][cap][2] = the
+ *   fp32 tuple np.round(cell * cell_size - 0.5, 2) the reference uses as dictionary key (cell_size 0: the raw keypoint).
+ * imw_nearest_point: `assign_keypoints(update=False)` (:52-59): id of the nearest of `points` [M][2] per query, -1 beyond
+ *   max_error.
+ * imw_unique_matches: `kpids_to_matches0` (:99-121) for a batch of pairs: ids0/ids1/scores [P][cap] (ids -1 = unassigned,
+ *   < id_cap), counts [P] -> matches0 [P][id_cap] (-1 = none), scores0 [P][id_cap] fp16, n_kps0 [P] (= max kept id0 + 1,
+ *   the length the reference's arrays have).  n-to-1 conflicts keep the best-scoring match per id on BOTH sides.
+ * ---------------------------------------------------------------------------------------------- */
+int imw_quantize_keypoints(int n_sets, int cap, const float* keypoints, const int* counts, float cell_size, int* cells,
+                           float* coords, imw_stream_t stream);
+int imw_nearest_point(int n_query, const float* query, int n_points, const float* points, float max_error, int* ids,
+                      imw_stream_t stream);
+size_t imw_unique_matches_workspace_bytes(int n_pairs, int id_cap);
+int imw_unique_matches(int n_pairs, int cap, int id_cap, const int* ids0, const int* ids1, const float* scores, const int* counts,
+                       int* matches0, void* scores0_f16, int* n_kps0, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
 /* keypoints [n_sets][cap][2], counts [n_sets] (nullable: all cap rows), scales [n_sets][2] -> out = (k + 0.5) * s - 0.5
  * (hloc/match_features.py:251-254, hloc/match_dense.py:655-659) */
 int imw_rescale_keypoints(int n_sets, int cap, const float* keypoints, const int* counts, const float* scales, float* out,

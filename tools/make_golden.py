@@ -292,6 +292,76 @@ def matcher_case(name, pairs):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def dense_agg_case(name):
+    """hloc/match_dense.py aggregate_matches / assign_keypoints / kpids_to_matches0 of the UNMODIFIED reference on seeded
+    semi-dense matches of four images (six pairs), run against an in-memory stand-in for h5py.File (h5py is not installed)."""
+    import importlib
+    import types
+    store = {}
+
+    class DS:
+        def __init__(self, a): self.a = np.asarray(a)
+        def __array__(self, *a, **k): return self.a
+
+    class Grp(dict):
+        def create_dataset(self, k, data=None): self[k] = DS(data)
+
+    class File:
+        def __init__(self, path, *a, **k): self.d = store.setdefault(str(path), {})
+        def __enter__(self): return self
+        def __exit__(self, *e): return False
+        def __getitem__(self, k): return self.d[k]
+        def __contains__(self, k): return k in self.d
+        def __delitem__(self, k): del self.d[k]
+        def create_group(self, k): self.d[k] = Grp(); return self.d[k]
+        def visititems(self, fn): [fn(g, v) for g, grp in self.d.items() for v in grp.values()]
+    h5 = types.ModuleType("h5py"); h5.File = File; h5.Dataset = DS
+    sys.modules["h5py"] = h5
+    sys.path.insert(0, str(R.REF))
+    importlib.import_module("imcui.hloc")
+    pc = types.ModuleType("pycolmap"); pc.__version__ = "0.0"; sys.modules.setdefault("pycolmap", pc)
+    md = importlib.import_module("imcui.hloc.match_dense")
+    md.list_h5_names = lambda path: list(store.get(str(path), {}).keys())
+    rng = np.random.default_rng(11)
+    names = ["q/a.jpg", "db/b.jpg", "db/c.jpg", "db/d.jpg"]
+    pairs = [(names[i], names[j]) for i in range(4) for j in range(i + 1, 4)]
+    out = {}
+    for case, conf, max_kps, fixed in (("sfm", {"max_error": 1, "cell_size": 1}, None, False), ("coarse", {"max_error": 2, "cell_size": 8}, 300, False),
+                                       ("loc", {"max_error": 4, "cell_size": 4}, None, True)):
+        store.clear()
+        mfile = File("m.h5")
+        base = {n: rng.uniform([0, 0], [320, 240], (500, 2)).astype(np.float32) for n in names}
+        for a, b in pairs:
+            k = int(rng.integers(200, 420))
+            ia, ib = rng.integers(0, 500, k), rng.integers(0, 500, k)
+            g = mfile.create_group(md.names_to_pair(a, b))
+            k0 = (base[a][ia] + rng.normal(0, 0.4, (k, 2))).astype(np.float32); k1 = (base[b][ib] + rng.normal(0, 0.4, (k, 2))).astype(np.float32)
+            sc = rng.uniform(0.2, 1.0, k).astype(np.float32)
+            sc[::7] = sc[1::7][: len(sc[::7])] if len(sc[1::7]) >= len(sc[::7]) else sc[::7]     # some exactly equal scores
+            g.create_dataset("keypoints0", data=k0); g.create_dataset("keypoints1", data=k1); g.create_dataset("scores", data=sc)
+            for key, v in (("keypoints0", k0), ("keypoints1", k1), ("scores", sc)):
+                out[f"{case}/in/{md.names_to_pair(a, b)}/{key}"] = v
+        kw = {}
+        if fixed:   # localisation: db keypoints are fixed arrays, only the query (name0 of its pairs) is aggregated, unbinned
+            cp = {n: rng.uniform([0, 0], [320, 240], (400, 2)).astype(np.float32) for n in names[1:]}
+            for n, v in cp.items():
+                out[f"{case}/fixed/{n}"] = v
+            cpd = md.defaultdict(list); cpd.update(cp)
+            kw = dict(required_queries={names[0]}, cpdict=cpd, bindict=md.defaultdict(list))
+            use_pairs = [p for p in pairs if p[0] == names[0]]
+        else:
+            kw = dict(cpdict=md.defaultdict(list), bindict=md.defaultdict(list))
+            use_pairs = pairs
+        md.aggregate_matches(conf, list(use_pairs), "m.h5", "f.h5", max_kps=max_kps, **kw)
+        for a, b in use_pairs:
+            g = store["m.h5"][md.names_to_pair(a, b)]
+            out[f"{case}/out/{md.names_to_pair(a, b)}/matches0"] = np.asarray(g["matches0"]); out[f"{case}/out/{md.names_to_pair(a, b)}/matching_scores0"] = np.asarray(g["matching_scores0"])
+        for n, g in store.get("f.h5", {}).items():
+            out[f"{case}/feat/{n}/keypoints"] = np.asarray(g["keypoints"]); out[f"{case}/feat/{n}/score"] = np.asarray(g["score"])
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(f"[golden] {name}: {len(out)} arrays")
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     (OUT / "data").mkdir(exist_ok=True)
@@ -334,6 +404,7 @@ def main():
     plugin_contract_case("plugins")
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
+    dense_agg_case("dense_agg")
 
 
 if __name__ == "__main__":
@@ -345,6 +416,6 @@ if __name__ == "__main__":
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
                 lg_proj_case("lg_proj", [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
             else:
-                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case}[sys.argv[1]](sys.argv[1])
+                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case}[sys.argv[1]](sys.argv[1])
     else:
         main()

@@ -33,7 +33,7 @@ class LGWeights(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("input_dim", C.c_int), ("posenc_wr", C.c_void_p),
                 ("token_w", C.c_void_p), ("token_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
                 ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS),
-                ("input_proj_w", C.c_void_p), ("input_proj_b", C.c_void_p)]
+                ("input_proj_w", C.c_void_p), ("input_proj_b", C.c_void_p), ("has_lo_planes", C.c_int), ("pad_", C.c_int)]
 
 
 IMW_SG_MAX_LAYERS = 32

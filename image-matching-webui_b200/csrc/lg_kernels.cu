@@ -478,6 +478,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
       TcGemmArgs t{};
       t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.counts; t.skip = skip; t.skip_shift = 1;
       t.wsel_minus1 = wsel; t.wsel_shift = 1; t.wsel_rows = N;
+      t.wlo_rows = W->has_lo_planes ? w_rows : 0;     // host pre-split weights: [W ; W - trunc_tf32(W)]
       if (use_tc == 2) return launch_tc_gemm<128, 1>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
       return launch_tc_gemm<128, 3>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
     }

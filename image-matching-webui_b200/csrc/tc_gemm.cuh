@@ -1,11 +1,15 @@
 // tcgen05 TF32 GEMM   C[M,N] = A[M,K] * W[N,K]^T   (fp32 accumulate in TMEM).
 //
 // SPLIT = 1: operands read as single TF32 (10-bit mantissa): fast mode.
-// SPLIT = 3: 3xTF32 split precision = fp32-equivalent products: after TMA lands the fp32 tiles, four splitter warps
-//            rewrite them in shared memory as x_hi (low 13 mantissa bits cleared, exactly TF32-representable) and
-//            x_lo = x - x_hi (same swizzled offsets, lo slot right behind the hi slot), and the MMA warp issues
-//            A_hi x [W_hi | W_lo] (one MMA of N = 2 BN) and A_lo x W_hi  (dropped lo*lo term and the TF32 rounding
-//            of the lo parts are <= 2^-21 relative).  This is the default: LightGlue scores stay within the 1e-3
+// SPLIT = 3: 3xTF32 split precision = fp32-equivalent products  x = x_hi + x_lo  with x_hi = x truncated to TF32 and
+//            x_lo = x - x_hi.  kind::tf32 ignores the 13 low mantissa bits of its fp32 operands, so the tile TMA landed IS
+//            the x_hi operand as it stands; four splitter warps only compute x_lo into the slot right behind it (same
+//            swizzled offsets).  Constant weights come with their lo plane pre-computed by the host (rows
+//            [wlo_rows, 2 wlo_rows) of W, TcGemmArgs::wlo_rows), so the splitters touch the activation tile only: one
+//            16-byte shared-memory load and one store per four elements instead of two loads and four stores (the
+//            round-1 kernel, bound by exactly this LSU traffic: 63 % of the shared-memory wavefront peak).  The MMA warp
+//            issues A_hi x [W_hi | W_lo] (one MMA of N = 2 BN) and A_lo x W_hi (dropped lo*lo term and the TF32
+//            rounding of the lo parts are <= 2^-21 relative).  This is the default: LightGlue scores stay within the 1e-3
 //            parity tolerance, which single TF32 does not (measured 1.4e-2 on the golden pairs).
 //
 // Persistent: one CTA per SM walks the (m-tile, n-tile) list; the smem ring runs across tile boundaries and two TMEM
@@ -35,6 +39,8 @@ struct TcGemmArgs {
   int wsel_rows;
   int pair_product;      // 1: "W" is the OTHER slot of the pair in the same row space as A (rows (z^1)*cap + n0) and
                          //    only even slots produce output: C[pair] = X_0 X_1^T (score matrices)
+  long long wlo_rows;    // > 0: W holds a second plane W_lo = W - trunc_tf32(W) wlo_rows rows below W (host pre-split);
+                         //      0: W_lo is computed in the kernel like A_lo
 };
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 448;
@@ -49,7 +55,7 @@ constexpr size_t tc_gemm_smem_bytes() {
 // together and hit L2).  Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 hi/lo splitters (SPLIT == 3),
 // 6-13 epilogue (two warps per TMEM sub-partition, half of the tile's columns each).  The smem ring runs across tile boundaries and two TMEM accumulator sets alternate, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int SPLIT, class Epi>
+template <int BN, int SPLIT, bool WLO, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi,
                                                                     int m_tiles) {
@@ -107,9 +113,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
         for (int kb = 0; kb < KB; kb++, c++) {
           const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
           tc::mbar_wait(empty + s, ph ^ 1);
-          tc::mbar_expect_tx(full + s, TILE_BYTES);
+          tc::mbar_expect_tx(full + s, TILE_BYTES + (WLO ? B_BYTES : 0));
           tc::tma_load_2d(smem + s * STAGE, &tmA, full + s, kb * TC_BK, m_tile * TC_BM);
           tc::tma_load_2d(smem + s * STAGE + W_OFF, &tmW, full + s, kb * TC_BK, w_row0);
+          if (WLO) tc::tma_load_2d(smem + s * STAGE + W_OFF + B_BYTES, &tmW, full + s, kb * TC_BK, (int)(g.wlo_rows + w_row0));
         }
       }
     }
@@ -152,7 +159,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
     }
   } else if (warp < 6) {
     if (SPLIT == 3) {
-      // splitter: x -> (x_hi in place, x_lo in the twin tile); elementwise, so the TMA swizzle is irrelevant
+      // splitter: x_lo = x - trunc_tf32(x) into the twin tile (the landed tile itself is the hi operand: the tensor core ignores
+      // the low 13 mantissa bits); elementwise, so the TMA swizzle is irrelevant.  With a host-provided W_lo plane only the
+      // activation tile is touched.
       const int t = threadIdx.x - 64;  // 0..127
       int c = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -163,18 +172,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
           tc::mbar_wait(full + s, ph);
           uint4* base = reinterpret_cast<uint4*>(smem + s * STAGE);
 #pragma unroll 8
-          for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
+          for (int idx = t; idx < (WLO ? A_BYTES : TILE_BYTES) / 16; idx += 128) {
             // A region: hi at idx, lo A_BYTES behind; W region: hi at W_OFF + .., lo B_BYTES behind
             const bool in_a = idx < A_BYTES / 16;
-            uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
-            uint4* lo = hi + (in_a ? A_BYTES : B_BYTES) / 16;
-            uint4 v = *hi, h, l;
-            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            *hi = h;
+            const uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
+            uint4* lo = const_cast<uint4*>(hi) + (in_a ? A_BYTES : B_BYTES) / 16;
+            const uint4 v = *hi;
+            uint4 l;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
             *lo = l;
           }
           tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -235,19 +243,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
   if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
-// A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32.
+// A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32 (followed by its lo plane when g.wlo_rows > 0).
+template <int BN, int SPLIT, bool WLO, class Epi>
+static inline int launch_tc_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmW, long long rows_total, TcGemmArgs g, Epi epi, cudaStream_t st) {
+  constexpr size_t smem = tc_gemm_smem_bytes<BN, SPLIT>();
+  IMW_SMEM_ATTR_ONCE((tc_gemm_tf32_kernel<BN, SPLIT, WLO, Epi>), smem);
+  const int num_sms = imw_num_sms();
+  const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
+  dim3 grid((unsigned)(total < num_sms ? total : num_sms));
+  tc_gemm_tf32_kernel<BN, SPLIT, WLO, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
 template <int BN, int SPLIT, class Epi>
 static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, const float* W, long long w_rows, TcGemmArgs g,
                                  Epi epi, cudaStream_t st) {
   CUtensorMap tmA, tmW;
+  const bool wlo = SPLIT == 3 && g.wlo_rows > 0 && !g.pair_product;
+  if (!wlo) g.wlo_rows = 0;
   if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, TC_BK, TC_BM)) return e;
-  if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)w_rows, (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
-  constexpr size_t smem = tc_gemm_smem_bytes<BN, SPLIT>();
-  IMW_SMEM_ATTR_ONCE((tc_gemm_tf32_kernel<BN, SPLIT, Epi>), smem);
-  const int num_sms = imw_num_sms();
-  const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
-  dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-  tc_gemm_tf32_kernel<BN, SPLIT, Epi><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);
-  IMW_CHECK_LAUNCH();
-  return IMW_OK;
+  if (int e = tc_make_map_2d_f32(&tmW, W, (uint64_t)(wlo ? g.wlo_rows + w_rows : w_rows), (uint64_t)g.K, (uint64_t)g.K, TC_BK, BN)) return e;
+  if (SPLIT == 3 && wlo) return launch_tc_gemm_t<BN, SPLIT, (SPLIT == 3), Epi>(tmA, tmW, rows_total, g, epi, st);
+  return launch_tc_gemm_t<BN, SPLIT, false, Epi>(tmA, tmW, rows_total, g, epi, st);
 }

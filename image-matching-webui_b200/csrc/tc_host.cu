@@ -40,7 +40,8 @@ extern "C" int imw_debug_gemm_tf32(const float* A, const float* W, const float* 
   IMW_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 32 == 0, "imw_debug_gemm_tf32: M%%128, N%%128, K%%32");
   TcGemmArgs g{};
   g.K = K; g.N = N; g.tiles_per_slot = M / 128;
-  if (split == 3) return launch_tc_gemm<128, 3>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
+  if (split == 4) g.wlo_rows = N;   // W is [2N][K]: the weights followed by their pre-computed lo plane
+  if (split >= 3) return launch_tc_gemm<128, 3>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
   return launch_tc_gemm<128, 1>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
 }
 

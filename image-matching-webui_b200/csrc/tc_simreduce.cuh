@@ -6,7 +6,7 @@
 //
 //   warp 0      TMA producer: own-row tile [128 x 32 f32] and other-slot tile [128 x 32 f32] per k-block (SWIZZLE_128B)
 //   warp 1      TMEM allocation + MMA issue: hi*hi into the main accumulator, hi*lo + lo*hi into the cross accumulator
-//   warps 2..5  hi/lo splitters (x_hi = low 13 mantissa bits cleared, x_lo = x - x_hi, twin tile)
+//   warps 2..5  lo splitters (x_lo = x - trunc_tf32(x) into the twin tile; the landed fp32 tile itself is the hi operand)
 //   warps 6..13 reduction: one TMEM lane = one row i per thread, two warps per TMEM sub-partition (columns 0..63 /
 //               64..127 of the tile); a thread walks its columns in 32-wide chunks (op.accum32 when the functor has a
 //               chunked form, else op.accum per element); the state lives in registers across all column tiles of the
@@ -132,15 +132,15 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_simreduce_kernel(const __gr
 #pragma unroll 8
           for (int idx = t; idx < TILE_BYTES / 16; idx += 128) {
             const bool in_a = idx < A_BYTES / 16;
-            uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
-            uint4* lo = hi + (in_a ? A_BYTES : B_BYTES) / 16;
-            uint4 v = *hi, h, l;
-            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            *hi = h;
+            // the landed tile is the hi operand as it stands (kind::tf32 ignores the 13 low mantissa bits): only x_lo is written
+            const uint4* hi = base + (in_a ? idx : idx + (W_OFF - A_BYTES) / 16);
+            uint4* lo = const_cast<uint4*>(hi) + (in_a ? A_BYTES : B_BYTES) / 16;
+            const uint4 v = *hi;
+            uint4 l;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
             *lo = l;
           }
           tc::fence_proxy_async();

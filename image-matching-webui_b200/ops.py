@@ -246,12 +246,29 @@ def lg_pack_weights(sd, n_layers=9, heads=4):
     out["match_b"] = torch.stack([sd[f"log_assignment.{i}.matchability.bias"].float().reshape(()) for i in range(n_layers)])
     if "input_proj.weight" in sd:  # Linear(input_dim -> 256) for 128-d features (lightglue.py:392-395)
         out["input_proj_w"], out["input_proj_b"] = sd["input_proj.weight"].float(), sd["input_proj.bias"].float()
+    # 3xTF32 tcgen05 GEMM: every linear weight matrix carries its TF32 lo plane behind it ([W ; W - trunc_tf32(W)]), so the
+    # kernel splits activations only.  The fp32 CUDA-core path reads the first N rows.
+    for k in list(out):
+        if k.endswith(("qkv_w", "out_w", "ffn0_w", "ffn3_w")) or k == "input_proj_w":
+            out[k] = with_tf32_lo_plane(out[k])
     return {k: v.contiguous() for k, v in out.items()}
+
+
+def tf32_lo(w):
+    """w - trunc_tf32(w): what kind::tf32 drops when it ignores the 13 low mantissa bits of an fp32 operand"""
+    w = w.float().contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return w - hi
+
+
+def with_tf32_lo_plane(w):
+    return torch.cat([w.float(), tf32_lo(w)], 0).contiguous()
 
 
 def lg_weights_struct(bufs, n_layers=9):
     s = L.LGWeights()
     s.n_layers, s.input_dim = n_layers, 256
+    s.has_lo_planes = 1
     if "input_proj_w" in bufs:
         s.input_dim = bufs["input_proj_w"].shape[1]
         s.input_proj_w, s.input_proj_b = bufs["input_proj_w"].data_ptr(), bufs["input_proj_b"].data_ptr()
@@ -271,6 +288,7 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
     L.require_cuda(keypoints, "lightglue_forward(keypoints)")
     S, cap, _ = keypoints.shape
     in_dim = bufs["input_proj_w"].shape[1] if "input_proj_w" in bufs else 256
+    assert bufs["l0.self.out_w"].shape[0] == 512, "lg_pack_weights output expected (weights followed by their TF32 lo planes)"
     assert S % 2 == 0 and descriptors.shape == (S, cap, in_dim) and counts.numel() == S and counts.dtype == torch.int32
     assert keypoints.is_contiguous() and descriptors.is_contiguous() and counts.is_contiguous()
     P, dev = S // 2, keypoints.device
@@ -648,17 +666,20 @@ def magsac(pts0, pts1, counts, geometry_type="Homography", threshold=3.0, confid
 
 
 def debug_gemm(A, W, bias, mode="3xtf32"):
-    """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32") or the CUDA-core GEMM ("fp32")."""
+    """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32" / "3xtf32_wlo": host-provided W lo plane) or the
+    CUDA-core GEMM ("fp32")."""
     L.require_cuda(A, "debug_gemm(A)")
     M, K = A.shape
     N = W.shape[0]
     out = torch.empty(M, N, device=A.device)
+    if mode == "3xtf32_wlo":
+        W = with_tf32_lo_plane(W)
     args = (L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K)
     with torch.cuda.device(A.device):
         if mode == "fp32":
             L.check(L.lib().imw_debug_gemm_fp32(*args, L.stream_ptr(A.device)))
         else:
-            L.check(L.lib().imw_debug_gemm_tf32(*args, 3 if mode == "3xtf32" else 1, L.stream_ptr(A.device)))
+            L.check(L.lib().imw_debug_gemm_tf32(*args, {"3xtf32": 3, "3xtf32_wlo": 4, "tf32": 1}[mode], L.stream_ptr(A.device)))
     return out
 
 

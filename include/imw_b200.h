@@ -162,6 +162,10 @@ typedef struct {
   const float *match_w, *match_b; /* [L][256], [L]       log_assignment.matchability */
   imw_lg_layer layers[IMW_LG_MAX_LAYERS];
   const float *input_proj_w, *input_proj_b; /* [256][input_dim], [256]; used when input_dim != 256 */
+  /* 1: every linear weight matrix W [N][K] above (qkv_w, out_w, ffn0_w, ffn3_w, input_proj_w) is followed in memory by its
+     TF32 lo plane W - trunc_tf32(W) [N][K] (ops.lg_pack_weights): the 3xTF32 tcgen05 GEMM then splits activations only */
+  int has_lo_planes;
+  int pad_;
 } imw_lg_weights;
 
 typedef struct {
@@ -331,7 +335,8 @@ int imw_magsac(int n_sets, int cap, const float* pts0, const float* pts1, const 
                int* n_iters, imw_stream_t stream);
 
 /* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 path (split = 1: single TF32,
- * split = 3: 3xTF32 fp32-equivalent) and on the CUDA-core fp32 path. */
+ * split = 3: 3xTF32 fp32-equivalent, split = 4: the same with W [2N][K] = weights + host-computed lo plane) and on the
+ * CUDA-core fp32 path. */
 int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K, int split,
                         imw_stream_t stream);
 int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,

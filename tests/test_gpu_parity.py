@@ -212,13 +212,15 @@ def test_tcgen05_gemm_unit(dev):
         simt = ops.debug_gemm(A, Wt, b, "fp32")
         tf32 = ops.debug_gemm(A, Wt, b, "tf32")
         x3 = ops.debug_gemm(A, Wt, b, "3xtf32")
+        x3w = ops.debug_gemm(A, Wt, b, "3xtf32_wlo")      # host-provided W lo plane (what the LightGlue linears use)
         torch.cuda.synchronize()
-        e_simt, e_tf32, e_x3 = (float((t - ref).abs().max()) for t in (simt, tf32, x3))
-        print(f"[gemm] {M}x{N}x{K}: fp32 {e_simt:.2e} tf32 {e_tf32:.2e} 3xtf32 {e_x3:.2e}")
-        assert e_simt < 1e-4 and e_tf32 < 2e-2 and e_x3 < 3e-5, (M, N, K, e_simt, e_tf32, e_x3)
+        e_simt, e_tf32, e_x3, e_x3w = (float((t - ref).abs().max()) for t in (simt, tf32, x3, x3w))
+        print(f"[gemm] {M}x{N}x{K}: fp32 {e_simt:.2e} tf32 {e_tf32:.2e} 3xtf32 {e_x3:.2e} 3xtf32+wlo {e_x3w:.2e}")
+        assert e_simt < 1e-4 and e_tf32 < 2e-2 and e_x3 < 3e-5 and e_x3w < 3e-5, (M, N, K, e_simt, e_tf32, e_x3, e_x3w)
+        assert torch.equal(x3, x3w)                       # same products in the same order: bit-identical
     # exactly representable operands -> exact result (layout / descriptor correctness independent of rounding)
     A = torch.randint(-4, 5, (256, 64), device=dev).float(); Wt = torch.randint(-4, 5, (128, 64), device=dev).float()
-    for mode in ("tf32", "3xtf32"):
+    for mode in ("tf32", "3xtf32", "3xtf32_wlo"):
         assert torch.equal(ops.debug_gemm(A, Wt, torch.zeros(128, device=dev), mode), A @ Wt.t())
 
 

@@ -9,11 +9,14 @@
 //              softmax_j and P_j V_j run, V_{j+1} while S_{j+1} and softmax_{j+1} run)
 //   warp 1     MMA issuer: S_j = Q K_j^T into one of two TMEM buffers (main hi*hi and cross-term accumulators),
 //              O_j = P_j V_j into a fresh TMEM tile (never rescaled in place)
-//   warps 2-9  softmax / correction, two warps per TMEM sub-partition: a thread owns one q row and HALF of the columns
-//              (32 of the 64 keys of S_j, 32 of the 64 output dims of O): tcgen05.ld S_j, mask, row max (exchanged
-//              with the partner thread through shared memory), P_j = exp(S_j - m) written to shared memory as
-//              hi/lo K-major SWIZZLE_128B tiles for the second MMA, and the running output
-//              acc = (acc + O_{j-1}) * exp(m_{j-1} - m_j) kept in registers.
+//   warps 2-17 softmax / correction, FOUR warps per TMEM sub-partition: a thread owns one q row and a QUARTER of the columns
+//              (16 of the 64 keys of S_j, 16 of the 64 output dims of O): tcgen05.ld S_j, mask, row max (exchanged
+//              with the three partner threads through shared memory), P_j = exp(S_j - m) written to shared memory as
+//              K-major SWIZZLE_128B tiles (P itself = the hi operand, P - trunc_tf32(P) = the lo operand) for the second
+//              MMA, and the running output acc = (acc + O_{j-1}) * exp(m_{j-1} - m_j) kept in registers.
+//              (Round 1 ran 8 such warps with half a row each: the per-tile chain S -> softmax -> P -> PV was bound by
+//              the LATENCY of those warps -- 2 per scheduler, ~700 dependent instructions per tile, tensor pipe 29 % --
+//              not by any throughput; twice the warps with half the work each shortens exactly that chain.)
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -29,12 +32,12 @@ struct TcAttnArgs {
   long long plane_rows_vt;  // slots*4*64
 };
 
-constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 64 + 256;
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_SM_THREADS = 512, TA_THREADS = 64 + TA_SM_THREADS;
 constexpr int TA_Q_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 k-subtiles x [128 x 32 f32]  = 64 KB
 constexpr int TA_K_BYTES = 2 * 2 * TA_BKV * 128;    // hi/lo x 2 subtiles x [64 x 32]        = 32 KB
 constexpr int TA_V_BYTES = 2 * 2 * 64 * 128;        // hi/lo x 2 kv-subtiles x [64 d x 32 kv] = 32 KB
 constexpr int TA_P_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 kv-subtiles x [128 x 32]     = 64 KB
-constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256 + 2 * 2 * 128 * sizeof(float);
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256 + 2 * 4 * 128 * sizeof(float);
 
 // TMEM columns: S buffers 2 x (main 64 + cross 64) = 256, O main 64 + cross 64 -> 384 (allocate 512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
@@ -64,12 +67,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
            *s_full = bars + 5 /*[2]*/, *p_full = bars + 7, *o_full = bars + 8;
   uint32_t* tmem_slot = (uint32_t*)(bars + 9);
-  float* xchg = (float*)(sP + TA_P_BYTES + 256);   // [tile parity][half][128 rows]: row maxima / final sums of the partner thread
+  float* xchg = (float*)(sP + TA_P_BYTES + 256);   // [tile parity][quarter][128 rows]: row maxima / final sums of the partner threads
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
     tc::mbar_init(q_full, 1); tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
-    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, 256);
+    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, TA_SM_THREADS);
     tc::mbar_init(o_full, 1);
     tc::fence_barrier_init();
   }
@@ -154,69 +157,70 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     const int q = warp % 4, r = q * 32 + lane;           // TMEM lane = q row inside the tile
-    const int half = (warp - 2) / 4;                     // keys [32 half, +32) of S_j and dims [32 half, +32) of O
+    const int qt = (warp - 2) / 4;                       // keys [16 qt, +16) of S_j and dims [16 qt, +16) of O
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f, acc[32];
+    float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
-    for (int c = 0; c < 32; c++) acc[c] = 0.f;
+    for (int c = 0; c < 16; c++) acc[c] = 0.f;
     for (int j = 0; j < T; j++) {
       tc::mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc::fence_after_sync();
-      float s[32];
+      float s[16];
       {
-        float t[32];
-        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128 + half * 32;
-        tc::tmem_ld32(a, s);
-        tc::tmem_ld32(a + 64, t);
+        float t[16];
+        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128 + qt * 16;
+        tc::tmem_ld16(a, s);
+        tc::tmem_ld16(a + 64, t);
 #pragma unroll
-        for (int c = 0; c < 32; c++) s[c] += t[c];
+        for (int c = 0; c < 16; c++) s[c] += t[c];
       }
-      const int kv0 = j * TA_BKV + half * 32;
+      const int kv0 = j * TA_BKV + qt * 16;
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 32; c++) {
+      for (int c = 0; c < 16; c++) {
         s[c] = (kv0 + c < nk) ? s[c] * g.scale : -INFINITY;
         mx = fmaxf(mx, s[c]);
       }
-      // row maximum over both halves (partner thread = same row, other column half)
-      float* xb = xchg + (j & 1) * 256;
-      xb[half * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m_new = fmaxf(m, fmaxf(mx, xb[(half ^ 1) * 128 + r]));   // finite: the tile holds at least one valid key
+      // row maximum over the four column quarters (partner threads = same row, other quarters)
+      float* xb = xchg + (j & 1) * 512;
+      xb[qt * 128 + r] = mx;
+      asm volatile("bar.sync 1, %0;" ::"n"(TA_SM_THREADS) : "memory");
+      const float m_new = fmaxf(m, fmaxf(fmaxf(xb[r], xb[128 + r]), fmaxf(xb[256 + r], xb[384 + r])));   // finite: the tile holds a valid key
       const float alpha = __expf(m - m_new);     // 0 on the first tile (m = -inf)
       float ps = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
+      for (int c = 0; c < 16; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
       l = l * alpha + ps;                        // partial sum over this thread's columns
       m = m_new;
       if (j > 0) {  // fold in O_{j-1} (computed relative to m_{j-1}), then move the reference to m_j
         tc::mbar_wait(o_full, (j - 1) & 1);
         tc::fence_after_sync();
-        float t[32];
-        tc::tmem_ld32(lane_addr + TA_O_COL + half * 32, t);        // main
+        float t[16];
+        tc::tmem_ld16(lane_addr + TA_O_COL + qt * 16, t);        // main
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c] += t[c];
-        tc::tmem_ld32(lane_addr + TA_O_COL + 64 + half * 32, t);   // cross terms
+        for (int c = 0; c < 16; c++) acc[c] += t[c];
+        tc::tmem_ld16(lane_addr + TA_O_COL + 64 + qt * 16, t);   // cross terms
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c] += t[c];
+        for (int c = 0; c < 16; c++) acc[c] += t[c];
       }
 #pragma unroll
-      for (int c = 0; c < 32; c++) acc[c] *= alpha;
-      // P_j -> shared memory, hi/lo planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk c of
-      // row r lives at chunk c ^ (r & 7)); the previous P V MMA has completed (o_full above)
+      for (int c = 0; c < 16; c++) acc[c] *= alpha;
+      // P_j -> shared memory: P (= hi operand: kind::tf32 ignores the 13 low mantissa bits) and P - trunc_tf32(P) (lo), K-major
+      // rows of 128 B with the 128B swizzle (16-byte chunk c of row r lives at chunk c ^ (r & 7)); keys [32 sub, +32) form
+      // k-subtile `sub`; the previous P V MMA has completed (o_full above)
       tc::fence_before_sync();
       {
-        uint8_t* ph = sP + (0 * 2 + half) * TA_BQ * 128 + r * 128;
-        uint8_t* pl = sP + (1 * 2 + half) * TA_BQ * 128 + r * 128;
+        const int sub = qt >> 1, ch0 = (qt & 1) * 4;
+        uint8_t* ph = sP + (0 * 2 + sub) * TA_BQ * 128 + r * 128;
+        uint8_t* pl = sP + (1 * 2 + sub) * TA_BQ * 128 + r * 128;
 #pragma unroll
-        for (int ch = 0; ch < 8; ch++) {
+        for (int ch = 0; ch < 4; ch++) {
           uint4 h4, l4;
           const float* v = &s[ch * 4];
-          h4.x = __float_as_uint(v[0]) & 0xFFFFE000u; h4.y = __float_as_uint(v[1]) & 0xFFFFE000u;
-          h4.z = __float_as_uint(v[2]) & 0xFFFFE000u; h4.w = __float_as_uint(v[3]) & 0xFFFFE000u;
-          l4.x = __float_as_uint(v[0] - __uint_as_float(h4.x)); l4.y = __float_as_uint(v[1] - __uint_as_float(h4.y));
-          l4.z = __float_as_uint(v[2] - __uint_as_float(h4.z)); l4.w = __float_as_uint(v[3] - __uint_as_float(h4.w));
-          const int pos = (ch ^ (r & 7)) * 16;
+          h4.x = __float_as_uint(v[0]); h4.y = __float_as_uint(v[1]); h4.z = __float_as_uint(v[2]); h4.w = __float_as_uint(v[3]);
+          l4.x = __float_as_uint(v[0] - __uint_as_float(h4.x & 0xFFFFE000u)); l4.y = __float_as_uint(v[1] - __uint_as_float(h4.y & 0xFFFFE000u));
+          l4.z = __float_as_uint(v[2] - __uint_as_float(h4.z & 0xFFFFE000u)); l4.w = __float_as_uint(v[3] - __uint_as_float(h4.w & 0xFFFFE000u));
+          const int pos = ((ch0 + ch) ^ (r & 7)) * 16;
           *reinterpret_cast<uint4*>(ph + pos) = h4;
           *reinterpret_cast<uint4*>(pl + pos) = l4;
         }
@@ -228,23 +232,23 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc::mbar_wait(o_full, (T - 1) & 1);
     tc::fence_after_sync();
     {
-      float t[32];
-      tc::tmem_ld32(lane_addr + TA_O_COL + half * 32, t);
+      float t[16];
+      tc::tmem_ld16(lane_addr + TA_O_COL + qt * 16, t);
 #pragma unroll
-      for (int c = 0; c < 32; c++) acc[c] += t[c];
-      tc::tmem_ld32(lane_addr + TA_O_COL + 64 + half * 32, t);
+      for (int c = 0; c < 16; c++) acc[c] += t[c];
+      tc::tmem_ld16(lane_addr + TA_O_COL + 64 + qt * 16, t);
 #pragma unroll
-      for (int c = 0; c < 32; c++) acc[c] += t[c];
+      for (int c = 0; c < 16; c++) acc[c] += t[c];
     }
-    float* xb = xchg + (T & 1) * 256;   // the buffer the last tile did not use
-    xb[half * 128 + r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* xb = xchg + (T & 1) * 512;   // the buffer the last tile did not use
+    xb[qt * 128 + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(TA_SM_THREADS) : "memory");
     const int row = q0 + r;
     if (row < nq) {
-      const float inv = 1.f / (l + xb[(half ^ 1) * 128 + r]);
-      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + half * 32);
+      const float inv = 1.f / ((xb[r] + xb[128 + r]) + (xb[256 + r] + xb[384 + r]));
+      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + qt * 16);
 #pragma unroll
-      for (int c = 0; c < 8; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      for (int c = 0; c < 4; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
     }
   }
   tc::fence_before_sync();

@@ -288,50 +288,6 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
   for (int c = lane; c < dim; c += 32) o[c] = __fdiv_rn(p[c], nrm);
 }
 
-struct OpRowMaxSum {  // softmax statistics of inv_temperature * sim along the other image
-  using State = MaxSumState;
-  float* rmax; float* rsum; int cap; float scale;
-  __device__ void init(State& s) const { s.m = -INFINITY; s.s = 0.f; }
-  __device__ void accum(State& s, float v, int, int, int, int) const { lse_accum(s, v * scale); }
-  __device__ void accum32(State& s, const float (&v)[32], int, int, int jn, int, int) const { lse_accum32(s, v, jn, scale); }
-  __device__ State shfl_xor(const State& s, int o) const {
-    State t; t.m = __shfl_xor_sync(0xffffffffu, s.m, o); t.s = __shfl_xor_sync(0xffffffffu, s.s, o); return t;
-  }
-  __device__ void merge(State& a, const State& b) const { lse_merge(a, b); }
-  __device__ void store(const State& s, int own, int i) const {
-    rmax[(long long)own * cap + i] = s.m;
-    rsum[(long long)own * cap + i] = s.s;
-  }
-};
-
-// P = softmax(sim, dim=-2) * softmax(sim, dim=-1) (dual_softmax.py:23); arg-max along the other image.
-struct OpDSMArgmax {
-  // arg-max over the other image of softmax(x, dim 1)[i,j] * softmax(x, dim 2)[i,j].  The factor normalised along the
-  // OTHER image's statistics is <= 1, so exp(x - max_own) / sum_own bounds the product: once a candidate is held, any
-  // x below  max_own + log(best * sum_own)  (minus a safety margin) cannot win and skips the exp / divide work.
-  struct State { float v; int j; float xmin; };
-  const float *rmax, *rsum; float* best_v; int* best_j; int cap; float scale;
-  __device__ void init(State& s) const { s.v = -INFINITY; s.j = 0x7fffffff; s.xmin = -INFINITY; }
-  __device__ void accum(State& s, float v, int i, int j, int own, int other) const {
-    const float x = v * scale;
-    if (x < s.xmin) return;
-    const long long io = (long long)own * cap + i, jo = (long long)other * cap + j;
-    const long long i0 = (own & 1) ? jo : io, i1 = (own & 1) ? io : jo;   // image-0 / image-1 statistics
-    // softmax over image-0 positions (statistics kept per image-1 column) times softmax over image-1 positions
-    const float p1 = __fdiv_rn(expf(x - rmax[i1]), rsum[i1]), p2 = __fdiv_rn(expf(x - rmax[i0]), rsum[i0]);
-    const float p = __fmul_rn(p1, p2);
-    if (p > s.v || (p == s.v && j < s.j)) {
-      s.v = p; s.j = j;
-      s.xmin = rmax[io] + logf(p * rsum[io]) - 1e-3f;   // -inf while p underflows to 0: nothing is skipped
-    }
-  }
-  __device__ State shfl_xor(const State& s, int o) const {
-    State t; t.v = __shfl_xor_sync(0xffffffffu, s.v, o); t.j = __shfl_xor_sync(0xffffffffu, s.j, o); t.xmin = s.xmin; return t;
-  }
-  __device__ void merge(State& a, const State& b) const { if (b.v > a.v || (b.v == a.v && b.j < a.j)) { a.v = b.v; a.j = b.j; } }
-  __device__ void store(const State& s, int own, int i) const { best_v[(long long)own * cap + i] = s.v; best_j[(long long)own * cap + i] = s.j; }
-};
-
 // (P == row max) & (P == col max) & (P > thr)  (dual_softmax.py:24-28)
 __global__ void dsm_finish_kernel(const float* __restrict__ best_v, const int* __restrict__ best_j, const int* __restrict__ counts,
                                   int* __restrict__ matches0, float* __restrict__ scores0, int cap, float thr) {
@@ -395,11 +351,11 @@ extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, cons
   IMW_CHECK_LAUNCH_T("normalize_rows_kernel");
   SimArgs sa{b.norm, cap, dim, dim, counts, nullptr};
   if (use_tensor_cores && tc_simreduce_ok(sa)) {
-    if (int e = launch_tc_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st)) return e;
-    if (int e = launch_tc_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, OpSoftmaxStats{b.f0, b.f1, (float*)b.m, cap, inv_temperature}, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, OpDualSoftmaxArgmax{b.f0, b.f1, (const float*)b.m, b.bv, b.bj, cap, inv_temperature}, st)) return e;
   } else {
-    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpRowMaxSum{b.f0, b.f1, cap, inv_temperature}, st));
-    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDSMArgmax{b.f0, b.f1, b.bv, b.bj, cap, inv_temperature}, st));
+    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpSoftmaxStats{b.f0, b.f1, (float*)b.m, cap, inv_temperature}, st));
+    IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDualSoftmaxArgmax{b.f0, b.f1, (const float*)b.m, b.bv, b.bj, cap, inv_temperature}, st));
   }
   dsm_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.bv, b.bj, counts, matches0, scores0, cap, match_threshold);
   IMW_CHECK_LAUNCH_T("dsm_finish_kernel");

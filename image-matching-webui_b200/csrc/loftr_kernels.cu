@@ -289,45 +289,6 @@ __global__ void lf_parity_kernel(int* skip_even, int* skip_odd, int S) {
 
 // ---- coarse matching ---------------------------------------------------------------------------------------------------
 // conf = softmax(sim, 1) * softmax(sim, 2), sim = <f0/16, f1/16> / 0.1  (coarse_matching.py:108-119): two streaming passes
-struct OpConfStats {
-  using State = MaxSumState;
-  float* rmax; float* rsum; int cap; float scale;
-  __device__ void init(State& s) const { s.m = -INFINITY; s.s = 0.f; }
-  __device__ void accum(State& s, float v, int, int, int, int) const { lse_accum(s, v * scale); }
-  __device__ void accum32(State& s, const float (&v)[32], int, int, int jn, int, int) const { lse_accum32(s, v, jn, scale); }
-  __device__ State shfl_xor(const State& s, int o) const {
-    State t; t.m = __shfl_xor_sync(0xffffffffu, s.m, o); t.s = __shfl_xor_sync(0xffffffffu, s.s, o); return t;
-  }
-  __device__ void merge(State& a, const State& b) const { lse_merge(a, b); }
-  __device__ void store(const State& s, int own, int i) const { rmax[(long long)own * cap + i] = s.m; rsum[(long long)own * cap + i] = s.s; }
-};
-struct OpConfArgmax {
-  // arg-max over the other image of softmax(x, dim 1)[i,j] * softmax(x, dim 2)[i,j].  The factor normalised along the
-  // OTHER image's statistics is <= 1, so exp(x - max_own) / sum_own bounds the product: once a candidate is held, any
-  // x below  max_own + log(best * sum_own)  (minus a safety margin) cannot win and skips the exp / divide work.
-  struct State { float v; int j; float xmin; };
-  const float *rmax, *rsum; float* best_v; int* best_j; int cap; float scale;
-  __device__ void init(State& s) const { s.v = -INFINITY; s.j = 0x7fffffff; s.xmin = -INFINITY; }
-  __device__ void accum(State& s, float v, int i, int j, int own, int other) const {
-    const float x = v * scale;
-    if (x < s.xmin) return;
-    const long long io = (long long)own * cap + i, jo = (long long)other * cap + j;
-    const long long i0 = (own & 1) ? jo : io, i1 = (own & 1) ? io : jo;   // image-0 / image-1 statistics
-    // softmax over image-0 positions (statistics kept per image-1 column) times softmax over image-1 positions
-    const float p1 = __fdiv_rn(expf(x - rmax[i1]), rsum[i1]), p2 = __fdiv_rn(expf(x - rmax[i0]), rsum[i0]);
-    const float p = __fmul_rn(p1, p2);
-    if (p > s.v || (p == s.v && j < s.j)) {
-      s.v = p; s.j = j;
-      s.xmin = rmax[io] + logf(p * rsum[io]) - 1e-3f;   // -inf while p underflows to 0: nothing is skipped
-    }
-  }
-  __device__ State shfl_xor(const State& s, int o) const {
-    State t; t.v = __shfl_xor_sync(0xffffffffu, s.v, o); t.j = __shfl_xor_sync(0xffffffffu, s.j, o); t.xmin = s.xmin; return t;
-  }
-  __device__ void merge(State& a, const State& b) const { if (b.v > a.v || (b.v == a.v && b.j < a.j)) { a.v = b.v; a.j = b.j; } }
-  __device__ void store(const State& s, int own, int i) const { best_v[(long long)own * cap + i] = s.v; best_j[(long long)own * cap + i] = s.j; }
-};
-
 // threshold + border + mutual max, ordered compaction by i (coarse_matching.py:176-195,241-250); one CTA per pair
 __global__ void __launch_bounds__(1024) lf_coarse_select_kernel(const float* __restrict__ best_v, const int* __restrict__ best_j,
                                                                 int L, int cap, int hc, int wc, float thr, int border,
@@ -430,7 +391,7 @@ constexpr int LF_KV_SPLIT = 32;   // token chunks per (slot, head) in the coarse
 
 struct LFBuffers {
   void *pa, *pb, *pc, *pd, *pe2;   // backbone plane scratch
-  float *fc, *ff, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *kv_part, *ksum_part, *rmax, *rsum, *best_v;
+  float *fc, *ff, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *kv_part, *ksum_part, *rmax, *rsum, *rlog, *best_v;
   int *best_j, *skip_even, *skip_odd, *cntL, *rows25, *fcnt;
   float *U, *G, *ctx, *fx, *fq, *fk, *fv, *fmsg, *ftmp, *fh, *fkv, *fksum;
 };
@@ -447,7 +408,7 @@ size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H, int W, int cap, int m
   b.msg = ws.take<float>(T * CD); b.tmp = ws.take<float>(T * CD); b.h = ws.take<float>(T * 512);
   b.kv = ws.take<float>(S * NH * 32 * 32); b.ksum = ws.take<float>(S * NH * 32);
   b.kv_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32 * 32); b.ksum_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32);
-  b.rmax = ws.take<float>(T); b.rsum = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
+  b.rmax = ws.take<float>(T); b.rsum = ws.take<float>(T); b.rlog = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
   b.skip_even = ws.take<int>(S); b.skip_odd = ws.take<int>(S); b.cntL = ws.take<int>(S); b.rows25 = ws.take<int>(S); b.fcnt = ws.take<int>(S * mcap);
   const size_t FT = 2 * (size_t)P * mcap * 25;  // fine tokens
   b.U = ws.take<float>(FT * FD); b.G = ws.take<float>(2 * (size_t)P * mcap * CD); b.ctx = ws.take<float>(2 * (size_t)P * mcap * 256);
@@ -593,11 +554,11 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     SimArgs sa{b.xm, cap, 512, CD, b.cntL, nullptr};
     const float scale = 1.f / (16.f * 16.f * conf->temperature);
     if (conf->use_tensor_cores && tc_simreduce_ok(sa)) {
-      RUN(launch_tc_simreduce(sa, S, OpConfStats{b.rmax, b.rsum, cap, scale}, st));
-      RUN(launch_tc_simreduce(sa, S, OpConfArgmax{b.rmax, b.rsum, b.best_v, b.best_j, cap, scale}, st));
+      RUN(launch_tc_simreduce(sa, S, OpSoftmaxStats{b.rmax, b.rsum, b.rlog, cap, scale}, st));
+      RUN(launch_tc_simreduce(sa, S, OpDualSoftmaxArgmax{b.rmax, b.rsum, b.rlog, b.best_v, b.best_j, cap, scale}, st));
     } else {
-      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfStats{b.rmax, b.rsum, cap, scale}, st));
-      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpConfArgmax{b.rmax, b.rsum, b.best_v, b.best_j, cap, scale}, st));
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpSoftmaxStats{b.rmax, b.rsum, b.rlog, cap, scale}, st));
+      IMW_CHECK_CUDA(launch_simreduce(sa, S, OpDualSoftmaxArgmax{b.rmax, b.rsum, b.rlog, b.best_v, b.best_j, cap, scale}, st));
     }
     int* i_ids = b.fcnt;               // [P][mcap]
     int* j_ids = b.fcnt + (size_t)P * mcap;

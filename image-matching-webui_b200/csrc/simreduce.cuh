@@ -142,3 +142,61 @@ __device__ __forceinline__ void lse_accum32(MaxSumState& st, const float (&v)[32
 __device__ __forceinline__ void argmax_accum(ArgMaxState& st, float v, int j) {
   if (v > st.v || (v == st.v && j < st.j)) { st.v = v; st.j = j; }
 }
+
+// ---- dual-softmax confidence  P = softmax(x, dim 1) * softmax(x, dim 2)  (hloc dual_softmax.py:23, LoFTR coarse_matching.py:115-119)
+// pass 1: per-row softmax statistics of scale * sim along the other image: max, sum of exp, and max + log(sum)
+struct OpSoftmaxStats {
+  using State = MaxSumState;
+  float *rmax, *rsum, *rlog; int cap; float scale;
+  __device__ void init(State& s) const { s.m = -INFINITY; s.s = 0.f; }
+  __device__ void accum(State& s, float v, int, int, int, int) const { lse_accum(s, v * scale); }
+  __device__ void accum32(State& s, const float (&v)[32], int, int, int jn, int, int) const { lse_accum32(s, v, jn, scale); }
+  __device__ State shfl_xor(const State& s, int o) const {
+    State t; t.m = __shfl_xor_sync(0xffffffffu, s.m, o); t.s = __shfl_xor_sync(0xffffffffu, s.s, o); return t;
+  }
+  __device__ void merge(State& a, const State& b) const { lse_merge(a, b); }
+  __device__ void store(const State& s, int own, int i) const {
+    const long long o = (long long)own * cap + i;
+    rmax[o] = s.m; rsum[o] = s.s; rlog[o] = s.m + logf(s.s);
+  }
+};
+// pass 2: arg-max over the other image of P[i,j] = exp(x - m_i) / s_i * exp(x - m_j) / s_j.  log P = 2x - c_i - c_j with
+// c = max + log(sum), so along a row the winner maximises y_j = 2 x_ij - c_j: candidates are screened with one FMA per element
+// and the exact fp32 product (same operations, same order as the reference: exp, divide, multiply) is evaluated only for
+// elements within a safety margin of the best y seen so far -- a handful per row instead of all of them (round 1 evaluated two
+// exp + two divides + four gathers for every element that passed a looser bound: 4x the cost of the statistics pass).
+// The margin (1e-3 + 4e-6 |y| in log units) exceeds every fp32 rounding in y and in P by orders of magnitude, so the exact
+// arg-max (first index among equal P) is always among the evaluated candidates.
+struct OpDualSoftmaxArgmax {
+  struct State { float v; int j; float ylim; };
+  const float *rmax, *rsum, *rlog; float* best_v; int* best_j; int cap; float scale;
+  __device__ void init(State& s) const { s.v = -INFINITY; s.j = 0x7fffffff; s.ylim = -INFINITY; }
+  __device__ __forceinline__ void exact(State& s, float x, float y, int i, int j, int own, int other) const {
+    const long long io = (long long)own * cap + i, jo = (long long)other * cap + j;
+    const long long i0 = (own & 1) ? jo : io, i1 = (own & 1) ? io : jo;   // image-0 / image-1 statistics
+    // softmax over image-0 positions (statistics kept per image-1 column) times softmax over image-1 positions
+    const float p1 = __fdiv_rn(expf(x - rmax[i1]), rsum[i1]), p2 = __fdiv_rn(expf(x - rmax[i0]), rsum[i0]);
+    const float p = __fmul_rn(p1, p2);
+    if (p > s.v || (p == s.v && j < s.j)) { s.v = p; s.j = j; }
+    s.ylim = fmaxf(s.ylim, y - (1e-3f + 4e-6f * fabsf(y)));
+  }
+  __device__ void accum(State& s, float v, int i, int j, int own, int other) const {
+    const float x = v * scale, y = 2.f * x - rlog[(long long)other * cap + j];
+    if (y >= s.ylim) exact(s, x, y, i, j, own, other);
+  }
+  __device__ void accum32(State& s, const float (&v)[32], int i, int j0, int jn, int own, int other) const {
+    const float* cl = rlog + (long long)other * cap + j0;    // the same 32 columns for every row of the warp: broadcast loads
+    float y[32], ym = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { y[j] = j < jn ? fmaf(2.f * scale, v[j], -cl[j]) : -INFINITY; ym = fmaxf(ym, y[j]); }
+    if (ym < s.ylim) return;
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+      if (y[j] >= s.ylim && j < jn) exact(s, v[j] * scale, y[j], i, j0 + j, own, other);
+  }
+  __device__ State shfl_xor(const State& s, int o) const {
+    State t; t.v = __shfl_xor_sync(0xffffffffu, s.v, o); t.j = __shfl_xor_sync(0xffffffffu, s.j, o); t.ylim = s.ylim; return t;
+  }
+  __device__ void merge(State& a, const State& b) const { if (b.v > a.v || (b.v == a.v && b.j < a.j)) { a.v = b.v; a.j = b.j; } }
+  __device__ void store(const State& s, int own, int i) const { best_v[(long long)own * cap + i] = s.v; best_j[(long long)own * cap + i] = s.j; }
+};

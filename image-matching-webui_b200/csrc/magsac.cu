@@ -13,6 +13,8 @@
 #include <math_constants.h>
 
 #include "../../include/imw_b200.h"
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -251,13 +253,21 @@ __device__ T block_sum(T v, T* scratch) {  // scratch: MS_THREADS/32 entries
 }
 
 // model_type 0 = homography (4-point), 1 = fundamental matrix (7-point)
+// G = CTAs per correspondence set.  G > 1: the G CTAs of a set form a thread-block CLUSTER; each draws its own 256 hypotheses
+// per round and the round's winner is agreed on through distributed shared memory (every CTA reads the G candidate scores,
+// copies the winning model and carries the same best_score / required-iterations state, so the CTAs leave the loop together).
+// Few sets (the single-pair API call: F and H of one pair) then still fill the GPU: 8 x 256 hypotheses per round and set.
+template <int G>
 __global__ void __launch_bounds__(MS_THREADS) magsac_kernel(const float* __restrict__ pts0, const float* __restrict__ pts1,
                                                             const int* __restrict__ counts, int cap, int model_type,
                                                             float threshold, float confidence, int max_iters, unsigned seed,
                                                             double* __restrict__ models, unsigned char* __restrict__ masks,
                                                             int* __restrict__ n_inliers, int* __restrict__ n_iters) {
   extern __shared__ __align__(16) float ms_smem[];
-  const int set = blockIdx.x, tid = threadIdx.x, K = counts[set];
+  namespace cg = cooperative_groups;
+  const int set = blockIdx.x / G, crank = blockIdx.x % G, tid = threadIdx.x, K = counts[set];
+  __shared__ float s_cl_score;        // this CTA's best candidate of the round, read by the other CTAs of the cluster
+  __shared__ float s_cl_model[9];
   float* X0 = ms_smem; float* Y0 = X0 + cap; float* X1 = Y0 + cap; float* Y1 = X1 + cap;
   __shared__ double s_red[MS_THREADS / 32];
   __shared__ float s_best_score[MS_THREADS / 32];
@@ -270,10 +280,12 @@ __global__ void __launch_bounds__(MS_THREADS) magsac_kernel(const float* __restr
   const int S = model_type == 0 ? 4 : 7;
   double* out_model = models + (long long)set * 9;
   unsigned char* out_mask = masks + (long long)set * cap;
-  if (K < S + (model_type == 0 ? 0 : 1)) {  // cv2: not enough points -> no model
-    for (int i = tid; i < cap; i += MS_THREADS) out_mask[i] = 0;
-    if (tid < 9) out_model[tid] = 0.0;
-    if (tid == 0) { n_inliers[set] = 0; n_iters[set] = 0; }
+  if (K < S + (model_type == 0 ? 0 : 1)) {  // cv2: not enough points -> no model (all CTAs of the cluster leave together)
+    if (crank == 0) {
+      for (int i = tid; i < cap; i += MS_THREADS) out_mask[i] = 0;
+      if (tid < 9) out_model[tid] = 0.0;
+      if (tid == 0) { n_inliers[set] = 0; n_iters[set] = 0; }
+    }
     return;
   }
   for (int i = tid; i < K; i += MS_THREADS) {
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(MS_THREADS) magsac_kernel(const float* __restr
   for (int round = 0; iters < required && iters < max_iters; round++) {
     // ---- one hypothesis per thread
     double smp[7][4];
-    unsigned st = pcg_hash(seed ^ (set * 9781u + round * 6271u + tid * 0x9E3779B9u));
+    unsigned st = pcg_hash(seed ^ (set * 9781u + (round * G + crank) * 6271u + tid * 0x9E3779B9u));
     int idx[7];
     for (int s = 0; s < S; s++) {
       bool dup;
@@ -361,13 +373,32 @@ __global__ void __launch_bounds__(MS_THREADS) magsac_kernel(const float* __restr
     __syncthreads();
     bs = s_best_score[0]; bt = s_best_tid[0];
     for (int w = 1; w < MS_THREADS / 32; w++) if (s_best_score[w] < bs) { bs = s_best_score[w]; bt = s_best_tid[w]; }
-    iters += MS_THREADS;
-    const bool improved = bs < best_score;
-    if (improved) {
-      best_score = bs;
-      if (tid == bt) for (int k = 0; k < 9; k++) s_model[k] = my_model[k];
+    iters += MS_THREADS * G;
+    bool improved;
+    if (G == 1) {
+      improved = bs < best_score;
+      if (improved) {
+        best_score = bs;
+        if (tid == bt) for (int k = 0; k < 9; k++) s_model[k] = my_model[k];
+      }
+      __syncthreads();
+    } else {
+      // publish this CTA's candidate, then every CTA of the cluster picks the same winner (lowest score, lowest rank on ties)
+      if (tid == bt) { s_cl_score = bs; for (int k = 0; k < 9; k++) s_cl_model[k] = my_model[k]; }
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();
+      float ws = CUDART_INF_F; int wr = 0;
+      for (int r = 0; r < G; r++) {
+        const float sr = *cluster.map_shared_rank(&s_cl_score, r);
+        if (sr < ws) { ws = sr; wr = r; }
+      }
+      improved = ws < best_score;
+      if (improved) {
+        best_score = ws;
+        if (tid < 9) s_model[tid] = cluster.map_shared_rank(s_cl_model, wr)[tid];
+      }
+      cluster.sync();     // nobody overwrites its candidate while a neighbour still reads it; also orders s_model for the block
     }
-    __syncthreads();
     if (improved) {  // inlier count of the new best model -> adaptive termination
       int cnt = 0;
       for (int i = tid; i < K; i += MS_THREADS) cnt += resid(s_model, i) <= mc.thr2_inl ? 1 : 0;
@@ -437,7 +468,8 @@ __global__ void __launch_bounds__(MS_THREADS) magsac_kernel(const float* __restr
       __syncthreads();
     }
   }
-  // ---- outputs: inlier mask at `threshold`, model scaled like OpenCV (last element 1 when possible)
+  // ---- outputs: inlier mask at `threshold`, model scaled like OpenCV (last element 1 when possible); CTA 0 of the cluster writes
+  if (crank != 0) return;
   int cnt = 0;
   for (int i = tid; i < cap; i += MS_THREADS) {
     const bool in = (i < K) && best_score < CUDART_INF_F && resid(s_model, i) <= mc.thr2_inl;
@@ -460,9 +492,30 @@ extern "C" int imw_magsac(int n_sets, int cap, const float* pts0, const float* p
   IMW_REQUIRE(model_type == 0 || model_type == 1, "imw_magsac: model_type 0 (homography) or 1 (fundamental)");
   IMW_REQUIRE(threshold > 0.f && confidence > 0.f && confidence < 1.f && max_iters > 0, "imw_magsac: bad threshold/confidence/max_iters");
   const size_t smem = (size_t)4 * cap * sizeof(float);
-  IMW_CHECK_CUDA(cudaFuncSetAttribute(magsac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  magsac_kernel<<<n_sets, MS_THREADS, smem, st>>>(pts0, pts1, counts, cap, model_type, threshold, confidence, max_iters, seed, models,
-                                                  masks, n_inliers, n_iters);
+  // CTAs per set: fill the SMs when there are few sets (cluster of up to 8 CTAs = portable cluster size)
+  const int sms = imw_num_sms();
+  const int G = n_sets * 8 <= sms ? 8 : (n_sets * 4 <= sms ? 4 : (n_sets * 2 <= sms ? 2 : 1));
+  if (G == 1) {
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(magsac_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    magsac_kernel<1><<<n_sets, MS_THREADS, smem, st>>>(pts0, pts1, counts, cap, model_type, threshold, confidence, max_iters, seed, models,
+                                                       masks, n_inliers, n_iters);
+    IMW_CHECK_LAUNCH();
+    return IMW_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_sets * G)); cfg.blockDim = dim3(MS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#define MS_LAUNCH(GG)                                                                                                             \
+  do {                                                                                                                            \
+    IMW_CHECK_CUDA(cudaFuncSetAttribute(magsac_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    IMW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, magsac_kernel<GG>, pts0, pts1, counts, cap, model_type, threshold, confidence, max_iters, \
+                                      seed, models, masks, n_inliers, n_iters));                                                  \
+  } while (0)
+  if (G == 8) MS_LAUNCH(8); else if (G == 4) MS_LAUNCH(4); else MS_LAUNCH(2);
+#undef MS_LAUNCH
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -87,7 +87,7 @@ def test_magsac_batched_and_degenerate(dev=None):
         assert _f1(mask[i, :len(gt)].cpu().numpy(), gt) > 0.95
         assert not mask[i, len(gt):].any()
     assert int(n_inl[3]) == 0 and not mask[3].any() and float(M[3].abs().sum()) == 0.0
-    assert (n_it[:3] > 0).all() and (n_it[:3] <= 10000 + 256).all()
+    assert (n_it[:3] > 0).all() and (n_it[:3] <= 10000 + 8 * 256).all()   # up to 8 CTAs x 256 hypotheses per round
 
 
 def test_filter_matches_contract_on_real_matches(golden):

@@ -130,6 +130,13 @@ def lib():
                                          C.c_size_t, C.c_void_p]
         L.imw_loftr_workspace_bytes.restype = C.c_size_t
         L.imw_loftr_workspace_bytes.argtypes = [C.c_int] * 4
+        L.imw_loftr_workspace_bytes_hw.restype = C.c_size_t
+        L.imw_loftr_workspace_bytes_hw.argtypes = [C.c_int] * 6
+        L.imw_loftr_forward_hw.restype = C.c_int
+        L.imw_loftr_forward_hw.argtypes = [C.POINTER(LoftrWeights), C.POINTER(LoftrConf), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]
         L.imw_loftr_forward.restype = C.c_int
         L.imw_loftr_forward.argtypes = [C.POINTER(LoftrWeights), C.POINTER(LoftrConf), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -26,14 +26,14 @@ __device__ __forceinline__ float lf_merge(const plane_t* p, size_t plane, size_t
 
 // ---- conv1: 7x7 stride 2 pad 3, 1 -> 128 channels, BN folded, ReLU (resnet_fpn.py:60-62,102) -> bf16 planes ----------
 __global__ void __launch_bounds__(256) lf_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[49][128]*/,
-                                                       const float* __restrict__ bias, plane_t* __restrict__ out, int B,
+                                                       const float* __restrict__ bias, plane_t* __restrict__ out, int B, size_t img_stride,
                                                        int H, int W) {
   __shared__ __align__(16) float s_in[37][38];
   __shared__ __align__(16) float s_w[49][128];
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int tiles_x = (Wo + 15) / 16;
   const int ox0 = (blockIdx.x % tiles_x) * 16, oy0 = (blockIdx.x / tiles_x) * 16, b = blockIdx.z, tid = threadIdx.x;
-  const float* im = img + (size_t)b * H * W;
+  const float* im = img + (size_t)b * img_stride;   // images of one side of the pairs may be interleaved with the other side's
   for (int i = tid; i < 37 * 37; i += 256) {
     int yy = i / 37, xx = i % 37, gy = oy0 * 2 - 3 + yy, gx = ox0 * 2 - 3 + xx;
     s_in[yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? im[(size_t)gy * W + gx] : 0.f;
@@ -109,29 +109,35 @@ __global__ void lf_planes_to_f32_kernel(const plane_t* __restrict__ in, float* _
 }
 
 // tokens: xm[z][l][0:256] = coarse_feat[z][l][:] + pe[l][:]   (loftr.py:58-59)
-__global__ void lf_tokens_kernel(const float* __restrict__ fc, const float* __restrict__ pe, float* __restrict__ xm, int L, int cap) {
-  const int z = blockIdx.y;
+// slot z = 2 * pair + side; the two sides may have different sizes (loftr.py:48-56): fc0 [P][L0][256], fc1 [P][L1][256]
+__global__ void lf_tokens_kernel(const float* __restrict__ fc0, const float* __restrict__ fc1, const float* __restrict__ pe0,
+                                 const float* __restrict__ pe1, float* __restrict__ xm, int L0, int L1, int cap) {
+  const int z = blockIdx.y, side = z & 1, L = side ? L1 : L0;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)L * CD) return;
   const int l = (int)(i / CD), c = (int)(i % CD);
-  xm[((size_t)z * cap + l) * 512 + c] = fc[((size_t)z * L + l) * CD + c] + pe[i];
+  const float* fc = (side ? fc1 : fc0) + (size_t)(z >> 1) * L * CD;
+  xm[((size_t)z * cap + l) * 512 + c] = fc[(size_t)l * CD + c] + (side ? pe1 : pe0)[i];
 }
 
 // ---- linear attention (linear_attention.py:31-47) ------------------------------------------------------------------------
 // projection epilogue: q -> elu+1, k -> elu+1, v -> v / S   (three [rows][dm] buffers)
 struct EpiLinAttnQKV {
   float *q, *k, *v; int dm; long long slot_stride; float kv_len;   // values are divided by the source length (:38-39)
+  const int* kv_counts = nullptr;                                  // per-slot token count (a slot's values serve as ITS OWN source rows)
   __device__ __forceinline__ float fmap(float x) const { return x > 0.f ? x + 1.f : expf(x); }  // elu(x) + 1
-  __device__ __forceinline__ float conv(int which, float x) const { return which < 2 ? fmap(x) : __fdiv_rn(x, kv_len); }
+  __device__ __forceinline__ float conv(int which, float x, int z) const {
+    return which < 2 ? fmap(x) : __fdiv_rn(x, kv_counts ? (float)kv_counts[z] : kv_len);
+  }
   __device__ void operator()(int z, int row, int col, float4 a, int) const {
     const int which = col / dm, c = col % dm;
     float* dst = (which == 0 ? q : which == 1 ? k : v) + z * slot_stride + (long long)row * dm + c;
-    *reinterpret_cast<float4*>(dst) = make_float4(conv(which, a.x), conv(which, a.y), conv(which, a.z), conv(which, a.w));
+    *reinterpret_cast<float4*>(dst) = make_float4(conv(which, a.x, z), conv(which, a.y, z), conv(which, a.z, z), conv(which, a.w, z));
   }
   __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
   __device__ void elem(int z, int row, int col, float a, float2) const {
     const int which = col / dm, c = col % dm;
-    (which == 0 ? q : which == 1 ? k : v)[z * slot_stride + (long long)row * dm + c] = conv(which, a);
+    (which == 0 ? q : which == 1 ? k : v)[z * slot_stride + (long long)row * dm + c] = conv(which, a, z);
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
@@ -291,7 +297,7 @@ __global__ void lf_parity_kernel(int* skip_even, int* skip_odd, int S) {
 // conf = softmax(sim, 1) * softmax(sim, 2), sim = <f0/16, f1/16> / 0.1  (coarse_matching.py:108-119): two streaming passes
 // threshold + border + mutual max, ordered compaction by i (coarse_matching.py:176-195,241-250); one CTA per pair
 __global__ void __launch_bounds__(1024) lf_coarse_select_kernel(const float* __restrict__ best_v, const int* __restrict__ best_j,
-                                                                int L, int cap, int hc, int wc, float thr, int border,
+                                                                int L, int L1, int cap, int hc, int wc, int hc1, int wc1, float thr, int border,
                                                                 int* __restrict__ i_ids, int* __restrict__ j_ids,
                                                                 float* __restrict__ mconf, int* __restrict__ mcount, int mcap) {
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid % 32, wid = tid / 32;
@@ -299,14 +305,14 @@ __global__ void __launch_bounds__(1024) lf_coarse_select_kernel(const float* __r
   __shared__ int s_base;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  auto inner = [&](int idx) { int y = idx / wc, x = idx % wc; return y >= border && y < hc - border && x >= border && x < wc - border; };
+  auto inner = [&](int idx, int hh, int ww) { int y = idx / ww, x = idx % ww; return y >= border && y < hh - border && x >= border && x < ww - border; };
   for (int i0 = 0; i0 < L; i0 += 1024) {
     const int i = i0 + tid;
     bool ok = false; int j = 0; float v = 0.f;
     if (i < L) {
       v = best_v[(long long)(2 * p) * cap + i];
       j = best_j[(long long)(2 * p) * cap + i];
-      ok = v > thr && (unsigned)j < (unsigned)L && inner(i) && inner(j) && best_j[(long long)(2 * p + 1) * cap + j] == i;   // NaN rows: j = init
+      ok = v > thr && (unsigned)j < (unsigned)L1 && inner(i, hc, wc) && inner(j, hc1, wc1) && best_j[(long long)(2 * p + 1) * cap + j] == i;   // NaN rows: j = init
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (lane == 0) s_w[wid] = __popc(bal);
@@ -325,14 +331,16 @@ __global__ void __launch_bounds__(1024) lf_coarse_select_kernel(const float* __r
 // ---- fine level -----------------------------------------------------------------------------------------------------------
 // 5x5 windows of the 1/2-resolution map around the matched coarse cells (F.unfold k=5, stride=4, pad=2 restricted to the
 // matches), fine_preprocess.py:40-50.  U[side][m][ww][c], side 0 <- feat_f0 at i_ids, side 1 <- feat_f1 at j_ids.
-__global__ void __launch_bounds__(128) lf_gather_windows_kernel(const float* __restrict__ ff, const int* __restrict__ i_ids,
-                                                                const int* __restrict__ j_ids, const int* __restrict__ mcount,
-                                                                float* __restrict__ U, int hf, int wf, int wc, int stride, int mcap, int P) {
+__global__ void __launch_bounds__(128) lf_gather_windows_kernel(const float* __restrict__ ff0, const float* __restrict__ ff1,
+                                                                const int* __restrict__ i_ids, const int* __restrict__ j_ids,
+                                                                const int* __restrict__ mcount, float* __restrict__ U, int hf0, int wf0, int wc0,
+                                                                int hf1, int wf1, int wc1, int stride, int mcap, int P) {
   const int m = blockIdx.x, side = blockIdx.y, p = blockIdx.z, c = threadIdx.x;
   if (m >= mcount[p]) return;
   const int id = side == 0 ? i_ids[(long long)p * mcap + m] : j_ids[(long long)p * mcap + m];
+  const int hf = side ? hf1 : hf0, wf = side ? wf1 : wf0, wc = side ? wc1 : wc0;
   const int cy = id / wc, cx = id % wc;
-  const float* f = ff + (size_t)(2 * p + side) * hf * wf * FD;
+  const float* f = (side ? ff1 : ff0) + (size_t)p * hf * wf * FD;
   float* o = U + ((((size_t)side * P + p) * mcap + m) * 25) * FD;
   for (int ww = 0; ww < 25; ww++) {
     const int y = cy * stride - 2 + ww / 5, x = cx * stride - 2 + ww % 5;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(256) lf_gather_coarse_kernel(const float* __re
 // sub-pixel expectation (fine_matching.py:46-49,66-77): one warp per match
 __global__ void __launch_bounds__(256) lf_fine_match_kernel(const float* __restrict__ X /*[2][P][mcap][25][256]*/, const int* __restrict__ i_ids,
                                                             const int* __restrict__ j_ids, const int* __restrict__ mcount,
-                                                            float* __restrict__ kpts0, float* __restrict__ kpts1, int wc, float scale_c,
+                                                            float* __restrict__ kpts0, float* __restrict__ kpts1, int wc, int wc1, float scale_c,
                                                             float scale_f, int mcap, int P) {
   const int p = blockIdx.y, m = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (m >= mcount[p]) return;
@@ -374,13 +382,13 @@ __global__ void __launch_bounds__(256) lf_fine_match_kernel(const float* __restr
     float* k0 = kpts0 + ((long long)p * mcap + m) * 2;
     float* k1 = kpts1 + ((long long)p * mcap + m) * 2;
     k0[0] = (i % wc) * scale_c; k0[1] = (i / wc) * scale_c;
-    k1[0] = (j % wc) * scale_c + ex * 2.f * scale_f; k1[1] = (j / wc) * scale_c + ey * 2.f * scale_f;
+    k1[0] = (j % wc1) * scale_c + ex * 2.f * scale_f; k1[1] = (j / wc1) * scale_c + ey * 2.f * scale_f;
   }
 }
 
-__global__ void lf_fill_int_kernel(int* p, int n, int v) {
+__global__ void lf_fill_counts_kernel(int* p, int n, int v_even, int v_odd) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) p[i] = (i & 1) ? v_odd : v_even;
 }
 __global__ void lf_scale_counts_kernel(const int* mcount, int* rows25, int P) {  // rows of the fine token matrices
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,18 +399,23 @@ constexpr int LF_KV_SPLIT = 32;   // token chunks per (slot, head) in the coarse
 
 struct LFBuffers {
   void *pa, *pb, *pc, *pd, *pe2;   // backbone plane scratch
-  float *fc, *ff, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *kv_part, *ksum_part, *rmax, *rsum, *rlog, *best_v;
+  float *fc, *fc1, *ff, *ff1, *xm, *q, *k, *v, *msg, *tmp, *h, *kv, *ksum, *kv_part, *ksum_part, *rmax, *rsum, *rlog, *best_v;
   int *best_j, *skip_even, *skip_odd, *cntL, *rows25, *fcnt;
   float *U, *G, *ctx, *fx, *fq, *fk, *fv, *fmsg, *ftmp, *fh, *fkv, *fksum;
 };
 }  // namespace
 
-size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H, int W, int cap, int mcap) {
-  const size_t S = 2 * (size_t)P, h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2, h8 = (h4 + 1) / 2, w8 = (w4 + 1) / 2;
-  const size_t big = S * h2 * w2 * 256 * NP;  // fp16 elements of the largest plane set (1/2 res, 256 padded channels)
+// The backbone runs one SIDE of the pairs at a time (P images of one size): its plane scratch is sized for P images of the
+// larger side -- half of what a 2P-image pass needs -- and the two sides may have different sizes.
+size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H0, int W0, int H1, int W1, int cap, int mcap) {
+  const size_t S = 2 * (size_t)P;
+  auto px = [](int H, int W, int d) { return (size_t)(H / d) * (W / d); };
+  const size_t a2 = px(H0, W0, 2) > px(H1, W1, 2) ? px(H0, W0, 2) : px(H1, W1, 2), a4 = px(H0, W0, 4) > px(H1, W1, 4) ? px(H0, W0, 4) : px(H1, W1, 4);
+  const size_t big = (size_t)P * a2 * 256 * NP;  // fp16 elements of the largest plane set (1/2 res, 256 padded channels)
   b.pa = ws.take<plane_t>(big); b.pb = ws.take<plane_t>(big); b.pc = ws.take<plane_t>(big);
-  b.pd = ws.take<plane_t>(S * h4 * w4 * 256 * NP); b.pe2 = ws.take<plane_t>(S * h4 * w4 * 256 * NP);
-  b.fc = ws.take<float>(S * h8 * w8 * CD); b.ff = ws.take<float>(S * h2 * w2 * FD);
+  b.pd = ws.take<plane_t>((size_t)P * a4 * 256 * NP); b.pe2 = ws.take<plane_t>((size_t)P * a4 * 256 * NP);
+  b.fc = ws.take<float>((size_t)P * px(H0, W0, 8) * CD); b.fc1 = ws.take<float>((size_t)P * px(H1, W1, 8) * CD);
+  b.ff = ws.take<float>((size_t)P * px(H0, W0, 2) * FD); b.ff1 = ws.take<float>((size_t)P * px(H1, W1, 2) * FD);
   const size_t T = S * cap;
   b.xm = ws.take<float>(T * 512); b.q = ws.take<float>(T * CD); b.k = ws.take<float>(T * CD); b.v = ws.take<float>(T * CD);
   b.msg = ws.take<float>(T * CD); b.tmp = ws.take<float>(T * CD); b.h = ws.take<float>(T * 512);
@@ -418,86 +431,112 @@ size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H, int W, int cap, int m
   return ws.off;
 }
 
-extern "C" size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_matches) {
+extern "C" size_t imw_loftr_workspace_bytes_hw(int n_pairs, int height0, int width0, int height1, int width1, int max_matches) {
   Workspace ws(nullptr, 0);
   LFBuffers b;
-  const int L = ((height + 7) / 8) * ((width + 7) / 8), cap = (L + 127) / 128 * 128;
-  return lf_carve(ws, b, n_pairs, height, width, cap, max_matches) + 256;
+  const int L0 = (height0 / 8) * (width0 / 8), L1 = (height1 / 8) * (width1 / 8), L = L0 > L1 ? L0 : L1, cap = (L + 127) / 128 * 128;
+  return lf_carve(ws, b, n_pairs, height0, width0, height1, width1, cap, max_matches) + 256;
+}
+extern "C" size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_matches) {
+  return imw_loftr_workspace_bytes_hw(n_pairs, height, width, height, width, max_matches);
 }
 
 // images [2P][H][W] fp32: slot 2p = the image whose cells index the ROWS of the confidence matrix ("image0" of the LoFTR
 // module; hloc passes its image1 there, hloc/matchers/loftr.py:43-51).  H, W multiples of 8.
 // Outputs per pair: keypoints0/1 [P][max_matches][2] (in i order), confidence [P][max_matches], counts [P].
-extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_conf* conf, int n_pairs, int height, int width,
-                                 const float* images, int max_matches, float* keypoints0, float* keypoints1, float* confidence,
-                                 int* counts, float* dbg_feat_c, float* dbg_backbone_c, void* workspace, size_t workspace_bytes,
-                                 cudaStream_t st) {
-  IMW_REQUIRE(W && conf && n_pairs > 0 && height % 8 == 0 && width % 8 == 0, "imw_loftr_forward: H, W must be multiples of 8");
+namespace {
+struct LFGeom { int H, W, h2, w2, h4, w4, hc, wc, L; };
+LFGeom lf_geom(int H, int W) { return LFGeom{H, W, H / 2, W / 2, H / 4, W / 4, H / 8, W / 8, (H / 8) * (W / 8)}; }
+}  // namespace
+
+// Pairs whose two images have DIFFERENT sizes (the LoFTR module runs the backbone per image then, loftr.py:48-56; hloc's
+// `minima_loftr` / `loftr_aachen`-style confs do not force a common size): images0 [P] frames of height0 x width0 (the image whose
+// cells index the ROWS of the confidence matrix), images1 [P] frames of height1 x width1; `stride*` = floats between consecutive
+// frames of a side (so that both the interleaved [2P][H][W] layout and two separate arrays fit).  weights->pos_enc is the
+// position encoding of side 0 ([hc0*wc0][256]), pos_enc1 that of side 1.
+extern "C" int imw_loftr_forward_hw(const imw_loftr_weights* W, const imw_loftr_conf* conf, int n_pairs, int height0, int width0,
+                                    int height1, int width1, const float* images0, long long stride0, const float* images1,
+                                    long long stride1, const float* pos_enc1, int max_matches, float* keypoints0, float* keypoints1,
+                                    float* confidence, int* counts, float* dbg_feat_c, float* dbg_backbone_c, void* workspace,
+                                    size_t workspace_bytes, cudaStream_t st) {
+  IMW_REQUIRE(W && conf && n_pairs > 0 && height0 % 8 == 0 && width0 % 8 == 0 && height1 % 8 == 0 && width1 % 8 == 0,
+              "imw_loftr_forward: H, W must be multiples of 8");
   IMW_REQUIRE(max_matches > 0, "imw_loftr_forward: max_matches must be positive");
   IMW_REQUIRE((long long)n_pairs * max_matches <= 65535, "imw_loftr_forward: n_pairs * max_matches must not exceed 65535 (got %d x %d); "
               "split the batch (ops.loftr_forward does)", n_pairs, max_matches);
-  const int P = n_pairs, S = 2 * P, H = height, Wd = width;
-  const int h2 = H / 2, w2 = Wd / 2, h4 = H / 4, w4 = Wd / 4, hc = H / 8, wc = Wd / 8, L = hc * wc, cap = (L + 127) / 128 * 128, mcap = max_matches;
+  const int P = n_pairs, S = 2 * P;
+  const LFGeom g0 = lf_geom(height0, width0), g1 = lf_geom(height1, width1);
+  const int L0 = g0.L, L1 = g1.L, Lmax = L0 > L1 ? L0 : L1, cap = (Lmax + 127) / 128 * 128, mcap = max_matches;
+  const int H = height0, hc = g0.hc, wc = g0.wc, h2 = g0.h2;    // side-0 names used by the scale factors below (8 and 2 on both sides)
   Workspace ws(workspace, workspace_bytes);
   LFBuffers b;
-  lf_carve(ws, b, P, H, Wd, cap, mcap);
+  lf_carve(ws, b, P, height0, width0, height1, width1, cap, mcap);
   if (ws.overflow) { imw_set_error("imw_loftr_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return IMW_ERR_WORKSPACE; }
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
-  // ---------------- backbone (resnet_fpn.py:100-118); 196-channel tensors are zero-padded to 256 channels ----------------
+  // ---------------- backbone (resnet_fpn.py:100-118), one side at a time; 196-channel tensors are zero-padded to 256 channels ------
   const imw_loftr_backbone& bb = W->backbone;
-  {
-    dim3 grid(ceil_div(w2, 16) * ceil_div(h2, 16), 1, S);
-    lf_conv1_kernel<<<grid, 256, 0, st>>>(images, bb.conv1_w, bb.conv1_b, (plane_t*)b.pa, S, H, Wd);
-    IMW_CHECK_LAUNCH_T("lf_conv1_kernel");
-  }
-  auto conv = [&](const void* in, const imw_loftr_conv& c, const void* res, void* out, int Hin, int Win, int act, int f32) {
-    return tc_conv_general(in, c.w, c.b, res, out, S, Hin, Win, c.cin, c.cout, c.ksize, c.stride, act, f32, st);
-  };
-  // layer1 (1/2): two BasicBlocks 128 -> 128
-  RUN(conv(b.pa, bb.l1[0], nullptr, b.pb, h2, w2, 1, 0));  RUN(conv(b.pb, bb.l1[1], b.pa, b.pc, h2, w2, 1, 0));   // x = relu(x + y)
-  RUN(conv(b.pc, bb.l1[2], nullptr, b.pb, h2, w2, 1, 0));  RUN(conv(b.pb, bb.l1[3], b.pc, b.pa, h2, w2, 1, 0));   // x1 = pa
-  // layer2 (1/4): 128 -> 196(256)
-  void *x2a = b.pd, *x2t = b.pe2;
-  RUN(conv(b.pa, bb.l2_down, nullptr, x2a, h2, w2, 0, 0));                                                        // downsample(x1)
-  RUN(conv(b.pa, bb.l2[0], nullptr, x2t, h2, w2, 1, 0));   RUN(conv(x2t, bb.l2[1], x2a, b.pb, h4, w4, 1, 0));      // block 0 -> pb (1/4)
-  RUN(conv(b.pb, bb.l2[2], nullptr, x2t, h4, w4, 1, 0));   RUN(conv(x2t, bb.l2[3], b.pb, x2a, h4, w4, 1, 0));      // x2 = x2a (pd)
-  // layer3 (1/8): 196(256) -> 256 ; reuse pb / pe2 / pc halves as scratch (all large enough)
-  void *x3d = b.pb, *x3t = b.pe2, *x3 = b.pc;
-  RUN(conv(x2a, bb.l3_down, nullptr, x3d, h4, w4, 0, 0));
-  RUN(conv(x2a, bb.l3[0], nullptr, x3t, h4, w4, 1, 0));
-  {
-    // block 0 second conv reads x3t (1/8) with residual x3d -> x3
-    RUN(conv(x3t, bb.l3[1], x3d, x3, hc, wc, 1, 0));
+  auto backbone = [&](const LFGeom& g, const float* images, long long img_stride, float* fc_out, float* ff_out) -> int {
+    const int nimg = P, h2 = g.h2, w2 = g.w2, h4 = g.h4, w4 = g.w4, hc = g.hc, wc = g.wc;
+    {
+      dim3 grid(ceil_div(w2, 16) * ceil_div(h2, 16), 1, nimg);
+      lf_conv1_kernel<<<grid, 256, 0, st>>>(images, bb.conv1_w, bb.conv1_b, (plane_t*)b.pa, nimg, (size_t)img_stride, g.H, g.W);
+      IMW_CHECK_LAUNCH_T("lf_conv1_kernel");
+    }
+    auto conv = [&](const void* in, const imw_loftr_conv& c, const void* res, void* out, int Hin, int Win, int act, int f32) {
+      return tc_conv_general(in, c.w, c.b, res, out, nimg, Hin, Win, c.cin, c.cout, c.ksize, c.stride, act, f32, st);
+    };
+    // layer1 (1/2): two BasicBlocks 128 -> 128
+    RUN(conv(b.pa, bb.l1[0], nullptr, b.pb, h2, w2, 1, 0));  RUN(conv(b.pb, bb.l1[1], b.pa, b.pc, h2, w2, 1, 0));   // x = relu(x + y)
+    RUN(conv(b.pc, bb.l1[2], nullptr, b.pb, h2, w2, 1, 0));  RUN(conv(b.pb, bb.l1[3], b.pc, b.pa, h2, w2, 1, 0));   // x1 = pa
+    // layer2 (1/4): 128 -> 196(256)
+    void *x2a = b.pd, *x2t = b.pe2;
+    RUN(conv(b.pa, bb.l2_down, nullptr, x2a, h2, w2, 0, 0));                                                        // downsample(x1)
+    RUN(conv(b.pa, bb.l2[0], nullptr, x2t, h2, w2, 1, 0));   RUN(conv(x2t, bb.l2[1], x2a, b.pb, h4, w4, 1, 0));      // block 0 -> pb (1/4)
+    RUN(conv(b.pb, bb.l2[2], nullptr, x2t, h4, w4, 1, 0));   RUN(conv(x2t, bb.l2[3], b.pb, x2a, h4, w4, 1, 0));      // x2 = x2a (pd)
+    // layer3 (1/8): 196(256) -> 256 ; reuse pb / pe2 / pc halves as scratch (all large enough)
+    void *x3d = b.pb, *x3t = b.pe2, *x3 = b.pc;
+    RUN(conv(x2a, bb.l3_down, nullptr, x3d, h4, w4, 0, 0));
+    RUN(conv(x2a, bb.l3[0], nullptr, x3t, h4, w4, 1, 0));
+    RUN(conv(x3t, bb.l3[1], x3d, x3, hc, wc, 1, 0));       // block 0 second conv reads x3t (1/8) with residual x3d -> x3
     RUN(conv(x3, bb.l3[2], nullptr, x3t, hc, wc, 1, 0));   RUN(conv(x3t, bb.l3[3], x3, x3d, hc, wc, 1, 0));          // x3 = x3d (pb)
+    // FPN
+    void* x3_out = b.pc;
+    RUN(conv(x3d, bb.l3_out, nullptr, fc_out, hc, wc, 0, 1));               // fp32 coarse feature map [nimg][hc][wc][256]
+    RUN(conv(x3d, bb.l3_out, nullptr, x3_out, hc, wc, 0, 0));               // same as planes for the upsampling path
+    RUN(conv(x2a, bb.l2_out, nullptr, b.pe2, h4, w4, 0, 0));                // layer2_outconv(x2) -> pe2
+    {
+      const size_t n = (size_t)nimg * h4 * w4 * 256;
+      lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pe2, (const plane_t*)x3_out,
+                                                                         (plane_t*)b.pb, nimg, h4, w4, 256);
+      IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
+    }
+    RUN(conv(b.pb, bb.l2_out2[0], nullptr, b.pe2, h4, w4, 2, 0));  RUN(conv(b.pe2, bb.l2_out2[1], nullptr, x2a, h4, w4, 0, 0));  // x2_out -> pd
+    RUN(conv(b.pa, bb.l1_out, nullptr, b.pb, h2, w2, 0, 0));                // layer1_outconv(x1) -> pb (256 padded)
+    {
+      const size_t n = (size_t)nimg * h2 * w2 * 256;
+      lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pb, (const plane_t*)x2a,
+                                                                         (plane_t*)b.pc, nimg, h2, w2, 256);
+      IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
+    }
+    RUN(conv(b.pc, bb.l1_out2[0], nullptr, b.pb, h2, w2, 2, 0));   RUN(conv(b.pb, bb.l1_out2[1], nullptr, ff_out, h2, w2, 0, 1));  // fine map fp32
+    return IMW_OK;
+  };
+  RUN(backbone(g0, images0, stride0, b.fc, b.ff));
+  RUN(backbone(g1, images1, stride1, b.fc1, b.ff1));
+  if (dbg_backbone_c) {   // [2P][Lmax][256] in slot order (side-major maps -> strided copies)
+    IMW_CHECK_CUDA(cudaMemcpy2DAsync(dbg_backbone_c, sizeof(float) * 2 * (size_t)Lmax * CD, b.fc, sizeof(float) * (size_t)L0 * CD,
+                                     sizeof(float) * (size_t)L0 * CD, P, cudaMemcpyDeviceToDevice, st));
+    IMW_CHECK_CUDA(cudaMemcpy2DAsync(dbg_backbone_c + (size_t)Lmax * CD, sizeof(float) * 2 * (size_t)Lmax * CD, b.fc1, sizeof(float) * (size_t)L1 * CD,
+                                     sizeof(float) * (size_t)L1 * CD, P, cudaMemcpyDeviceToDevice, st));
   }
-  // FPN
-  void* x3_out = b.pc;
-  RUN(conv(x3d, bb.l3_out, nullptr, b.fc, hc, wc, 0, 1));                 // fp32 coarse feature map [S][hc][wc][256]
-  RUN(conv(x3d, bb.l3_out, nullptr, x3_out, hc, wc, 0, 0));               // same as planes for the upsampling path
-  RUN(conv(x2a, bb.l2_out, nullptr, b.pe2, h4, w4, 0, 0));                // layer2_outconv(x2) -> pe2
-  {
-    const size_t n = (size_t)S * h4 * w4 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pe2, (const plane_t*)x3_out,
-                                                                       (plane_t*)b.pb, S, h4, w4, 256);
-    IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
-  }
-  RUN(conv(b.pb, bb.l2_out2[0], nullptr, b.pe2, h4, w4, 2, 0));  RUN(conv(b.pe2, bb.l2_out2[1], nullptr, x2a, h4, w4, 0, 0));  // x2_out -> pd
-  RUN(conv(b.pa, bb.l1_out, nullptr, b.pb, h2, w2, 0, 0));                // layer1_outconv(x1) -> pb (256 padded)
-  {
-    const size_t n = (size_t)S * h2 * w2 * 256;
-    lf_upsample_add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const plane_t*)b.pb, (const plane_t*)x2a,
-                                                                       (plane_t*)b.pc, S, h2, w2, 256);
-    IMW_CHECK_LAUNCH_T("lf_upsample_add_kernel");
-  }
-  RUN(conv(b.pc, bb.l1_out2[0], nullptr, b.pb, h2, w2, 2, 0));   RUN(conv(b.pb, bb.l1_out2[1], nullptr, b.ff, h2, w2, 0, 1));  // fine map fp32
-  if (dbg_backbone_c) IMW_CHECK_CUDA(cudaMemcpyAsync(dbg_backbone_c, b.fc, sizeof(float) * (size_t)S * L * CD, cudaMemcpyDeviceToDevice, st));
 
   // ---------------- coarse transformer -----------------------------------------------------------------------------------
-  lf_tokens_kernel<<<dim3((unsigned)(((size_t)L * CD + 255) / 256), S), 256, 0, st>>>(b.fc, W->pos_enc, b.xm, L, cap);
+  lf_tokens_kernel<<<dim3((unsigned)(((size_t)Lmax * CD + 255) / 256), S), 256, 0, st>>>(b.fc, b.fc1, W->pos_enc, pos_enc1 ? pos_enc1 : W->pos_enc,
+                                                                                         b.xm, L0, L1, cap);
   IMW_CHECK_LAUNCH_T("lf_tokens_kernel");
-  lf_fill_int_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.cntL, S, L);
-  IMW_CHECK_LAUNCH_T("lf_fill_int_kernel");
+  lf_fill_counts_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.cntL, S, L0, L1);
+  IMW_CHECK_LAUNCH_T("lf_fill_counts_kernel");
   // per-slot skip masks for the sequential cross layers: skip_even[z] = (z even), skip_odd[z] = (z odd)
   lf_parity_kernel<<<ceil_div(S, 256), 256, 0, st>>>(b.skip_even, b.skip_odd, S);
   IMW_CHECK_LAUNCH_T("lf_parity_kernel");
@@ -519,24 +558,24 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
   // one encoder layer applied to the slots NOT skipped by `skip_q`; keys / values come from slot z ^ kv_xor
   auto encoder = [&](const imw_loftr_layer& ly, const int* skip_q, int kv_xor) -> int {
     // projections for every slot (q of the updated slots, k/v of their sources)
-    if (int e = tok_linear(b.xm, 512, ly.qkv_w, 3 * CD, CD, EpiLinAttnQKV{b.q, b.k, b.v, CD, (long long)cap * CD, (float)L}, nullptr)) return e;
-    la_kv_kernel<32><<<dim3(S, NH, kv_split), 1024, 0, st>>>(b.k, b.v, b.kv_part, b.ksum_part, nullptr, L, (long long)cap * CD, CD, skip_q, kv_xor);
+    if (int e = tok_linear(b.xm, 512, ly.qkv_w, 3 * CD, CD, EpiLinAttnQKV{b.q, b.k, b.v, CD, (long long)cap * CD, 0.f, b.cntL}, nullptr)) return e;
+    la_kv_kernel<32><<<dim3(S, NH, kv_split), 1024, 0, st>>>(b.k, b.v, b.kv_part, b.ksum_part, b.cntL, 0, (long long)cap * CD, CD, skip_q, kv_xor);
     IMW_CHECK_LAUNCH_T("la_kv_kernel<32>");
     la_kv_reduce_kernel<<<ceil_div(S * NH * 32 * 32, 256), 256, 0, st>>>(b.kv_part, b.kv, (long long)S * NH, 32 * 32, kv_split, skip_q, NH);
     IMW_CHECK_LAUNCH_T("la_kv_reduce_kernel");
     la_kv_reduce_kernel<<<ceil_div(S * NH * 32, 256), 256, 0, st>>>(b.ksum_part, b.ksum, (long long)S * NH, 32, kv_split, skip_q, NH);
     IMW_CHECK_LAUNCH_T("la_kv_reduce_kernel");
-    la_apply_kernel<32><<<dim3(ceil_div(L, 8 * 16), S), 256, 0, st>>>(b.q, b.kv, b.ksum, b.msg, nullptr, L, (long long)cap * CD, CD, CD,
+    la_apply_kernel<32><<<dim3(ceil_div(Lmax, 8 * 16), S), 256, 0, st>>>(b.q, b.kv, b.ksum, b.msg, b.cntL, 0, (long long)cap * CD, CD, CD,
                                                                     (long long)cap * CD, skip_q, kv_xor);
     IMW_CHECK_LAUNCH_T("la_apply_kernel<32>");
     if (int e = tok_linear(b.msg, CD, ly.merge_w, CD, CD, EpiPlain{b.tmp, CD, (long long)cap * CD, 0, nullptr}, skip_q)) return e;
-    lf_layernorm_kernel<CD><<<dim3(ceil_div(L, 8), S), 256, 0, st>>>(b.tmp, CD, (long long)cap * CD, b.xm + CD, 512, (long long)cap * 512,
-                                                                   ly.norm1_g, ly.norm1_b, nullptr, L, skip_q, 0);
+    lf_layernorm_kernel<CD><<<dim3(ceil_div(Lmax, 8), S), 256, 0, st>>>(b.tmp, CD, (long long)cap * CD, b.xm + CD, 512, (long long)cap * 512,
+                                                                   ly.norm1_g, ly.norm1_b, b.cntL, 0, skip_q, 0);
     IMW_CHECK_LAUNCH();
     if (int e = tok_linear(b.xm, 512, ly.mlp0_w, 512, 512, EpiPlain{b.h, 512, (long long)cap * 512, 1, nullptr}, skip_q)) return e;
     if (int e = tok_linear(b.h, 512, ly.mlp2_w, CD, 512, EpiPlain{b.tmp, CD, (long long)cap * CD, 0, nullptr}, skip_q)) return e;
-    lf_layernorm_kernel<CD><<<dim3(ceil_div(L, 8), S), 256, 0, st>>>(b.tmp, CD, (long long)cap * CD, b.xm, 512, (long long)cap * 512,
-                                                                   ly.norm2_g, ly.norm2_b, nullptr, L, skip_q, 1);
+    lf_layernorm_kernel<CD><<<dim3(ceil_div(Lmax, 8), S), 256, 0, st>>>(b.tmp, CD, (long long)cap * CD, b.xm, 512, (long long)cap * 512,
+                                                                   ly.norm2_g, ly.norm2_b, b.cntL, 0, skip_q, 1);
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   };
@@ -562,12 +601,13 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
     }
     int* i_ids = b.fcnt;               // [P][mcap]
     int* j_ids = b.fcnt + (size_t)P * mcap;
-    lf_coarse_select_kernel<<<P, 1024, 0, st>>>(b.best_v, b.best_j, L, cap, hc, wc, conf->match_threshold, conf->border_rm, i_ids, j_ids,
+    lf_coarse_select_kernel<<<P, 1024, 0, st>>>(b.best_v, b.best_j, L0, L1, cap, g0.hc, g0.wc, g1.hc, g1.wc, conf->match_threshold, conf->border_rm, i_ids, j_ids,
                                                 confidence, counts, mcap);
     IMW_CHECK_LAUNCH_T("lf_coarse_select_kernel");
     // ---------------- fine level ---------------------------------------------------------------------------------------
     const int stride_f = h2 / hc;
-    lf_gather_windows_kernel<<<dim3(mcap, 2, P), FD, 0, st>>>(b.ff, i_ids, j_ids, counts, b.U, h2, w2, wc, stride_f, mcap, P);
+    lf_gather_windows_kernel<<<dim3(mcap, 2, P), FD, 0, st>>>(b.ff, b.ff1, i_ids, j_ids, counts, b.U, g0.h2, g0.w2, g0.wc, g1.h2, g1.w2, g1.wc,
+                                                              stride_f, mcap, P);
     IMW_CHECK_LAUNCH_T("lf_gather_windows_kernel");
     lf_gather_coarse_kernel<<<dim3(mcap, 2, P), CD, 0, st>>>(b.xm, i_ids, j_ids, counts, b.G, cap, mcap, P);
     IMW_CHECK_LAUNCH_T("lf_gather_coarse_kernel");
@@ -632,10 +672,21 @@ extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_con
       if (!ly.is_cross) { RUN(fine_encoder(ly, 0, 2, 0)); }
       else { RUN(fine_encoder(ly, 0, 1, 1)); RUN(fine_encoder(ly, 1, 2, 1)); }
     }
-    lf_fine_match_kernel<<<dim3(ceil_div(mcap, 8), P), 256, 0, st>>>(b.fx, i_ids, j_ids, counts, keypoints0, keypoints1, wc, (float)H / hc,
+    lf_fine_match_kernel<<<dim3(ceil_div(mcap, 8), P), 256, 0, st>>>(b.fx, i_ids, j_ids, counts, keypoints0, keypoints1, g0.wc, g1.wc, (float)H / hc,
                                                                     (float)H / h2, mcap, P);
     IMW_CHECK_LAUNCH_T("lf_fine_match_kernel");
   }
 #undef RUN
   return IMW_OK;
+}
+
+// images [2P][H][W] fp32 (slot 2p+side, both sides of one size): the interleaved layout is side 0 / side 1 with a 2 H W stride
+extern "C" int imw_loftr_forward(const imw_loftr_weights* W, const imw_loftr_conf* conf, int n_pairs, int height, int width,
+                                 const float* images, int max_matches, float* keypoints0, float* keypoints1, float* confidence,
+                                 int* counts, float* dbg_feat_c, float* dbg_backbone_c, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t st) {
+  const long long hw = (long long)height * width;
+  return imw_loftr_forward_hw(W, conf, n_pairs, height, width, height, width, images, 2 * hw, images ? images + hw : nullptr, 2 * hw, nullptr,
+                              max_matches, keypoints0, keypoints1, confidence, counts, dbg_feat_c, dbg_backbone_c, workspace,
+                              workspace_bytes, st);
 }

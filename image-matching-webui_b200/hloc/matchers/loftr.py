@@ -46,12 +46,15 @@ class LoFTR(BaseModel):
     def _forward(self, data):
         # hloc refines the keypoints of ITS image0: the LoFTR module sees (image1, image0) (hloc/matchers/loftr.py:43-51)
         im0, im1 = data["image1"], data["image0"]
-        assert im0.shape == im1.shape and im0.shape[0] == 1 and im0.shape[1] == 1, "same-size grayscale pair expected"
-        imgs = torch.stack([im0[0, 0], im1[0, 0]]).float()
+        assert im0.shape[0] == 1 and im0.shape[1] == 1 and im1.shape[:2] == (1, 1), "grayscale pair expected"
         tc = {False: 0, True: 1, "3xtf32": 1, "tf32": 2}[self.conf["tensor_cores"]]
-        out = ops.loftr_forward(self._weights(imgs.device), imgs,
-                                {"match_threshold": self.conf["match_threshold"], "use_tensor_cores": tc},
-                                self.conf["max_matches"], temp_bug_fix=self.temp_bug_fix)
+        kconf = {"match_threshold": self.conf["match_threshold"], "use_tensor_cores": tc}
+        if im0.shape == im1.shape:
+            out = ops.loftr_forward(self._weights(im0.device), torch.stack([im0[0, 0], im1[0, 0]]).float(), kconf,
+                                    self.conf["max_matches"], temp_bug_fix=self.temp_bug_fix)
+        else:   # the two images keep their own sizes (kornia LoFTR == SE2LoFTR loftr.py:48-56 runs the backbone per image then)
+            out = ops.loftr_forward(self._weights(im0.device), im0[0].float(), kconf, self.conf["max_matches"],
+                                    temp_bug_fix=self.temp_bug_fix, images1=im1[0].float())
         n = int(out["counts"][0])
         k0, k1, scores = out["keypoints0"][0, :n], out["keypoints1"][0, :n], out["confidence"][0, :n]
         top_k = self.conf["max_keypoints"]

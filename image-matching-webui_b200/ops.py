@@ -572,40 +572,56 @@ def _loftr_struct(wd, pos_enc):
     return s
 
 
-def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=False, max_workspace_bytes=48 << 30):
-    """images [2P,H,W] fp32 CUDA (slot 2p = rows of the confidence matrix).  Returns dict of device tensors:
-    keypoints0/1 [P,mcap,2], confidence [P,mcap], counts [P] (+ debug features)."""
+def loftr_forward(wd, images, conf, max_matches=None, debug=False, temp_bug_fix=False, max_workspace_bytes=48 << 30, images1=None):
+    """images [2P,H,W] fp32 CUDA (slot 2p = rows of the confidence matrix), or -- for pairs whose two images differ in size --
+    images [P,H0,W0] with images1 [P,H1,W1].  Returns dict of device tensors: keypoints0/1 [P,mcap,2], confidence [P,mcap],
+    counts [P] (+ debug features)."""
     L.require_cuda(images, "loftr_forward(images)")
-    S, H, W = images.shape
-    assert S % 2 == 0 and H % 8 == 0 and W % 8 == 0
-    P, dev = S // 2, images.device
-    hc, wc = H // 8, W // 8
-    Lc = hc * wc
+    images = images.contiguous()
+    if images1 is None:
+        S, H0, W0 = images.shape
+        assert S % 2 == 0
+        P, H1, W1 = S // 2, H0, W0
+        im0, st0, im1, st1 = images, 2 * H0 * W0, images.view(-1)[H0 * W0:], 2 * H0 * W0
+    else:
+        images1 = images1.contiguous()
+        P, H0, W0 = images.shape
+        assert images1.shape[0] == P and images1.device == images.device
+        H1, W1 = images1.shape[1:]
+        im0, st0, im1, st1 = images, H0 * W0, images1, H1 * W1
+    assert H0 % 8 == 0 and W0 % 8 == 0 and H1 % 8 == 0 and W1 % 8 == 0
+    dev = images.device
+    L0, L1 = (H0 // 8) * (W0 // 8), (H1 // 8) * (W1 // 8)
+    Lc = max(L0, L1)
     cap = (Lc + 127) // 128 * 128
-    mcap = int(max_matches or Lc)
-    key = ("pe", hc, wc, temp_bug_fix)
-    if key not in wd:
-        wd[key] = loftr_position_encoding(256, hc, wc, temp_bug_fix).to(dev)
+    mcap = int(max_matches or L0)
+    pes = []
+    for (hc, wc) in ((H0 // 8, W0 // 8), (H1 // 8, W1 // 8)):
+        key = ("pe", hc, wc, temp_bug_fix)
+        if key not in wd:
+            wd[key] = loftr_position_encoding(256, hc, wc, temp_bug_fix).to(dev)
+        pes.append(wd[key])
     out = {"keypoints0": torch.zeros(P, mcap, 2, device=dev), "keypoints1": torch.zeros(P, mcap, 2, device=dev),
            "confidence": torch.zeros(P, mcap, device=dev), "counts": torch.zeros(P, dtype=torch.int32, device=dev)}
-    dbg_c = torch.zeros(S, cap, 256, device=dev) if debug else None
-    dbg_b = torch.zeros(S, Lc, 256, device=dev) if debug else None
+    dbg_c = torch.zeros(2 * P, cap, 256, device=dev) if debug else None
+    dbg_b = torch.zeros(2 * P, Lc, 256, device=dev) if debug else None
     lib = L.lib()
-    # pairs per library call: bound the workspace (~4 GB per 1024x1024 pair) -- BASELINE configs[2] is batch = 32
-    per_pair = lib.imw_loftr_workspace_bytes(1, H, W, mcap)
+    # pairs per library call: bound the workspace -- BASELINE configs[2] is batch = 32
+    per_pair = lib.imw_loftr_workspace_bytes_hw(1, H0, W0, H1, W1, mcap)
     chunk = max(1, min(P, int(max_workspace_bytes // max(per_pair, 1)), 65535 // mcap))   # grid.y of the fine stage = pairs * mcap
-    ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes(chunk, H, W, mcap), "loftr")
+    ws = L.workspaces.get(dev, lib.imw_loftr_workspace_bytes_hw(chunk, H0, W0, H1, W1, mcap), "loftr")
     c = L.LoftrConf(float(conf.get("match_threshold", 0.2)), float(conf.get("temperature", 0.1)), int(conf.get("border_rm", 2)),
                     int(conf.get("use_tensor_cores", 1)))
-    wstruct = _loftr_struct(wd, wd[key])
-    images = images.contiguous()
+    wstruct = _loftr_struct(wd, pes[0])
+    f0, f1 = im0.view(-1), im1.view(-1)
     with torch.cuda.device(dev):
         for p0 in range(0, P, chunk):
             n = min(chunk, P - p0)
-            rc = lib.imw_loftr_forward(C.byref(wstruct), C.byref(c), n, H, W, L.ptr(images[2 * p0:]), mcap, L.ptr(out["keypoints0"][p0:]),
-                                       L.ptr(out["keypoints1"][p0:]), L.ptr(out["confidence"][p0:]), L.ptr(out["counts"][p0:]),
-                                       L.ptr(dbg_c[2 * p0:]) if debug else None, L.ptr(dbg_b[2 * p0:]) if debug else None,
-                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+            rc = lib.imw_loftr_forward_hw(C.byref(wstruct), C.byref(c), n, H0, W0, H1, W1, L.ptr(f0[p0 * st0:]), st0, L.ptr(f1[p0 * st1:]), st1,
+                                          L.ptr(pes[1]), mcap, L.ptr(out["keypoints0"][p0:]), L.ptr(out["keypoints1"][p0:]),
+                                          L.ptr(out["confidence"][p0:]), L.ptr(out["counts"][p0:]),
+                                          L.ptr(dbg_c[2 * p0:]) if debug else None, L.ptr(dbg_b[2 * p0:]) if debug else None,
+                                          L.ptr(ws), ws.numel(), L.stream_ptr(dev))
             L.check(rc)
     if debug:
         out["feat_c"], out["backbone_c"] = dbg_c[:, :Lc], dbg_b

@@ -313,6 +313,7 @@ typedef struct {
 } imw_loftr_conf;
 
 size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_matches);
+size_t imw_loftr_workspace_bytes_hw(int n_pairs, int height0, int width0, int height1, int width1, int max_matches);
 
 /* images [2P][H][W] fp32 (H, W multiples of 8): slot 2p indexes the rows of the confidence matrix ("image0" of the LoFTR
  * module), slot 2p+1 its columns; the sub-pixel refinement moves the slot-2p+1 keypoint.
@@ -322,6 +323,16 @@ size_t imw_loftr_workspace_bytes(int n_pairs, int height, int width, int max_mat
 int imw_loftr_forward(const imw_loftr_weights* weights, const imw_loftr_conf* conf, int n_pairs, int height, int width,
                       const float* images, int max_matches, float* keypoints0, float* keypoints1, float* confidence, int* counts,
                       float* dbg_feat_c, float* dbg_backbone_c, void* workspace, size_t workspace_bytes, imw_stream_t stream);
+
+/* The same for pairs whose two images differ in size (the LoFTR module then runs its backbone per image,
+ * third_party/SE2LoFTR/src/loftr/loftr.py:48-56; hloc's minima_loftr / loftr_aachen-style confs do not force a common size).
+ * images0 [P] frames of height0 x width0 (rows of the confidence matrix), images1 [P] frames of height1 x width1; stride0 /
+ * stride1 = floats between consecutive frames of a side.  weights->pos_enc is the position encoding of side 0
+ * ([height0/8 * width0/8][256]), pos_enc1 that of side 1 (NULL: same as side 0).  dbg_* are laid out for max(L0, L1). */
+int imw_loftr_forward_hw(const imw_loftr_weights* weights, const imw_loftr_conf* conf, int n_pairs, int height0, int width0,
+                         int height1, int width1, const float* images0, long long stride0, const float* images1, long long stride1,
+                         const float* pos_enc1, int max_matches, float* keypoints0, float* keypoints1, float* confidence, int* counts,
+                         float* dbg_feat_c, float* dbg_backbone_c, void* workspace, size_t workspace_bytes, imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MAGSAC++ geometric verification.

@@ -151,20 +151,24 @@ def fine_matching(u0, u1, mk0_c, mk1_c, scale, W=5):
 
 
 def forward(w, image0, image1, thr=0.2, cfg=None):
-    """LoFTR.forward, loftr.py:29-75 (B = 1, same-size images).  Returns dict with keypoints0/1 [M,2], confidence [M],
-    plus intermediates for staged parity checks."""
+    """LoFTR.forward, loftr.py:29-75 (B = 1; the two images may differ in size: the backbone then runs per image, :48-56).
+    Returns dict with keypoints0/1 [M,2], confidence [M], plus intermediates for staged parity checks."""
     c = {**CFG, **(cfg or {})}
-    fc, ff = backbone(w, torch.cat([image0, image1], 0))
-    fc0, fc1, ff0, ff1 = fc[:1], fc[1:], ff[:1], ff[1:]
+    if image0.shape == image1.shape:
+        fc, ff = backbone(w, torch.cat([image0, image1], 0))
+        fc0, fc1, ff0, ff1 = fc[:1], fc[1:], ff[:1], ff[1:]
+    else:
+        (fc0, ff0), (fc1, ff1) = backbone(w, image0), backbone(w, image1)
+        fc = None
     hc, wc = fc0.shape[2:]
-    pe = position_encoding(c["d_model"], hc, wc, c["temp_bug_fix"])[None]
-    t0 = (fc0 + pe).flatten(2).transpose(1, 2)
-    t1 = (fc1 + pe).flatten(2).transpose(1, 2)
+    hc1, wc1 = fc1.shape[2:]
+    t0 = (fc0 + position_encoding(c["d_model"], hc, wc, c["temp_bug_fix"])[None]).flatten(2).transpose(1, 2)
+    t1 = (fc1 + position_encoding(c["d_model"], hc1, wc1, c["temp_bug_fix"])[None]).flatten(2).transpose(1, 2)
     t0, t1 = transformer(w, "loftr_coarse.", t0, t1, c["coarse_layers"], c["nhead"])
-    conf, i_ids, j_ids, mconf = coarse_matching(t0, t1, (hc, wc), (hc, wc), thr, c["border_rm"], c["temperature"])
+    conf, i_ids, j_ids, mconf = coarse_matching(t0, t1, (hc, wc), (hc1, wc1), thr, c["border_rm"], c["temperature"])
     scale_c = image0.shape[2] / hc
     mk0_c = torch.stack([i_ids % wc, i_ids // wc], 1) * scale_c
-    mk1_c = torch.stack([j_ids % wc, j_ids // wc], 1) * scale_c
+    mk1_c = torch.stack([j_ids % wc1, j_ids // wc1], 1) * scale_c
     stride = ff0.shape[2] // hc
     u0, u1 = fine_preprocess(w, ff0, ff1, t0, t1, i_ids, j_ids, stride, c["fine_window"])
     if u0.size(0) != 0:

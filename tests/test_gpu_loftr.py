@@ -100,3 +100,34 @@ def test_loftr_ragged_sizes_vs_oracle(hw):
     assert np.array_equal(out["keypoints0"][0, :n].cpu().numpy(), o["keypoints0"].numpy())
     np.testing.assert_allclose(out["keypoints1"][0, :n].cpu().numpy(), o["keypoints1"].numpy(), atol=2e-3)
     np.testing.assert_allclose(out["confidence"][0, :n].cpu().numpy(), o["confidence"].numpy(), rtol=2e-3)
+
+
+@pytest.mark.parametrize("tag", ["d", "e"])
+def test_loftr_different_sizes_vs_reference(golden, tag):
+    """The two images of a pair keep their own sizes (no force_resize in the `minima_loftr` / `loftr_aachen`-style confs): the
+    module runs its backbone per image (loftr.py:48-56).  Library entry (imw_loftr_forward_hw) and plugin vs the goldens of the
+    unmodified module; a batch of two such pairs == the pairs one by one."""
+    from imcui_b200 import ops
+    from imcui_b200.hloc import matchers
+    from imcui_b200.hloc.utils.base_model import dynamic_load
+    from oracle import loftr as ol
+    dev = torch.device("cuda:0")
+    g = golden("loftr_hw")
+    thr = float(g[tag + "/thr"])
+    x0 = torch.from_numpy(g[tag + "/image0"].astype(np.float32) / 255.0).to(dev)
+    x1 = torch.from_numpy(g[tag + "/image1"].astype(np.float32) / 255.0).to(dev)
+    sd = ol.random_weights(0)
+    wd = ops.loftr_to_device(ops.loftr_pack_weights(sd), dev)
+    out = ops.loftr_forward(wd, torch.stack([x0, x0]), {"match_threshold": thr}, images1=torch.stack([x1, x1]))
+    for p in range(2):
+        n = int(out["counts"][p])
+        print(f"[loftr hw] {tag} pair {p}: {tuple(x0.shape)} x {tuple(x1.shape)} -> {n} matches (reference {len(g[tag + '/confidence'])})")
+        assert n == len(g[tag + "/confidence"]) and n > 0
+        assert np.array_equal(out["keypoints0"][p, :n].cpu().numpy(), g[tag + "/keypoints0"])
+        np.testing.assert_allclose(out["keypoints1"][p, :n].cpu().numpy(), g[tag + "/keypoints1"], atol=2e-3)
+        np.testing.assert_allclose(out["confidence"][p, :n].cpu().numpy(), g[tag + "/confidence"], rtol=2e-3)
+    # plugin: hloc hands the module (image1, image0) (hloc/matchers/loftr.py:43-51)
+    model = dynamic_load(matchers, "loftr")({"state_dict": sd, "match_threshold": thr, "max_keypoints": None}).eval().to(dev)
+    pred = model({"image0": x1[None, None], "image1": x0[None, None]})
+    assert np.array_equal(pred["keypoints1"].cpu().numpy(), g[tag + "/keypoints0"])
+    np.testing.assert_allclose(pred["keypoints0"].cpu().numpy(), g[tag + "/keypoints1"], atol=2e-3)

@@ -135,6 +135,21 @@ def test_loftr_oracle_matches_reference(golden, tag):
     np.testing.assert_allclose(o["conf_matrix"][0].max(1)[0].numpy(), g[tag + "/conf_rowmax"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("tag", ["d", "e"])
+def test_loftr_oracle_different_sizes(golden, tag):
+    """Pairs whose two images differ in size (backbone per image, loftr.py:48-56): oracle == the unmodified module."""
+    from oracle import loftr as ol
+    g = golden("loftr_hw")
+    x0 = torch.from_numpy(g[tag + "/image0"].astype(np.float32) / 255.0)[None, None]
+    x1 = torch.from_numpy(g[tag + "/image1"].astype(np.float32) / 255.0)[None, None]
+    o = ol.forward(ol.random_weights(0), x0, x1, thr=float(g[tag + "/thr"]))
+    assert len(g[tag + "/i_ids"]) > 0
+    assert np.array_equal(o["i_ids"].numpy(), g[tag + "/i_ids"]) and np.array_equal(o["j_ids"].numpy(), g[tag + "/j_ids"])
+    assert np.array_equal(o["keypoints0"].numpy(), g[tag + "/keypoints0"])
+    np.testing.assert_allclose(o["keypoints1"].numpy(), g[tag + "/keypoints1"], atol=1e-4)
+    np.testing.assert_allclose(o["confidence"].numpy(), g[tag + "/confidence"], rtol=1e-4)
+
+
 def _matcher_inputs(golden, p):
     g = golden("matchers")
     if p == 0:

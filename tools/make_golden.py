@@ -210,6 +210,26 @@ def loftr_case(name):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def loftr_hw_case(name):
+    """LoFTR on a pair whose two images have DIFFERENT sizes (the module then runs the backbone per image, loftr.py:48-56)."""
+    w = synth_weights.loftr_random_weights(0)
+    blob = {}
+    for tag, hw0, hw1, thr in (("d", (240, 320), (256, 288), 1e-5), ("e", (192, 256), (320, 240), 1e-5)):
+        net = R.make_loftr(0, thr=thr)
+        net.load_state_dict(w, strict=False)
+        a = synth.make_pair(0, *hw0)[0]
+        b = synth.make_pair(1, *hw1)[1]
+        d = {"image0": torch.from_numpy(a.astype(np.float32) / 255.0)[None, None], "image1": torch.from_numpy(b.astype(np.float32) / 255.0)[None, None]}
+        net(d)
+        blob[tag + "/thr"] = np.float32(thr); blob[tag + "/hw0"] = np.array(hw0); blob[tag + "/hw1"] = np.array(hw1)
+        blob[tag + "/image0"] = a; blob[tag + "/image1"] = b
+        blob[tag + "/keypoints0"] = d["mkpts0_f"].numpy(); blob[tag + "/keypoints1"] = d["mkpts1_f"].numpy()
+        blob[tag + "/confidence"] = d["mconf"].numpy()
+        blob[tag + "/i_ids"] = d["i_ids"].numpy().astype(np.int32); blob[tag + "/j_ids"] = d["j_ids"].numpy().astype(np.int32)
+        print(name, tag, "matches", len(d["mconf"]))
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 sys.path.insert(0, str(ROOT / "tests"))
 from aliked_cases import ALIKED_CASES  # noqa: E402
 
@@ -405,6 +425,7 @@ def main():
     d0, d1 = synth.make_descriptor_pair(0, n=768, dim=128)
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
     dense_agg_case("dense_agg")
+    loftr_hw_case("loftr_hw")
 
 
 if __name__ == "__main__":
@@ -416,6 +437,6 @@ if __name__ == "__main__":
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
                 lg_proj_case("lg_proj", [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
             else:
-                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case}[sys.argv[1]](sys.argv[1])
+                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case, "loftr_hw": loftr_hw_case}[sys.argv[1]](sys.argv[1])
     else:
         main()

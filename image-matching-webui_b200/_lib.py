@@ -33,7 +33,7 @@ class LGWeights(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("input_dim", C.c_int), ("posenc_wr", C.c_void_p),
                 ("token_w", C.c_void_p), ("token_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
                 ("match_w", C.c_void_p), ("match_b", C.c_void_p), ("layers", LGLayer * IMW_LG_MAX_LAYERS),
-                ("input_proj_w", C.c_void_p), ("input_proj_b", C.c_void_p), ("has_lo_planes", C.c_int), ("pad_", C.c_int)]
+                ("input_proj_w", C.c_void_p), ("input_proj_b", C.c_void_p), ("has_lo_planes", C.c_int), ("posenc_dim", C.c_int)]
 
 
 IMW_SG_MAX_LAYERS = 32
@@ -148,6 +148,9 @@ def lib():
         L.imw_lightglue_forward.restype = C.c_int
         L.imw_lightglue_forward.argtypes = [C.POINTER(LGWeights), C.POINTER(LGConf), C.c_int, C.c_int, vp, vp, vp, vp,
                                             vp, vp, vp, vp, C.c_size_t, vp]
+        L.imw_lightglue_forward_so.restype = C.c_int
+        L.imw_lightglue_forward_so.argtypes = [C.POINTER(LGWeights), C.POINTER(LGConf), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                               vp, vp, vp, vp, C.c_size_t, vp]
         L.imw_superglue_forward.restype = C.c_int
         L.imw_superglue_forward.argtypes = [C.POINTER(SGWeights), C.POINTER(SGConf), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
                                             vp, C.c_size_t, vp]

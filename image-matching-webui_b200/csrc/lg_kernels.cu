@@ -22,8 +22,10 @@ namespace {
 // ---- keypoint normalisation + learnable Fourier positional encoding -----------------------------
 // lightglue.py:31-43 (size=None: 1 + max - min of the keypoints) and :68-81.
 // enc[slot][tok][0..31] = cos, [32..63] = sin.
+// M = 2: (x, y); M = 4: (x, y, scale, orientation) for the add_scale_ori features (sift / doghardnet, lightglue.py:500-506)
 __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ kpts, const int* __restrict__ counts,
-                                                     const float* __restrict__ Wr, float* __restrict__ enc, int cap) {
+                                                     const float* __restrict__ Wr, float* __restrict__ enc, int cap, int M,
+                                                     const float* __restrict__ scales, const float* __restrict__ oris) {
   const int z = blockIdx.x, tid = threadIdx.x, n = counts[z];
   if (n == 0) return;
   const float* kp = kpts + (long long)z * cap * 2;
@@ -43,7 +45,8 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ k
   for (int idx = tid; idx < n * NF; idx += 256) {
     int i = idx / NF, f = idx % NF;
     float x = __fdiv_rn(__fsub_rn(kp[2 * i], shx), scale), y = __fdiv_rn(__fsub_rn(kp[2 * i + 1], shy), scale);
-    float p = fmaf(y, Wr[2 * f + 1], __fmul_rn(x, Wr[2 * f]));
+    float p = fmaf(y, Wr[M * f + 1], __fmul_rn(x, Wr[M * f]));
+    if (M == 4) p = fmaf(oris[(long long)z * cap + i], Wr[M * f + 3], fmaf(scales[(long long)z * cap + i], Wr[M * f + 2], p));
     float* e = enc + ((long long)z * cap + i) * 64;
     e[f] = cosf(p);
     e[32 + f] = sinf(p);
@@ -439,7 +442,17 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
                                      const float* kpts, const float* desc, const int* counts_in, int* matches,
                                      float* mscores, int* stop, int* prune, void* workspace, size_t workspace_bytes,
                                      cudaStream_t st) {
+  return imw_lightglue_forward_so(W, conf, n_pairs, cap, kpts, nullptr, nullptr, desc, counts_in, matches, mscores, stop, prune, workspace,
+                                  workspace_bytes, st);
+}
+
+extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_conf* conf, int n_pairs, int cap,
+                                        const float* kpts, const float* scales, const float* oris, const float* desc,
+                                        const int* counts_in, int* matches, float* mscores, int* stop, int* prune, void* workspace,
+                                        size_t workspace_bytes, cudaStream_t st) {
   IMW_REQUIRE(W && conf && n_pairs > 0 && cap > 0, "imw_lightglue_forward: bad arguments");
+  const int pe_dim = W->posenc_dim == 4 ? 4 : 2;
+  IMW_REQUIRE(pe_dim == 2 || (scales && oris), "imw_lightglue_forward: add_scale_ori weights (posenc_dim 4) need the scales / oris inputs");
   IMW_REQUIRE(W->n_layers >= 1 && W->n_layers <= IMW_LG_MAX_LAYERS, "imw_lightglue_forward: n_layers %d", W->n_layers);
   IMW_REQUIRE(W->input_dim == 256 || (W->input_dim == 128 && W->input_proj_w && W->input_proj_b),
               "imw_lightglue_forward: input_dim must be 256 (identity) or 128 with input_proj weights (got %d)", W->input_dim);
@@ -461,7 +474,7 @@ extern "C" int imw_lightglue_forward(const imw_lg_weights* W, const imw_lg_conf*
   init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(W->input_dim == D ? desc : nullptr, b.xm[0], b.ind[0], matches, mscores, prune, b.counts, cap,
                                                                 prune_semantics ? 1 : L);
   IMW_CHECK_LAUNCH_T("init_tokens_kernel");
-  posenc_kernel<<<S, 256, 0, st>>>(kpts, b.counts, W->posenc_wr, b.enc[0], cap);
+  posenc_kernel<<<S, 256, 0, st>>>(kpts, b.counts, W->posenc_wr, b.enc[0], cap, pe_dim, scales, oris);
   IMW_CHECK_LAUNCH_T("posenc_kernel");
 
   const size_t at_smem = (size_t)4 * 64 * ATP * sizeof(float);

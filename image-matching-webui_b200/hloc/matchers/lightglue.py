@@ -30,7 +30,8 @@ class LightGlue(BaseModel):
     }
     required_inputs = ["image0", "keypoints0", "scores0", "descriptors0", "image1", "keypoints1", "scores1",
                        "descriptors1"]
-    input_dims = {"superpoint": 256, "aliked": 128, "disk": 128}  # lightglue.py:350-373 (features with add_scale_ori are not built)
+    input_dims = {"superpoint": 256, "aliked": 128, "disk": 128, "raco-aliked": 128, "sift": 128, "doghardnet": 128}   # lightglue.py:350-377
+    scale_ori = {"sift", "doghardnet"}                                                                          # add_scale_ori features
 
     def _init(self, conf):
         logger.info("Loading lightglue model, {}".format(conf["model_name"]))
@@ -45,6 +46,10 @@ class LightGlue(BaseModel):
         self.input_dim = self.input_dims[conf["features"]]
         if (self.input_dim != 256) != ("input_proj.weight" in sd):
             raise ValueError(f"features={conf['features']} needs {'an' if self.input_dim != 256 else 'no'} input_proj in the checkpoint")
+        want_so = bool(conf["add_scale_ori"]) or conf["features"] in self.scale_ori
+        if (sd["posenc.Wr.weight"].shape[1] == 4) != want_so:
+            raise ValueError(f"features={conf['features']}: add_scale_ori={want_so} but posenc.Wr is {tuple(sd['posenc.Wr.weight'].shape)}")
+        self.add_scale_ori = want_so
         conf["filter_threshold"] = conf["match_threshold"]  # hloc/matchers/lightglue.py:50
         self.conf["filter_threshold"] = conf["match_threshold"]
         for k, v in ops.lg_pack_weights(sd, conf["n_layers"]).items():
@@ -77,7 +82,14 @@ class LightGlue(BaseModel):
         kp[0, :m], kp[1, :n] = k0[0].float(), k1[0].float()
         ds[0, :m], ds[1, :n] = d0[0].float(), d1[0].float()
         counts = torch.tensor([m, n], dtype=torch.int32, device=dev)
-        out = ops.lightglue_forward(self._bufs(), self.conf["n_layers"], kp, ds, counts, self._kernel_conf())
+        so = {}
+        if self.add_scale_ori:   # hloc/matchers/lightglue.py:61-73 forwards scales0/1, oris0/1 when the extractor provides them
+            for name in ("scales", "oris"):
+                assert name + "0" in data and name + "1" in data, f"features with add_scale_ori need {name}0 / {name}1"
+                t = torch.zeros(2, cap, device=dev)
+                t[0, :m], t[1, :n] = data[name + "0"].reshape(-1).float(), data[name + "1"].reshape(-1).float()
+                so[name] = t
+        out = ops.lightglue_forward(self._bufs(), self.conf["n_layers"], kp, ds, counts, self._kernel_conf(), **so)
         m0, m1 = out["matches"][0, :m].long()[None], out["matches"][1, :n].long()[None]
         ms0, ms1 = out["scores"][0, :m][None], out["scores"][1, :n][None]
         valid = m0[0] > -1
@@ -100,6 +112,7 @@ class LightGlue(BaseModel):
         """Many pairs in one library call (hloc/pairs_stream.py): batch = {keypoints [2P,cap,2], descriptors [2P,cap,D] token-major,
         scores [2P,cap], counts [2P] int32, image_wh [2P,2]} (slot 2p+side, cap % 128 == 0) -> (matches0 [P,cap] int32,
         matching_scores0 [P,cap]).  Every pair keeps the reference's B = 1 semantics (own early exit, own pruning)."""
+        so = {k: batch[k] for k in ("scales", "oris") if self.add_scale_ori}
         out = ops.lightglue_forward(self._bufs(), self.conf["n_layers"], batch["keypoints"], batch["descriptors"], batch["counts"],
-                                    self._kernel_conf())
+                                    self._kernel_conf(), **so)
         return out["matches"][0::2], out["scores"][0::2]

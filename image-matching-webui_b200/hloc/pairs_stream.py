@@ -178,6 +178,7 @@ class _PairLoader(threading.Thread):
                 S = 2 * len(chunk)
                 kp = torch.zeros(S, cap, 2).pin_memory(); ds = torch.zeros(S, cap, dim).pin_memory(); sc = torch.zeros(S, cap).pin_memory()
                 counts = torch.zeros(S, dtype=torch.int32); wh = torch.zeros(S, 2, dtype=torch.int32)
+                extra = {k: torch.zeros(S, cap).pin_memory() for k in ("scales", "oris") if k in feats[0][0]}   # add_scale_ori features
                 for p, pr in enumerate(feats):
                     for side, f in enumerate(pr):
                         n = len(f["keypoints"])
@@ -186,9 +187,11 @@ class _PairLoader(threading.Thread):
                         ds[z, :n] = torch.from_numpy(np.ascontiguousarray(f["descriptors"].T).astype(np.float32))
                         if "scores" in f:
                             sc[z, :n] = torch.from_numpy(f["scores"].astype(np.float32))
+                        for k, t in extra.items():
+                            t[z, :n] = torch.from_numpy(f[k].astype(np.float32))
                         counts[z] = n
                         wh[z] = torch.from_numpy(np.asarray(f["image_size"]).astype(np.int32))    # "some matchers ... only use its size"
-                self.q.put((chunk, {"keypoints": kp, "descriptors": ds, "scores": sc, "counts": counts, "image_wh": wh}))
+                self.q.put((chunk, {"keypoints": kp, "descriptors": ds, "scores": sc, "counts": counts, "image_wh": wh, **extra}))
         except Exception as e:  # noqa: BLE001  (re-raised in the consumer)
             self.error = e
         finally:

@@ -269,6 +269,7 @@ def lg_weights_struct(bufs, n_layers=9):
     s = L.LGWeights()
     s.n_layers, s.input_dim = n_layers, 256
     s.has_lo_planes = 1
+    s.posenc_dim = bufs["posenc_wr"].shape[1]
     if "input_proj_w" in bufs:
         s.input_dim = bufs["input_proj_w"].shape[1]
         s.input_proj_w, s.input_proj_b = bufs["input_proj_w"].data_ptr(), bufs["input_proj_b"].data_ptr()
@@ -282,8 +283,9 @@ def lg_weights_struct(bufs, n_layers=9):
     return s
 
 
-def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=None):
-    """keypoints [2P,cap,2], descriptors [2P,cap,input_dim], counts [2P] int32 (all CUDA, contiguous).
+def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=None, scales=None, oris=None):
+    """keypoints [2P,cap,2], descriptors [2P,cap,input_dim], counts [2P] int32 (all CUDA, contiguous); scales / oris [2P,cap]
+    for the add_scale_ori features (posenc over (x, y, scale, orientation), lightglue.py:500-506).
     Returns dict: matches [2P,cap] int32, scores [2P,cap], stop [P] int32, prune [2P,cap] int32."""
     L.require_cuda(keypoints, "lightglue_forward(keypoints)")
     S, cap, _ = keypoints.shape
@@ -305,9 +307,10 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
                  int(conf["pruning_min_kpts"]), int(conf.get("use_tensor_cores", 1)) if cap % 128 == 0 else 0)
     wstruct = lg_weights_struct(bufs, n_layers)
     with torch.cuda.device(dev):
-        rc = lib.imw_lightglue_forward(C.byref(wstruct), C.byref(c), P, cap, L.ptr(keypoints), L.ptr(descriptors), L.ptr(counts),
-                                       L.ptr(out["matches"]), L.ptr(out["scores"]), L.ptr(out["stop"]), L.ptr(out["prune"]),
-                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+        rc = lib.imw_lightglue_forward_so(C.byref(wstruct), C.byref(c), P, cap, L.ptr(keypoints),
+                                          L.ptr(scales.contiguous() if scales is not None else None), L.ptr(oris.contiguous() if oris is not None else None),
+                                          L.ptr(descriptors), L.ptr(counts), L.ptr(out["matches"]), L.ptr(out["scores"]), L.ptr(out["stop"]),
+                                          L.ptr(out["prune"]), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc)
     return out
 

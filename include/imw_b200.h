@@ -165,7 +165,8 @@ typedef struct {
   /* 1: every linear weight matrix W [N][K] above (qkv_w, out_w, ffn0_w, ffn3_w, input_proj_w) is followed in memory by its
      TF32 lo plane W - trunc_tf32(W) [N][K] (ops.lg_pack_weights): the 3xTF32 tcgen05 GEMM then splits activations only */
   int has_lo_planes;
-  int pad_;
+  int posenc_dim;   /* 2 (0 is read as 2): posenc_wr [32][2]; 4: add_scale_ori features (sift / doghardnet, lightglue.py:366-377,
+                       500-506): posenc_wr [32][4] over (x, y, scale, orientation) */
 } imw_lg_weights;
 
 typedef struct {
@@ -186,6 +187,11 @@ int imw_lightglue_forward(const imw_lg_weights* weights, const imw_lg_conf* conf
                           const float* keypoints, const float* descriptors, const int* counts, int* matches,
                           float* matching_scores, int* stop, int* prune, void* workspace, size_t workspace_bytes,
                           imw_stream_t stream);
+/* the same with the per-keypoint scales / orientations [2P][cap] of the add_scale_ori features (NULL otherwise) */
+int imw_lightglue_forward_so(const imw_lg_weights* weights, const imw_lg_conf* conf, int n_pairs, int cap,
+                             const float* keypoints, const float* scales, const float* oris, const float* descriptors,
+                             const int* counts, int* matches, float* matching_scores, int* stop, int* prune, void* workspace,
+                             size_t workspace_bytes, imw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SuperGlue matcher.

@@ -152,7 +152,7 @@ def filter_matches(scores, th):
     return m0, m1, ms0, ms1
 
 
-def forward(w, kpts0, desc0, kpts1, desc1, conf=None, trace=None):
+def forward(w, kpts0, desc0, kpts1, desc1, conf=None, trace=None, scale_ori=None):
     """LightGlue._forward for one pair, lightglue.py:488-634.
     kpts* [1,N,2] pixels, desc* [1,N,256].  Returns the reference's dict (tensors with batch dim 1).
     `trace`, if a list, receives per-layer dicts (descriptor states, token confidences)."""
@@ -170,6 +170,9 @@ def forward(w, kpts0, desc0, kpts1, desc1, conf=None, trace=None):
     if "input_proj.weight" in w:
         d0 = F.linear(d0, w["input_proj.weight"], w["input_proj.bias"])
         d1 = F.linear(d1, w["input_proj.weight"], w["input_proj.bias"])
+    if scale_ori is not None:   # add_scale_ori (lightglue.py:500-506): (scales0, oris0, scales1, oris1), each [1,N]
+        s0, o0, s1, o1 = scale_ori
+        k0, k1 = torch.cat([k0, s0[..., None], o0[..., None]], -1), torch.cat([k1, s1[..., None], o1[..., None]], -1)
     e0, e1 = posenc(w, k0), posenc(w, k1)
     do_stop = c["depth_confidence"] > 0
     do_prune = c["width_confidence"] > 0

@@ -202,6 +202,33 @@ def test_lightglue_input_proj_128d(golden, dev, tc):
             assert f1 >= 0.999
 
 
+@pytest.mark.parametrize("tc", [False, "3xtf32"], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
+def test_lightglue_scale_ori_inputs(golden, dev, tc):
+    """features="sift" architecture: 128-d descriptors + per-keypoint scales / orientations in the
+    positional encoding (lightglue.py:500-506), forwarded by the plugin exactly as hloc/matchers/lightglue.py:61-73 does."""
+    import oracle
+    from imcui_b200.hloc import matchers
+    g = golden("lg_so")
+    sd = dict(oracle.load_weights("superpoint_lightglue.pt"))
+    sd["input_proj.weight"], sd["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])
+    sd["posenc.Wr.weight"] = torch.from_numpy(g["posenc_wr"])
+    model = _load(matchers, "lightglue", {"match_threshold": 0.2, "features": "sift", "state_dict": sd, "tensor_cores": tc, **LG_MODES["cuda"]}, dev)
+    for p, src in enumerate(g["sources"]):
+        k0, _, k1, _ = lg_pair_from_source(golden, src)
+        data = _lg_inputs(k0, np.ascontiguousarray(g[f"{p}/descriptors0"].T), k1, np.ascontiguousarray(g[f"{p}/descriptors1"].T), dev)
+        for n in ("scales0", "oris0", "scales1", "oris1"):
+            data[n] = torch.from_numpy(g[f"{p}/{n}"])[None].to(dev)
+        out = model(data)
+        m0 = out["matches0"][0].cpu().numpy()
+        f1 = match_f1(m0, g[f"{p}/matches0"])
+        both = (m0 > -1) & (g[f"{p}/matches0"] > -1)
+        err = np.abs(out["matching_scores0"][0].cpu().numpy() - g[f"{p}/matching_scores0"])[both].max()
+        print(f"[lg-so tc={tc}] pair {p}: F1 {f1:.4f} stop {out['stop']}/{int(g[f'{p}/stop'])} score err {err:.2e}")
+        assert out["stop"] == int(g[f"{p}/stop"]) and err < SCORE_TOL and f1 >= 0.995
+    with pytest.raises(AssertionError):
+        model(_lg_inputs(k0, np.ascontiguousarray(g["0/descriptors0"].T)[:, :len(k0)], k1, np.ascontiguousarray(g["0/descriptors1"].T)[:, :len(k1)], dev))   # scales / oris missing
+
+
 def test_tcgen05_gemm_unit(dev):
     """tcgen05/TMA GEMM against the CUDA-core GEMM and torch fp64."""
     from imcui_b200 import ops

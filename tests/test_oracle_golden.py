@@ -92,6 +92,22 @@ def test_lightglue_input_proj_oracle_matches_reference(golden):
         np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{p}/matching_scores0"], atol=1e-4)
 
 
+def test_lightglue_scale_ori_oracle_matches_reference(golden):
+    """LightGlue with add_scale_ori (sift / doghardnet architecture, lightglue.py:366-377,500-506): posenc over
+    (x, y, scale, orientation)."""
+    g = golden("lg_so")
+    w = _lg_proj_weights(g)
+    w["posenc.Wr.weight"] = torch.from_numpy(g["posenc_wr"])
+    for p, src in enumerate(g["sources"]):
+        k0, _, k1, _ = lg_pair_from_source(golden, src)
+        so = tuple(torch.from_numpy(g[f"{p}/{n}"])[None] for n in ("scales0", "oris0", "scales1", "oris1"))
+        out = olg.forward(w, torch.from_numpy(k0)[None], torch.from_numpy(g[f"{p}/descriptors0"])[None],
+                          torch.from_numpy(k1)[None], torch.from_numpy(g[f"{p}/descriptors1"])[None], MODES["cuda"], scale_ori=so)
+        assert out["stop"] == int(g[f"{p}/stop"])
+        assert np.array_equal(out["matches0"][0].numpy(), g[f"{p}/matches0"])
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{p}/matching_scores0"], atol=1e-4)
+
+
 def _sg_data(golden, src):
     f, conf, i, j = str(src).split(":")
     b = golden(f)

@@ -165,6 +165,40 @@ def lg_proj_case(name, pairs, sources):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+def lg_so_case(name, pairs, sources):
+    """LightGlue with add_scale_ori (the sift / doghardnet architecture, lightglue.py:366-377,500-506): 128-d inputs through
+    input_proj as in lg_proj_case, posenc over (x, y, scale, orientation) with Wr = [GIM Wr | seeded extra columns]."""
+    lgm = R.lightglue_module()
+    blob = {"sources": np.array(sources)}
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = LG_MODES["cuda"]["prune_th"]
+    net = lgm.LightGlue(features=None, input_dim=128, add_scale_ori=True, weights=None, filter_threshold=0.2, depth_confidence=0.95, width_confidence=0.99)
+    sd, q = R.lightglue_proj_state(128)
+    g = torch.Generator().manual_seed(11)
+    sd["posenc.Wr.weight"] = torch.cat([sd["posenc.Wr.weight"], 0.3 * torch.randn(32, 2, generator=g)], 1).contiguous()
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all("confidence_thresholds" in m for m in missing), (missing, unexpected)
+    net.eval()
+    blob["input_proj_w"], blob["input_proj_b"], blob["posenc_wr"] = sd["input_proj.weight"].numpy(), sd["input_proj.bias"].numpy(), sd["posenc.Wr.weight"].numpy()
+    rng = np.random.default_rng(5)
+    for p, (k0, d0, k1, d1) in enumerate(pairs):
+        c0 = torch.nn.functional.normalize(torch.from_numpy(d0).t() @ q.t(), dim=-1)
+        c1 = torch.nn.functional.normalize(torch.from_numpy(d1).t() @ q.t(), dim=-1)
+        so = [torch.from_numpy(rng.uniform(lo, hi, n).astype(np.float32))[None] for n in (len(k0), len(k1)) for lo, hi in ((1.0, 4.0), (-3.14, 3.14))]
+        out = net({"image0": {"keypoints": torch.from_numpy(k0).float()[None], "descriptors": c0[None], "scales": so[0], "oris": so[1]},
+                   "image1": {"keypoints": torch.from_numpy(k1).float()[None], "descriptors": c1[None], "scales": so[2], "oris": so[3]}})
+        pre = f"{p}/"
+        blob[pre + "descriptors0"], blob[pre + "descriptors1"] = c0.numpy(), c1.numpy()
+        for nm, t in zip(("scales0", "oris0", "scales1", "oris1"), so):
+            blob[pre + nm] = t[0].numpy()
+        for k in ("matches0", "matches1"):
+            blob[pre + k] = out[k][0].numpy().astype(np.int32)
+        blob[pre + "matching_scores0"] = out["matching_scores0"][0].numpy()
+        blob[pre + "stop"] = np.int32(out["stop"])
+        print(name, p, "stop", out["stop"], "matches", int((out["matches0"] > -1).sum()))
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = -1
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def sg_case(name, pairs):
     """pairs: list of (kpts0 [N,2], scores0 [N], desc0 [256,N], kpts1, scores1, desc1, source)."""
     blob = {"sources": np.array([p[-1] for p in pairs])}
@@ -411,6 +445,7 @@ def main():
     lg_case("lg_synth", [pair(sb, "max1024", 0, 1), pair(sb, "max1024", 2, 3), pair(sb, "max2048", 0, 1)],
             ["sp_synth:max1024:0:1", "sp_synth:max1024:2:3", "sp_synth:max2048:0:1"])
     lg_proj_case("lg_proj", [pair(sb, "max1024", 0, 1), pair(rb, "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
+    lg_so_case("lg_so", [pair(sb, "max1024", 0, 1), pair(rb, "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
 
     def sg_pair(blob, src):
         f, conf, i, j = src.split(":")
@@ -431,11 +466,11 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1:   # python make_golden.py aliked -> only that family
         with torch.no_grad():
-            if sys.argv[1] == "lg_proj":   # inputs come from the stored SuperPoint goldens
+            if sys.argv[1] in ("lg_proj", "lg_so"):   # inputs come from the stored SuperPoint goldens
                 gb = {n: np.load(OUT / f"{n}.npz") for n in ("sp_synth", "sp_real")}
                 pr = lambda f, c, i, j: (gb[f][f"{c}/{i}/keypoints"].astype(np.float32), gb[f][f"{c}/{i}/descriptors"],
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
-                lg_proj_case("lg_proj", [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
+                {"lg_proj": lg_proj_case, "lg_so": lg_so_case}[sys.argv[1]](sys.argv[1], [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
             else:
                 {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case, "loftr_hw": loftr_hw_case}[sys.argv[1]](sys.argv[1])
     else:

@@ -335,12 +335,10 @@ class Config1(_Base):
         from imcui_b200.hloc.utils.base_model import dynamic_load
         self.sp = dynamic_load(extractors, "superpoint")(dict(self.SP)).eval().to(dev)
         self.nn = dynamic_load(matchers, "nearest_neighbor")({"do_mutual_check": True}).eval().to(dev)
-        from imcui_b200.hloc import extract_features as ef
-        from types import SimpleNamespace
-        import cv2
-        pre = [ef.preprocess(cv2.cvtColor(r, cv2.COLOR_RGB2GRAY), SimpleNamespace(**self.PRE), dev) for r in self.rgb]
-        self.d_img = torch.cat([p["image"] for p in pre])            # [2,1,480,640] resident
-        self.scales = [p["original_size"] / p["size"] for p in pre]
+        from imcui_b200.hloc.pipeline import FramePrep
+        pre = FramePrep(self.PRE, dev)(self.rgb)
+        self.d_img = torch.cat([p[0] for p in pre])            # [2,1,480,640] resident
+        self.scales = [p[1] / p[2] for p in pre]
 
     def _match_device(self):
         from imcui_b200 import ops

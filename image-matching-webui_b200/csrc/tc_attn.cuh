@@ -92,17 +92,26 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int p = 0; p < 2; p++)
         for (int sub = 0; sub < 2; sub++)
           tc::tma_load_2d(sQ + (p * 2 + sub) * TA_BQ * 128, &tmQ, q_full, sub * 32, (int)(p * g.plane_rows_qk) + q_row);
-      for (int j = 0; j < T; j++) {
-        if (j > 0) tc::mbar_wait(k_empty, (j - 1) & 1);
-        tc::mbar_expect_tx(k_full, TA_K_BYTES);
-        for (int p = 0; p < 2; p++)
-          for (int sub = 0; sub < 2; sub++)
-            tc::tma_load_2d(sK + (sub * 2 + p) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + j * TA_BKV);
-        if (j > 0) tc::mbar_wait(v_empty, (j - 1) & 1);
-        tc::mbar_expect_tx(v_full, TA_V_BYTES);
-        for (int p = 0; p < 2; p++)
-          for (int sub = 0; sub < 2; sub++)
-            tc::tma_load_2d(sV + (sub * 2 + p) * 64 * 128, &tmV, v_full, j * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
+      // K and V tiles are refilled INDEPENDENTLY, each as soon as its own consumer MMAs have completed (round 1 walked
+      // K_j, V_j, K_{j+1} ... in one sequence, so the K_{j+1} load -- and with it S_{j+1} -- waited for P_{j-1} V_{j-1}).
+      // A barrier cannot run ahead of the phase polled here: S_{j+1} needs K_{j+1}, which is only requested after
+      // k_empty(j) was observed (same for V), so a non-blocking parity test never misses a phase.
+      int jk = 0, jv = 0;
+      while (jk < T || jv < T) {
+        if (jk < T && (jk == 0 || tc::mbar_try_wait(k_empty, (jk - 1) & 1))) {
+          tc::mbar_expect_tx(k_full, TA_K_BYTES);
+          for (int p = 0; p < 2; p++)
+            for (int sub = 0; sub < 2; sub++)
+              tc::tma_load_2d(sK + (sub * 2 + p) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + jk * TA_BKV);
+          jk++;
+        }
+        if (jv < T && (jv == 0 || tc::mbar_try_wait(v_empty, (jv - 1) & 1))) {
+          tc::mbar_expect_tx(v_full, TA_V_BYTES);
+          for (int p = 0; p < 2; p++)
+            for (int sub = 0; sub < 2; sub++)
+              tc::tma_load_2d(sV + (sub * 2 + p) * 64 * 128, &tmV, v_full, jv * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
+          jv++;
+        }
       }
     }
   } else if (warp == 1) {
@@ -110,8 +119,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const bool leader = tc::elect_one();
       constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64), idesc2 = tc::make_idesc(tc::FMT_TF32, 128, 128);
       const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
-      auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi
-        tc::mbar_wait(k_full, j & 1);
+      auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi   (k_full(j) already observed)
         tc::fence_after_sync();
         const uint32_t d_main = tmem_base + TA_S_COL + (j & 1) * 128, d_cross = d_main + 64;
 #pragma unroll
@@ -130,16 +138,11 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         __syncwarp();
       };
-      tc::mbar_wait(q_full, 0);
-      issue_S(0);
-      for (int j = 0; j < T; j++) {
-        if (j + 1 < T) issue_S(j + 1);
-        tc::mbar_wait(v_full, j & 1);
-        tc::mbar_wait(p_full, j & 1);
+      auto issue_PV = [&](int j) {  // O_j = P_j V_j, K = 64 keys   (p_full(j), v_full(j) already observed)
         tc::fence_after_sync();
         const uint32_t d_main = tmem_base + TA_O_COL, d_cross = d_main + 64;
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {  // O_j = P_j V_j, K = 64 keys
+        for (int ks = 0; ks < 8; ks++) {
           const int sub = ks / 4, ko = (ks % 4) * 32;
           uint64_t ph = tc::make_smem_desc_sw128(aP + (0 * 2 + sub) * TA_BQ * 128 + ko), pl = tc::make_smem_desc_sw128(aP + (1 * 2 + sub) * TA_BQ * 128 + ko);
           uint64_t vh = tc::make_smem_desc_sw128(aV + (sub * 2 + 0) * 64 * 128 + ko);       // [V_hi | V_lo]
@@ -153,6 +156,27 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc::mma_commit(o_full);
         }
         __syncwarp();
+      };
+      // Whichever of S_{js} / P_{jp} V_{jp} has its operands ready is issued next (round 1 issued S_{j+1} strictly before
+      // P_j V_j and blocked on K_{j+1} while P_j was already waiting).  S_{js} writes TMEM buffer js & 1, free once softmax(js-2)
+      // has read it = p_full(js-2) observed = jp >= js - 1.  The polls are warp-uniform (same barrier, same parity in every lane).
+      tc::mbar_wait(q_full, 0);
+      int js = 0, jp = 0;
+      uint32_t spins = 0;
+      const int lead_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+      // the issuing lane polls, the warp follows its verdict (a per-lane poll could split the warp around the __syncwarp()s)
+      auto ready = [&](bool cond_s) -> bool {
+        unsigned r = 0;
+        if (leader) r = cond_s ? (tc::mbar_try_wait(k_full, js & 1) ? 1u : 0u)
+                               : ((tc::mbar_try_wait(p_full, jp & 1) && tc::mbar_try_wait(v_full, jp & 1)) ? 1u : 0u);
+        return __shfl_sync(0xffffffffu, r, lead_lane) != 0;
+      };
+      while (jp < T) {
+        bool did = false;
+        if (js < T && js <= jp + 1 && ready(true)) { issue_S(js); js++; did = true; }
+        if (jp < js && ready(false)) { issue_PV(jp); jp++; did = true; }
+        if (did) spins = 0;
+        else if (++spins > (1u << 24)) { printf("tc_attn MMA scheduler timeout block (%d,%d,%d) js %d jp %d\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp); __trap(); }
       }
     }
   } else {

@@ -235,6 +235,9 @@ constexpr int C64_B_STAGE = NP * 64 * 128;        // NP weight planes of one tap
 constexpr int C64_B_STAGES = 4;
 constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256 + 2 * 240 * sizeof(float) /*fused: image patches*/;
 constexpr int C64_FUSE_PROD = 256;   // conv1a producer threads (8 warps)
+constexpr int C64_HALO_PX = 18 * 10;                       // conv1a outputs one tile needs: rows y0-1..y0+16, cols x0-1..x0+8
+constexpr int C64_STG_BYTES = NP * C64_HALO_PX * 128;      // staging of the split conv1a outputs (fused kernel only)
+constexpr size_t C64_FUSE_SMEM = C64_SMEM + C64_STG_BYTES;
 constexpr int C64_FUSE_THREADS = CV_THREADS + C64_FUSE_PROD;
 
 // Persistent: one CTA per SM walks the tile list.  The three dx-copy slots, the weight ring and two TMEM
@@ -348,6 +351,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
     for (int k = 0; k < 8; k++) bv[k] = g.b1a[chunk * 8 + k];
     float* s_img = (float*)((uint8_t*)tmem_slot + 64);   // [2][20 rows][12 cols], double-buffered by tile parity
+    uint8_t* stg = (uint8_t*)s_img + 2 * 240 * sizeof(float);   // [plane][180 halo pixels][128 B] (16-byte aligned: see C64_SMEM)
     int i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, i++) {
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
@@ -359,41 +363,56 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         im[idx] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? src[(size_t)gy * g.W + gx] : 0.f;
       }
       asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");
+      // conv1a ONCE per halo pixel (18 x 10), split, into a linear staging buffer [plane][pixel][8 units of 16 B].  (Round 1
+      // evaluated it once per dx-shifted copy: 3 x 144 pixel evaluations per tile, which became the kernel's bottleneck -- issue
+      // slots of the producer warps -- once the tensor work was halved.)  Runs ahead of the a_empty waits: overlaps the MMAs of
+      // the previous tile.
+#pragma unroll 1
+      for (int k = 0; k < (C64_HALO_PX + C64_FUSE_PROD / 8 - 1) / (C64_FUSE_PROD / 8); k++) {
+        const int pidx = t / 8 + (C64_FUSE_PROD / 8) * k;   // halo pixel: row pidx / 10, column pidx % 10
+        if (pidx >= C64_HALO_PX) break;
+        const int hy = pidx / 10, hx = pidx % 10;
+        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;       // conv1a output position
+        float a[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) a[c] = 0.f;
+        const bool inside = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;   // conv1b's zero padding: outside -> 0
+        if (inside) {
+#pragma unroll
+          for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+              const float v = im[(hy + dy) * 12 + hx + dx];
+#pragma unroll
+              for (int c = 0; c < 8; c++) a[c] = fmaf(v, w[dy * 3 + dx][c], a[c]);
+            }
+#pragma unroll
+          for (int c = 0; c < 8; c++) a[c] = fmaxf(a[c] + bv[c], 0.f);
+        }
+        __align__(16) plane_t p0[8], p1[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) split2(a[c], p0[c], p1[c]);
+        *reinterpret_cast<uint4*>(stg + pidx * 128 + chunk * 16) = *reinterpret_cast<const uint4*>(p0);
+        *reinterpret_cast<uint4*>(stg + C64_HALO_PX * 128 + pidx * 128 + chunk * 16) = *reinterpret_cast<const uint4*>(p1);
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");
+      // three dx-shifted SWIZZLE_128B copies (the layout TMA would have produced): copy dx row (hy, cx) = halo pixel (hy, cx + dx)
       for (int dxi = 0; dxi < 3; dxi++) {
         tc::mbar_wait(a_empty + dxi, (i & 1) ^ 1);   // the MMAs of the previous tile have read this dx slot
         uint8_t* copy = sA + dxi * NP * C64_COPY;
 #pragma unroll 1
         for (int k = 0; k < (144 + C64_FUSE_PROD / 8 - 1) / (C64_FUSE_PROD / 8); k++) {
-          const int pidx = t / 8 + (C64_FUSE_PROD / 8) * k;   // pixel of the copy: halo row pidx / 8, column pidx % 8
+          const int pidx = t / 8 + (C64_FUSE_PROD / 8) * k;   // row of the copy: halo row pidx / 8, column pidx % 8
           if (pidx >= 144) break;
-          const int hy = pidx / 8, cx = pidx % 8;
-          const int gy = y0 - 1 + hy, gx = x0 + dxi - 1 + cx;   // conv1a output position held by this operand row
-          float a[8];
-#pragma unroll
-          for (int c = 0; c < 8; c++) a[c] = 0.f;
-          const bool inside = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;   // conv1b's zero padding: outside -> 0
-          if (inside) {
-#pragma unroll
-            for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-              for (int dx = 0; dx < 3; dx++) {
-                const float v = im[(hy + dy) * 12 + cx + dxi + dx];
-#pragma unroll
-                for (int c = 0; c < 8; c++) a[c] = fmaf(v, w[dy * 3 + dx][c], a[c]);
-              }
-#pragma unroll
-            for (int c = 0; c < 8; c++) a[c] = fmaxf(a[c] + bv[c], 0.f);
-          }
-          __align__(16) plane_t p0[8], p1[8];
-#pragma unroll
-          for (int c = 0; c < 8; c++) split2(a[c], p0[c], p1[c]);
+          const int src_px = (pidx / 8) * 10 + (pidx % 8) + dxi;
           const int off = pidx * 128 + ((chunk ^ (pidx & 7)) * 16);   // SWIZZLE_128B: 16-byte unit c of row r sits at c ^ (r & 7)
-          *reinterpret_cast<uint4*>(copy + off) = *reinterpret_cast<const uint4*>(p0);
-          *reinterpret_cast<uint4*>(copy + C64_COPY + off) = *reinterpret_cast<const uint4*>(p1);
+          *reinterpret_cast<uint4*>(copy + off) = *reinterpret_cast<const uint4*>(stg + src_px * 128 + chunk * 16);
+          *reinterpret_cast<uint4*>(copy + C64_COPY + off) = *reinterpret_cast<const uint4*>(stg + C64_HALO_PX * 128 + src_px * 128 + chunk * 16);
         }
         tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
         tc::mbar_arrive(a_full + dxi);
       }
+      asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");   // staging is rewritten for the next tile
     }
   } else {
     const int q = warp % 4;
@@ -561,10 +580,10 @@ int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const
   if (int e = make_map_wgt(&tmW, w1b_planes, NP * 9 * 64, 64, 64)) return e;
   ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (plane_t*)out, (float*)out};
   g.img = img; g.w1a = w1a; g.b1a = b1a;
-  IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<true>, C64_SMEM);
+  IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<true>, C64_FUSE_SMEM);
   const int num_sms = imw_num_sms();
   const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
-  tc_conv3x3_c64_kernel<true><<<dim3((unsigned)(total < num_sms ? total : num_sms)), C64_FUSE_THREADS, C64_SMEM, st>>>(tmW, tmW, g, total);
+  tc_conv3x3_c64_kernel<true><<<dim3((unsigned)(total < num_sms ? total : num_sms)), C64_FUSE_THREADS, C64_FUSE_SMEM, st>>>(tmW, tmW, g, total);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -17,7 +17,7 @@ class SPWeights(C.Structure):
 
 class SPConf(C.Structure):
     _fields_ = [("nms_radius", C.c_int), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int),
-                ("remove_borders", C.c_int), ("use_tensor_cores", C.c_int)]
+                ("remove_borders", C.c_int), ("use_tensor_cores", C.c_int), ("fix_sampling", C.c_int)]
 
 
 class LGBlock(C.Structure):

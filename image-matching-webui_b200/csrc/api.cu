@@ -209,7 +209,7 @@ extern "C" int imw_superpoint_forward(const imw_sp_weights* wt, const imw_sp_con
   RUN(sp_nms(b.dense, b.nms, B, H, W, conf->nms_radius, st));
   RUN(sp_select(b.nms, b.keys, (int)b.key_cap, keypoints, scores, counts, B, H, W, conf->keypoint_threshold, conf->remove_borders,
                 conf->max_keypoints, cap, st));
-  RUN(sp_sample_desc(b.dd, keypoints, counts, descriptors, B, h, w, cap, 256, st));
+  RUN(sp_sample_desc(b.dd, keypoints, counts, descriptors, B, h, w, cap, 256, conf->fix_sampling, st));
 #undef RUN
   return IMW_OK;
 }

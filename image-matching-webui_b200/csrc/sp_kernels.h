@@ -21,8 +21,9 @@ size_t sp_select_key_cap(int H, int W);
 // in-place L2 normalisation of rows of 256 ([cells][256])
 int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st);
 // bilinear sample of dense descriptors [B][h][w][256] at kpts, then L2 norm -> desc [B][cap][256]
+// fix_sampling: hloc/extractors/superpoint.py:16-30 (align_corners=False at (k + 0.5) / 8 - 0.5) instead of superpoint.py:80-92
 int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts, float* desc, int B, int h, int w,
-                   int cap, int C, cudaStream_t st);
+                   int cap, int C, int fix_sampling, cudaStream_t st);
 
 // tcgen05 split-precision conv (tc_conv.cu): activations / weights as three bf16 planes
 int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, void* out, int B, int H, int W, int Cin,

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x,
 // warp per keypoint; C = 256 -> 8 channels per lane.
 __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restrict__ dd, const float* __restrict__ kpts,
                                                           const int* __restrict__ counts, float* __restrict__ desc, int h,
-                                                          int w, int cap, int C) {
+                                                          int w, int cap, int C, int fix_sampling) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -289,6 +289,14 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restric
   float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(ky, s / 2), 0.5f), (h * s - s / 2 - 0.5f)), 2.f), 1.f);
   float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1));
   float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
+  if (fix_sampling) {
+    // hloc/extractors/superpoint.py:19-27: (k + 0.5) / ([w, h] * s) * 2 - 1, grid_sample(align_corners=False):
+    // unnormalise ((g + 1) * size - 1) / 2
+    gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(kx, 0.5f), (w * s)), 2.f), 1.f);
+    gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(ky, 0.5f), (h * s)), 2.f), 1.f);
+    ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 2.f);
+    iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 2.f);
+  }
   float fx = floorf(ix), fy = floorf(iy);
   int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
   float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
@@ -368,10 +376,10 @@ int sp_l2norm_rows(float* x, long long rows, int C, cudaStream_t st) {
 }
 
 int sp_sample_desc(const float* dense_desc, const float* kpts, const int* counts, float* desc, int B, int h, int w, int cap,
-                   int C, cudaStream_t st) {
+                   int C, int fix_sampling, cudaStream_t st) {
   IMW_REQUIRE(C == 256, "sp_sample_desc: descriptor_dim must be 256");
   dim3 grid(ceil_div(cap, 8), B);
-  sample_desc_kernel<<<grid, 256, 0, st>>>(dense_desc, kpts, counts, desc, h, w, cap, C);
+  sample_desc_kernel<<<grid, 256, 0, st>>>(dense_desc, kpts, counts, desc, h, w, cap, C, fix_sampling);
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

@@ -24,8 +24,6 @@ class SuperPoint(BaseModel):
     detection_noise = 2.0
 
     def _init(self, conf):
-        if conf["fix_sampling"]:
-            raise NotImplementedError("fix_sampling=True is not built into the B200 engine (reference default: False)")
         mk = conf["max_keypoints"]
         if mk == 0 or mk < -1:  # superpoint.py:139-141
             raise ValueError('"max_keypoints" must be positive or "-1"')

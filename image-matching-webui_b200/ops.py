@@ -202,7 +202,7 @@ def superpoint_forward(bufs, image, conf, cap, out=None, want_dense=False):
     ws = L.workspaces.get(dev, nbytes, "sp")
     use_tc = bool(conf.get("tensor_cores", True)) and W % 16 == 0
     c = L.SPConf(int(conf["nms_radius"]), float(conf["keypoint_threshold"]), int(conf["max_keypoints"]),
-                 int(conf["remove_borders"]), int(use_tc))
+                 int(conf["remove_borders"]), int(use_tc), int(bool(conf.get("fix_sampling", False))))
     wstruct = sp_weights_struct(bufs)
     with torch.cuda.device(dev):
         rc = lib.imw_superpoint_forward(C.byref(wstruct), C.byref(c), B, H, W, L.ptr(image), cap, L.ptr(out["keypoints"]),

@@ -121,6 +121,8 @@ typedef struct {
   int max_keypoints;        /* conf["max_keypoints"]; -1 = no cap; 0 or < -1 -> error (superpoint.py:139-141) */
   int remove_borders;       /* conf["remove_borders"] */
   int use_tensor_cores;     /* 1: encoder convs on tcgen05 (two fp16 planes per operand, three products = fp32-equivalent), 0: fp32 CUDA cores */
+  int fix_sampling;         /* conf["fix_sampling"] (hloc/extractors/superpoint.py:16-30,46-47): descriptors sampled at
+                               (k + 0.5) / (8 [w, h]) with align_corners=False instead of superpoint.py:80-92 */
 } imw_sp_conf;
 
 size_t imw_superpoint_workspace_bytes(int batch, int height, int width);

@@ -100,6 +100,15 @@ def sample_descriptors(kpts, desc, s=8):
     return F.normalize(d.reshape(b, c, -1), p=2, dim=1)
 
 
+def sample_descriptors_fix_sampling(kpts, desc, s=8):
+    """hloc/extractors/superpoint.py:16-30 (fix_sampling=True): (k + 0.5) / ([w, h] * s), align_corners=False."""
+    b, c, h, w = desc.shape
+    k = (kpts + 0.5) / (torch.tensor([w, h]).to(kpts) * s)
+    k = k * 2 - 1
+    d = F.grid_sample(desc, k.view(b, 1, -1, 2), mode="bilinear", align_corners=False)
+    return F.normalize(d.reshape(b, c, -1), p=2, dim=1)
+
+
 def forward(w, image, conf=None, return_dense=False):
     """superpoint.py:145-206.  image [B,1,H,W] fp32 in [0,1].
     Returns {"keypoints": [ [N,2] ], "scores": ( [N] ), "descriptors": [ [256,N] ]}."""
@@ -116,7 +125,8 @@ def forward(w, image, conf=None, return_dense=False):
         kpts.append(k)
         scores.append(s)
     dd = dense_descriptors(w, feat)
-    descs = [sample_descriptors(k[None], d[None], 8)[0] for k, d in zip(kpts, dd)]
+    sample = sample_descriptors_fix_sampling if conf.get("fix_sampling") else sample_descriptors
+    descs = [sample(k[None], d[None], 8)[0] for k, d in zip(kpts, dd)]
     out = {"keypoints": kpts, "scores": tuple(scores), "descriptors": descs}
     if return_dense:
         out["dense_scores"] = dense

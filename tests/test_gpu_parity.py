@@ -48,6 +48,26 @@ def test_superpoint_matches_reference(golden, dev, case, confs, tc):
                 assert moved == 0  # row-major order: exact
 
 
+SP_FIX_CONF = {"nms_radius": 3, "max_keypoints": 256, "keypoint_threshold": 0.005, "remove_borders": 4, "fix_sampling": True}
+
+
+def test_superpoint_fix_sampling_matches_reference_plugin(golden, dev):
+    """conf["fix_sampling"] = True (hloc/extractors/superpoint.py:16-30,46-47): goldens from the unmodified reference PLUGIN."""
+    from imcui_b200.hloc import extractors
+    g = golden("sp_fix")
+    images = torch.from_numpy(g["images"]).to(dev)
+    model = _load(extractors, "superpoint", dict(SP_FIX_CONF), dev)
+    plain = _load(extractors, "superpoint", {**SP_FIX_CONF, "fix_sampling": False}, dev)
+    for b in range(images.shape[0]):
+        out = model({"image": images[b:b + 1]})
+        assert_keypoints_equivalent(
+            out["keypoints"][0].cpu().numpy(), out["scores"][0].cpu().numpy(), out["descriptors"][0].cpu().numpy(),
+            g[f"{b}/keypoints"], g[f"{b}/scores"], g[f"{b}/descriptors"], score_tol=SCORE_TOL, desc_tol=DESC_TOL, order_noise=5e-5,
+            what=f"sp_fix/{b}")
+        other = plain({"image": images[b:b + 1]})["descriptors"][0]
+        assert (other - out["descriptors"][0]).abs().max() > 1e-2      # the switch does change the sampling
+
+
 @pytest.mark.parametrize("hw", [(136, 208), (200, 336), (136, 200), (64, 64)], ids=lambda v: f"{v[0]}x{v[1]}")
 def test_superpoint_ragged_sizes_vs_oracle(dev, hw):
     """Sizes that leave partial tiles in every conv kernel (H % 16 != 0, W % 16 != 0 -> CUDA-core convs, tiny maps):

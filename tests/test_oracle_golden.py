@@ -32,6 +32,20 @@ def test_superpoint_oracle_matches_reference(golden, case, confs):
             np.testing.assert_allclose(out["descriptors"][0].numpy(), g[f"{c}/{b}/descriptors"], atol=1e-4)
 
 
+def test_superpoint_oracle_fix_sampling(golden):
+    """oracle.sample_descriptors_fix_sampling against the unmodified reference plugin with fix_sampling=True."""
+    g = golden("sp_fix")
+    w = oracle.load_weights("superpoint_v1.pt")
+    conf = {"nms_radius": 3, "max_keypoints": 256, "keypoint_threshold": 0.005, "remove_borders": 4, "fix_sampling": True}
+    images = torch.from_numpy(g["images"])
+    for b in range(images.shape[0]):
+        out = osp.forward(w, images[b:b + 1], conf)
+        assert np.array_equal(out["keypoints"][0].numpy().astype(np.int16), g[f"{b}/keypoints"])
+        np.testing.assert_allclose(out["descriptors"][0].numpy(), g[f"{b}/descriptors"], atol=1e-4)
+        plain = osp.forward(w, images[b:b + 1], {**conf, "fix_sampling": False})
+        assert np.abs(plain["descriptors"][0].numpy() - g[f"{b}/descriptors"]).max() > 1e-2
+
+
 def test_superpoint_oracle_dense_maps(golden):
     g = golden("sp_real")
     w = oracle.load_weights("superpoint_v1.pt")

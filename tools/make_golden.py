@@ -99,6 +99,28 @@ def sp_case(name, images, confs, dense_for=()):
     return blob
 
 
+def sp_fix_case(name, images):
+    """The reference PLUGIN (imcui/hloc/extractors/superpoint.py, unmodified) with fix_sampling=True: _init swaps the module's
+    sample_descriptors for sample_descriptors_fix_sampling (:16-30,46-47)."""
+    if str(R.REF) not in sys.path:
+        sys.path.insert(0, str(R.REF))
+    from imcui.hloc.extractors import superpoint as plug
+    plug.SuperPoint._download_model = lambda self, repo_id=None, filename=None: str(R.SP_WEIGHTS)
+    import contextlib, io
+    conf = {"nms_radius": 3, "max_keypoints": 256, "keypoint_threshold": 0.005, "remove_borders": 4, "fix_sampling": True}
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = plug.SuperPoint(dict(conf)).eval()
+    blob = {"images": images.numpy()}
+    for b in range(images.shape[0]):
+        out = net({"image": images[b:b + 1]})
+        blob[f"{b}/keypoints"] = out["keypoints"][0].numpy().astype(np.int16)
+        blob[f"{b}/scores"] = out["scores"][0].numpy()
+        blob[f"{b}/descriptors"] = out["descriptors"][0].numpy()
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+    print("wrote", name, {k: v.shape for k, v in list(blob.items())[:4]})
+    plug.superpoint.sample_descriptors = None  # never reuse the patched module in this process
+
+
 LG_MODES = {
     # oracle A: full depth, no pruning (deterministic compute graph)
     "full": dict(depth_confidence=-1, width_confidence=-1, prune_th=-1),
@@ -436,6 +458,7 @@ def main():
     syn_u8 = np.stack([a[0], b[0], a[1], b[1]])
     syn = torch.from_numpy(syn_u8.astype(np.float32) / 255.0)[:, None]
     sb = sp_case("sp_synth", syn, {k: SP_CONFS[k] for k in ("max1024", "max2048")})
+    sp_fix_case("sp_fix", torch.cat([real[:1, :, :240, :320], syn[1:2, :, 100:340, 64:384]], 0))
 
     def pair(blob, conf, i, j):
         return (blob[f"{conf}/{i}/keypoints"].astype(np.float32), blob[f"{conf}/{i}/descriptors"],
@@ -466,7 +489,10 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1:   # python make_golden.py aliked -> only that family
         with torch.no_grad():
-            if sys.argv[1] in ("lg_proj", "lg_so"):   # inputs come from the stored SuperPoint goldens
+            if sys.argv[1] == "sp_fix":
+                gr, gs = np.load(OUT / "sp_real.npz")["images"], np.load(OUT / "sp_synth.npz")["images"]
+                sp_fix_case("sp_fix", torch.from_numpy(np.concatenate([gr[:1, :, :240, :320], gs[1:2, :, 100:340, 64:384]], 0)))
+            elif sys.argv[1] in ("lg_proj", "lg_so"):   # inputs come from the stored SuperPoint goldens
                 gb = {n: np.load(OUT / f"{n}.npz") for n in ("sp_synth", "sp_real")}
                 pr = lambda f, c, i, j: (gb[f][f"{c}/{i}/keypoints"].astype(np.float32), gb[f][f"{c}/{i}/descriptors"],
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])

@@ -85,7 +85,7 @@ class LoftrLayer(C.Structure):
 class LoftrWeights(C.Structure):
     _fields_ = [("backbone", LoftrBackbone), ("pos_enc", C.c_void_p), ("n_coarse", C.c_int), ("n_fine", C.c_int),
                 ("coarse", LoftrLayer * 8), ("fine", LoftrLayer * 2), ("down_proj_w", C.c_void_p), ("down_proj_b", C.c_void_p),
-                ("merge_feat_w", C.c_void_p), ("merge_feat_b", C.c_void_p)]
+                ("merge_feat_w", C.c_void_p), ("merge_feat_b", C.c_void_p), ("has_f16_planes", C.c_int)]
 
 
 class LoftrConf(C.Structure):

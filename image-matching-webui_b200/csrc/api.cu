@@ -306,11 +306,12 @@ __global__ void dsm_finish_kernel(const float* __restrict__ best_v, const int* _
   scores0[(long long)p * cap + i] = s;
 }
 
-struct MatcherBuffers { float *norm, *f0, *f1, *bv; int *bj, *m; };
+struct MatcherBuffers { float *norm, *f0, *f1, *bv; int *bj, *m; plane_t* planes; };
 size_t matcher_carve(Workspace& ws, MatcherBuffers& b, int P, int cap) {
   const size_t T = (size_t)2 * P * cap;
   b.norm = ws.take<float>(T * 256); b.f0 = ws.take<float>(T); b.f1 = ws.take<float>(T); b.bv = ws.take<float>(T);
   b.bj = ws.take<int>(T); b.m = ws.take<int>(T);
+  b.planes = ws.take<plane_t>(T * 256 * 2);   // split-fp16 planes of the descriptors for the tcgen05 similarity kernel
   return ws.off;
 }
 }  // namespace
@@ -332,8 +333,10 @@ extern "C" int imw_nearest_neighbor(int P, int cap, int dim, const float* desc, 
   SimArgs sa{desc, cap, dim, dim, counts, nullptr};
   OpTop2 op{b.m, b.f0, counts, cap, ratio_threshold > 0.f ? ratio_threshold * ratio_threshold : 0.f,
             distance_threshold > 0.f ? distance_threshold * distance_threshold : 0.f};
-  if (use_tensor_cores && tc_simreduce_ok(sa)) { if (int e = launch_tc_simreduce(sa, 2 * P, op, st)) return e; }
-  else IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, op, st));
+  if (use_tensor_cores && tc_simreduce_ok(sa)) {
+    if (int e = tc_simreduce_split(sa, 2 * P, b.planes, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, b.planes, op, st)) return e;
+  } else IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, op, st));
   nn_finish_kernel<<<dim3(ceil_div(cap, 256), P), 256, 0, st>>>(b.m, b.f0, counts, matches0, scores0, cap, do_mutual_check);
   IMW_CHECK_LAUNCH_T("nn_finish_kernel");
   return IMW_OK;
@@ -351,8 +354,9 @@ extern "C" int imw_dual_softmax(int P, int cap, int dim, const float* desc, cons
   IMW_CHECK_LAUNCH_T("normalize_rows_kernel");
   SimArgs sa{b.norm, cap, dim, dim, counts, nullptr};
   if (use_tensor_cores && tc_simreduce_ok(sa)) {
-    if (int e = launch_tc_simreduce(sa, 2 * P, OpSoftmaxStats{b.f0, b.f1, (float*)b.m, cap, inv_temperature}, st)) return e;
-    if (int e = launch_tc_simreduce(sa, 2 * P, OpDualSoftmaxArgmax{b.f0, b.f1, (const float*)b.m, b.bv, b.bj, cap, inv_temperature}, st)) return e;
+    if (int e = tc_simreduce_split(sa, 2 * P, b.planes, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, b.planes, OpSoftmaxStats{b.f0, b.f1, (float*)b.m, cap, inv_temperature}, st)) return e;
+    if (int e = launch_tc_simreduce(sa, 2 * P, b.planes, OpDualSoftmaxArgmax{b.f0, b.f1, (const float*)b.m, b.bv, b.bj, cap, inv_temperature}, st)) return e;
   } else {
     IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpSoftmaxStats{b.f0, b.f1, (float*)b.m, cap, inv_temperature}, st));
     IMW_CHECK_CUDA(launch_simreduce(sa, 2 * P, OpDualSoftmaxArgmax{b.f0, b.f1, (const float*)b.m, b.bv, b.bj, cap, inv_temperature}, st));

@@ -491,7 +491,8 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
       TcGemmArgs t{};
       t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.counts; t.skip = skip; t.skip_shift = 1;
       t.wsel_minus1 = wsel; t.wsel_shift = 1; t.wsel_rows = N;
-      t.wlo_rows = W->has_lo_planes ? w_rows : 0;     // host pre-split weights: [W ; W - trunc_tf32(W)]
+      if (W->has_lo_planes == 2) { t.w_planes = Wt + (size_t)w_rows * K; t.w_plane_rows = w_rows; }   // [W fp32 ; split-fp16 planes]
+      else t.wlo_rows = W->has_lo_planes ? w_rows : 0;     // host pre-split weights: [W ; W - trunc_tf32(W)]
       if (use_tc == 2) return launch_tc_gemm<128, 1>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
       return launch_tc_gemm<128, 3>(A, (long long)S * cap, lda, Wt, w_rows, t, epi, st);
     }
@@ -503,7 +504,7 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
   };
   // attention: tcgen05 flash attention on hi/lo planes (tensor-core modes) or the fp32 CUDA-core kernel
   const long long plane = use_tc ? (long long)S * cap * D : 0;
-  if (use_tc) IMW_CHECK_CUDA(cudaMemsetAsync(b.v, 0, sizeof(float) * 2 * plane, st));  // V^T tail columns must be finite
+  if (use_tc) IMW_CHECK_CUDA(cudaMemsetAsync(b.v, 0, sizeof(plane_t) * 2 * plane, st));  // V^T tail columns must be finite
   auto attention = [&](const float* q, const float* k, const float* v, float scale, int cross) -> int {
     if (use_tc) {
       TcAttnArgs a{b.ctx, b.counts, b.done, cap, S, scale, cross, (long long)S * HEADS * cap, (long long)S * HEADS * HD};
@@ -576,9 +577,11 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
     logsigmoid_kernel<<<dim3(ceil_div(cap, 256), S), 256, 0, st>>>(b.zl, b.counts, b.empty, cap);
     IMW_CHECK_LAUNCH_T("logsigmoid_kernel");
     SimArgs sa{b.md, cap, D, D, b.counts, b.empty};
-    if (use_tc && tc_simreduce_ok(sa)) {  // 3xTF32 similarity tiles in TMEM, same reduction functors
-      if (int e = launch_tc_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st)) return e;
-      if (int e = launch_tc_simreduce(sa, S, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st)) return e;
+    if (use_tc && tc_simreduce_ok(sa)) {  // split-fp16 similarity tiles in TMEM, same reduction functors
+      plane_t* planes = reinterpret_cast<plane_t*>(b.q);   // q/k/v are dead after the last layer: [2][S * cap][D] fp16 fits in q
+      if (int e = tc_simreduce_split(sa, S, planes, st)) return e;
+      if (int e = launch_tc_simreduce(sa, S, planes, OpRowLSE{b.rmax, b.rlse, cap}, st)) return e;
+      if (int e = launch_tc_simreduce(sa, S, planes, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st)) return e;
     } else {
       IMW_CHECK_CUDA(launch_simreduce(sa, S, OpRowLSE{b.rmax, b.rlse, cap}, st));
       IMW_CHECK_CUDA(launch_simreduce(sa, S, OpAssignArgmax{b.rmax, b.rlse, b.zl, b.best_v, b.best_j, cap}, st));
@@ -599,14 +602,11 @@ __global__ void attn_prep_planes_kernel(const float* __restrict__ q, const float
                                         int cap) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float hi, lo;
-  split_hi_lo(q[i], hi, lo); qp[i] = hi; qp[n + i] = lo;
-  split_hi_lo(k[i], hi, lo); kp[i] = hi; kp[n + i] = lo;
+  store_planes(qp, n, i, q[i]);
+  store_planes(kp, n, i, k[i]);
   const int d = (int)(i % HD);
   const long long row = (i / HD) % cap, zh = i / ((long long)HD * cap);
-  split_hi_lo(v[i], hi, lo);
-  const long long o = (zh * HD + d) * cap + row;
-  vtp[o] = hi; vtp[n + o] = lo;
+  store_planes(vtp, n, (zh * HD + d) * cap + row, v[i]);
 }
 }  // namespace
 

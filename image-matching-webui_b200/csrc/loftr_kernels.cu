@@ -546,6 +546,7 @@ extern "C" int imw_loftr_forward_hw(const imw_loftr_weights* W, const imw_loftr_
     if (use_tc) {
       TcGemmArgs t{};
       t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.cntL; t.skip = skip; t.skip_shift = 0;
+      if (W->has_f16_planes) { t.w_planes = Wt + (size_t)N * K; t.w_plane_rows = N; }   // [W fp32 ; split-fp16 planes]
       if (use_tc == 2) return launch_tc_gemm<128, 1>(A, (long long)S * cap, lda, Wt, N, t, epi, st);
       return launch_tc_gemm<128, 3>(A, (long long)S * cap, lda, Wt, N, t, epi, st);
     }
@@ -593,8 +594,10 @@ extern "C" int imw_loftr_forward_hw(const imw_loftr_weights* W, const imw_loftr_
     SimArgs sa{b.xm, cap, 512, CD, b.cntL, nullptr};
     const float scale = 1.f / (16.f * 16.f * conf->temperature);
     if (conf->use_tensor_cores && tc_simreduce_ok(sa)) {
-      RUN(launch_tc_simreduce(sa, S, OpSoftmaxStats{b.rmax, b.rsum, b.rlog, cap, scale}, st));
-      RUN(launch_tc_simreduce(sa, S, OpDualSoftmaxArgmax{b.rmax, b.rsum, b.rlog, b.best_v, b.best_j, cap, scale}, st));
+      plane_t* planes = reinterpret_cast<plane_t*>(b.q);   // q is dead after the coarse transformer: [2][S * cap][CD] fp16 fits
+      RUN(tc_simreduce_split(sa, S, planes, st));
+      RUN(launch_tc_simreduce(sa, S, planes, OpSoftmaxStats{b.rmax, b.rsum, b.rlog, cap, scale}, st));
+      RUN(launch_tc_simreduce(sa, S, planes, OpDualSoftmaxArgmax{b.rmax, b.rsum, b.rlog, b.best_v, b.best_j, cap, scale}, st));
     } else {
       IMW_CHECK_CUDA(launch_simreduce(sa, S, OpSoftmaxStats{b.rmax, b.rsum, b.rlog, cap, scale}, st));
       IMW_CHECK_CUDA(launch_simreduce(sa, S, OpDualSoftmaxArgmax{b.rmax, b.rsum, b.rlog, b.best_v, b.best_j, cap, scale}, st));

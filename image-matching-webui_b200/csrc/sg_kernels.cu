@@ -254,7 +254,7 @@ extern "C" int imw_superglue_forward(const imw_sg_weights* W, const imw_sg_conf*
     return IMW_OK;
   };
   const long long plane = use_tc ? (long long)S * cap * D : 0;
-  if (use_tc) IMW_CHECK_CUDA(cudaMemsetAsync(b.v, 0, sizeof(float) * 2 * plane, st));
+  if (use_tc) IMW_CHECK_CUDA(cudaMemsetAsync(b.v, 0, sizeof(plane_t) * 2 * plane, st));   // V^T tail columns must be finite
   // ---- attentional GNN (superglue.py:112-140)
   for (int i = 0; i < W->n_layers; i++) {
     const imw_sg_layer& ly = W->layers[i];

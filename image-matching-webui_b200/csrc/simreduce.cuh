@@ -185,10 +185,16 @@ struct OpDualSoftmaxArgmax {
     if (y >= s.ylim) exact(s, x, y, i, j, own, other);
   }
   __device__ void accum32(State& s, const float (&v)[32], int i, int j0, int jn, int own, int other) const {
-    const float* cl = rlog + (long long)other * cap + j0;    // the same 32 columns for every row of the warp: broadcast loads
-    float y[32], ym = -INFINITY;
+    // the same 32 columns for every row of the warp: eight 16-byte broadcast loads (j0 % 32 == 0 and cap % 128 == 0 on the
+    // tensor-core path: aligned, and in bounds even when jn < 32)
+    const float4* cl4 = reinterpret_cast<const float4*>(rlog + (long long)other * cap + j0);
+    float cl[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) { y[j] = j < jn ? fmaf(2.f * scale, v[j], -cl[j]) : -INFINITY; ym = fmaxf(ym, y[j]); }
+    for (int q = 0; q < 8; q++) { const float4 t = __ldg(cl4 + q); cl[4 * q] = t.x; cl[4 * q + 1] = t.y; cl[4 * q + 2] = t.z; cl[4 * q + 3] = t.w; }
+    float y[32], ym = -INFINITY;
+    const float s2 = 2.f * scale;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { y[j] = j < jn ? fmaf(s2, v[j], -cl[j]) : -INFINITY; ym = fmaxf(ym, y[j]); }
     if (ym < s.ylim) return;
 #pragma unroll
     for (int j = 0; j < 32; j++)

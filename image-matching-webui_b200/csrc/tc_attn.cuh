@@ -1,24 +1,30 @@
-// tcgen05 flash attention for LightGlue (head dim 64, fp32-equivalent via 3xTF32 split operands).
+// tcgen05 flash attention for LightGlue / SuperGlue (head dim 64, fp32-equivalent via split-fp16 operands).
 //
 //   ctx[z][row][h*64 + d] = softmax_j(scale * <q_row, k_j>) v_j      self: k,v of slot z; cross: of slot z^1
 //
-// Operands arrive pre-split from the projection epilogues as hi/lo planes (hi = 13 low mantissa bits cleared,
-// lo = x - hi): q, k  [plane][slot][head][cap][64],  v transposed  [plane][slot][head][64][cap]  (kv contiguous,
-// so that V^T is a plain K-major B operand).  Per CTA: one (slot, head, 128-row q tile).
-//   warp 0     TMA producer: Q once, then K_j / V_j tiles of 64 keys (single-buffered; K_{j+1} is fetched while
-//              softmax_j and P_j V_j run, V_{j+1} while S_{j+1} and softmax_{j+1} run)
-//   warp 1     MMA issuer: S_j = Q K_j^T into one of two TMEM buffers (main hi*hi and cross-term accumulators),
-//              O_j = P_j V_j into a fresh TMEM tile (never rescaled in place)
-//   warps 2-17 softmax / correction, FOUR warps per TMEM sub-partition: a thread owns one q row and a QUARTER of the columns
-//              (16 of the 64 keys of S_j, 16 of the 64 output dims of O): tcgen05.ld S_j, mask, row max (exchanged
-//              with the three partner threads through shared memory), P_j = exp(S_j - m) written to shared memory as
-//              K-major SWIZZLE_128B tiles (P itself = the hi operand, P - trunc_tf32(P) = the lo operand) for the second
-//              MMA, and the running output acc = (acc + O_{j-1}) * exp(m_{j-1} - m_j) kept in registers.
-//              (Round 1 ran 8 such warps with half a row each: the per-tile chain S -> softmax -> P -> PV was bound by
-//              the LATENCY of those warps -- 2 per scheduler, ~700 dependent instructions per tile, tensor pipe 29 % --
-//              not by any throughput; twice the warps with half the work each shortens exactly that chain.)
+// Operands arrive pre-split from the projection epilogues as two fp16 planes (split_planes.cuh: hi = fp16(x),
+// lo = fp16((x - hi) 2^11)):  q, k  [plane][slot][head][cap][64],  v transposed  [plane][slot][head][64][cap]  (keys contiguous,
+// so that V^T is a plain K-major B operand).  Per CTA: one (slot, head, 128-row q tile); key tiles of 64.
+//
+// Round-2 structure (the round-1 kernel ran 3xTF32 with 16 softmax warps that each owned a QUARTER of a row: one 512-thread
+// barrier and a shared-memory max exchange per key tile, O read back from TMEM and rescaled in registers every tile -- 2.2 us
+// per key tile against 0.8 us of MMA time, tensor pipe 40 %):
+//   * TWO independent softmax streams: stream A owns the even key tiles, stream B the odd ones; each has its own S buffer, P
+//     buffer and O accumulator, so S_{j+1} / P_{j+1} are produced while P_j V_j runs and nothing is exchanged between threads
+//     until the end.  A thread owns one whole q row of its stream's tile (64 scores): row max and row sum are thread-local.
+//   * O stays in TMEM and is accumulated by the tensor core across the stream's tiles (use_acc); it is rescaled in place
+//     (tcgen05.ld / st) only when a row's running reference maximum has to move by more than 2^8 (lazy rescaling: P <= 256
+//     stays far inside fp16 / fp32 range and the final division by the row sum, taken with the same reference, cancels it).
+//   * kind::f16 MMAs (K = 16 per instruction): S = Q_hi x [K_hi | K_lo] + Q_lo x K_hi, O = P_hi x [V_hi | V_lo] + P_lo x V_hi,
+//     scaled cross terms in their own accumulator columns.  Half the tensor time and half the operand bytes of 3xTF32.
+//   * the two streams are merged once: O = (O_a w_a + O_b w_b) / (l_a w_a + l_b w_b), w = 2^(m - max(m_a, m_b)).
+//
+//   warp 0      TMA producer: Q once, K / V^T tiles through two independent 3-deep rings
+//   warp 1      MMA issuer (whichever of S_js / P_jp V_jp has its operands ready is issued next)
+//   warps 2-5   softmax stream A, warps 6-9 stream B (one TMEM sub-partition = 32 rows per warp)
 #pragma once
 #include "common.cuh"
+#include "split_planes.cuh"
 #include "tc_common.cuh"
 
 struct TcAttnArgs {
@@ -32,15 +38,35 @@ struct TcAttnArgs {
   long long plane_rows_vt;  // slots*4*64
 };
 
-constexpr int TA_BQ = 128, TA_BKV = 64, TA_SM_THREADS = 512, TA_THREADS = 64 + TA_SM_THREADS;
-constexpr int TA_Q_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 k-subtiles x [128 x 32 f32]  = 64 KB
-constexpr int TA_K_BYTES = 2 * 2 * TA_BKV * 128;    // hi/lo x 2 subtiles x [64 x 32]        = 32 KB
-constexpr int TA_V_BYTES = 2 * 2 * 64 * 128;        // hi/lo x 2 kv-subtiles x [64 d x 32 kv] = 32 KB
-constexpr int TA_P_BYTES = 2 * 2 * TA_BQ * 128;     // hi/lo x 2 kv-subtiles x [128 x 32]     = 64 KB
-constexpr size_t TA_SMEM = TA_Q_BYTES + TA_K_BYTES + TA_V_BYTES + TA_P_BYTES + 1024 + 256 + 2 * 4 * 128 * sizeof(float);
-
-// TMEM columns: S buffers 2 x (main 64 + cross 64) = 256, O main 64 + cross 64 -> 384 (allocate 512)
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_NK = 3, TA_NV = 3, TA_THREADS = 64 + 256;
+constexpr int TA_Q_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 f16]   = 32 KB
+constexpr int TA_K_BYTES = 2 * TA_BKV * 128;        // hi | lo x [64 keys x 64 f16]    = 16 KB per stage
+constexpr int TA_V_BYTES = 2 * 64 * 128;            // hi | lo x [64 d x 64 keys f16]  = 16 KB per stage
+constexpr int TA_P_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 keys]  = 32 KB per stream
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_NK * TA_K_BYTES + TA_NV * TA_V_BYTES + 2 * TA_P_BYTES + 1024 + 256 + 4 * 128 * sizeof(float);
+// TMEM columns: S_a [0,128) = main 64 | cross 64, S_b [128,256), O_a [256,384) = main 64 | cross 64, O_b [384,512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
+constexpr float TA_LAZY = 8.f;   // log2 units: the reference maximum of a row moves only when it would grow by more than this
+
+namespace tc {
+// 32 lanes x 32 consecutive fp32 columns, registers -> TMEM
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+}  // namespace tc
 
 static __global__ void __launch_bounds__(TA_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -59,21 +85,21 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   extern __shared__ uint8_t ta_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)ta_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                 // [plane][sub][128 rows][128 B]
-  uint8_t* sK = sQ + TA_Q_BYTES;      // [sub][plane][64 rows][128 B]   (hi | lo of one k-subtile adjacent: one N = 128 operand)
-  uint8_t* sV = sK + TA_K_BYTES;      // [sub][plane][64 d rows][128 B]
-  uint8_t* sP = sV + TA_V_BYTES;      // [plane][sub][128 rows][128 B]
-  uint64_t* bars = (uint64_t*)(sP + TA_P_BYTES);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-           *s_full = bars + 5 /*[2]*/, *p_full = bars + 7, *o_full = bars + 8;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
-  float* xchg = (float*)(sP + TA_P_BYTES + 256);   // [tile parity][quarter][128 rows]: row maxima / final sums of the partner threads
+  uint8_t* sQ = smem;                          // [hi | lo][128 rows][128 B]
+  uint8_t* sK = sQ + TA_Q_BYTES;               // [stage][hi | lo][64 keys][128 B]     (hi | lo adjacent: one N = 128 operand)
+  uint8_t* sV = sK + TA_NK * TA_K_BYTES;       // [stage][hi | lo][64 d rows][128 B]
+  uint8_t* sP = sV + TA_NV * TA_V_BYTES;       // [stream][hi | lo][128 rows][128 B]
+  uint64_t* bars = (uint64_t*)(sP + 2 * TA_P_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1 /*[3]*/, *k_empty = bars + 4 /*[3]*/, *v_full = bars + 7 /*[3]*/, *v_empty = bars + 10 /*[3]*/,
+           *s_full = bars + 13 /*[2]*/, *s_free = bars + 15 /*[2]*/, *p_full = bars + 17 /*[2]*/, *o_done = bars + 19 /*[2]*/;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 21);
+  float* xchg = (float*)((uint8_t*)bars + 256);   // [2][128]: (m, l) of stream B for the final merge
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
-    tc::mbar_init(q_full, 1); tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
-    tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1); tc::mbar_init(s_full + 1, 1); tc::mbar_init(p_full, TA_SM_THREADS);
-    tc::mbar_init(o_full, 1);
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 3; i++) { tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); }
+    for (int i = 0; i < 2; i++) { tc::mbar_init(s_full + i, 1); tc::mbar_init(s_free + i, 128); tc::mbar_init(p_full + i, 128); tc::mbar_init(o_done + i, 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TA_TMEM_COLS);
@@ -82,197 +108,217 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int T = (nk + TA_BKV - 1) / TA_BKV;
-  const int q_row = (z * 4 + head) * g.cap + q0;          // row in the [slots*4*cap][64] q/k tensors
+  const int q_row = (z * 4 + head) * g.cap + q0;          // row in the [2][slots*4*cap][64] q/k tensors
   const int k_row0 = (zk * 4 + head) * g.cap;
-  const int v_row = (zk * 4 + head) * 64;                 // row in the [slots*4*64][cap] v^T tensor
+  const int v_row = (zk * 4 + head) * 64;                 // row in the [2][slots*4*64][cap] v^T tensor
 
   if (warp == 0) {
     if (lane == 0) {
       tc::mbar_expect_tx(q_full, TA_Q_BYTES);
-      for (int p = 0; p < 2; p++)
-        for (int sub = 0; sub < 2; sub++)
-          tc::tma_load_2d(sQ + (p * 2 + sub) * TA_BQ * 128, &tmQ, q_full, sub * 32, (int)(p * g.plane_rows_qk) + q_row);
-      // K and V tiles are refilled INDEPENDENTLY, each as soon as its own consumer MMAs have completed (round 1 walked
-      // K_j, V_j, K_{j+1} ... in one sequence, so the K_{j+1} load -- and with it S_{j+1} -- waited for P_{j-1} V_{j-1}).
-      // A barrier cannot run ahead of the phase polled here: S_{j+1} needs K_{j+1}, which is only requested after
-      // k_empty(j) was observed (same for V), so a non-blocking parity test never misses a phase.
+      tc::tma_load_2d(sQ, &tmQ, q_full, 0, q_row);
+      tc::tma_load_2d(sQ + TA_Q_BYTES / 2, &tmQ, q_full, 0, (int)g.plane_rows_qk + q_row);
+      // K and V rings are refilled independently, each stage as soon as its own consumer MMAs have completed.  A barrier cannot
+      // run ahead of the phase polled here: stage reuse n+1 is only requested after reuse n was observed empty.
       int jk = 0, jv = 0;
+      uint32_t spins = 0;
       while (jk < T || jv < T) {
-        if (jk < T && (jk == 0 || tc::mbar_try_wait(k_empty, (jk - 1) & 1))) {
-          tc::mbar_expect_tx(k_full, TA_K_BYTES);
-          for (int p = 0; p < 2; p++)
-            for (int sub = 0; sub < 2; sub++)
-              tc::tma_load_2d(sK + (sub * 2 + p) * TA_BKV * 128, &tmK, k_full, sub * 32, (int)(p * g.plane_rows_qk) + k_row0 + jk * TA_BKV);
-          jk++;
+        bool did = false;
+        if (jk < T && (jk < TA_NK || tc::mbar_try_wait(k_empty + jk % TA_NK, ((jk / TA_NK) - 1) & 1))) {
+          uint8_t* dst = sK + (jk % TA_NK) * TA_K_BYTES;
+          tc::mbar_expect_tx(k_full + jk % TA_NK, TA_K_BYTES);
+          tc::tma_load_2d(dst, &tmK, k_full + jk % TA_NK, 0, k_row0 + jk * TA_BKV);
+          tc::tma_load_2d(dst + TA_K_BYTES / 2, &tmK, k_full + jk % TA_NK, 0, (int)g.plane_rows_qk + k_row0 + jk * TA_BKV);
+          jk++; did = true;
         }
-        if (jv < T && (jv == 0 || tc::mbar_try_wait(v_empty, (jv - 1) & 1))) {
-          tc::mbar_expect_tx(v_full, TA_V_BYTES);
-          for (int p = 0; p < 2; p++)
-            for (int sub = 0; sub < 2; sub++)
-              tc::tma_load_2d(sV + (sub * 2 + p) * 64 * 128, &tmV, v_full, jv * TA_BKV + sub * 32, (int)(p * g.plane_rows_vt) + v_row);
-          jv++;
+        if (jv < T && (jv < TA_NV || tc::mbar_try_wait(v_empty + jv % TA_NV, ((jv / TA_NV) - 1) & 1))) {
+          uint8_t* dst = sV + (jv % TA_NV) * TA_V_BYTES;
+          tc::mbar_expect_tx(v_full + jv % TA_NV, TA_V_BYTES);
+          tc::tma_load_2d(dst, &tmV, v_full + jv % TA_NV, jv * TA_BKV, v_row);
+          tc::tma_load_2d(dst + TA_V_BYTES / 2, &tmV, v_full + jv % TA_NV, jv * TA_BKV, (int)g.plane_rows_vt + v_row);
+          jv++; did = true;
         }
+        if (did) spins = 0;
+        else if (++spins > (1u << 24)) { printf("tc_attn producer timeout block (%d,%d,%d) jk %d jv %d\n", blockIdx.x, blockIdx.y, blockIdx.z, jk, jv); __trap(); }
       }
     }
   } else if (warp == 1) {
-    {
-      const bool leader = tc::elect_one();
-      constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64), idesc2 = tc::make_idesc(tc::FMT_TF32, 128, 128);
-      const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
-      auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = hi*lo + lo*hi   (k_full(j) already observed)
-        tc::fence_after_sync();
-        const uint32_t d_main = tmem_base + TA_S_COL + (j & 1) * 128, d_cross = d_main + 64;
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc64 = tc::make_idesc(tc::FMT_F16, 128, 64), idesc128 = tc::make_idesc(tc::FMT_F16, 128, 128);
+    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+    auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = (hi*lo + lo*hi) 2^11
+      tc::fence_after_sync();
+      const uint32_t d_main = tmem_base + TA_S_COL + (j & 1) * 128, d_cross = d_main + 64;
+      const uint32_t kb = aK + (j % TA_NK) * TA_K_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-          const int sub = ks / 4, ko = (ks % 4) * 32;
-          uint64_t qh = tc::make_smem_desc_sw128(aQ + (0 * 2 + sub) * TA_BQ * 128 + ko), ql = tc::make_smem_desc_sw128(aQ + (1 * 2 + sub) * TA_BQ * 128 + ko);
-          uint64_t kh = tc::make_smem_desc_sw128(aK + (sub * 2 + 0) * TA_BKV * 128 + ko);   // [K_hi | K_lo]: 128 adjacent rows
-          if (leader) {
-            tc::mma_tf32(d_main, qh, kh, idesc2, ks ? 1u : 0u);   // Q_hi x [K_hi | K_lo] -> [main | cross]
-            tc::mma_tf32(d_cross, ql, kh, idesc, 1u);             // Q_lo x K_hi -> cross
-          }
-        }
+      for (int ks = 0; ks < 4; ks++) {
+        uint64_t qh = tc::make_smem_desc_sw128(aQ + ks * 32), ql = tc::make_smem_desc_sw128(aQ + TA_Q_BYTES / 2 + ks * 32);
+        uint64_t kh = tc::make_smem_desc_sw128(kb + ks * 32);   // [K_hi | K_lo]: 128 adjacent rows
         if (leader) {
-          tc::mma_commit(k_empty);
-          tc::mma_commit(s_full + (j & 1));
+          tc::mma_f16(d_main, qh, kh, idesc128, ks ? 1u : 0u);   // Q_hi x [K_hi | K_lo] -> [main | cross]
+          tc::mma_f16(d_cross, ql, kh, idesc64, 1u);             // Q_lo x K_hi -> cross
         }
-        __syncwarp();
-      };
-      auto issue_PV = [&](int j) {  // O_j = P_j V_j, K = 64 keys   (p_full(j), v_full(j) already observed)
-        tc::fence_after_sync();
-        const uint32_t d_main = tmem_base + TA_O_COL, d_cross = d_main + 64;
-#pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-          const int sub = ks / 4, ko = (ks % 4) * 32;
-          uint64_t ph = tc::make_smem_desc_sw128(aP + (0 * 2 + sub) * TA_BQ * 128 + ko), pl = tc::make_smem_desc_sw128(aP + (1 * 2 + sub) * TA_BQ * 128 + ko);
-          uint64_t vh = tc::make_smem_desc_sw128(aV + (sub * 2 + 0) * 64 * 128 + ko);       // [V_hi | V_lo]
-          if (leader) {
-            tc::mma_tf32(d_main, ph, vh, idesc2, ks ? 1u : 0u);
-            tc::mma_tf32(d_cross, pl, vh, idesc, 1u);
-          }
-        }
-        if (leader) {
-          tc::mma_commit(v_empty);
-          tc::mma_commit(o_full);
-        }
-        __syncwarp();
-      };
-      // Whichever of S_{js} / P_{jp} V_{jp} has its operands ready is issued next (round 1 issued S_{j+1} strictly before
-      // P_j V_j and blocked on K_{j+1} while P_j was already waiting).  S_{js} writes TMEM buffer js & 1, free once softmax(js-2)
-      // has read it = p_full(js-2) observed = jp >= js - 1.  The polls are warp-uniform (same barrier, same parity in every lane).
-      tc::mbar_wait(q_full, 0);
-      int js = 0, jp = 0;
-      uint32_t spins = 0;
-      const int lead_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
-      // the issuing lane polls, the warp follows its verdict (a per-lane poll could split the warp around the __syncwarp()s)
-      auto ready = [&](bool cond_s) -> bool {
-        unsigned r = 0;
-        if (leader) r = cond_s ? (tc::mbar_try_wait(k_full, js & 1) ? 1u : 0u)
-                               : ((tc::mbar_try_wait(p_full, jp & 1) && tc::mbar_try_wait(v_full, jp & 1)) ? 1u : 0u);
-        return __shfl_sync(0xffffffffu, r, lead_lane) != 0;
-      };
-      while (jp < T) {
-        bool did = false;
-        if (js < T && js <= jp + 1 && ready(true)) { issue_S(js); js++; did = true; }
-        if (jp < js && ready(false)) { issue_PV(jp); jp++; did = true; }
-        if (did) spins = 0;
-        else if (++spins > (1u << 24)) { printf("tc_attn MMA scheduler timeout block (%d,%d,%d) js %d jp %d\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp); __trap(); }
       }
+      if (leader) {
+        tc::mma_commit(k_empty + j % TA_NK);
+        tc::mma_commit(s_full + (j & 1));
+      }
+      __syncwarp();
+    };
+    auto issue_PV = [&](int j) {  // O_stream += P_j V_j  (K = 64 keys)
+      tc::fence_after_sync();
+      const int st = j & 1;
+      const uint32_t d_main = tmem_base + TA_O_COL + st * 128, d_cross = d_main + 64;
+      const uint32_t vb = aV + (j % TA_NV) * TA_V_BYTES, pb = aP + st * TA_P_BYTES;
+      const uint32_t first = (j < 2) ? 0u : 1u;   // the stream's first tile overwrites its accumulator
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        uint64_t ph = tc::make_smem_desc_sw128(pb + ks * 32), pl = tc::make_smem_desc_sw128(pb + TA_P_BYTES / 2 + ks * 32);
+        uint64_t vh = tc::make_smem_desc_sw128(vb + ks * 32);   // [V_hi | V_lo]
+        if (leader) {
+          tc::mma_f16(d_main, ph, vh, idesc128, ks ? 1u : first);
+          tc::mma_f16(d_cross, pl, vh, idesc64, 1u);
+        }
+      }
+      if (leader) {
+        tc::mma_commit(v_empty + j % TA_NV);
+        tc::mma_commit(o_done + st);
+      }
+      __syncwarp();
+    };
+    tc::mbar_wait(q_full, 0);
+    int js = 0, jp = 0;
+    uint32_t spins = 0;
+    const int lead_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+    // the issuing lane polls, the warp follows its verdict.  S_js needs K_js landed and its S buffer drained by the softmax of
+    // tile js-2; P_jp V_jp needs P_jp written (which implies the stream's previous P V has completed) and V_jp landed.
+    auto ready_S = [&]() -> bool {
+      unsigned r = 0;
+      if (leader) r = (tc::mbar_try_wait(k_full + js % TA_NK, (js / TA_NK) & 1) &&
+                       (js < 2 || tc::mbar_try_wait(s_free + (js & 1), ((js >> 1) - 1) & 1))) ? 1u : 0u;
+      return __shfl_sync(0xffffffffu, r, lead_lane) != 0;
+    };
+    auto ready_PV = [&]() -> bool {
+      unsigned r = 0;
+      if (leader) r = (tc::mbar_try_wait(p_full + (jp & 1), (jp >> 1) & 1) && tc::mbar_try_wait(v_full + jp % TA_NV, (jp / TA_NV) & 1)) ? 1u : 0u;
+      return __shfl_sync(0xffffffffu, r, lead_lane) != 0;
+    };
+    while (jp < T) {
+      bool did = false;
+      if (js < T && js <= jp + 2 && ready_S()) { issue_S(js); js++; did = true; }
+      if (jp < js && ready_PV()) { issue_PV(jp); jp++; did = true; }
+      if (did) spins = 0;
+      else if (++spins > (1u << 24)) { printf("tc_attn MMA scheduler timeout block (%d,%d,%d) js %d jp %d\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp); __trap(); }
     }
   } else {
+    const int st = (warp - 2) / 4;                       // stream: key tiles j = st, st + 2, ...
     const int q = warp % 4, r = q * 32 + lane;           // TMEM lane = q row inside the tile
-    const int qt = (warp - 2) / 4;                       // keys [16 qt, +16) of S_j and dims [16 qt, +16) of O
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f, acc[16];
-#pragma unroll
-    for (int c = 0; c < 16; c++) acc[c] = 0.f;
-    for (int j = 0; j < T; j++) {
-      tc::mbar_wait(s_full + (j & 1), (j >> 1) & 1);
+    const float c2 = g.scale * 1.4426950408889634f;      // softmax in base 2: p = 2^(s c2 - m)
+    float m = -INFINITY, l = 0.f;                        // reference maximum (log2 units) and row sum relative to it
+    int n = 0;                                           // tiles of this stream processed so far
+    uint8_t* pP = sP + st * TA_P_BYTES + r * 128;
+    for (int j = st; j < T; j += 2, n++) {
+      tc::mbar_wait(s_full + st, n & 1);
       tc::fence_after_sync();
-      float s[16];
+      float s[64];
       {
-        float t[16];
-        const uint32_t a = lane_addr + TA_S_COL + (j & 1) * 128 + qt * 16;
-        tc::tmem_ld16(a, s);
-        tc::tmem_ld16(a + 64, t);
+        const uint32_t a = lane_addr + TA_S_COL + st * 128;
 #pragma unroll
-        for (int c = 0; c < 16; c++) s[c] += t[c];
-      }
-      const int kv0 = j * TA_BKV + qt * 16;
-      float mx = -INFINITY;
+        for (int hlf = 0; hlf < 2; hlf++) {
+          float mn[32], cr[32];
+          tc::tmem_ld32(a + hlf * 32, mn);
+          tc::tmem_ld32(a + 64 + hlf * 32, cr);
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
-        s[c] = (kv0 + c < nk) ? s[c] * g.scale : -INFINITY;
-        mx = fmaxf(mx, s[c]);
-      }
-      // row maximum over the four column quarters (partner threads = same row, other quarters)
-      float* xb = xchg + (j & 1) * 512;
-      xb[qt * 128 + r] = mx;
-      asm volatile("bar.sync 1, %0;" ::"n"(TA_SM_THREADS) : "memory");
-      const float m_new = fmaxf(m, fmaxf(fmaxf(xb[r], xb[128 + r]), fmaxf(xb[256 + r], xb[384 + r])));   // finite: the tile holds a valid key
-      const float alpha = __expf(m - m_new);     // 0 on the first tile (m = -inf)
-      float ps = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; c++) { s[c] = __expf(s[c] - m_new); ps += s[c]; }
-      l = l * alpha + ps;                        // partial sum over this thread's columns
-      m = m_new;
-      if (j > 0) {  // fold in O_{j-1} (computed relative to m_{j-1}), then move the reference to m_j
-        tc::mbar_wait(o_full, (j - 1) & 1);
-        tc::fence_after_sync();
-        float t[16];
-        tc::tmem_ld16(lane_addr + TA_O_COL + qt * 16, t);        // main
-#pragma unroll
-        for (int c = 0; c < 16; c++) acc[c] += t[c];
-        tc::tmem_ld16(lane_addr + TA_O_COL + 64 + qt * 16, t);   // cross terms
-#pragma unroll
-        for (int c = 0; c < 16; c++) acc[c] += t[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 16; c++) acc[c] *= alpha;
-      // P_j -> shared memory: P (= hi operand: kind::tf32 ignores the 13 low mantissa bits) and P - trunc_tf32(P) (lo), K-major
-      // rows of 128 B with the 128B swizzle (16-byte chunk c of row r lives at chunk c ^ (r & 7)); keys [32 sub, +32) form
-      // k-subtile `sub`; the previous P V MMA has completed (o_full above)
-      tc::fence_before_sync();
-      {
-        const int sub = qt >> 1, ch0 = (qt & 1) * 4;
-        uint8_t* ph = sP + (0 * 2 + sub) * TA_BQ * 128 + r * 128;
-        uint8_t* pl = sP + (1 * 2 + sub) * TA_BQ * 128 + r * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
-          uint4 h4, l4;
-          const float* v = &s[ch * 4];
-          h4.x = __float_as_uint(v[0]); h4.y = __float_as_uint(v[1]); h4.z = __float_as_uint(v[2]); h4.w = __float_as_uint(v[3]);
-          l4.x = __float_as_uint(v[0] - __uint_as_float(h4.x & 0xFFFFE000u)); l4.y = __float_as_uint(v[1] - __uint_as_float(h4.y & 0xFFFFE000u));
-          l4.z = __float_as_uint(v[2] - __uint_as_float(h4.z & 0xFFFFE000u)); l4.w = __float_as_uint(v[3] - __uint_as_float(h4.w & 0xFFFFE000u));
-          const int pos = ((ch0 + ch) ^ (r & 7)) * 16;
-          *reinterpret_cast<uint4*>(ph + pos) = h4;
-          *reinterpret_cast<uint4*>(pl + pos) = l4;
+          for (int c = 0; c < 32; c++) s[hlf * 32 + c] = fmaf(cr[c], PLANE_LO_INV, mn[c]);
         }
       }
+      tc::fence_before_sync();
+      tc::mbar_arrive(s_free + st);                      // S buffer may take tile j + 2
+      const int kv0 = j * TA_BKV;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c++) {
+        s[c] = (kv0 + c < nk) ? s[c] * c2 : -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      // lazy reference: move it only when this tile's maximum exceeds it by more than TA_LAZY (always on the first tile)
+      const bool move = mx > m + TA_LAZY;                // false for NaN rows (rows beyond the count read unwritten memory)
+      const float m_new = move ? mx : m;
+      const float alpha = move ? exp2f(m - m_new) : 1.f; // 0 on the first tile (m = -inf)
+      if (n > 0) {
+        tc::mbar_wait(o_done + st, (n - 1) & 1);         // P_{j-2} V_{j-2} complete: O is stable, the P buffer is free
+        tc::fence_after_sync();
+        if (__any_sync(0xffffffffu, move)) {             // rescale this warp's 32 rows of O in place (rare after the first tiles)
+#pragma unroll 1
+          for (int cc = 0; cc < 4; cc++) {               // main 0..63, cross 64..127
+            float o[32];
+            const uint32_t oa = lane_addr + TA_O_COL + st * 128 + cc * 32;
+            tc::tmem_ld32(oa, o);
+#pragma unroll
+            for (int c = 0; c < 32; c++) o[c] *= alpha;
+            tc::tmem_st32(oa, o);
+          }
+        }
+      }
+      l *= alpha;
+      m = m_new;
+      float ps = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c++) { s[c] = exp2f(s[c] - m); ps += s[c]; }
+      l += ps;
+      // P_j -> shared memory as the two fp16 operand planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk ch of
+      // row r lives at chunk ch ^ (r & 7))
+#pragma unroll
+      for (int ch = 0; ch < 8; ch++) {
+        __align__(16) plane_t h[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const float p = s[ch * 8 + e];
+          h[e] = __float2half_rn(p);
+          lo[e] = __float2half_rn((p - __half2float(h[e])) * PLANE_LO_SCALE);
+        }
+        const int pos = (ch ^ (r & 7)) * 16;
+        *reinterpret_cast<uint4*>(pP + pos) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(pP + TA_P_BYTES / 2 + pos) = *reinterpret_cast<const uint4*>(lo);
+      }
+      tc::fence_before_sync();                           // orders the tcgen05.st of the rescale before the MMA that accumulates on top
       tc::fence_proxy_async();
-      tc::mbar_arrive(p_full);
+      tc::mbar_arrive(p_full + st);
     }
-    // last tile's O, normalise, store
-    tc::mbar_wait(o_full, (T - 1) & 1);
-    tc::fence_after_sync();
-    {
-      float t[16];
-      tc::tmem_ld16(lane_addr + TA_O_COL + qt * 16, t);
-#pragma unroll
-      for (int c = 0; c < 16; c++) acc[c] += t[c];
-      tc::tmem_ld16(lane_addr + TA_O_COL + 64 + qt * 16, t);
-#pragma unroll
-      for (int c = 0; c < 16; c++) acc[c] += t[c];
+    // the stream's last P V
+    if (n > 0) {
+      tc::mbar_wait(o_done + st, (n - 1) & 1);
+      tc::fence_after_sync();
     }
-    float* xb = xchg + (T & 1) * 512;   // the buffer the last tile did not use
-    xb[qt * 128 + r] = l;
-    asm volatile("bar.sync 1, %0;" ::"n"(TA_SM_THREADS) : "memory");
+    // merge the two streams: stream A writes dims 0..31 of every row, stream B dims 32..63
+    if (st == 1) { xchg[r] = m; xchg[128 + r] = l; }
+    float* xa = xchg + 256;                              // (m, l) of stream A
+    if (st == 0) { xa[r] = m; xa[128 + r] = l; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float ma = xa[r], la = xa[128 + r], mb = xchg[r], lb = xchg[128 + r];
+    const float mm = fmaxf(ma, mb);                      // stream A always has a tile (T >= 1): finite for valid rows
+    const float wa = exp2f(ma - mm), wb = (lb > 0.f) ? exp2f(mb - mm) : 0.f;
+    const float inv = 1.f / (la * wa + lb * wb);
     const int row = q0 + r;
-    if (row < nq) {
-      const float inv = 1.f / ((xb[r] + xb[128 + r]) + (xb[256 + r] + xb[384 + r]));
-      float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + qt * 16);
+    {
+      float acc[32], t[32];
+      const uint32_t oa = lane_addr + TA_O_COL + st * 32;            // this warp's 32 output dims
+      tc::tmem_ld32(oa, acc);
+      tc::tmem_ld32(oa + 64, t);
 #pragma unroll
-      for (int c = 0; c < 4; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      for (int c = 0; c < 32; c++) acc[c] = fmaf(t[c], PLANE_LO_INV, acc[c]) * wa;
+      if (T > 1) {                                                   // stream B ran: its accumulator holds data
+        float ob[32];
+        tc::tmem_ld32(oa + 128, ob);
+        tc::tmem_ld32(oa + 128 + 64, t);
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc[c] = fmaf(fmaf(t[c], PLANE_LO_INV, ob[c]), wb, acc[c]);
+      }
+      if (row < nq) {
+        float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + st * 32);
+#pragma unroll
+        for (int c = 0; c < 8; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      }
     }
   }
   tc::fence_before_sync();
@@ -280,13 +326,13 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1) tc::tmem_dealloc(tmem_base, TA_TMEM_COLS);
 }
 
-// q_planes / k_planes: [2][slots*4*cap][64] fp32, vt_planes: [2][slots*4*64][cap] fp32
-static inline int launch_tc_attn(const float* q_planes, const float* k_planes, const float* vt_planes, TcAttnArgs g, cudaStream_t st) {
+// q_planes / k_planes: [2][slots*4*cap][64] fp16, vt_planes: [2][slots*4*64][cap] fp16
+static inline int launch_tc_attn(const void* q_planes, const void* k_planes, const void* vt_planes, TcAttnArgs g, cudaStream_t st) {
   CUtensorMap tmQ, tmK, tmV;
   const long long rows_qk = 2 * g.plane_rows_qk, rows_vt = 2 * g.plane_rows_vt;
-  if (int e = tc_make_map_2d_f32(&tmQ, q_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BQ)) return e;
-  if (int e = tc_make_map_2d_f32(&tmK, k_planes, (uint64_t)rows_qk, 64, 64, 32, TA_BKV)) return e;
-  if (int e = tc_make_map_2d_f32(&tmV, vt_planes, (uint64_t)rows_vt, (uint64_t)g.cap, (uint64_t)g.cap, 32, 64)) return e;
+  if (int e = tc_make_map_2d_f16(&tmQ, q_planes, (uint64_t)rows_qk, 64, 64, TA_BQ)) return e;
+  if (int e = tc_make_map_2d_f16(&tmK, k_planes, (uint64_t)rows_qk, 64, 64, TA_BKV)) return e;
+  if (int e = tc_make_map_2d_f16(&tmV, vt_planes, (uint64_t)rows_vt, (uint64_t)g.cap, 64, 64)) return e;
   IMW_SMEM_ATTR_ONCE(tc_attn_kernel, TA_SMEM);
   dim3 grid(g.cap / TA_BQ, 4, g.slots);
   tc_attn_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(tmQ, tmK, tmV, g);

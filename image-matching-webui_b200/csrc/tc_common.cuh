@@ -60,6 +60,34 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- thread-block clusters: TMA multicast + cross-CTA barrier traffic ----------------------------------------
+// A tile that several CTAs of a cluster need (the weight / column tile of a streaming contraction) is fetched from L2 ONCE:
+// every CTA loads a different slice and multicasts it to the same shared-memory offset of all CTAs in `mask`; the bytes
+// are counted on the mbarrier at the same offset in each destination CTA.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (barrier init visible before any peer multicasts into this CTA; no CTA exits while a
+// peer may still write into its shared memory)
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// all previously issued MMAs of this thread arrive, when complete, on the mbarrier at this offset in EVERY CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
 // one elected lane of a converged warp (elect.sync): lets the MMA warp run its loop warp-uniformly, so that
 // descriptors live in uniform registers and each tcgen05.mma is a single predicated instruction instead of a
 // per-instruction vote/broadcast sequence
@@ -161,3 +189,5 @@ PFN_encodeTiled tc_get_encode_fn();
 // 2-D row-major fp32 [rows][ld] tensor, box = {box_cols (inner), box_rows}, 128B swizzle, zero OOB fill.
 int tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols,
                        uint32_t box_rows);
+// 2-D row-major fp16 [rows][cols] tensor (dense rows), box = {box_cols (64 = one 128-byte swizzled row), box_rows}
+int tc_make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);

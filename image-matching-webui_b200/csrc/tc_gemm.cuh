@@ -25,6 +25,7 @@
 // slot's count are skipped on the device.
 #pragma once
 #include "common.cuh"
+#include "split_planes.cuh"
 #include "tc_common.cuh"
 
 struct TcGemmArgs {
@@ -41,6 +42,8 @@ struct TcGemmArgs {
                          //    only even slots produce output: C[pair] = X_0 X_1^T (score matrices)
   long long wlo_rows;    // > 0: W holds a second plane W_lo = W - trunc_tf32(W) wlo_rows rows below W (host pre-split);
                          //      0: W_lo is computed in the kernel like A_lo
+  const void* w_planes;  // non-null: the weights as split-fp16 planes [2][w_plane_rows][K] (split_planes.cuh, packed by the host):
+  long long w_plane_rows;  //         the GEMM runs on kind::f16 (tc_gemm_f16_kernel) -- half the tensor time and 2/3 of the L2 -> SM bytes
 };
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 448;
@@ -243,6 +246,217 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
   if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Split-fp16 variant (the default for every linear with host-packed weights):  x = hi + lo 2^-11, three kind::f16 products per
+// fp32-equivalent product (split_planes.cuh).  Why: the 3xTF32 kernel above is bound by the L2 -> SM stream of its fp32 operand
+// tiles (ncu round 2: 9 TB/s, 1.58 us per 64 elements of K at 96 KB) with the tensor pipe half idle.  Here
+//   * weights arrive as fp16 planes [W_hi ; W_lo] (4 B per element instead of 8 B): TMA, adjacent tiles -> one N = 2 BN operand;
+//   * the activation tile lands as fp32 (TMA, two 32-column boxes per 64-element k-block) and four splitter warps convert it
+//     to the two fp16 operand tiles (K-major, SWIZZLE_128B written by hand: 16-byte chunk c of row r sits at c ^ (r & 7));
+//   * MMAs are kind::f16 (K = 16 per instruction): A_hi x [W_hi | W_lo] -> [main | cross], A_lo x W_hi -> cross; the epilogue adds
+//     main + cross 2^-11.
+// Same persistent tile walk, roles and functor epilogues as the kernel above.
+constexpr int TH_BKE = 64, TH_STAGES = 2, TH_SPLIT_WARPS = 4, TH_THREADS = 64 + 32 * TH_SPLIT_WARPS + 256;
+
+template <int BN>
+constexpr size_t tc_gemm_f16_smem_bytes() {
+  return (size_t)TH_STAGES * (2 * TC_BM * 128 /*fp32 landing*/ + 2 * TC_BM * 128 /*A planes*/ + 2 * BN * 128 /*W planes*/) + 1024 + 256 +
+         8 * 32 * 33 * sizeof(float);
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi,
+                                                                   int m_tiles) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int LAND_BYTES = 2 * TC_BM * 128, AP_BYTES = TC_BM * 128, WP_BYTES = BN * 128;
+  constexpr int A_OFF = LAND_BYTES, W_OFF = LAND_BYTES + 2 * AP_BYTES, STAGE = W_OFF + 2 * WP_BYTES;
+  constexpr int ACC_COLS = 2 * BN;
+  uint64_t* full = (uint64_t*)(smem + TH_STAGES * STAGE);
+  uint64_t* empty = full + TH_STAGES;
+  uint64_t* ready = empty + TH_STAGES;
+  uint64_t* tmem_full = ready + TH_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* epi_tiles = (float*)(smem + TH_STAGES * STAGE + 256);  // [8 warps][32][33]
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+    for (int s = 0; s < TH_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); tc::mbar_init(ready + s, 32 * TH_SPLIT_WARPS); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 256); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int KB = g.K / TH_BKE, n_tiles = g.N / BN, total = m_tiles * n_tiles;
+
+  auto tile_info = [&](int tile, int& m_tile, int& n0, int& z, int& row0, int& nrows) -> bool {
+    m_tile = tile / n_tiles; n0 = (tile % n_tiles) * BN;
+    z = m_tile / g.tiles_per_slot; row0 = (m_tile % g.tiles_per_slot) * TC_BM;
+    if (g.skip && g.skip[z >> g.skip_shift]) return false;
+    nrows = g.counts ? g.counts[z] : (g.tiles_per_slot * TC_BM);
+    return row0 < nrows;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int c = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int m_tile, n0, z, row0, nrows;
+        if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+        for (int kb = 0; kb < KB; kb++, c++) {
+          const int s = c % TH_STAGES, ph = (c / TH_STAGES) & 1;
+          tc::mbar_wait(empty + s, ph ^ 1);
+          tc::mbar_expect_tx(full + s, LAND_BYTES + 2 * WP_BYTES);
+          uint8_t* st = smem + s * STAGE;
+          tc::tma_load_2d(st, &tmA, full + s, kb * TH_BKE, m_tile * TC_BM);
+          tc::tma_load_2d(st + LAND_BYTES / 2, &tmA, full + s, kb * TH_BKE + 32, m_tile * TC_BM);
+          tc::tma_load_2d(st + W_OFF, &tmW, full + s, kb * TH_BKE, n0);
+          tc::tma_load_2d(st + W_OFF + WP_BYTES, &tmW, full + s, kb * TH_BKE, (int)(g.w_plane_rows + n0));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_F16, TC_BM, BN), idesc2 = tc::make_idesc(tc::FMT_F16, TC_BM, 2 * BN);
+    int c = 0, i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int m_tile, n0, z, row0, nrows;
+      if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+      const int acc = i & 1;
+      tc::mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_main = tmem_base + acc * ACC_COLS, d_cross = d_main + BN;
+      for (int kb = 0; kb < KB; kb++, c++) {
+        const int s = c % TH_STAGES, ph = (c / TH_STAGES) & 1;
+        tc::mbar_wait(ready + s, ph);   // splitters done (they waited for the TMA bytes: W planes have landed too)
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + s * STAGE + A_OFF), b_addr = tc::smem_u32(smem + s * STAGE + W_OFF);
+#pragma unroll
+        for (int k = 0; k < TH_BKE / 16; k++) {
+          uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32), bd = tc::make_smem_desc_sw128(b_addr + k * 32);
+          uint64_t adl = tc::make_smem_desc_sw128(a_addr + AP_BYTES + k * 32);
+          if (leader) {
+            tc::mma_f16(d_main, ad, bd, idesc2, (kb | k) ? 1u : 0u);   // A_hi x [W_hi | W_lo] -> [main | cross]
+            tc::mma_f16(d_cross, adl, bd, idesc, 1u);                  // A_lo x W_hi -> cross
+          }
+        }
+        if (leader) tc::mma_commit(empty + s);
+        __syncwarp();
+      }
+      if (leader) tc::mma_commit(tmem_full + acc);
+      __syncwarp();
+      i++;
+    }
+  } else if (warp < 2 + TH_SPLIT_WARPS) {
+    // splitters: item = (row r, box b, chunk pair j): 8 fp32 (two 16-byte chunks of the landed row) -> 8 hi + 8 lo halves
+    const int t = threadIdx.x - 64;  // 0 .. 32 * TH_SPLIT_WARPS - 1
+    constexpr int NT = 32 * TH_SPLIT_WARPS, ROUNDS = 1024 / (4 * NT);
+    int c = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int m_tile, n0, z, row0, nrows;
+      if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+      for (int kb = 0; kb < KB; kb++, c++) {
+        const int s = c % TH_STAGES, ph = (c / TH_STAGES) & 1;
+        tc::mbar_wait(full + s, ph);
+        uint8_t* st = smem + s * STAGE;
+#pragma unroll 1
+       for (int rd = 0; rd < ROUNDS; rd++) {
+        uint4 v[4][2];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          const int item = t + (rd * 4 + it) * NT, r = item >> 3, b = (item >> 2) & 1, j = item & 3;
+          const uint8_t* src = st + b * (LAND_BYTES / 2) + r * 128;
+          v[it][0] = *reinterpret_cast<const uint4*>(src + (((2 * j) ^ (r & 7)) << 4));
+          v[it][1] = *reinterpret_cast<const uint4*>(src + (((2 * j + 1) ^ (r & 7)) << 4));
+        }
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          const int item = t + (rd * 4 + it) * NT, r = item >> 3, b = (item >> 2) & 1, j = item & 3;
+          const float x[8] = {__uint_as_float(v[it][0].x), __uint_as_float(v[it][0].y), __uint_as_float(v[it][0].z), __uint_as_float(v[it][0].w),
+                              __uint_as_float(v[it][1].x), __uint_as_float(v[it][1].y), __uint_as_float(v[it][1].z), __uint_as_float(v[it][1].w)};
+          __align__(16) plane_t h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) split2(x[e], h[e], l[e]);
+          const int off = r * 128 + (((b * 4 + j) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(st + A_OFF + off) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(st + A_OFF + AP_BYTES + off) = *reinterpret_cast<const uint4*>(l);
+        }
+       }
+        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        tc::mbar_arrive(ready + s);
+      }
+    }
+  } else {
+    const int ew = warp - 2 - TH_SPLIT_WARPS;   // 0..7
+    const int q = warp % 4;          // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    const int half = ew / 4;         // two warps per sub-partition: columns [0, BN/2) and [BN/2, BN)
+    float* T = epi_tiles + ew * 32 * 33;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int m_tile, n0, z, row0, nrows;
+      if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
+      const int acc = i & 1;
+      tc::mbar_wait(tmem_full + acc, (i >> 1) & 1);
+      tc::fence_after_sync();
+      const int row_base = row0 + q * 32;
+      const uint32_t lane_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(lane_addr + c0, v);
+        {
+          float t[32];
+          tc::tmem_ld32(lane_addr + BN + c0, t);
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaf(t[j], PLANE_LO_INV, v[j]);
+        }
+        if (c0 + 32 >= (half + 1) * (BN / 2)) {
+          tc::fence_before_sync();
+          tc::mbar_arrive(tmem_empty + acc);
+        }
+        if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int rmax = min(32, nrows - row_base);  // warp-uniform
+        float2 pre[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+          if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
+      }
+      i++;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+template <int BN, class Epi>
+static inline int launch_tc_gemm_f16(const float* A, long long rows_total, int lda, TcGemmArgs g, Epi epi, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, 32, TC_BM)) return e;
+  if (int e = tc_make_map_2d_f16(&tmW, g.w_planes, (uint64_t)(2 * g.w_plane_rows), (uint64_t)g.K, TH_BKE, BN)) return e;
+  constexpr size_t smem = tc_gemm_f16_smem_bytes<BN>();
+  IMW_SMEM_ATTR_ONCE((tc_gemm_f16_kernel<BN, Epi>), smem);
+  const int num_sms = imw_num_sms();
+  const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
+  dim3 grid((unsigned)(total < num_sms ? total : num_sms));
+  tc_gemm_f16_kernel<BN, Epi><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+
 // A: [slots*cap][lda] fp32 (rows_total x K view), W: [w_rows][K] fp32 (followed by its lo plane when g.wlo_rows > 0).
 template <int BN, int SPLIT, bool WLO, class Epi>
 static inline int launch_tc_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmW, long long rows_total, TcGemmArgs g, Epi epi, cudaStream_t st) {
@@ -259,6 +473,8 @@ static inline int launch_tc_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tm
 template <int BN, int SPLIT, class Epi>
 static inline int launch_tc_gemm(const float* A, long long rows_total, int lda, const float* W, long long w_rows, TcGemmArgs g,
                                  Epi epi, cudaStream_t st) {
+  if (SPLIT == 3 && g.w_planes && !g.pair_product && !g.wsel_minus1 && g.K % TH_BKE == 0)
+    return launch_tc_gemm_f16<BN, Epi>(A, rows_total, lda, g, epi, st);
   CUtensorMap tmA, tmW;
   const bool wlo = SPLIT == 3 && g.wlo_rows > 0 && !g.pair_product;
   if (!wlo) g.wlo_rows = 0;

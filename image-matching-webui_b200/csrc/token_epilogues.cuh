@@ -2,6 +2,7 @@
 // form: 4 columns per call; tcgen05 form: elem()/prefetch()/rowwise(), see tc_gemm.cuh).
 #pragma once
 #include "common.cuh"
+#include "split_planes.cuh"
 
 namespace {
 constexpr int D = 256, HEADS = 4, HD = 64, NF = 32;
@@ -9,10 +10,12 @@ constexpr int D = 256, HEADS = 4, HD = 64, NF = 32;
 // ---- GEMM epilogues ---------------------------------------------------------------------------------
 // Self-attention projection: columns [q | k | v] x [head][dim]; rotary on q,k (lightglue.py:58-65,
 // 165-169).  Output buffers [slots][HEADS][cap][HD].
-// hi/lo split used by the tcgen05 attention operands: hi = 13 low mantissa bits cleared, lo = x - hi
-__device__ __forceinline__ void split_hi_lo(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+// tcgen05 attention operands: two fp16 planes per tensor (split_planes.cuh), `plane` elements apart
+__device__ __forceinline__ void store_planes(float* base, long long plane, long long off, float x) {
+  plane_t hi, lo;
+  split2(x, hi, lo);
+  plane_t* p = reinterpret_cast<plane_t*>(base);
+  p[off] = hi; p[plane + off] = lo;
 }
 
 struct EpiQKVRotary {
@@ -49,7 +52,7 @@ struct EpiQKVRotary {
     }
     float* dst = (which == 0 ? q : which == 1 ? k : v);
     const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
-    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    if (plane) store_planes(dst, plane, off, r);
     else dst[off] = r;
   }
   // tcgen05 attention wants V transposed ([head][d][token], tokens contiguous): taken straight from the
@@ -59,12 +62,8 @@ struct EpiQKVRotary {
     const int c = col0 - 2 * D, head = c / HD, d0 = c % HD;
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        float hi, lo;
-        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
-        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
-        v[off] = hi; v[plane + off] = lo;
-      }
+      for (int j = 0; j < 32; j++)
+        store_planes(v, plane, (((long long)z * HEADS + head) * HD + d0 + j) * cap + row, a[j] + bias[col0 + j]);
     }
     return true;
   }
@@ -89,7 +88,7 @@ struct EpiCrossQKV {
     if (which == 0) r *= qk_scale;
     float* dst = (which == 0 ? qk : v);
     const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
-    if (plane) { float hi, lo; split_hi_lo(r, hi, lo); dst[off] = hi; dst[plane + off] = lo; }
+    if (plane) store_planes(dst, plane, off, r);
     else dst[off] = r;
   }
   __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
@@ -97,12 +96,8 @@ struct EpiCrossQKV {
     const int c = col0 - D, head = c / HD, d0 = c % HD;
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        float hi, lo;
-        split_hi_lo(a[j] + bias[col0 + j], hi, lo);
-        const long long off = (((long long)z * HEADS + head) * HD + d0 + j) * cap + row;
-        v[off] = hi; v[plane + off] = lo;
-      }
+      for (int j = 0; j < 32; j++)
+        store_planes(v, plane, (((long long)z * HEADS + head) * HD + d0 + j) * cap + row, a[j] + bias[col0 + j]);
     }
     return true;
   }

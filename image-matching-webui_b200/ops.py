@@ -246,11 +246,11 @@ def lg_pack_weights(sd, n_layers=9, heads=4):
     out["match_b"] = torch.stack([sd[f"log_assignment.{i}.matchability.bias"].float().reshape(()) for i in range(n_layers)])
     if "input_proj.weight" in sd:  # Linear(input_dim -> 256) for 128-d features (lightglue.py:392-395)
         out["input_proj_w"], out["input_proj_b"] = sd["input_proj.weight"].float(), sd["input_proj.bias"].float()
-    # 3xTF32 tcgen05 GEMM: every linear weight matrix carries its TF32 lo plane behind it ([W ; W - trunc_tf32(W)]), so the
-    # kernel splits activations only.  The fp32 CUDA-core path reads the first N rows.
+    # split-fp16 tcgen05 GEMM: every linear weight matrix carries its two fp16 planes behind it ([W fp32 ; hi | lo]: the same
+    # bytes as a second fp32 matrix), so the kernel splits activations only.  The fp32 CUDA-core path reads the first N rows.
     for k in list(out):
         if k.endswith(("qkv_w", "out_w", "ffn0_w", "ffn3_w")) or k == "input_proj_w":
-            out[k] = with_tf32_lo_plane(out[k])
+            out[k] = with_f16_planes(out[k])
     return {k: v.contiguous() for k, v in out.items()}
 
 
@@ -265,10 +265,24 @@ def with_tf32_lo_plane(w):
     return torch.cat([w.float(), tf32_lo(w)], 0).contiguous()
 
 
+def f16_planes(w):
+    """csrc/split_planes.cuh on the host: hi = fp16(w), lo = fp16((w - hi) * 2^11) -> [2, N, K] float16"""
+    w = w.float().clamp(-65504.0, 65504.0).contiguous()
+    hi = w.half()
+    lo = ((w - hi.float()) * 2048.0).half()
+    return torch.stack([hi, lo]).contiguous()
+
+
+def with_f16_planes(w):
+    """[N, K] fp32 -> [2N, K] fp32 storage: the matrix followed by its split-fp16 planes (2 * N * K halves = N * K floats)"""
+    n, k = w.shape
+    return torch.cat([w.float(), f16_planes(w).view(torch.float32).reshape(n, k)], 0).contiguous()
+
+
 def lg_weights_struct(bufs, n_layers=9):
     s = L.LGWeights()
     s.n_layers, s.input_dim = n_layers, 256
-    s.has_lo_planes = 1
+    s.has_lo_planes = 2
     s.posenc_dim = bufs["posenc_wr"].shape[1]
     if "input_proj_w" in bufs:
         s.input_dim = bufs["input_proj_w"].shape[1]
@@ -290,7 +304,7 @@ def lightglue_forward(bufs, n_layers, keypoints, descriptors, counts, conf, out=
     L.require_cuda(keypoints, "lightglue_forward(keypoints)")
     S, cap, _ = keypoints.shape
     in_dim = bufs["input_proj_w"].shape[1] if "input_proj_w" in bufs else 256
-    assert bufs["l0.self.out_w"].shape[0] == 512, "lg_pack_weights output expected (weights followed by their TF32 lo planes)"
+    assert bufs["l0.self.out_w"].shape[0] == 512, "lg_pack_weights output expected (weights followed by their split-fp16 planes)"
     assert S % 2 == 0 and descriptors.shape == (S, cap, in_dim) and counts.numel() == S and counts.dtype == torch.int32
     assert keypoints.is_contiguous() and descriptors.is_contiguous() and counts.is_contiguous()
     P, dev = S // 2, keypoints.device
@@ -516,10 +530,11 @@ def loftr_pack_weights(sd):
     for prefix, n, tag in (("loftr_coarse.", 8, "c"), ("loftr_fine.", 2, "f")):
         for i in range(n):
             p = f"{prefix}layers.{i}."
-            out[f"{tag}{i}.qkv_w"] = torch.cat([sd[p + "q_proj.weight"], sd[p + "k_proj.weight"], sd[p + "v_proj.weight"]], 0).float().contiguous()
-            out[f"{tag}{i}.merge_w"] = sd[p + "merge.weight"].float().contiguous()
-            out[f"{tag}{i}.mlp0_w"] = sd[p + "mlp.0.weight"].float().contiguous()
-            out[f"{tag}{i}.mlp2_w"] = sd[p + "mlp.2.weight"].float().contiguous()
+            # every matrix is followed by its split-fp16 planes (tcgen05 GEMM operands); the fp32 paths read the first N rows
+            out[f"{tag}{i}.qkv_w"] = with_f16_planes(torch.cat([sd[p + "q_proj.weight"], sd[p + "k_proj.weight"], sd[p + "v_proj.weight"]], 0).float())
+            out[f"{tag}{i}.merge_w"] = with_f16_planes(sd[p + "merge.weight"].float())
+            out[f"{tag}{i}.mlp0_w"] = with_f16_planes(sd[p + "mlp.0.weight"].float())
+            out[f"{tag}{i}.mlp2_w"] = with_f16_planes(sd[p + "mlp.2.weight"].float())
             for nm, k in (("norm1.weight", "norm1_g"), ("norm1.bias", "norm1_b"), ("norm2.weight", "norm2_g"), ("norm2.bias", "norm2_b")):
                 out[f"{tag}{i}.{k}"] = sd[p + nm].float().contiguous()
     for k in ("down_proj.weight", "down_proj.bias", "merge_feat.weight", "merge_feat.bias"):
@@ -572,6 +587,7 @@ def _loftr_struct(wd, pos_enc):
             arr[i].is_cross = i % 2  # layer_names = ['self', 'cross'] * n
     s.down_proj_w, s.down_proj_b = wd["down_proj_w"].data_ptr(), wd["down_proj_b"].data_ptr()
     s.merge_feat_w, s.merge_feat_b = wd["merge_feat_w"].data_ptr(), wd["merge_feat_b"].data_ptr()
+    s.has_f16_planes = 1
     return s
 
 
@@ -685,20 +701,22 @@ def magsac(pts0, pts1, counts, geometry_type="Homography", threshold=3.0, confid
 
 
 def debug_gemm(A, W, bias, mode="3xtf32"):
-    """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32" / "3xtf32_wlo": host-provided W lo plane) or the
-    CUDA-core GEMM ("fp32")."""
+    """out = A @ W.T + bias through the tcgen05 GEMM ("tf32" / "3xtf32" / "3xtf32_wlo": host-provided W lo plane / "f16x2":
+    split-fp16 with host-packed weight planes, what the LightGlue / LoFTR linears run) or the CUDA-core GEMM ("fp32")."""
     L.require_cuda(A, "debug_gemm(A)")
     M, K = A.shape
     N = W.shape[0]
     out = torch.empty(M, N, device=A.device)
     if mode == "3xtf32_wlo":
         W = with_tf32_lo_plane(W)
+    if mode == "f16x2":
+        W = with_f16_planes(W)
     args = (L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K)
     with torch.cuda.device(A.device):
         if mode == "fp32":
             L.check(L.lib().imw_debug_gemm_fp32(*args, L.stream_ptr(A.device)))
         else:
-            L.check(L.lib().imw_debug_gemm_tf32(*args, {"3xtf32": 3, "3xtf32_wlo": 4, "tf32": 1}[mode], L.stream_ptr(A.device)))
+            L.check(L.lib().imw_debug_gemm_tf32(*args, {"3xtf32": 3, "3xtf32_wlo": 4, "f16x2": 5, "tf32": 1}[mode], L.stream_ptr(A.device)))
     return out
 
 

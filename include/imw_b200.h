@@ -165,7 +165,9 @@ typedef struct {
   imw_lg_layer layers[IMW_LG_MAX_LAYERS];
   const float *input_proj_w, *input_proj_b; /* [256][input_dim], [256]; used when input_dim != 256 */
   /* 1: every linear weight matrix W [N][K] above (qkv_w, out_w, ffn0_w, ffn3_w, input_proj_w) is followed in memory by its
-     TF32 lo plane W - trunc_tf32(W) [N][K] (ops.lg_pack_weights): the 3xTF32 tcgen05 GEMM then splits activations only */
+     TF32 lo plane W - trunc_tf32(W) [N][K]: the 3xTF32 tcgen05 GEMM then splits activations only.
+     2 (ops.lg_pack_weights): followed by its split-fp16 planes [2][N][K] __half (hi = fp16(w), lo = fp16((w - hi) 2^11); the same
+     N*K*4 bytes): the linears run on the split-fp16 tcgen05 GEMM (kind::f16, three products per fp32-equivalent product) */
   int has_lo_planes;
   int posenc_dim;   /* 2 (0 is read as 2): posenc_wr [32][2]; 4: add_scale_ori features (sift / doghardnet, lightglue.py:366-377,
                        500-506): posenc_wr [32][4] over (x, y, scale, orientation) */
@@ -312,6 +314,9 @@ typedef struct {
   int n_coarse, n_fine;
   imw_loftr_layer coarse[8], fine[2];
   const float *down_proj_w, *down_proj_b, *merge_feat_w, *merge_feat_b; /* [128][256],[128],[128][256],[128] */
+  /* 1 (ops.loftr_pack_weights): every encoder weight matrix W [N][K] (qkv_w, merge_w, mlp0_w, mlp2_w) is followed in memory by its
+     split-fp16 planes [2][N][K] __half: the coarse linears then run on the split-fp16 tcgen05 GEMM (see imw_lg_weights) */
+  int has_f16_planes;
 } imw_loftr_weights;
 typedef struct {
   float match_threshold; /* match_coarse.thr */

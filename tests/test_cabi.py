@@ -92,9 +92,11 @@ def test_qkv_permutation_is_a_relabelling():
     w = sd["transformers.0.self_attn.Wqkv.weight"]
     x = torch.randn(5, 256)
     ref = (x @ w.t()).unflatten(-1, (4, 64, 3))          # lightglue.py:166
-    assert packed["l0.self.qkv_w"].shape == (2 * 768, 256)            # weights followed by their TF32 lo plane
-    hi = (packed["l0.self.qkv_w"][:768].view(torch.int32) & -8192).view(torch.float32)
-    assert torch.equal(packed["l0.self.qkv_w"][768:], packed["l0.self.qkv_w"][:768] - hi)
+    assert packed["l0.self.qkv_w"].shape == (2 * 768, 256)            # weights followed by their split-fp16 planes (same bytes)
+    w = packed["l0.self.qkv_w"][:768]
+    planes = packed["l0.self.qkv_w"][768:].contiguous().view(torch.float16).reshape(2, 768, 256)
+    assert torch.equal(planes[0], w.half()) and torch.equal(planes[1], ((w - w.half().float()) * 2048.0).half())
+    assert float((planes[0].double() + planes[1].double() / 2048.0 - w.double()).abs().max()) < 2.0 ** -22 * float(w.abs().max())
     mine = (x @ packed["l0.self.qkv_w"][:768].t()).view(5, 3, 4, 64)
     for which in range(3):
         assert torch.allclose(ref[..., which], mine[:, which], atol=1e-5)

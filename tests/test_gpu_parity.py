@@ -223,6 +223,51 @@ def test_lightglue_input_proj_128d(golden, dev, tc):
 
 
 @pytest.mark.parametrize("tc", [False, "3xtf32"], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
+def test_aliked_lightglue_composition(golden, dev, tc):
+    """BASELINE configs[3] composition: ALIKED (CUDA) -> LightGlue features="aliked" with the fitted input_proj, against the
+    UNMODIFIED reference modules run end to end on the same two synthetic pairs (tests/golden/aliked_lg.npz)."""
+    import oracle
+    from imcui_b200 import ops
+    from imcui_b200.hloc import matchers
+    from imcui_b200.utils import synth, synth_weights
+    g = golden("aliked_lg")
+    sd = dict(oracle.load_weights("superpoint_lightglue.pt"))
+    sd["input_proj.weight"], sd["input_proj.bias"] = torch.from_numpy(g["input_proj_w"]), torch.from_numpy(g["input_proj_b"])
+    model = _load(matchers, "lightglue", {"match_threshold": 0.2, "features": "aliked", "state_dict": sd, "tensor_cores": tc, **LG_MODES["cuda"]}, dev)
+    aw = {k: v.to(dev) for k, v in ops.aliked_pack_weights(synth_weights.aliked_random_weights(0)).items()}
+    for p, seed in enumerate(g["eval_seeds"]):
+        a, c, _ = synth.make_pair(int(seed), 480, 640)
+        rgb = torch.from_numpy(synth.to_rgb(np.stack([a, c])).astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(dev)
+        f = ops.aliked_forward(aw, rgb, {"detection_threshold": 0.1, "max_num_keypoints": 1024, "nms_radius": 2}, 1024)
+        n = [int(v) for v in f["counts"][0].cpu()]
+        kp = [f["keypoints"][i, :n[i]] for i in range(2)]
+        ds = [f["descriptors"][i, :n[i]] for i in range(2)]
+        # the extractor against the reference's features (score-sorted selection: same set, near-tie swaps allowed)
+        for i in range(2):
+            rk = g[f"{p}/keypoints{i}"]
+            assert n[i] == len(rk)
+            d = np.abs(kp[i].cpu().numpy()[:, None] - rk[None]).max(-1)
+            j = d.argmin(1)
+            assert d[np.arange(len(j)), j].max() < 2e-3 and len(set(j.tolist())) == len(j)
+            assert np.abs(ds[i].cpu().numpy() - g[f"{p}/descriptors{i}"][j]).max() < 1e-3
+        # the matcher on the reference's features: indices comparable one to one
+        out = model(_lg_inputs(g[f"{p}/keypoints0"], np.ascontiguousarray(g[f"{p}/descriptors0"].T), g[f"{p}/keypoints1"],
+                               np.ascontiguousarray(g[f"{p}/descriptors1"].T), dev))
+        m0 = out["matches0"][0].cpu().numpy()
+        f1 = match_f1(m0, g[f"{p}/matches0"])
+        print(f"[aliked-lg tc={tc}] pair {p}: F1 {f1:.4f} stop {out['stop']}/{int(g[f'{p}/stop'])} matches {(m0 > -1).sum()}")
+        assert out["stop"] == int(g[f"{p}/stop"])
+        assert np.array_equal(m0, g[f"{p}/matches0"]) if tc is False else f1 >= 0.999
+        # and end to end on our own features: the matches are geometrically real
+        out = model(_lg_inputs(kp[0].cpu().numpy(), np.ascontiguousarray(ds[0].t().cpu().numpy()), kp[1].cpu().numpy(),
+                               np.ascontiguousarray(ds[1].t().cpu().numpy()), dev))
+        m = out["matches0"][0].cpu().numpy(); v = m > -1
+        q = np.concatenate([kp[0].cpu().numpy()[v], np.ones((v.sum(), 1))], 1) @ g[f"{p}/H"].T
+        err = np.linalg.norm(q[:, :2] / q[:, 2:] - kp[1].cpu().numpy()[m[v]], axis=1)
+        assert v.sum() > 300 and (err < 3).mean() > 0.8
+
+
+@pytest.mark.parametrize("tc", [False, "3xtf32"], ids=["cuda-core-fp32", "tcgen05-3xtf32"])
 def test_lightglue_scale_ori_inputs(golden, dev, tc):
     """features="sift" architecture: 128-d descriptors + per-keypoint scales / orientations in the
     positional encoding (lightglue.py:500-506), forwarded by the plugin exactly as hloc/matchers/lightglue.py:61-73 does."""
@@ -259,16 +304,25 @@ def test_tcgen05_gemm_unit(dev):
         simt = ops.debug_gemm(A, Wt, b, "fp32")
         tf32 = ops.debug_gemm(A, Wt, b, "tf32")
         x3 = ops.debug_gemm(A, Wt, b, "3xtf32")
-        x3w = ops.debug_gemm(A, Wt, b, "3xtf32_wlo")      # host-provided W lo plane (what the LightGlue linears use)
+        x3w = ops.debug_gemm(A, Wt, b, "3xtf32_wlo")      # host-provided W lo plane
+        f16 = ops.debug_gemm(A, Wt, b, "f16x2")           # split-fp16 with host-packed weight planes (what the LightGlue / LoFTR linears use)
         torch.cuda.synchronize()
+        e_f16 = float((f16 - ref).abs().max())
+        print(f"[gemm] {M}x{N}x{K}: split-fp16 {e_f16:.2e}")
+        assert e_f16 < 3e-5, (M, N, K, e_f16)
         e_simt, e_tf32, e_x3, e_x3w = (float((t - ref).abs().max()) for t in (simt, tf32, x3, x3w))
         print(f"[gemm] {M}x{N}x{K}: fp32 {e_simt:.2e} tf32 {e_tf32:.2e} 3xtf32 {e_x3:.2e} 3xtf32+wlo {e_x3w:.2e}")
         assert e_simt < 1e-4 and e_tf32 < 2e-2 and e_x3 < 3e-5 and e_x3w < 3e-5, (M, N, K, e_simt, e_tf32, e_x3, e_x3w)
         assert torch.equal(x3, x3w)                       # same products in the same order: bit-identical
     # exactly representable operands -> exact result (layout / descriptor correctness independent of rounding)
     A = torch.randint(-4, 5, (256, 64), device=dev).float(); Wt = torch.randint(-4, 5, (128, 64), device=dev).float()
-    for mode in ("tf32", "3xtf32", "3xtf32_wlo"):
+    for mode in ("tf32", "3xtf32", "3xtf32_wlo", "f16x2"):
         assert torch.equal(ops.debug_gemm(A, Wt, torch.zeros(128, device=dev), mode), A @ Wt.t())
+    # split-fp16 over a wide dynamic range (LightGlue residual-stream magnitudes, tiny values next to large ones)
+    A = torch.randn(256, 512, device=dev) * torch.logspace(-4, 2, 512, device=dev)[None]; Wt = torch.randn(256, 512, device=dev) / 512 ** 0.5
+    ref = (A.double() @ Wt.double().t()).float()
+    out = ops.debug_gemm(A, Wt, torch.zeros(256, device=dev), "f16x2")
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-6
 
 
 def test_tcgen05_conv_unit(dev):

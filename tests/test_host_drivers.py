@@ -88,7 +88,7 @@ def test_loftr_weight_packing_layout():
     rec = c["w"][0].float() + c["w"][1].float() / 2048.0
     assert float((rec[:, :196] - w).abs().max()) < 1e-6 * float(w.abs().max()) + 1e-7 and float(rec[:, 196:].abs().max()) == 0.0
     assert float(c["b"][196:].abs().max()) == 0.0 and pk["convs"]["l3_out"]["b"] is None
-    assert tuple(pk["conv1_w"].shape) == (49, 128) and tuple(pk["c0.qkv_w"].shape) == (768, 256) and tuple(pk["f1.mlp0_w"].shape) == (256, 256)
+    assert tuple(pk["conv1_w"].shape) == (49, 128) and tuple(pk["c0.qkv_w"].shape) == (2 * 768, 256) and tuple(pk["f1.mlp0_w"].shape) == (2 * 256, 256)   # [W ; split-fp16 planes]
     pe = ops.loftr_position_encoding(256, 30, 40)
     assert torch.allclose(pe, ol.position_encoding(256, 30, 40).permute(1, 2, 0).reshape(1200, 256))
 

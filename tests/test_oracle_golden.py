@@ -106,6 +106,25 @@ def test_lightglue_input_proj_oracle_matches_reference(golden):
         np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{p}/matching_scores0"], atol=1e-4)
 
 
+def test_aliked_lightglue_fitted_input_proj_oracle_matches_reference(golden):
+    """BASELINE configs[3] composition on the reference's own outputs: reference ALIKED features -> LightGlue(input_dim=128) with the
+    fitted input_proj (tools/make_golden.py aliked_lg_case).  The oracle reproduces matches0 / stop, and the matches are real:
+    most of them lie within 3 px of the ground-truth warp."""
+    g = golden("aliked_lg")
+    w = _lg_proj_weights(g)
+    for p in range(len(g["eval_seeds"])):
+        t = lambda n: torch.from_numpy(g[f"{p}/{n}"])[None]
+        out = olg.forward(w, t("keypoints0"), t("descriptors0"), t("keypoints1"), t("descriptors1"), MODES["cuda"])
+        assert out["stop"] == int(g[f"{p}/stop"])
+        m = out["matches0"][0].numpy()
+        assert np.array_equal(m, g[f"{p}/matches0"])
+        np.testing.assert_allclose(out["matching_scores0"][0].numpy(), g[f"{p}/matching_scores0"], atol=1e-4)
+        v = m > -1
+        q = np.concatenate([g[f"{p}/keypoints0"][v], np.ones((v.sum(), 1))], 1) @ g[f"{p}/H"].T
+        err = np.linalg.norm(q[:, :2] / q[:, 2:] - g[f"{p}/keypoints1"][m[v]], axis=1)
+        assert v.sum() > 300 and (err < 3).mean() > 0.8
+
+
 def test_lightglue_scale_ori_oracle_matches_reference(golden):
     """LightGlue with add_scale_ori (sift / doghardnet architecture, lightglue.py:366-377,500-506): posenc over
     (x, y, scale, orientation)."""

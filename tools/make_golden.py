@@ -313,6 +313,72 @@ def aliked_case(name):
     np.savez_compressed(OUT / f"{name}.npz", **blob)
 
 
+ALIKED_LG_CONF = {"detection_threshold": 0.1, "max_num_keypoints": 1024, "nms_radius": 2}   # BASELINE configs[3] (bench_configs.Config4)
+
+
+def aliked_lg_case(name, train_seeds=range(5000, 5016), eval_seeds=(2, 65)):
+    """BASELINE configs[3] without its checkpoints (aliked-n16.pth / aliked_lightglue.pth are not in the tree): the
+    LightGlue `input_proj` (Linear 128 -> 256, lightglue.py:392-395) is FITTED so that the GIM SuperPoint-LightGlue weights
+    see SuperPoint-like descriptors -- ridge regression from the descriptors of the reference ALIKED module (seeded random
+    weights, utils/synth_weights.py) to the reference SuperPoint descriptors sampled at the same keypoints, on synthetic
+    images outside the bench stream.  With it the composition ALIKED -> LightGlue -> MAGSAC produces hundreds of (mostly
+    correct) matches per pair instead of none.  Also stores two evaluation pairs run through the UNMODIFIED reference
+    modules end to end (ALIKED features -> LightGlue(input_dim=128) with this input_proj): parity goldens."""
+    w = synth_weights.aliked_random_weights(0)
+    anet = R.make_aliked(w, **ALIKED_LG_CONF)
+    sp_mod = R.superpoint_module()
+    snet = R.make_superpoint({"nms_radius": 4, "max_keypoints": -1, "keypoint_threshold": 0.005})
+
+    def feats(gray_u8):
+        rgb = torch.from_numpy(synth.to_rgb(gray_u8).astype(np.float32) / 255.0).permute(2, 0, 1)[None]
+        out = anet({"image": rgb})
+        k, d = out["keypoints"][0], out["descriptors"][0]                       # [N,2] pixels, [N,128]
+        x = torch.from_numpy(gray_u8.astype(np.float32) / 255.0)[None, None]
+        r = snet.relu
+        h = r(snet.conv1a(x)); h = r(snet.conv1b(h)); h = snet.pool(h)
+        h = r(snet.conv2a(h)); h = r(snet.conv2b(h)); h = snet.pool(h)
+        h = r(snet.conv3a(h)); h = r(snet.conv3b(h)); h = snet.pool(h)
+        h = r(snet.conv4a(h)); h = r(snet.conv4b(h))
+        dd = torch.nn.functional.normalize(snet.convDb(r(snet.convDa(h))), p=2, dim=1)
+        return k, d, sp_mod.sample_descriptors(k[None], dd, 8)[0].t()            # SuperPoint descriptors at the ALIKED keypoints
+
+    X, Y = [], []
+    for s_ in train_seeds:
+        a, c, _ = synth.make_pair(s_, 480, 640)
+        for g in (a, c):
+            _, d, y = feats(g)
+            X.append(d); Y.append(y)
+    X = torch.cat(X).double(); Y = torch.cat(Y).double()
+    Xb = torch.cat([X, torch.ones(len(X), 1, dtype=torch.float64)], 1)
+    Wb = torch.linalg.solve(Xb.t() @ Xb + 1e-3 * torch.eye(129, dtype=torch.float64), Xb.t() @ Y)
+    W, b = Wb[:128].t().float().contiguous(), Wb[128].float().contiguous()
+    blob = {"input_proj_w": W.numpy(), "input_proj_b": b.numpy(), "train_seeds": np.array(list(train_seeds)), "eval_seeds": np.array(eval_seeds)}
+    lgm = R.lightglue_module()
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = LG_MODES["cuda"]["prune_th"]
+    net = lgm.LightGlue(features=None, input_dim=128, weights=None, filter_threshold=0.2, depth_confidence=0.95, width_confidence=0.99)
+    sd = dict(R.lightglue_state_dict()); sd["input_proj.weight"], sd["input_proj.bias"] = W, b
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all("confidence_thresholds" in m for m in missing)
+    net = net.eval()
+    for p_, s_ in enumerate(eval_seeds):
+        a, c, Hm = synth.make_pair(s_, 480, 640)
+        (k0, d0, _), (k1, d1, _) = feats(a), feats(c)
+        out = net({"image0": {"keypoints": k0[None], "descriptors": d0[None]}, "image1": {"keypoints": k1[None], "descriptors": d1[None]}})
+        pre = f"{p_}/"
+        blob[pre + "keypoints0"], blob[pre + "keypoints1"] = k0.numpy(), k1.numpy()
+        blob[pre + "descriptors0"], blob[pre + "descriptors1"] = d0.numpy(), d1.numpy()
+        blob[pre + "matches0"] = out["matches0"][0].numpy().astype(np.int32)
+        blob[pre + "matching_scores0"] = out["matching_scores0"][0].numpy()
+        blob[pre + "stop"] = np.int32(out["stop"])
+        blob[pre + "H"] = np.asarray(Hm, dtype=np.float64)
+        m = blob[pre + "matches0"]; v = m > -1
+        q = np.concatenate([k0.numpy()[v], np.ones((v.sum(), 1))], 1) @ blob[pre + "H"].T
+        err = np.linalg.norm(q[:, :2] / q[:, 2:] - k1.numpy()[m[v]], axis=1)
+        print(name, "seed", s_, "stop", out["stop"], "matches", int(v.sum()), "within 3 px of the ground-truth warp", int((err < 3).sum()))
+    lgm.LightGlue.pruning_keypoint_thresholds["cpu"] = -1
+    np.savez_compressed(OUT / f"{name}.npz", **blob)
+
+
 def confs_case(name):
     """The reference's registry entries (imcui/hloc/configs) for every conf name the B200 package provides."""
     import json
@@ -484,6 +550,7 @@ def main():
     matcher_case("matchers", [(rb["api/0/descriptors"], rb["api/1/descriptors"]), (d0, d1[:, :700].copy())])
     dense_agg_case("dense_agg")
     loftr_hw_case("loftr_hw")
+    aliked_lg_case("aliked_lg")
 
 
 if __name__ == "__main__":
@@ -498,6 +565,6 @@ if __name__ == "__main__":
                                          gb[f][f"{c}/{j}/keypoints"].astype(np.float32), gb[f][f"{c}/{j}/descriptors"])
                 {"lg_proj": lg_proj_case, "lg_so": lg_so_case}[sys.argv[1]](sys.argv[1], [pr("sp_synth", "max1024", 0, 1), pr("sp_real", "api", 0, 1)], ["sp_synth:max1024:0:1", "sp_real:api:0:1"])
             else:
-                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case, "loftr_hw": loftr_hw_case}[sys.argv[1]](sys.argv[1])
+                {"aliked": aliked_case, "loftr": loftr_case, "confs": confs_case, "plugins": plugin_contract_case, "dense_agg": dense_agg_case, "loftr_hw": loftr_hw_case, "aliked_lg": aliked_lg_case}[sys.argv[1]](sys.argv[1])
     else:
         main()

@@ -139,6 +139,14 @@ struct EpiLinAttnQKV {
     const int which = col / dm, c = col % dm;
     (which == 0 ? q : which == 1 ? k : v)[z * slot_stride + (long long)row * dm + c] = conv(which, a, z);
   }
+  // pair form (col, dm even)
+  __device__ float4 pair_prefetch(int z, int, int) const { return make_float4(kv_counts ? (float)kv_counts[z] : kv_len, 0.f, 0.f, 0.f); }
+  __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
+    const int which = col / dm, c = col - which * dm;
+    float* dst = (which == 0 ? q : which == 1 ? k : v) + z * slot_stride + (long long)row * dm + c;
+    const float2 o = which < 2 ? make_float2(fmap(a0), fmap(a1)) : make_float2(__fdiv_rn(a0, pre.x), __fdiv_rn(a1, pre.x));
+    *reinterpret_cast<float2*>(dst) = o;
+  }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
 
@@ -276,6 +284,16 @@ struct EpiPlain {
   __device__ void elem(int z, int row, int col, float a, float2) const {
     const float x = a + (bias ? bias[col] : 0.f);
     out[z * strideOut + (long long)row * ldo + col] = relu ? fmaxf(x, 0.f) : x;
+  }
+  // pair form (col, ldo, strideOut even; `out` 8-byte aligned)
+  __device__ float4 pair_prefetch(int, int, int col) const {
+    const float2 b = bias ? *reinterpret_cast<const float2*>(bias + col) : make_float2(0.f, 0.f);
+    return make_float4(b.x, b.y, 0.f, 0.f);
+  }
+  __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
+    float x0 = a0 + pre.x, x1 = a1 + pre.y;
+    if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    *reinterpret_cast<float2*>(out + z * strideOut + (long long)row * ldo + col) = make_float2(x0, x1);
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };

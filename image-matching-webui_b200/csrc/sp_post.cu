@@ -140,6 +140,155 @@ __global__ void __launch_bounds__(512) nms_kernel(const float* __restrict__ dens
     }
 }
 
+// ---- simple_nms, restructured (radius 1..5) --------------------------------------------------------------------------------
+// Same arithmetic as nms_kernel (exact float equality, -inf outside the image, results valid 5r inside the staged region), but
+//   * max-pools are register-blocked: the row pass produces 4 outputs from three (five at r = 5) 16-byte shared-memory loads, the
+//     column pass slides a 2r+1 window down 8 rows per thread (8 + 2r loads for 8 outputs) -- the old kernel read 2r+1 values
+//     per output per pass, ten passes over the tile: 2.3 ms per 128 images = 150 GB/s of the 6.5 TB/s HBM peak, bound by
+//     shared-memory wavefronts;
+//   * masks are bit rows (one ballot per 32 pixels): the two dilations are shifts and ORs on a few hundred words;
+//   * supp_scores = where(supp, 0, scores) is never materialised: both passes rebuild it from the scores and the supp bits.
+// Layout: S / A float [R][RS] with 8 pad columns on either side (float4-aligned windows), bit rows [R][NW + 2] with one zero pad
+// word on either side.
+constexpr int NF_T = 64, NF_THREADS = 512;
+template <int RAD> struct NmsFast {
+  static constexpr int R = NF_T + 10 * RAD;                 // staged rows / columns
+  static constexpr int RP = (R + 31) / 32 * 32;             // columns rounded up to whole bit words
+  static constexpr int NW = RP / 32, BW = NW + 2;           // words per bit row (+ pads)
+  static constexpr int RS = RP + 16;                        // float row stride (8 pad columns each side)
+  static constexpr size_t smem = (size_t)2 * R * RS * sizeof(float) + (size_t)4 * R * BW * sizeof(unsigned);
+};
+
+template <int RAD>
+__global__ void __launch_bounds__(NF_THREADS) nms_fast_kernel(const float* __restrict__ dense, float* __restrict__ out, int H, int W) {
+  using C = NmsFast<RAD>;
+  constexpr int R = C::R, RP = C::RP, NW = C::NW, BW = C::BW, RS = C::RS, r = RAD, halo = 5 * RAD;
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  float* S = reinterpret_cast<float*>(nms_smem);            // scores, -inf outside the image / in the pads
+  float* A = S + R * RS;                                    // row-pooled temp
+  unsigned* M = reinterpret_cast<unsigned*>(A + R * RS);    // max_mask bits
+  unsigned* SUP = M + R * BW;                               // supp bits
+  unsigned* TMP = SUP + R * BW;                             // row-dilated mask
+  unsigned* NEWM = TMP + R * BW;                            // unused words stay zero (pads)
+
+  const int tiles_x = (W + NF_T - 1) / NF_T;
+  const int x0 = (blockIdx.x % tiles_x) * NF_T - halo, y0 = (blockIdx.x / tiles_x) * NF_T - halo;
+  const float* img = dense + (long long)blockIdx.z * H * W;
+  const int tid = threadIdx.x, lane = tid % 32, wrp = tid / 32;
+  constexpr int NWARPS = NF_THREADS / 32;
+  const float NINF = -CUDART_INF_F;
+
+  for (int i = tid; i < R * RS; i += NF_THREADS) {
+    const int yy = i / RS, xx = i % RS - 8;
+    const int gy = y0 + yy, gx = x0 + xx;
+    S[i] = (xx >= 0 && xx < R && gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(long long)gy * W + gx] : NINF;
+  }
+  for (int i = tid; i < 4 * R * BW; i += NF_THREADS) M[i] = 0u;
+  __syncthreads();
+
+  // value of pixel (yy, xx) in the current score map: scores (SUPP = false) or where(supp, 0, scores)
+  // row pass: A = max over [x - r, x + r]; four outputs per item from aligned 16-byte loads
+  auto row_pass = [&](bool use_supp) {
+    constexpr int NV = RAD <= 4 ? 3 : 5, LEFT = RAD <= 4 ? 4 : 8;        // float4 loads, first column relative to x
+    for (int it = tid; it < R * (RP / 4); it += NF_THREADS) {
+      const int yy = it / (RP / 4), x = (it % (RP / 4)) * 4;
+      float v[4 * NV];
+      const float4* src = reinterpret_cast<const float4*>(S + yy * RS + 8 + x - LEFT);
+#pragma unroll
+      for (int q = 0; q < NV; q++) { const float4 t = src[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+      if (use_supp) {
+        const int bp = x - LEFT + 32;                                      // bit position in the padded bit row
+        const unsigned* wr = SUP + yy * BW + (bp >> 5);
+        const unsigned long long bits = (((unsigned long long)wr[1] << 32) | wr[0]) >> (bp & 31);
+#pragma unroll
+        for (int k = 0; k < 4 * NV; k++)
+          if ((bits >> k) & 1ull) v[k] = (v[k] == NINF) ? NINF : 0.f;
+      }
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float m = v[LEFT + i - r];
+#pragma unroll
+        for (int d = -r + 1; d <= r; d++) m = fmaxf(m, v[LEFT + i + d]);
+        o[i] = m;
+      }
+      *reinterpret_cast<float4*>(A + yy * RS + 8 + x) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  };
+  // column pass: m = max over rows [y - r, y + r] of A; bit = (value == m) && value != -inf.  One warp = 32 columns x 8 rows.
+  auto col_pass = [&](bool use_supp) {
+    constexpr int RUN = 8, NRUN = (R + RUN - 1) / RUN;
+    for (int task = wrp; task < NW * NRUN; task += NWARPS) {
+      const int cb = task % NW, yb = (task / NW) * RUN;
+      const int xx = cb * 32 + lane;
+      float win[RUN + 2 * RAD];
+#pragma unroll
+      for (int k = 0; k < RUN + 2 * RAD; k++) {
+        const int yy = yb - r + k;
+        win[k] = (yy >= 0 && yy < R) ? A[yy * RS + 8 + xx] : NINF;
+      }
+#pragma unroll
+      for (int k = 0; k < RUN; k++) {
+        const int yy = yb + k;
+        if (yy >= R) break;                                   // warp-uniform
+        float m = win[k];
+#pragma unroll
+        for (int d = 1; d <= 2 * RAD; d++) m = fmaxf(m, win[k + d]);
+        float c = S[yy * RS + 8 + xx];
+        const unsigned sup = use_supp ? SUP[yy * BW + 1 + cb] : 0u;
+        if ((sup >> lane) & 1u) c = (c == NINF) ? NINF : 0.f;
+        const unsigned bal = __ballot_sync(0xffffffffu, (c == m) && (c != NINF) && xx < R);
+        if (lane == 0) {
+          if (use_supp) M[yy * BW + 1 + cb] |= bal & ~sup;    // max_mask | (new_max_mask & ~supp_mask)
+          else M[yy * BW + 1 + cb] = bal;
+        }
+      }
+    }
+  };
+  // supp = max_pool(max_mask) > 0: dilation by r along the row (shifts across word boundaries), then along the column
+  auto dilate = [&]() {
+    for (int i = tid; i < R * NW; i += NF_THREADS) {
+      const int yy = i / NW, w = 1 + i % NW;
+      const unsigned lo = M[yy * BW + w - 1], mid = M[yy * BW + w], hi = M[yy * BW + w + 1];
+      unsigned d = mid;
+#pragma unroll
+      for (int k = 1; k <= RAD; k++) d |= (mid << k) | (lo >> (32 - k)) | (mid >> k) | (hi << (32 - k));
+      TMP[yy * BW + w] = d;
+    }
+    __syncthreads();
+    for (int i = tid; i < R * NW; i += NF_THREADS) {
+      const int yy = i / NW, w = 1 + i % NW;
+      unsigned d = 0u;
+#pragma unroll
+      for (int k = -RAD; k <= RAD; k++)
+        if (yy + k >= 0 && yy + k < R) d |= TMP[(yy + k) * BW + w];
+      SUP[yy * BW + w] = d;
+    }
+    __syncthreads();
+  };
+
+  row_pass(false);
+  __syncthreads();
+  col_pass(false);
+  __syncthreads();
+  for (int it = 0; it < 2; it++) {
+    dilate();
+    row_pass(true);
+    __syncthreads();
+    col_pass(true);
+    __syncthreads();
+  }
+  float* o = out + (long long)blockIdx.z * H * W;
+  for (int i = tid; i < NF_T * NF_T; i += NF_THREADS) {
+    const int yy = i / NF_T + halo, xx = i % NF_T + halo;
+    const int gy = y0 + yy, gx = x0 + xx;
+    if (gy < H && gx < W) {
+      const bool keep = (M[yy * BW + 1 + (xx >> 5)] >> (xx & 31)) & 1u;
+      o[(long long)gy * W + gx] = keep ? S[yy * RS + 8 + xx] : 0.f;
+    }
+  }
+}
+
 // ---- threshold / border / ordered compaction / top-k -------------------------------------------
 // key = score bits (positive float => order-preserving) << 32 | (~pixel index): sorting keys in
 // descending order yields descending score with ascending row-major index on ties.
@@ -335,6 +484,24 @@ int sp_softmax_d2s(const float* logits, float* dense, int B, int h, int w, cudaS
 
 int sp_nms(const float* dense, float* nms, int B, int H, int W, int radius, cudaStream_t st) {
   IMW_REQUIRE(radius >= 0 && radius <= 8, "sp_nms: nms_radius must be in [0,8] (got %d)", radius);
+  if (radius >= 1 && radius <= 5) {   // register-blocked / bit-mask kernel
+    dim3 fgrid(ceil_div(W, NF_T) * ceil_div(H, NF_T), 1, B);
+    auto flaunch = [&](auto kern, size_t fsmem) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (e != cudaSuccess) return e;
+      kern<<<fgrid, NF_THREADS, fsmem, st>>>(dense, nms, H, W);
+      return cudaSuccess;
+    };
+    switch (radius) {
+      case 1: IMW_CHECK_CUDA(flaunch(nms_fast_kernel<1>, NmsFast<1>::smem)); break;
+      case 2: IMW_CHECK_CUDA(flaunch(nms_fast_kernel<2>, NmsFast<2>::smem)); break;
+      case 3: IMW_CHECK_CUDA(flaunch(nms_fast_kernel<3>, NmsFast<3>::smem)); break;
+      case 4: IMW_CHECK_CUDA(flaunch(nms_fast_kernel<4>, NmsFast<4>::smem)); break;
+      default: IMW_CHECK_CUDA(flaunch(nms_fast_kernel<5>, NmsFast<5>::smem)); break;
+    }
+    IMW_CHECK_LAUNCH();
+    return IMW_OK;
+  }
   const int NMS_T = radius <= 5 ? NMS_T_LARGE : NMS_T_SMALL;   // halo redundancy (T + 10 r)^2 / T^2: 2.6x instead of 5x at r = 4
   int R = NMS_T + 10 * radius;
   size_t smem = (size_t)R * R * (3 * sizeof(float) + 3);

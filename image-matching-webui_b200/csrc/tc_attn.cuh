@@ -11,7 +11,9 @@
 // per key tile against 0.8 us of MMA time, tensor pipe 40 %):
 //   * TWO independent softmax streams: stream A owns the even key tiles, stream B the odd ones; each has its own S buffer, P
 //     buffer and O accumulator, so S_{j+1} / P_{j+1} are produced while P_j V_j runs and nothing is exchanged between threads
-//     until the end.  A thread owns one whole q row of its stream's tile (64 scores): row max and row sum are thread-local.
+//     until the end.  Two threads share one q row of their stream's tile: both read all 64 scores for the row maximum (so the
+//     maximum -- and the lazy-rescale decision -- is computed identically, without an exchange) and each exponentiates, splits and
+//     stores its own 32 columns of P.
 //   * O stays in TMEM and is accumulated by the tensor core across the stream's tiles (use_acc); it is rescaled in place
 //     (tcgen05.ld / st) only when a row's running reference maximum has to move by more than 2^8 (lazy rescaling: P <= 256
 //     stays far inside fp16 / fp32 range and the final division by the row sum, taken with the same reference, cancels it).
@@ -21,7 +23,7 @@
 //
 //   warp 0      TMA producer: Q once, K / V^T tiles through two independent 3-deep rings
 //   warp 1      MMA issuer (whichever of S_js / P_jp V_jp has its operands ready is issued next)
-//   warps 2-5   softmax stream A, warps 6-9 stream B (one TMEM sub-partition = 32 rows per warp)
+//   warps 2-9   softmax stream A, warps 10-17 stream B (two warps per TMEM sub-partition: columns 0..31 / 32..63 of P)
 #pragma once
 #include "common.cuh"
 #include "split_planes.cuh"
@@ -38,17 +40,40 @@ struct TcAttnArgs {
   long long plane_rows_vt;  // slots*4*64
 };
 
-constexpr int TA_BQ = 128, TA_BKV = 64, TA_NK = 3, TA_NV = 3, TA_THREADS = 64 + 256;
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_NK = 3, TA_NV = 3, TA_SM_THREADS = 512, TA_THREADS = 64 + TA_SM_THREADS;
 constexpr int TA_Q_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 f16]   = 32 KB
 constexpr int TA_K_BYTES = 2 * TA_BKV * 128;        // hi | lo x [64 keys x 64 f16]    = 16 KB per stage
 constexpr int TA_V_BYTES = 2 * 64 * 128;            // hi | lo x [64 d x 64 keys f16]  = 16 KB per stage
 constexpr int TA_P_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 keys]  = 32 KB per stream
-constexpr size_t TA_SMEM = TA_Q_BYTES + TA_NK * TA_K_BYTES + TA_NV * TA_V_BYTES + 2 * TA_P_BYTES + 1024 + 256 + 4 * 128 * sizeof(float);
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_NK * TA_K_BYTES + TA_NV * TA_V_BYTES + 2 * TA_P_BYTES + 1024 + 256 + 6 * 128 * sizeof(float);
 // TMEM columns: S_a [0,128) = main 64 | cross 64, S_b [128,256), O_a [256,384) = main 64 | cross 64, O_b [384,512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
 constexpr float TA_LAZY = 8.f;   // log2 units: the reference maximum of a row moves only when it would grow by more than this
 
 namespace tc {
+// 2^x on the SFU (ex2.approx.ftz: relative error 2^-22.5; -inf -> 0)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32 lanes x 16 consecutive fp32 columns WITHOUT the wait: issue several, then tmem_wait_ld() once (the loads pipeline)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// compiler-level dependency: values loaded by tmem_ld16_async may only be consumed after the wait (an empty volatile asm that
+// "rewrites" the registers; volatile asms keep their order, so every use is scheduled behind tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
 // 32 lanes x 32 consecutive fp32 columns, registers -> TMEM
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
@@ -93,13 +118,13 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t *q_full = bars, *k_full = bars + 1 /*[3]*/, *k_empty = bars + 4 /*[3]*/, *v_full = bars + 7 /*[3]*/, *v_empty = bars + 10 /*[3]*/,
            *s_full = bars + 13 /*[2]*/, *s_free = bars + 15 /*[2]*/, *p_full = bars + 17 /*[2]*/, *o_done = bars + 19 /*[2]*/;
   uint32_t* tmem_slot = (uint32_t*)(bars + 21);
-  float* xchg = (float*)((uint8_t*)bars + 256);   // [2][128]: (m, l) of stream B for the final merge
+  float* xchg = (float*)((uint8_t*)bars + 256);   // reference maxima [2][128] + partial row sums [2][2][128] for the final merge
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
     tc::mbar_init(q_full, 1);
     for (int i = 0; i < 3; i++) { tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); }
-    for (int i = 0; i < 2; i++) { tc::mbar_init(s_full + i, 1); tc::mbar_init(s_free + i, 128); tc::mbar_init(p_full + i, 128); tc::mbar_init(o_done + i, 1); }
+    for (int i = 0; i < 2; i++) { tc::mbar_init(s_full + i, 1); tc::mbar_init(s_free + i, 256); tc::mbar_init(p_full + i, 256); tc::mbar_init(o_done + i, 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TA_TMEM_COLS);
@@ -210,49 +235,55 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       else if (++spins > (1u << 24)) { printf("tc_attn MMA scheduler timeout block (%d,%d,%d) js %d jp %d\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp); __trap(); }
     }
   } else {
-    const int st = (warp - 2) / 4;                       // stream: key tiles j = st, st + 2, ...
+    const int st = (warp - 2) / 8;                       // stream: key tiles j = st, st + 2, ...
+    const int hf = ((warp - 2) / 4) & 1;                 // this thread's half of the tile's 64 columns
     const int q = warp % 4, r = q * 32 + lane;           // TMEM lane = q row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float c2 = g.scale * 1.4426950408889634f;      // softmax in base 2: p = 2^(s c2 - m)
-    float m = -INFINITY, l = 0.f;                        // reference maximum (log2 units) and row sum relative to it
+    float m = -INFINITY, l = 0.f;                        // reference maximum (log2 units) and this thread's part of the row sum
     int n = 0;                                           // tiles of this stream processed so far
     uint8_t* pP = sP + st * TA_P_BYTES + r * 128;
     for (int j = st; j < T; j += 2, n++) {
       tc::mbar_wait(s_full + st, n & 1);
       tc::fence_after_sync();
-      float s[64];
+      const int kv0 = j * TA_BKV;
+      float s[32];                                       // own half, scaled and masked
+      float mx = -INFINITY;                              // maximum over all 64 columns (both halves read: no exchange)
       {
         const uint32_t a = lane_addr + TA_S_COL + st * 128;
 #pragma unroll
-        for (int hlf = 0; hlf < 2; hlf++) {
-          float mn[32], cr[32];
-          tc::tmem_ld32(a + hlf * 32, mn);
-          tc::tmem_ld32(a + 64 + hlf * 32, cr);
+        for (int hh = 0; hh < 2; hh++) {                 // the other half first, the own half last: its values stay in registers
+          const int h2 = hh ^ hf ^ 1;
+          uint32_t mn[2][16], cr[2][16];                 // four loads in flight, one wait
+          tc::tmem_ld16_async(a + h2 * 32, mn[0]);
+          tc::tmem_ld16_async(a + 64 + h2 * 32, cr[0]);
+          tc::tmem_ld16_async(a + h2 * 32 + 16, mn[1]);
+          tc::tmem_ld16_async(a + 64 + h2 * 32 + 16, cr[1]);
+          tc::tmem_wait_ld();
+          tc::tmem_ld_fence(mn[0]); tc::tmem_ld_fence(cr[0]); tc::tmem_ld_fence(mn[1]); tc::tmem_ld_fence(cr[1]);
 #pragma unroll
-          for (int c = 0; c < 32; c++) s[hlf * 32 + c] = fmaf(cr[c], PLANE_LO_INV, mn[c]);
+          for (int c = 0; c < 32; c++) {
+            const float v = (kv0 + h2 * 32 + c < nk) ? fmaf(__uint_as_float(cr[c >> 4][c & 15]), PLANE_LO_INV, __uint_as_float(mn[c >> 4][c & 15])) * c2
+                                                     : -INFINITY;
+            mx = fmaxf(mx, v);
+            if (hh == 1) s[c] = v;
+          }
         }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(s_free + st);                      // S buffer may take tile j + 2
-      const int kv0 = j * TA_BKV;
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 64; c++) {
-        s[c] = (kv0 + c < nk) ? s[c] * c2 : -INFINITY;
-        mx = fmaxf(mx, s[c]);
-      }
       // lazy reference: move it only when this tile's maximum exceeds it by more than TA_LAZY (always on the first tile)
       const bool move = mx > m + TA_LAZY;                // false for NaN rows (rows beyond the count read unwritten memory)
       const float m_new = move ? mx : m;
-      const float alpha = move ? exp2f(m - m_new) : 1.f; // 0 on the first tile (m = -inf)
+      const float alpha = move ? tc::ex2(m - m_new) : 1.f; // 0 on the first tile (m = -inf)
       if (n > 0) {
         tc::mbar_wait(o_done + st, (n - 1) & 1);         // P_{j-2} V_{j-2} complete: O is stable, the P buffer is free
         tc::fence_after_sync();
-        if (__any_sync(0xffffffffu, move)) {             // rescale this warp's 32 rows of O in place (rare after the first tiles)
+        if (__any_sync(0xffffffffu, move)) {             // rescale this warp's 32 rows of O in place (rare after the first tiles):
 #pragma unroll 1
-          for (int cc = 0; cc < 4; cc++) {               // main 0..63, cross 64..127
+          for (int cc = 0; cc < 2; cc++) {               // half 0 rescales the main accumulator columns, half 1 the cross terms
             float o[32];
-            const uint32_t oa = lane_addr + TA_O_COL + st * 128 + cc * 32;
+            const uint32_t oa = lane_addr + TA_O_COL + st * 128 + hf * 64 + cc * 32;
             tc::tmem_ld32(oa, o);
 #pragma unroll
             for (int c = 0; c < 32; c++) o[c] *= alpha;
@@ -264,22 +295,27 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       m = m_new;
       float ps = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; c++) { s[c] = exp2f(s[c] - m); ps += s[c]; }
+      for (int c = 0; c < 32; c++) { s[c] = tc::ex2(s[c] - m); ps += s[c]; }
       l += ps;
       // P_j -> shared memory as the two fp16 operand planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk ch of
-      // row r lives at chunk ch ^ (r & 7))
+      // row r lives at chunk ch ^ (r & 7)); this thread's 32 keys = chunks 4 hf .. 4 hf + 3
 #pragma unroll
-      for (int ch = 0; ch < 8; ch++) {
-        __align__(16) plane_t h[8], lo[8];
+      for (int ch = 0; ch < 4; ch++) {
+        uint4 hv, lv;
+        uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+        uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          const float p = s[ch * 8 + e];
-          h[e] = __float2half_rn(p);
-          lo[e] = __float2half_rn((p - __half2float(h[e])) * PLANE_LO_SCALE);
+        for (int e = 0; e < 4; e++) {
+          const float p0 = s[ch * 8 + 2 * e], p1 = s[ch * 8 + 2 * e + 1];
+          const __half2 h2v = __floats2half2_rn(p0, p1);
+          const float2 hf2 = __half22float2(h2v);
+          const __half2 l2v = __floats2half2_rn((p0 - hf2.x) * PLANE_LO_SCALE, (p1 - hf2.y) * PLANE_LO_SCALE);
+          hp[e] = *reinterpret_cast<const uint32_t*>(&h2v);
+          lp[e] = *reinterpret_cast<const uint32_t*>(&l2v);
         }
-        const int pos = (ch ^ (r & 7)) * 16;
-        *reinterpret_cast<uint4*>(pP + pos) = *reinterpret_cast<const uint4*>(h);
-        *reinterpret_cast<uint4*>(pP + TA_P_BYTES / 2 + pos) = *reinterpret_cast<const uint4*>(lo);
+        const int pos = ((4 * hf + ch) ^ (r & 7)) * 16;
+        *reinterpret_cast<uint4*>(pP + pos) = hv;
+        *reinterpret_cast<uint4*>(pP + TA_P_BYTES / 2 + pos) = lv;
       }
       tc::fence_before_sync();                           // orders the tcgen05.st of the rescale before the MMA that accumulates on top
       tc::fence_proxy_async();
@@ -290,34 +326,37 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_wait(o_done + st, (n - 1) & 1);
       tc::fence_after_sync();
     }
-    // merge the two streams: stream A writes dims 0..31 of every row, stream B dims 32..63
-    if (st == 1) { xchg[r] = m; xchg[128 + r] = l; }
-    float* xa = xchg + 256;                              // (m, l) of stream A
-    if (st == 0) { xa[r] = m; xa[128 + r] = l; }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float ma = xa[r], la = xa[128 + r], mb = xchg[r], lb = xchg[128 + r];
+    // merge: every thread publishes (m, partial l); thread (stream st, half hf) writes output dims [32 st + 16 hf, +16) of its row
+    float* xm = xchg;            // [stream][128]     reference maxima (identical in both halves)
+    float* xl = xchg + 256;      // [stream][half][128] partial row sums
+    if (hf == 0) xm[st * 128 + r] = m;
+    xl[(st * 2 + hf) * 128 + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(TA_SM_THREADS) : "memory");
+    const float ma = xm[r], mb = xm[128 + r];
+    const float la = xl[r] + xl[128 + r], lb = xl[256 + r] + xl[384 + r];
     const float mm = fmaxf(ma, mb);                      // stream A always has a tile (T >= 1): finite for valid rows
-    const float wa = exp2f(ma - mm), wb = (lb > 0.f) ? exp2f(mb - mm) : 0.f;
+    const float wa = tc::ex2(ma - mm), wb = (lb > 0.f) ? tc::ex2(mb - mm) : 0.f;
     const float inv = 1.f / (la * wa + lb * wb);
     const int row = q0 + r;
     {
-      float acc[32], t[32];
-      const uint32_t oa = lane_addr + TA_O_COL + st * 32;            // this warp's 32 output dims
-      tc::tmem_ld32(oa, acc);
-      tc::tmem_ld32(oa + 64, t);
+      float acc[16], t[16];
+      const int d0 = st * 32 + hf * 16;
+      const uint32_t oa = lane_addr + TA_O_COL + d0;                 // this thread's 16 output dims
+      tc::tmem_ld16(oa, acc);
+      tc::tmem_ld16(oa + 64, t);
 #pragma unroll
-      for (int c = 0; c < 32; c++) acc[c] = fmaf(t[c], PLANE_LO_INV, acc[c]) * wa;
+      for (int c = 0; c < 16; c++) acc[c] = fmaf(t[c], PLANE_LO_INV, acc[c]) * wa;
       if (T > 1) {                                                   // stream B ran: its accumulator holds data
-        float ob[32];
-        tc::tmem_ld32(oa + 128, ob);
-        tc::tmem_ld32(oa + 128 + 64, t);
+        float ob[16];
+        tc::tmem_ld16(oa + 128, ob);
+        tc::tmem_ld16(oa + 128 + 64, t);
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c] = fmaf(fmaf(t[c], PLANE_LO_INV, ob[c]), wb, acc[c]);
+        for (int c = 0; c < 16; c++) acc[c] = fmaf(fmaf(t[c], PLANE_LO_INV, ob[c]), wb, acc[c]);
       }
       if (row < nq) {
-        float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + st * 32);
+        float4* o = reinterpret_cast<float4*>(g.ctx + ((long long)z * g.cap + row) * 256 + head * 64 + d0);
 #pragma unroll
-        for (int c = 0; c < 8; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+        for (int c = 0; c < 4; c++) o[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
       }
     }
   }

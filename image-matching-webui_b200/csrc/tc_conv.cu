@@ -58,6 +58,10 @@ constexpr size_t conv_smem_bytes() { return (size_t)conv_stages<BN>() * conv_sta
 
 // KS: kernel size (3 or 1) and RES: residual input are compile-time so that the SuperPoint instantiation <BN, 3, false>
 // keeps constant tap arithmetic in the single-thread producer / MMA loops and a lean epilogue.
+// (Round 2 tried a cluster of two pixel tiles with the weight planes TMA-multicast to both CTAs -- tc::tma_load_2d_mc, multicast
+// tcgen05.commit on both `empty` barriers: parity-green, but no faster (LoFTR backbone 177.9 vs 174.9 ms): requests of
+// neighbouring SMs for the same L2 lines are already merged below cluster size ~4 and the kernel is bound by the aggregate
+// L2 -> SM throughput, see DESIGN.md.  The single-CTA form stays.)
 template <int BN, int KS, bool RES>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g) {

@@ -24,6 +24,8 @@
 // Rows are [slots][cap] with cap % 128 == 0: a tile never straddles two slots; finished pairs / rows beyond the
 // slot's count are skipped on the device.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "split_planes.cuh"
 #include "tc_common.cuh"
@@ -252,15 +254,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
 // tiles (ncu round 2: 9 TB/s, 1.58 us per 64 elements of K at 96 KB) with the tensor pipe half idle.  Here
 //   * weights arrive as fp16 planes [W_hi ; W_lo] (4 B per element instead of 8 B): TMA, adjacent tiles -> one N = 2 BN operand;
 //   * the activation tile lands as fp32 (TMA, two 32-column boxes per 64-element k-block) and four splitter warps convert it
-//     to the two fp16 operand tiles (K-major, SWIZZLE_128B written by hand: 16-byte chunk c of row r sits at c ^ (r & 7));
+//     IN PLACE to the two fp16 operand tiles (K-major, SWIZZLE_128B written by hand: 16-byte chunk c of row r sits at c ^ (r & 7));
 //   * MMAs are kind::f16 (K = 16 per instruction): A_hi x [W_hi | W_lo] -> [main | cross], A_lo x W_hi -> cross; the epilogue adds
 //     main + cross 2^-11.
 // Same persistent tile walk, roles and functor epilogues as the kernel above.
-constexpr int TH_BKE = 64, TH_STAGES = 2, TH_SPLIT_WARPS = 4, TH_THREADS = 64 + 32 * TH_SPLIT_WARPS + 256;
+constexpr int TH_BKE = 64, TH_STAGES = 3, TH_SPLIT_WARPS = 4, TH_THREADS = 64 + 32 * TH_SPLIT_WARPS + 256;
+
+// Functors may provide a PAIR form of the epilogue -- two adjacent output columns per lane, sixteen column pairs x two rows per
+// warp instruction:  float4 pair_prefetch(z, row, col)  (every global read the pair needs)  and  pair(z, row, col, a0, a1, pre).
+// It halves the instruction count of the element-per-lane form (one address, one 8-byte store, no partner shuffle for the
+// rotary pairs); the QKV projections, whose epilogues write three re-laid-out tensors, were bound by exactly that count
+// (ncu round 2: 48.7 k warp instructions per 128 x 128 tile, tensor pipe 21 %).
+template <class Epi, class = void>
+struct tc_has_pair : std::false_type {};
+template <class Epi>
+struct tc_has_pair<Epi, std::void_t<decltype(&Epi::pair)>> : std::true_type {};
 
 template <int BN>
 constexpr size_t tc_gemm_f16_smem_bytes() {
-  return (size_t)TH_STAGES * (2 * TC_BM * 128 /*fp32 landing*/ + 2 * TC_BM * 128 /*A planes*/ + 2 * BN * 128 /*W planes*/) + 1024 + 256 +
+  return (size_t)TH_STAGES * (2 * TC_BM * 128 /*fp32 landing = A planes, split in place*/ + 2 * BN * 128 /*W planes*/) + 1024 + 256 +
          8 * 32 * 33 * sizeof(float);
 }
 
@@ -270,8 +282,12 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
                                                                    int m_tiles) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  // The fp32 tile lands as two 32-column boxes of 16 KB; the splitters rewrite it IN PLACE as the two fp16 operand tiles
+  // (A_hi over box 0, A_lo over box 1: 128 B of fp32 per row and box = 64 B of hi + 64 B of lo, so the bytes match).  One thread
+  // owns one whole row (256 B in registers before the first store): no cross-thread hazard, no separate landing buffer --
+  // three stages of 64 KB fit where two of 96 KB did (the kernel is bound by the bytes it keeps in flight, not by the tensor pipe).
   constexpr int LAND_BYTES = 2 * TC_BM * 128, AP_BYTES = TC_BM * 128, WP_BYTES = BN * 128;
-  constexpr int A_OFF = LAND_BYTES, W_OFF = LAND_BYTES + 2 * AP_BYTES, STAGE = W_OFF + 2 * WP_BYTES;
+  constexpr int A_OFF = 0, W_OFF = LAND_BYTES, STAGE = W_OFF + 2 * WP_BYTES;
   constexpr int ACC_COLS = 2 * BN;
   uint64_t* full = (uint64_t*)(smem + TH_STAGES * STAGE);
   uint64_t* empty = full + TH_STAGES;
@@ -355,9 +371,10 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
       i++;
     }
   } else if (warp < 2 + TH_SPLIT_WARPS) {
-    // splitters: item = (row r, box b, chunk pair j): 8 fp32 (two 16-byte chunks of the landed row) -> 8 hi + 8 lo halves
-    const int t = threadIdx.x - 64;  // 0 .. 32 * TH_SPLIT_WARPS - 1
-    constexpr int NT = 32 * TH_SPLIT_WARPS, ROUNDS = 1024 / (4 * NT);
+    // splitters: thread = row r of the tile: 64 fp32 (two landed 128-byte rows, SWIZZLE_128B: 16-byte chunk c at c ^ (r & 7))
+    // -> 64 hi halves (row r of A_hi, 128 B: element chunk cc at cc ^ (r & 7)) + 64 lo halves, written over the same bytes
+    const int r = threadIdx.x - 64;  // 0 .. 127
+    const int sw = r & 7;
     int c = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int m_tile, n0, z, row0, nrows;
@@ -365,30 +382,25 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
       for (int kb = 0; kb < KB; kb++, c++) {
         const int s = c % TH_STAGES, ph = (c / TH_STAGES) & 1;
         tc::mbar_wait(full + s, ph);
-        uint8_t* st = smem + s * STAGE;
-#pragma unroll 1
-       for (int rd = 0; rd < ROUNDS; rd++) {
-        uint4 v[4][2];
+        uint8_t* row_hi = smem + s * STAGE + r * 128;          // box 0 row r -> A_hi row r
+        uint8_t* row_lo = row_hi + AP_BYTES;                   // box 1 row r -> A_lo row r
+        uint4 v[16];
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-          const int item = t + (rd * 4 + it) * NT, r = item >> 3, b = (item >> 2) & 1, j = item & 3;
-          const uint8_t* src = st + b * (LAND_BYTES / 2) + r * 128;
-          v[it][0] = *reinterpret_cast<const uint4*>(src + (((2 * j) ^ (r & 7)) << 4));
-          v[it][1] = *reinterpret_cast<const uint4*>(src + (((2 * j + 1) ^ (r & 7)) << 4));
+        for (int ch = 0; ch < 8; ch++) {
+          v[ch] = *reinterpret_cast<const uint4*>(row_hi + ((ch ^ sw) << 4));        // elements 4 ch .. 4 ch + 3
+          v[8 + ch] = *reinterpret_cast<const uint4*>(row_lo + ((ch ^ sw) << 4));    // elements 32 + 4 ch ..
         }
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-          const int item = t + (rd * 4 + it) * NT, r = item >> 3, b = (item >> 2) & 1, j = item & 3;
-          const float x[8] = {__uint_as_float(v[it][0].x), __uint_as_float(v[it][0].y), __uint_as_float(v[it][0].z), __uint_as_float(v[it][0].w),
-                              __uint_as_float(v[it][1].x), __uint_as_float(v[it][1].y), __uint_as_float(v[it][1].z), __uint_as_float(v[it][1].w)};
+        for (int cc = 0; cc < 8; cc++) {   // output chunk cc = elements 8 cc .. 8 cc + 7 = input chunks 2 cc, 2 cc + 1
+          const uint4 a = v[2 * cc], b = v[2 * cc + 1];
+          const float x[8] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+                              __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
           __align__(16) plane_t h[8], l[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) split2(x[e], h[e], l[e]);
-          const int off = r * 128 + (((b * 4 + j) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(st + A_OFF + off) = *reinterpret_cast<const uint4*>(h);
-          *reinterpret_cast<uint4*>(st + A_OFF + AP_BYTES + off) = *reinterpret_cast<const uint4*>(l);
+          *reinterpret_cast<uint4*>(row_hi + ((cc ^ sw) << 4)) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(row_lo + ((cc ^ sw) << 4)) = *reinterpret_cast<const uint4*>(l);
         }
-       }
         tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         tc::mbar_arrive(ready + s);
       }
@@ -427,12 +439,27 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
         for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
         __syncwarp();
         const int rmax = min(32, nrows - row_base);  // warp-uniform
-        float2 pre[32];
+        if constexpr (tc_has_pair<Epi>::value) {
+          // lane = (row parity, column pair): rows 2k + (lane >> 4), columns 2 (lane & 15), +1.  T reads are conflict-free
+          // (row stride 33 words: even rows hit the even banks, odd rows the odd ones)
+          const int cp = 2 * (lane & 15), ro = lane >> 4;
+          float4 pre[16];
 #pragma unroll
-        for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
+          for (int k = 0; k < 16; k++)
+            pre[k] = (2 * k + ro < rmax) ? epi.pair_prefetch(z, row_base + 2 * k + ro, n0 + c0 + cp) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < 32; r++)
-          if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
+          for (int k = 0; k < 16; k++) {
+            const int r = 2 * k + ro;
+            if (r < rmax) epi.pair(z, row_base + r, n0 + c0 + cp, T[r * 33 + cp], T[r * 33 + cp + 1], pre[k]);
+          }
+        } else {
+          float2 pre[32];
+#pragma unroll
+          for (int r = 0; r < 32; r++) pre[r] = (r < rmax) ? epi.prefetch(z, row_base + r, n0 + c0 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < 32; r++)
+            if (r < rmax) epi.elem(z, row_base + r, n0 + c0 + lane, T[r * 33 + lane], pre[r]);
+        }
       }
       i++;
     }

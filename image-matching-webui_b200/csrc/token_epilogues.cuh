@@ -10,6 +10,16 @@ constexpr int D = 256, HEADS = 4, HD = 64, NF = 32;
 // ---- GEMM epilogues ---------------------------------------------------------------------------------
 // Self-attention projection: columns [q | k | v] x [head][dim]; rotary on q,k (lightglue.py:58-65,
 // 165-169).  Output buffers [slots][HEADS][cap][HD].
+// two adjacent elements (off even): one 4-byte store per plane
+__device__ __forceinline__ void store_planes2(float* base, long long plane, long long off, float x0, float x1) {
+  x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+  const __half2 hi = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hi);
+  const __half2 lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
+  plane_t* p = reinterpret_cast<plane_t*>(base);
+  *reinterpret_cast<__half2*>(p + off) = hi;
+  *reinterpret_cast<__half2*>(p + plane + off) = lo;
+}
 // tcgen05 attention operands: two fp16 planes per tensor (split_planes.cuh), `plane` elements apart
 __device__ __forceinline__ void store_planes(float* base, long long plane, long long off, float x) {
   plane_t hi, lo;
@@ -55,6 +65,29 @@ struct EpiQKVRotary {
     if (plane) store_planes(dst, plane, off, r);
     else dst[off] = r;
   }
+  // pair form (col even): the rotary pair (d, d + 1) lives in one lane; (cos, sin, bias_d, bias_d+1) prefetched
+  __device__ float4 pair_prefetch(int z, int row, int col) const {
+    float2 cs = make_float2(1.f, 0.f);
+    if (col < 2 * D && enc) {
+      const float* e = enc + ((long long)z * cap + row) * 64 + (col % HD) / 2;
+      cs = make_float2(e[0], e[32]);
+    }
+    const float2 b = *reinterpret_cast<const float2*>(bias + col);
+    return make_float4(cs.x, cs.y, b.x, b.y);
+  }
+  __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
+    float r0 = a0 + pre.z, r1 = a1 + pre.w;
+    const int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which < 2) {   // same operations as elem(): even dim r cs - partner sn, odd dim r cs + partner sn
+      const float o0 = __fadd_rn(__fmul_rn(r0, pre.x), __fmul_rn(-r1, pre.y));
+      const float o1 = __fadd_rn(__fmul_rn(r1, pre.x), __fmul_rn(r0, pre.y));
+      r0 = o0; r1 = o1;
+    }
+    float* dst = (which == 0 ? q : which == 1 ? k : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) store_planes2(dst, plane, off, r0, r1);
+    else *reinterpret_cast<float2*>(dst + off) = make_float2(r0, r1);
+  }
   // tcgen05 attention wants V transposed ([head][d][token], tokens contiguous): taken straight from the
   // thread-per-row TMEM layout (lanes = consecutive tokens -> coalesced), before the epilogue transpose.
   __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
@@ -91,6 +124,19 @@ struct EpiCrossQKV {
     if (plane) store_planes(dst, plane, off, r);
     else dst[off] = r;
   }
+  __device__ float4 pair_prefetch(int, int, int col) const {
+    const float2 b = *reinterpret_cast<const float2*>(bias + col);
+    return make_float4(b.x, b.y, 0.f, 0.f);
+  }
+  __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
+    float r0 = a0 + pre.x, r1 = a1 + pre.y;
+    const int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which == 0) { r0 *= qk_scale; r1 *= qk_scale; }
+    float* dst = (which == 0 ? qk : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) store_planes2(dst, plane, off, r0, r1);
+    else *reinterpret_cast<float2*>(dst + off) = make_float2(r0, r1);
+  }
   __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
     if (!plane || col0 < D) return false;
     const int c = col0 - D, head = c / HD, d0 = c % HD;
@@ -123,6 +169,18 @@ struct EpiStore {
     float r = a * scale + (bias ? bias[col] : 0.f);
     if (relu) r = fmaxf(r, 0.f);
     out[z * strideOut + (long long)row * ldo + col] = r + res.x;
+  }
+  // pair form (col, ldo, strideOut even; `out` 8-byte aligned): (residual_0, residual_1, bias_0, bias_1) prefetched
+  __device__ float4 pair_prefetch(int z, int row, int col) const {
+    float2 r = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+    if (residual) r = *reinterpret_cast<const float2*>(out + z * strideOut + (long long)row * ldo + col);
+    if (bias) b = *reinterpret_cast<const float2*>(bias + col);
+    return make_float4(r.x, r.y, b.x, b.y);
+  }
+  __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
+    float r0 = a0 * scale + pre.z, r1 = a1 * scale + pre.w;
+    if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+    *reinterpret_cast<float2*>(out + z * strideOut + (long long)row * ldo + col) = make_float2(r0 + pre.x, r1 + pre.y);
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };

@@ -332,7 +332,8 @@ def test_tcgen05_conv_unit(dev):
     torch.manual_seed(1)
     for (B, H, W, Cin, Cout, pool) in ((1, 16, 32, 64, 64, False), (2, 48, 64, 64, 64, True), (1, 24, 48, 64, 64, True),
                                        (1, 40, 16, 64, 64, False), (1, 24, 32, 64, 128, False),
-                                       (2, 32, 48, 128, 128, True), (1, 60, 80, 128, 256, False)):
+                                       (2, 32, 48, 128, 128, True), (1, 60, 80, 128, 256, False),
+                                       (1, 24, 48, 128, 128, False)):   # 9 pixel tiles: odd count -> one padding CTA in the last cluster
         x = torch.rand(B, H, W, Cin, device=dev)
         w = torch.randn(9, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
         b = torch.randn(Cout, device=dev) * 0.1

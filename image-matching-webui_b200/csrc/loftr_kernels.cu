@@ -429,23 +429,35 @@ size_t lf_carve(Workspace& ws, LFBuffers& b, int P, int H0, int W0, int H1, int 
   const size_t S = 2 * (size_t)P;
   auto px = [](int H, int W, int d) { return (size_t)(H / d) * (W / d); };
   const size_t a2 = px(H0, W0, 2) > px(H1, W1, 2) ? px(H0, W0, 2) : px(H1, W1, 2), a4 = px(H0, W0, 4) > px(H1, W1, 4) ? px(H0, W0, 4) : px(H1, W1, 4);
-  const size_t big = (size_t)P * a2 * 256 * NP;  // fp16 elements of the largest plane set (1/2 res, 256 padded channels)
-  b.pa = ws.take<plane_t>(big); b.pb = ws.take<plane_t>(big); b.pc = ws.take<plane_t>(big);
-  b.pd = ws.take<plane_t>((size_t)P * a4 * 256 * NP); b.pe2 = ws.take<plane_t>((size_t)P * a4 * 256 * NP);
+  const size_t T = S * cap;
+  const size_t FT = 2 * (size_t)P * mcap * 25;  // fine tokens
+  // ---- alive across phases: backbone outputs, coarse-matching results, small tables
   b.fc = ws.take<float>((size_t)P * px(H0, W0, 8) * CD); b.fc1 = ws.take<float>((size_t)P * px(H1, W1, 8) * CD);
   b.ff = ws.take<float>((size_t)P * px(H0, W0, 2) * FD); b.ff1 = ws.take<float>((size_t)P * px(H1, W1, 2) * FD);
-  const size_t T = S * cap;
-  b.xm = ws.take<float>(T * 512); b.q = ws.take<float>(T * CD); b.k = ws.take<float>(T * CD); b.v = ws.take<float>(T * CD);
-  b.msg = ws.take<float>(T * CD); b.tmp = ws.take<float>(T * CD); b.h = ws.take<float>(T * 512);
   b.kv = ws.take<float>(S * NH * 32 * 32); b.ksum = ws.take<float>(S * NH * 32);
   b.kv_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32 * 32); b.ksum_part = ws.take<float>(S * NH * LF_KV_SPLIT * 32);
   b.rmax = ws.take<float>(T); b.rsum = ws.take<float>(T); b.rlog = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
   b.skip_even = ws.take<int>(S); b.skip_odd = ws.take<int>(S); b.cntL = ws.take<int>(S); b.rows25 = ws.take<int>(S); b.fcnt = ws.take<int>(S * mcap);
-  const size_t FT = 2 * (size_t)P * mcap * 25;  // fine tokens
+  b.xm = ws.take<float>(T * 512);               // coarse features: written by the tokeniser, read until the fine stage gathers its context
+  // ---- three phases share the rest (the stream orders them): (1) backbone plane scratch, (2) coarse transformer, (3) fine stage.
+  // Round 1 kept all three side by side: 4 GB per 1024 x 1024 pair; 2.5 GB after the per-side backbone passes; 1.4 GB aliased.
+  const size_t base = ws.off;
+  const size_t big = (size_t)P * a2 * 256 * NP;  // fp16 elements of the largest plane set (1/2 res, 256 padded channels)
+  b.pa = ws.take<plane_t>(big); b.pb = ws.take<plane_t>(big); b.pc = ws.take<plane_t>(big);
+  b.pd = ws.take<plane_t>((size_t)P * a4 * 256 * NP); b.pe2 = ws.take<plane_t>((size_t)P * a4 * 256 * NP);
+  size_t high = ws.off;
+  ws.off = base;                                // (2)
+  b.q = ws.take<float>(T * CD); b.k = ws.take<float>(T * CD); b.v = ws.take<float>(T * CD);
+  b.msg = ws.take<float>(T * CD); b.tmp = ws.take<float>(T * CD); b.h = ws.take<float>(T * 512);
+  if (ws.off > high) high = ws.off;
+  ws.off = base;                                // (3)
   b.U = ws.take<float>(FT * FD); b.G = ws.take<float>(2 * (size_t)P * mcap * CD); b.ctx = ws.take<float>(2 * (size_t)P * mcap * 256);
   b.fx = ws.take<float>(FT * 256); b.fq = ws.take<float>(FT * FD); b.fk = ws.take<float>(FT * FD); b.fv = ws.take<float>(FT * FD);
   b.fmsg = ws.take<float>(FT * FD); b.ftmp = ws.take<float>(FT * FD); b.fh = ws.take<float>(FT * 256);
   b.fkv = ws.take<float>(2 * (size_t)P * mcap * NH * 16 * 16); b.fksum = ws.take<float>(2 * (size_t)P * mcap * NH * 16);
+  if (ws.off > high) high = ws.off;
+  ws.off = high;
+  if (ws.base && ws.off > ws.size) ws.overflow = true;
   return ws.off;
 }
 

@@ -11,9 +11,10 @@
 // per key tile against 0.8 us of MMA time, tensor pipe 40 %):
 //   * TWO independent softmax streams: stream A owns the even key tiles, stream B the odd ones; each has its own S buffer, P
 //     buffer and O accumulator, so S_{j+1} / P_{j+1} are produced while P_j V_j runs and nothing is exchanged between threads
-//     until the end.  Two threads share one q row of their stream's tile: both read all 64 scores for the row maximum (so the
-//     maximum -- and the lazy-rescale decision -- is computed identically, without an exchange) and each exponentiates, splits and
-//     stores its own 32 columns of P.
+//     until the end.  Two threads (two warps of the same TMEM sub-partition) share one q row of their stream's tile: each reads,
+//     exponentiates, splits and stores its own 32 columns of P; the row maximum is the max of the two half maxima, exchanged
+//     through shared memory behind a 64-thread named barrier of the two warps (identical in both threads, so the lazy-rescale
+//     decision agrees).
 //   * O stays in TMEM and is accumulated by the tensor core across the stream's tiles (use_acc); it is rescaled in place
 //     (tcgen05.ld / st) only when a row's running reference maximum has to move by more than 2^8 (lazy rescaling: P <= 256
 //     stays far inside fp16 / fp32 range and the final division by the row sum, taken with the same reference, cancels it).
@@ -45,7 +46,7 @@ constexpr int TA_Q_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 
 constexpr int TA_K_BYTES = 2 * TA_BKV * 128;        // hi | lo x [64 keys x 64 f16]    = 16 KB per stage
 constexpr int TA_V_BYTES = 2 * 64 * 128;            // hi | lo x [64 d x 64 keys f16]  = 16 KB per stage
 constexpr int TA_P_BYTES = 2 * TA_BQ * 128;         // hi | lo x [128 rows x 64 keys]  = 32 KB per stream
-constexpr size_t TA_SMEM = TA_Q_BYTES + TA_NK * TA_K_BYTES + TA_NV * TA_V_BYTES + 2 * TA_P_BYTES + 1024 + 256 + 6 * 128 * sizeof(float);
+constexpr size_t TA_SMEM = TA_Q_BYTES + TA_NK * TA_K_BYTES + TA_NV * TA_V_BYTES + 2 * TA_P_BYTES + 1024 + 256 + (6 + 8) * 128 * sizeof(float);
 // TMEM columns: S_a [0,128) = main 64 | cross 64, S_b [128,256), O_a [256,384) = main 64 | cross 64, O_b [384,512)
 constexpr int TA_TMEM_COLS = 512, TA_S_COL = 0, TA_O_COL = 256;
 constexpr float TA_LAZY = 8.f;   // log2 units: the reference maximum of a row moves only when it would grow by more than this
@@ -119,6 +120,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
            *s_full = bars + 13 /*[2]*/, *s_free = bars + 15 /*[2]*/, *p_full = bars + 17 /*[2]*/, *o_done = bars + 19 /*[2]*/;
   uint32_t* tmem_slot = (uint32_t*)(bars + 21);
   float* xchg = (float*)((uint8_t*)bars + 256);   // reference maxima [2][128] + partial row sums [2][2][128] for the final merge
+  float* xhalf = xchg + 768;                      // [stream][tile parity][half][128] half-row maxima
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
@@ -247,31 +249,42 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_wait(s_full + st, n & 1);
       tc::fence_after_sync();
       const int kv0 = j * TA_BKV;
-      float s[32];                                       // own half, scaled and masked
-      float mx = -INFINITY;                              // maximum over all 64 columns (both halves read: no exchange)
+      float s[32];                                       // own half of the row: raw scores
+      float mx = -INFINITY;
       {
-        const uint32_t a = lane_addr + TA_S_COL + st * 128;
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {                 // the other half first, the own half last: its values stay in registers
-          const int h2 = hh ^ hf ^ 1;
-          uint32_t mn[2][16], cr[2][16];                 // four loads in flight, one wait
-          tc::tmem_ld16_async(a + h2 * 32, mn[0]);
-          tc::tmem_ld16_async(a + 64 + h2 * 32, cr[0]);
-          tc::tmem_ld16_async(a + h2 * 32 + 16, mn[1]);
-          tc::tmem_ld16_async(a + 64 + h2 * 32 + 16, cr[1]);
-          tc::tmem_wait_ld();
-          tc::tmem_ld_fence(mn[0]); tc::tmem_ld_fence(cr[0]); tc::tmem_ld_fence(mn[1]); tc::tmem_ld_fence(cr[1]);
+        const uint32_t a = lane_addr + TA_S_COL + st * 128 + hf * 32;
+        uint32_t mn[2][16], cr[2][16];                   // four loads in flight, one wait
+        tc::tmem_ld16_async(a, mn[0]);
+        tc::tmem_ld16_async(a + 64, cr[0]);
+        tc::tmem_ld16_async(a + 16, mn[1]);
+        tc::tmem_ld16_async(a + 64 + 16, cr[1]);
+        tc::tmem_wait_ld();
+        tc::tmem_ld_fence(mn[0]); tc::tmem_ld_fence(cr[0]); tc::tmem_ld_fence(mn[1]); tc::tmem_ld_fence(cr[1]);
+        tc::fence_before_sync();
+        tc::mbar_arrive(s_free + st);                    // S buffer may take tile j + 2
+        if (kv0 + TA_BKV <= nk) {                        // full tile (warp-uniform): no masking
 #pragma unroll
           for (int c = 0; c < 32; c++) {
-            const float v = (kv0 + h2 * 32 + c < nk) ? fmaf(__uint_as_float(cr[c >> 4][c & 15]), PLANE_LO_INV, __uint_as_float(mn[c >> 4][c & 15])) * c2
-                                                     : -INFINITY;
-            mx = fmaxf(mx, v);
-            if (hh == 1) s[c] = v;
+            s[c] = fmaf(__uint_as_float(cr[c >> 4][c & 15]), PLANE_LO_INV, __uint_as_float(mn[c >> 4][c & 15]));
+            mx = fmaxf(mx, s[c]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c++) {
+            const float v = fmaf(__uint_as_float(cr[c >> 4][c & 15]), PLANE_LO_INV, __uint_as_float(mn[c >> 4][c & 15]));
+            s[c] = (kv0 + hf * 32 + c < nk) ? v : -INFINITY;
+            mx = fmaxf(mx, s[c]);
           }
         }
       }
-      tc::fence_before_sync();
-      tc::mbar_arrive(s_free + st);                      // S buffer may take tile j + 2
+      // row maximum = max of the two halves: exchanged with the partner thread (same row, warp +-4) through shared memory and a
+      // 64-thread named barrier of the two warps; both threads then hold the identical value (max is commutative)
+      {
+        float* xb = xhalf + (st * 2 + (n & 1)) * 256;    // double-buffered by tile parity: the partner may run one tile ahead
+        xb[hf * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + st * 4 + q) : "memory");
+        mx = fmaxf(mx, xb[(hf ^ 1) * 128 + r]) * c2;     // log2 units (scale > 0 commutes with max)
+      }
       // lazy reference: move it only when this tile's maximum exceeds it by more than TA_LAZY (always on the first tile)
       const bool move = mx > m + TA_LAZY;                // false for NaN rows (rows beyond the count read unwritten memory)
       const float m_new = move ? mx : m;
@@ -295,7 +308,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       m = m_new;
       float ps = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; c++) { s[c] = tc::ex2(s[c] - m); ps += s[c]; }
+      for (int c = 0; c < 32; c++) { s[c] = tc::ex2(fmaf(s[c], c2, -m)); ps += s[c]; }   // masked columns: -inf -> 0
       l += ps;
       // P_j -> shared memory as the two fp16 operand planes, K-major rows of 128 B with the 128B swizzle (16-byte chunk ch of
       // row r lives at chunk ch ^ (r & 7)); this thread's 32 keys = chunks 4 hf .. 4 hf + 3

@@ -488,6 +488,218 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// ---- 3x3 stride-1 convs with Cin = 64 k, Cout = 64 / 128 n: the halo-copy scheme of the c64 kernel for any channel count ----
+// The generic kernel above fetches the activation tile once per tap: 9 x 32 KB of activations + 9 x 32 KB of weights per
+// 64-channel chunk and 128 pixels, and is bound by the chip's aggregate L2 -> SM throughput (ncu round 2: 7.4 TB/s, tensor pipe
+// 23-35 %).  Here the 16 x 8 pixel tile keeps, per 64-channel chunk, three dx-shifted halo copies (2 planes x 18 KB each) that
+// serve three taps each: 108 KB of activations instead of 288 KB per chunk.  The three dx slots ROLL: a slot is refilled with
+// the next chunk (or the next tile) as soon as its three taps have been issued, by a dedicated TMA warp, so activation loads
+// run six taps ahead of their use; weights stream through their own ring from a second TMA warp.  Persistent CTAs walk the
+// (tile, Cout slice) list; the accumulator (two alternating [main | cross] sets, see above) is single-buffered at BN = 128
+// (512 TMEM columns), so only the loads -- not the MMAs -- of the next tile overlap the epilogue.
+constexpr int HL_EPI_WARPS = 8;
+constexpr int HL_THREADS = (3 + HL_EPI_WARPS) * 32;   // warp 0: weight TMA, 1: MMA, 2: activation TMA, 3..10: epilogue (two warps per
+                                                       // TMEM sub-partition, half of the Cout slice each: the accumulator is single-buffered, so the
+                                                       // epilogue is exposed time)
+template <int BN> constexpr int hl_b_stage() { return NP * BN * 128; }
+template <int BN> constexpr int hl_b_stages() { return BN == 128 ? 3 : 6; }
+template <int BN> constexpr size_t hl_smem_bytes() { return (size_t)C64_A_BYTES + (size_t)hl_b_stages<BN>() * hl_b_stage<BN>() + 1024 + 256; }
+
+template <int BN, bool RES>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_items) {
+  constexpr int STAGES = hl_b_stages<BN>(), B_STAGE = hl_b_stage<BN>();
+  extern __shared__ uint8_t cv_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // [dx][plane][18*8 rows][128 B]
+  uint8_t* sB = smem + C64_A_BYTES;         // [stage][plane][BN rows][128 B]
+  uint64_t* a_full = (uint64_t*)(sB + STAGES * B_STAGE);  // [3] one per dx slot
+  uint64_t* a_empty = a_full + 3;
+  uint64_t* b_full = a_empty + 3;           // [stages]
+  uint64_t* b_empty = b_full + STAGES;
+  uint64_t* tmem_full = b_empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+
+  const int tiles_x = g.W / C64_TW, tiles_y = (g.H + C64_TH - 1) / C64_TH;
+  const int n_tiles = g.Cout / BN, chunks = g.Cin / CV_CK;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+    for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+    for (int s = 0; s < STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+    tc::mbar_init(tmem_full, 1); tc::mbar_init(tmem_empty, 32 * HL_EPI_WARPS);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 4 * BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& b, int& x0, int& y0, int& n0) {
+    const int tile = item / n_tiles;             // Cout slices of one tile are neighbours: its activations stay in L2
+    n0 = (item % n_tiles) * BN;
+    x0 = (tile % tiles_x) * C64_TW; y0 = ((tile / tiles_x) % tiles_y) * C64_TH; b = tile / (tiles_x * tiles_y);
+  };
+
+  if (warp == 2) {            // activation TMA: slot dx of (item, chunk) -- use number u = i * chunks + ck of every slot
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, i++) {
+        int b, x0, y0, n0;
+        decode(item, b, x0, y0, n0);
+        for (int ck = 0; ck < chunks; ck++) {
+          const int u = i * chunks + ck;
+          for (int dxi = 0; dxi < 3; dxi++) {
+            tc::mbar_wait(a_empty + dxi, (u & 1) ^ 1);
+            tc::mbar_expect_tx(a_full + dxi, NP * C64_COPY);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+              tc::tma_load_4d(sA + (dxi * NP + p) * C64_COPY, &tmA, a_full + dxi, ck * CV_CK, x0 + dxi - 1, y0 - 1, p * g.B + b);
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {     // weight TMA: one stage per (chunk, dx, dy) in the MMA's order
+    if (lane == 0) {
+      int c = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int b, x0, y0, n0;
+        decode(item, b, x0, y0, n0);
+        for (int ck = 0; ck < chunks; ck++)
+          for (int it = 0; it < 9; it++, c++) {
+            const int dxi = it / 3, dyi = it % 3, tap = dyi * 3 + dxi;
+            const int s = c % STAGES, ph = (c / STAGES) & 1;
+            tc::mbar_wait(b_empty + s, ph ^ 1);
+            tc::mbar_expect_tx(b_full + s, B_STAGE);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+              tc::tma_load_2d(sB + s * B_STAGE + p * BN * 128, &tmW, b_full + s, ck * CV_CK, (p * 9 + tap) * g.Cout + n0);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, BN), idesc2 = tc::make_idesc(tc::FMT_F16, 128, 2 * BN);
+    int i = 0, c = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, i++) {
+      tc::mbar_wait(tmem_empty, (i & 1) ^ 1);   // the epilogue has drained the previous item's accumulators
+      tc::fence_after_sync();
+      int step = 0;
+      for (int ck = 0; ck < chunks; ck++) {
+        const int u = i * chunks + ck;
+        for (int it = 0; it < 9; it++, c++, step++) {
+          const int dxi = it / 3, dyi = it % 3;
+          const int s = c % STAGES, ph = (c / STAGES) & 1;
+          if (dyi == 0) tc::mbar_wait(a_full + dxi, u & 1);
+          tc::mbar_wait(b_full + s, ph);
+          tc::fence_after_sync();
+          const uint32_t a0 = tc::smem_u32(sA + dxi * NP * C64_COPY) + dyi * 1024, b0 = tc::smem_u32(sB + s * B_STAGE);
+          const uint32_t d_set = tmem_base + (step & 1) * 2 * BN;     // [main | cross] sets alternate step by step
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint64_t a_hi = tc::make_smem_desc_sw128(a0 + k * 32), a_lo = tc::make_smem_desc_sw128(a0 + C64_COPY + k * 32);
+            const uint64_t b_hi = tc::make_smem_desc_sw128(b0 + k * 32);
+            if (leader) {
+              tc::mma_f16(d_set, a_hi, b_hi, idesc2, (step >= 2 || k) ? 1u : 0u);
+              tc::mma_f16(d_set + BN, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          if (leader) {
+            tc::mma_commit(b_empty + s);
+            if (dyi == 2) tc::mma_commit(a_empty + dxi);  // the three taps of this dx slot are done: it may take the next chunk
+          }
+          __syncwarp();
+        }
+      }
+      if (leader) tc::mma_commit(tmem_full);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp % 4, chalf = (warp - 3) / 4;   // TMEM sub-partition; columns [chalf * BN / 2, +BN / 2) of the slice
+    const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
+    const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
+    const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
+    const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
+    int i = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, i++) {
+      int b, x0, y0, n0;
+      decode(item, b, x0, y0, n0);
+      tc::mbar_wait(tmem_full, i & 1);
+      tc::fence_after_sync();
+      const int py = y0 + m / C64_TW, px = x0 + m % C64_TW;
+      const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
+      const bool in_img = (py < g.H) && (px < g.W);
+      const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
+#pragma unroll 1
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        float v[32], t[32], u[32];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+        tc::tmem_ld32(lane_base, v);              // set 0 main
+        tc::tmem_ld32(lane_base + 2 * BN, t);     // set 1 main
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] += t[j];
+        tc::tmem_ld32(lane_base + BN, u);         // set 0 cross (scaled by 2^11)
+        tc::tmem_ld32(lane_base + 3 * BN, t);     // set 1 cross
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaf(u[j] + t[j], PLANE_LO_INV, v[j]);
+        if (c0 + 32 >= (chalf + 1) * (BN / 2)) {  // this warp's last TMEM read of the item: hand the accumulators back to the MMA warp
+          tc::fence_before_sync();
+          tc::mbar_arrive(tmem_empty);
+        }
+        if (RES && in_img) {  // residual branch of a BasicBlock (added before the activation)
+          const plane_t* r0 = g.res_planes + opix + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 a = *reinterpret_cast<const uint4*>(r0 + j), bq = *reinterpret_cast<const uint4*>(r0 + plane_stride + j);
+            const plane_t *pa = reinterpret_cast<const plane_t*>(&a), *pb = reinterpret_cast<const plane_t*>(&bq);
+#pragma unroll
+            for (int e = 0; e < 8; e++) t[j + e] = merge2(pa[e], pb[e]);
+          }
+        } else if (RES) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) t[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float x = v[j] + (g.bias ? g.bias[n0 + c0 + j] : 0.f);
+          if (RES) x += t[j];
+          if (g.relu == 1) x = fmaxf(x, 0.f);
+          else if (g.relu == 2) x = x > 0.f ? x : 0.01f * x;
+          if (g.pool) {  // 2x2 window = lanes {l, l^1, l^8}: 4 image rows x 8 cols per warp
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+          }
+          v[j] = x;
+        }
+        if (writer && in_img) {
+          if (g.out_fp32) {
+            float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            __align__(16) plane_t p0[32], p1[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) split2(v[j], p0[j], p1[j]);
+            uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
+            uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              o0[j] = reinterpret_cast<const uint4*>(p0)[j];
+              o1[j] = reinterpret_cast<const uint4*>(p1)[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 4 * BN);
+}
+
 // fp32 NHWC -> two fp16 planes (and back): interop with the CUDA-core path and the unit tests
 __global__ void split_planes_kernel(const float* __restrict__ in, plane_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -541,6 +753,27 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs
   return IMW_OK;
 }
 
+template <int BN, bool RES>
+int launch_conv_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+  constexpr size_t smem = hl_smem_bytes<BN>();
+  IMW_SMEM_ATTR_ONCE((tc_conv3x3_halo_kernel<BN, RES>), smem);
+  const int total = g.B * ceil_div(g.H, C64_TH) * (g.W / C64_TW) * (g.Cout / BN);
+  const int num_sms = imw_num_sms();
+  tc_conv3x3_halo_kernel<BN, RES><<<dim3((unsigned)(total < num_sms ? total : num_sms)), HL_THREADS, smem, st>>>(tmA, tmW, g, total);
+  IMW_CHECK_LAUNCH();
+  return IMW_OK;
+}
+// 3x3, stride 1, W % 8 == 0: halo-copy kernel (activation map with the 8 x 18 halo box)
+int launch_conv_halo(const void* in_planes, const void* w_planes, const ConvArgs& g, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  const int BN = (g.Cout % 128 == 0) ? 128 : 64;
+  if (int e = make_map_act(&tmA, in_planes, NP * g.B, g.H, g.W, g.Cin, C64_TW, C64_TH + 2)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * g.Cout, g.Cin, BN)) return e;
+  if (g.res_planes) return BN == 128 ? launch_conv_halo_t<128, true>(tmA, tmW, g, st) : launch_conv_halo_t<64, true>(tmA, tmW, g, st);
+  return BN == 128 ? launch_conv_halo_t<128, false>(tmA, tmW, g, st) : launch_conv_halo_t<64, false>(tmA, tmW, g, st);
+}
+static int g_conv_halo = 1;   // imw_debug_set_conv_halo: 0 = generic kernel everywhere (A/B measurements, unit tests of both)
+
 template <int BN>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
   if (g.ksize == 1) return launch_conv_t<BN, 1, false>(tmA, tmW, g, st);   // (no 1x1 conv with a residual on the path)
@@ -548,6 +781,12 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& 
 }
 
 }  // namespace
+
+// A/B hook (unit tests, measurements): 1 = 3x3 stride-1 convs with W % 8 == 0 run on the halo-copy kernel (default), 0 = generic kernel
+extern "C" int imw_debug_set_conv_halo(int on) {
+  if (on >= 0) g_conv_halo = on ? 1 : 0;
+  return g_conv_halo;
+}
 
 // in_planes [NP][B][H][W][Cin] fp16, w_planes [NP][9][Cout][Cin] fp16 (split_planes.cuh), bias [Cout] fp32.
 // out: planes [NP][B][Ho][Wo][Cout] fp16 or fp32 [B][Ho][Wo][Cout].
@@ -570,9 +809,10 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   }
+  ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
+  if (g_conv_halo && W % C64_TW == 0) return launch_conv_halo(in_planes, w_planes, g, st);
   if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin)) return e;
   if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, BN)) return e;
-  ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 
@@ -605,6 +845,7 @@ int tc_conv_general(const void* in_planes, const void* w_planes, const float* bi
   if (int e = make_map_wgt(&tmW, w_planes, NP * ksize * ksize * Cout, Cin, BN)) return e;
   ConvArgs g{H, W, Cin, Cout, B, act, 0, out_fp32, bias, (plane_t*)out, (float*)out};
   g.ksize = ksize; g.stride = stride; g.res_planes = (const plane_t*)res_planes;
+  if (g_conv_halo && ksize == 3 && stride == 1 && W % C64_TW == 0) return launch_conv_halo(in_planes, w_planes, g, st);
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 

@@ -359,8 +359,8 @@ int imw_magsac(int n_sets, int cap, const float* pts0, const float* pts1, const 
                int* n_iters, imw_stream_t stream);
 
 /* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 path (split = 1: single TF32,
- * split = 3: 3xTF32 fp32-equivalent, split = 4: the same with W [2N][K] = weights + host-computed lo plane) and on the
- * CUDA-core fp32 path. */
+ * split = 3: 3xTF32 fp32-equivalent, split = 4: the same with W [2N][K] = weights + host-computed lo plane, split = 5: the
+ * split-fp16 GEMM the linears run on, W [2N][K] = weights + their two fp16 planes) and on the CUDA-core fp32 path. */
 int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K, int split,
                         imw_stream_t stream);
 int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
@@ -381,6 +381,8 @@ int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, con
  * w1b_planes [2][9][64][64] fp16 -> conv1b output planes [2][B][H/2][W/2][64] (pool = 1) */
 /* tuning hook: images per pass of the SuperPoint conv stack (default 8); returns the value in effect */
 int imw_debug_set_sp_sub(int n);
+/* 1 (default): 3x3 stride-1 tcgen05 convs with W % 8 == 0 use the halo-copy kernel, 0: the per-tap generic kernel; < 0: query */
+int imw_debug_set_conv_halo(int on);
 int imw_debug_conv1ab_fused(const float* image, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,
                             void* out_planes, int batch, int height, int width, int pool, imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,

@@ -328,21 +328,24 @@ def test_tcgen05_gemm_unit(dev):
 def test_tcgen05_conv_unit(dev):
     """tcgen05 split-fp16 implicit-GEMM conv == fp32 CUDA-core conv to fp32 rounding noise, incl. zero padding,
     fused ReLU / 2x2 max-pool, partial tiles (H % 8 != 0) and both Cout tile widths."""
-    from imcui_b200 import ops
+    from imcui_b200 import _lib, ops
     torch.manual_seed(1)
     for (B, H, W, Cin, Cout, pool) in ((1, 16, 32, 64, 64, False), (2, 48, 64, 64, 64, True), (1, 24, 48, 64, 64, True),
                                        (1, 40, 16, 64, 64, False), (1, 24, 32, 64, 128, False),
                                        (2, 32, 48, 128, 128, True), (1, 60, 80, 128, 256, False),
-                                       (1, 24, 48, 128, 128, False)):   # 9 pixel tiles: odd count -> one padding CTA in the last cluster
+                                       (1, 24, 48, 128, 128, False), (3, 40, 24, 256, 256, False), (1, 20, 40, 64, 256, True)):
         x = torch.rand(B, H, W, Cin, device=dev)
         w = torch.randn(9, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
         b = torch.randn(Cout, device=dev) * 0.1
         ref = ops.debug_conv3x3(x, w, b, relu=True, pool=pool, tensor_cores=False)
-        out = ops.debug_conv3x3(x, w, b, relu=True, pool=pool, tensor_cores=True)
-        torch.cuda.synchronize()
-        err = float((out - ref).abs().max())
-        print(f"[conv] {B}x{H}x{W} {Cin}->{Cout} pool={pool}: max |tc - fp32| = {err:.2e} (ref max {float(ref.abs().max()):.2f})")
-        assert err < 1e-5, (B, H, W, Cin, Cout, pool, err)
+        for halo in (1, 0):   # halo-copy kernel (default for W % 8 == 0) and the per-tap generic kernel
+            _lib.lib().imw_debug_set_conv_halo(halo)
+            out = ops.debug_conv3x3(x, w, b, relu=True, pool=pool, tensor_cores=True)
+            torch.cuda.synchronize()
+            err = float((out - ref).abs().max())
+            print(f"[conv] {B}x{H}x{W} {Cin}->{Cout} pool={pool} halo={halo}: max |tc - fp32| = {err:.2e} (ref max {float(ref.abs().max()):.2f})")
+            assert err < 1e-5, (B, H, W, Cin, Cout, pool, halo, err)
+        _lib.lib().imw_debug_set_conv_halo(1)
     # against torch (NCHW) once, to pin the CUDA-core conv itself
     x = torch.rand(1, 16, 32, 64, device=dev); w = torch.randn(9, 64, 64, device=dev) * 0.05; b = torch.zeros(64, device=dev)
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.view(3, 3, 64, 64).permute(3, 2, 0, 1).double(), padding=1).relu()

@@ -179,6 +179,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns WITHOUT the wait: issue several, then tmem_wait_ld() once (the loads pipeline)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// compiler-level dependency: values loaded by tmem_ld16_async may only be consumed after the wait (an empty volatile asm that
+// "rewrites" the registers; volatile asms keep their order, so every use is scheduled behind tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+// one 32-column chunk of a split-precision accumulator: (set0.main + set1.main) + (set0.cross + set1.cross) * lo_inv, with the two
+// [main | cross] sets `set_stride` columns apart and cross `cross_off` columns behind main.  Eight 16-column loads, two waits
+// (the element-wise order of the additions is the one the epilogues always used).
+__device__ __forceinline__ void tmem_ld_acc32(uint32_t lane_base, int cross_off, int set_stride, float lo_inv, float (&v)[32]) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t m0[16], m1[16], c0[16], c1[16];
+    tmem_ld16_async(lane_base + 16 * h, m0);
+    tmem_ld16_async(lane_base + set_stride + 16 * h, m1);
+    tmem_ld16_async(lane_base + cross_off + 16 * h, c0);
+    tmem_ld16_async(lane_base + set_stride + cross_off + 16 * h, c1);
+    tmem_wait_ld();
+    tmem_ld_fence(m0); tmem_ld_fence(m1); tmem_ld_fence(c0); tmem_ld_fence(c1);
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      v[16 * h + j] = fmaf(__uint_as_float(c0[j]) + __uint_as_float(c1[j]), lo_inv, __uint_as_float(m0[j]) + __uint_as_float(m1[j]));
+  }
+}
 }  // namespace tc
 
 // ---- host: tensor maps ----------------------------------------------------------------------------------

@@ -18,7 +18,7 @@
 // the conv's zero padding), 64 channels = one 128-byte swizzled row per pixel.
 //   warp 0: TMA producer (2 activation planes + 2 weight planes per (tap, 64-channel chunk) stage)
 //   warp 1: TMEM alloc + tcgen05.mma issue (8 MMAs per stage)
-//   warps 2-5: epilogue: tcgen05.ld, bias, optional residual planes, ReLU / LeakyReLU, optional fused 2x2 max-pool
+//   warps 2-9: epilogue (two per TMEM sub-partition): tcgen05.ld, bias, optional residual planes, ReLU / LeakyReLU, optional fused 2x2 max-pool
 //              (lane shuffles: the 2x2 window lives in one warp), re-split into fp16 planes (or fp32) and store NHWC.
 // Cin = Cout = 64 specialisation (tc_conv3x3_c64_kernel<FUSE>): persistent, halo tile as three dx-shifted copies,
 // double-buffered TMEM; FUSE evaluates SuperPoint's conv1a inside the CTA (see below).
@@ -33,7 +33,8 @@ namespace {
 constexpr int CV_TH = 8, CV_TW = 16;          // pixel tile (rows x cols) = 128 = MMA M
 constexpr int CV_CK = 64;                     // channels per stage (128 B of bf16)
 constexpr int CV_A_BYTES = 128 * 128;         // one activation plane tile
-constexpr int CV_THREADS = 192;
+constexpr int CV_EPI_WARPS = 8;               // two warps per TMEM sub-partition, half of the Cout slice each (the epilogue is exposed time)
+constexpr int CV_THREADS = 64 + 32 * CV_EPI_WARPS;
 
 struct ConvArgs {
   int H, W, Cin, Cout, B;     // H, W: INPUT size; output = ceil(H/stride) x ceil(W/stride) (then /2 if pooled)
@@ -147,7 +148,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
     }
   } else {
-    const int q = warp % 4;
+    const int q = warp % 4, chalf = (warp - 2) / 4;   // TMEM sub-partition; columns [chalf * BN / 2, +BN / 2) of the slice
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
     const int m = q * 32 + lane;              // pixel index in the tile: row m/16, col m%16
@@ -159,22 +160,17 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
     const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
       float v[32], t[32];
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-      float u[32];
-      tc::tmem_ld32(lane_base, v);          // set 0: [main | cross]
-      tc::tmem_ld32(lane_base + BN, u);
-      if (steps >= 2) {   // set 1 (odd k-steps)
-        tc::tmem_ld32(lane_base + 2 * BN, t);
+      if (steps >= 2) {   // both [main | cross] sets were written (set 1 = odd k-steps)
+        tc::tmem_ld_acc32(lane_base, BN, 2 * BN, PLANE_LO_INV, v);
+      } else {
+        tc::tmem_ld32(lane_base, v);
+        tc::tmem_ld32(lane_base + BN, t);
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += t[j];
-        tc::tmem_ld32(lane_base + 3 * BN, t);
-#pragma unroll
-        for (int j = 0; j < 32; j++) u[j] += t[j];
+        for (int j = 0; j < 32; j++) v[j] = fmaf(t[j], PLANE_LO_INV, v[j]);
       }
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = fmaf(u[j], PLANE_LO_INV, v[j]);
       if (RES && in_img) {  // residual branch of a BasicBlock (added before the activation)
         const plane_t* r0 = g.res_planes + opix + c0;
 #pragma unroll
@@ -238,20 +234,24 @@ constexpr int C64_A_BYTES = NP * 3 * C64_COPY;    // NP planes x 3 dx
 constexpr int C64_B_STAGE = NP * 64 * 128;        // NP weight planes of one tap
 constexpr int C64_B_STAGES = 4;
 constexpr size_t C64_SMEM = C64_A_BYTES + C64_B_STAGES * C64_B_STAGE + 1024 + 256 + 2 * 240 * sizeof(float) /*fused: image patches*/;
-constexpr int C64_FUSE_PROD = 256;   // conv1a producer threads (8 warps)
+constexpr int C64_FUSE_PROD = 192;   // conv1a producer threads (6 warps: 512 threads per CTA keep 128 registers per thread)
 constexpr int C64_HALO_PX = 18 * 10;                       // conv1a outputs one tile needs: rows y0-1..y0+16, cols x0-1..x0+8
 constexpr int C64_STG_BYTES = NP * C64_HALO_PX * 128;      // staging of the split conv1a outputs (fused kernel only)
 constexpr size_t C64_FUSE_SMEM = C64_SMEM + C64_STG_BYTES;
-constexpr int C64_FUSE_THREADS = CV_THREADS + C64_FUSE_PROD;
+// warps 0 (TMA), 1 (MMA), 2..9 (epilogue: two warps per TMEM sub-partition, 32 of the 64 output channels each -- with four warps
+// the epilogue of a tile took as long as the tile itself, 5 us, and bounded the kernel), 10..17 (FUSE: conv1a producers)
+constexpr int C64_EPI_WARPS = 8;
+constexpr int C64_THREADS = 64 + 32 * C64_EPI_WARPS;
+constexpr int C64_FUSE_THREADS = C64_THREADS + C64_FUSE_PROD;
 
 // Persistent: one CTA per SM walks the tile list.  The three dx-copy slots, the weight ring and two TMEM
 // accumulator sets (2 x 4 x 64 = 512 columns) are all recycled through mbarriers, so the next tile's loads and
 // MMAs run while the epilogue warps drain the previous tile.
-// FUSE: the input is the 1-channel image; warps 6..9 evaluate conv1a (3x3, Cin = 1, bias, ReLU; superpoint.py:152) on the halo
+// FUSE: the input is the 1-channel image; the producer warps (10..15) evaluate conv1a (3x3, Cin = 1, bias, ReLU; superpoint.py:152) on the halo
 // patch of every tile, split the result into the three bf16 planes and write the three dx-shifted SWIZZLE_128B copies
 // themselves (the layout TMA would have produced) -- conv1a's 118 MB / image of plane traffic never touches HBM.
 template <bool FUSE>
-__global__ void __launch_bounds__(FUSE ? C64_FUSE_THREADS : CV_THREADS, 1)
+__global__ void __launch_bounds__(FUSE ? C64_FUSE_THREADS : C64_THREADS, 1)
 tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles) {
   constexpr int BN = 64;
   extern __shared__ uint8_t cv_smem_raw[];
@@ -273,7 +273,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc::tma_prefetch_desc(&tmW);
     for (int i = 0; i < 3; i++) { tc::mbar_init(a_full + i, FUSE ? C64_FUSE_PROD : 1); tc::mbar_init(a_empty + i, 1); }
     for (int s = 0; s < C64_B_STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
-    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 128); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(tmem_full + a, 1); tc::mbar_init(tmem_empty + a, 32 * C64_EPI_WARPS); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -344,8 +344,8 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
       }
     }
-  } else if (FUSE && warp >= 6) {
-    const int t = threadIdx.x - CV_THREADS;   // 0..C64_FUSE_PROD-1
+  } else if (FUSE && warp >= 2 + C64_EPI_WARPS) {
+    const int t = threadIdx.x - C64_THREADS;   // 0..C64_FUSE_PROD-1
     const int chunk = t % 8;                  // output channels [8 chunk, +8) = one 16-byte unit of a pixel's 128-byte row
     float w[9][8], bv[8];
 #pragma unroll
@@ -419,7 +419,7 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       asm volatile("bar.sync 2, %0;" ::"n"(C64_FUSE_PROD) : "memory");   // staging is rewritten for the next tile
     }
   } else {
-    const int q = warp % 4;
+    const int q = warp % 4, chalf = (warp - 2) / 4;   // TMEM sub-partition; output channels [32 chalf, +32)
     const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
     const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
     const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
@@ -435,20 +435,12 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
       const bool in_img = (py < g.H) && (px < g.W);
       const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32], tt[32];
+      {
+        const int c0 = chalf * 32;
+        float v[32];
         const uint32_t lane_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + c0;
-        float u[32];
-        tc::tmem_ld32(lane_base, v);              // set 0 main
-        tc::tmem_ld32(lane_base + 2 * BN, tt);    // set 1 main
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += tt[j];
-        tc::tmem_ld32(lane_base + BN, u);         // set 0 cross (scaled by 2^11)
-        tc::tmem_ld32(lane_base + 3 * BN, tt);    // set 1 cross
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaf(u[j] + tt[j], PLANE_LO_INV, v[j]);
-        if (c0 + 32 >= BN) {  // last TMEM read of this accumulator set: hand it back to the MMA warp
+        tc::tmem_ld_acc32(lane_base, BN, 2 * BN, PLANE_LO_INV, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
+        {  // this warp's only TMEM read of the accumulator set: hand it back to the MMA warp
           tc::fence_before_sync();
           tc::mbar_arrive(tmem_empty + acc);
         }
@@ -635,16 +627,9 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
-        float v[32], t[32], u[32];
+        float v[32], t[32];
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-        tc::tmem_ld32(lane_base, v);              // set 0 main
-        tc::tmem_ld32(lane_base + 2 * BN, t);     // set 1 main
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] += t[j];
-        tc::tmem_ld32(lane_base + BN, u);         // set 0 cross (scaled by 2^11)
-        tc::tmem_ld32(lane_base + 3 * BN, t);     // set 1 cross
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaf(u[j] + t[j], PLANE_LO_INV, v[j]);
+        tc::tmem_ld_acc32(lane_base, BN, 2 * BN, PLANE_LO_INV, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
         if (c0 + 32 >= (chalf + 1) * (BN / 2)) {  // this warp's last TMEM read of the item: hand the accumulators back to the MMA warp
           tc::fence_before_sync();
           tc::mbar_arrive(tmem_empty);
@@ -805,7 +790,7 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
     const int num_sms = imw_num_sms();
     dim3 grid((unsigned)(total < num_sms ? total : num_sms), 1);
-    tc_conv3x3_c64_kernel<false><<<grid, CV_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
+    tc_conv3x3_c64_kernel<false><<<grid, C64_THREADS, C64_SMEM, st>>>(tmA, tmW, g, total);
     IMW_CHECK_LAUNCH();
     return IMW_OK;
   }

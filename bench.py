@@ -248,7 +248,7 @@ class Config2:
             except Exception:
                 pass
             return roofline_from_sites(prof, ["tc_conv1ab_fused"], (SP_LAYER_GFLOP["conv1a"] + SP_LAYER_GFLOP["conv1b"]) * n_img, "TFLOP/s", "tensor",
-                                       "tc_conv3x3_c64_kernel<fused conv1a> (SuperPoint conv1a 1->64 + conv1b 64->64 @480x640, tcgen05 split-fp16 = fp32-equivalent)",
+                                       "tc_conv3x3_c64_pair_kernel<fused conv1a> (SuperPoint conv1a 1->64 + conv1b 64->64 @480x640, tcgen05 cta_group::2 split-fp16 = fp32-equivalent)",
                                        note="split precision: three fp16 partial products per fp32-equivalent product (issued as two MMAs over N-concatenated weight planes): tensor-pipe FLOP/s = 3 x achieved",
                                        traffic=traffic)
         return roofline_from_sites(prof, ["sp_conv3x3"], 0.0, "TFLOP/s", "tensor", "conv3x3_nhwc_kernel (fp32 CUDA cores)")

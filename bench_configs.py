@@ -179,8 +179,8 @@ class Config3(_Base):
 
     def roofline(self, prof):
         # all tcgen05 implicit-GEMM conv launches of the ResNet-FPN backbone: 1.014 TFLOP / image minus the 7x7 stem (3.3 GFLOP, CUDA cores)
-        return roofline_from_sites(prof, ["launch_conv_t"], (1014.0 - 3.3) * 2 * self.P, "TFLOP/s", "tensor",
-                                   "tc_conv3x3_kernel<BN,KS,RES> (LoFTR ResNet-FPN backbone @1024x1024: every 3x3 / 1x1 conv, tcgen05 split-fp16 = fp32-equivalent)",
+        return roofline_from_sites(prof, ["tc_conv"], (1014.0 - 3.3) * 2 * self.P, "TFLOP/s", "tensor",
+                                   "tc_conv3x3_halo_pair_kernel / tc_conv3x3_kernel<BN,KS,RES> (LoFTR ResNet-FPN backbone @1024x1024: every 3x3 / 1x1 conv, tcgen05 split-fp16 = fp32-equivalent)",
                                    note="split precision: three fp16 partial products per fp32-equivalent product; 196-channel layers zero-padded to 256 (padding FLOPs not counted)")
 
     def cpu_unit(self):

@@ -480,6 +480,9 @@ tc_conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+#include "tc_conv_pair.cuh"   // the same conv on a CTA pair (cta_group::2): dense halo patch, resident weights
+#include "tc_conv_pair_halo.cuh"   // any channel count on a CTA pair: dense halo patch, weight stages split between the CTAs
+
 // ---- 3x3 stride-1 convs with Cin = 64 k, Cout = 64 / 128 n: the halo-copy scheme of the c64 kernel for any channel count ----
 // The generic kernel above fetches the activation tile once per tap: 9 x 32 KB of activations + 9 x 32 KB of weights per
 // 64-channel chunk and 128 pixels, and is bound by the chip's aggregate L2 -> SM throughput (ncu round 2: 7.4 TB/s, tensor pipe
@@ -757,6 +760,7 @@ int launch_conv_halo(const void* in_planes, const void* w_planes, const ConvArgs
   if (g.res_planes) return BN == 128 ? launch_conv_halo_t<128, true>(tmA, tmW, g, st) : launch_conv_halo_t<64, true>(tmA, tmW, g, st);
   return BN == 128 ? launch_conv_halo_t<128, false>(tmA, tmW, g, st) : launch_conv_halo_t<64, false>(tmA, tmW, g, st);
 }
+static int g_conv_pair = 1;   // imw_debug_set_conv_pair: 1 = Cin = Cout = 64 convs on CTA pairs (default), 0 = single-CTA c64 kernel, 2 = pair kernel with swapped B halves (probe)
 static int g_conv_halo = 1;   // imw_debug_set_conv_halo: 0 = generic kernel everywhere (A/B measurements, unit tests of both)
 
 template <int BN>
@@ -766,6 +770,44 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& 
 }
 
 }  // namespace
+
+// CTA-pair launch of the c64 conv (fused first layer when g.img is set)
+template <bool FUSE>
+static int launch_conv_c64_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+  IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_pair_kernel<FUSE>, P2_SMEM);
+  const int total = g.B * ceil_div(g.H, C64_TH) * (g.W / C64_TW);
+  const int pairs = (total + 1) / 2, max_clusters = imw_num_sms() / 2;
+  const int clusters = pairs < max_clusters ? pairs : max_clusters;
+  tc_conv3x3_c64_pair_kernel<FUSE><<<dim3((unsigned)(2 * clusters)), FUSE ? P2_FUSE_THREADS : P2_THREADS, P2_SMEM, st>>>(tmA, tmW, g, total,
+                                                                                                                        (g_conv_pair == 2) | (g_conv_pair & ~3));
+  IMW_CHECK_LAUNCH_T(FUSE ? "tc_conv1ab_fused -> tc_conv3x3_c64_pair_kernel<fused conv1a>" : "tc_conv3x3 -> tc_conv3x3_c64_pair_kernel");
+  return IMW_OK;
+}
+extern "C" int imw_debug_set_conv_pair(int mode) {
+  if (mode >= 0) g_conv_pair = mode;
+  return g_conv_pair;
+}
+
+template <int BN, bool RES>
+static int launch_conv_halo_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvArgs& g, cudaStream_t st) {
+  constexpr size_t smem = ph_smem_bytes<BN>();
+  IMW_SMEM_ATTR_ONCE((tc_conv3x3_halo_pair_kernel<BN, RES>), smem);
+  const int total = g.B * ceil_div(g.H, C64_TH) * (g.W / C64_TW);
+  const int items = ((total + 1) / 2) * (g.Cout / BN), max_clusters = imw_num_sms() / 2;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  tc_conv3x3_halo_pair_kernel<BN, RES><<<dim3((unsigned)(2 * clusters)), PH_THREADS, smem, st>>>(tmA, tmW, g, total);
+  IMW_CHECK_LAUNCH_T(BN == 128 ? "tc_conv3x3 -> tc_conv3x3_halo_pair_kernel<128>" : "tc_conv3x3 -> tc_conv3x3_halo_pair_kernel<64>");
+  return IMW_OK;
+}
+// 3x3, stride 1, W % 8 == 0 on CTA pairs: dense halo patch (10 x 18 box), each CTA fetches its half of the Cout slice
+static int launch_conv_halo_pair(const void* in_planes, const void* w_planes, const ConvArgs& g, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  const int BN = (g.Cout % 128 == 0) ? 128 : 64;
+  if (int e = make_map_act(&tmA, in_planes, NP * g.B, g.H, g.W, g.Cin, P2_HALO_W, P2_HALO_H)) return e;
+  if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * g.Cout, g.Cin, BN / 2)) return e;
+  if (g.res_planes) return BN == 128 ? launch_conv_halo_pair_t<128, true>(tmA, tmW, g, st) : launch_conv_halo_pair_t<64, true>(tmA, tmW, g, st);
+  return BN == 128 ? launch_conv_halo_pair_t<128, false>(tmA, tmW, g, st) : launch_conv_halo_pair_t<64, false>(tmA, tmW, g, st);
+}
 
 // A/B hook (unit tests, measurements): 1 = 3x3 stride-1 convs with W % 8 == 0 run on the halo-copy kernel (default), 0 = generic kernel
 extern "C" int imw_debug_set_conv_halo(int on) {
@@ -782,6 +824,12 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
   IMW_REQUIRE(!pool || (H % 2 == 0), "tc_conv3x3: pooled conv needs even H");
   CUtensorMap tmA, tmW;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
+  if (Cin == 64 && Cout == 64 && W % C64_TW == 0 && g_conv_pair) {  // CTA-pair kernel: dense halo patch (10 x 18 box), resident weights
+    if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin, P2_HALO_W, P2_HALO_H)) return e;
+    if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, 32)) return e;
+    ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
+    return launch_conv_c64_pair<false>(tmA, tmW, g, st);
+  }
   if (Cin == 64 && Cout == 64 && W % C64_TW == 0) {  // halo-copy specialisation
     if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin, C64_TW, C64_TH + 2)) return e;
     if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, 64)) return e;
@@ -795,7 +843,7 @@ int tc_conv3x3(const void* in_planes, const void* w_planes, const float* bias, v
     return IMW_OK;
   }
   ConvArgs g{H, W, Cin, Cout, B, relu, pool, out_fp32, bias, (plane_t*)out, (float*)out};
-  if (g_conv_halo && W % C64_TW == 0) return launch_conv_halo(in_planes, w_planes, g, st);
+  if (g_conv_halo && W % C64_TW == 0) return (g_conv_pair & 1) ? launch_conv_halo_pair(in_planes, w_planes, g, st) : launch_conv_halo(in_planes, w_planes, g, st);
   if (int e = make_map_act(&tmA, in_planes, NP * B, H, W, Cin)) return e;
   if (int e = make_map_wgt(&tmW, w_planes, NP * 9 * Cout, Cin, BN)) return e;
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
@@ -809,6 +857,11 @@ int tc_conv1ab_fused(const float* img, const float* w1a, const float* b1a, const
   if (int e = make_map_wgt(&tmW, w1b_planes, NP * 9 * 64, 64, 64)) return e;
   ConvArgs g{H, W, 64, 64, B, 1, pool, 0, b1b, (plane_t*)out, (float*)out};
   g.img = img; g.w1a = w1a; g.b1a = b1a;
+  if (g_conv_pair) {
+    CUtensorMap tmW32;
+    if (int e = make_map_wgt(&tmW32, w1b_planes, NP * 9 * 64, 64, 32)) return e;
+    return launch_conv_c64_pair<true>(tmW32, tmW32, g, st);
+  }
   IMW_SMEM_ATTR_ONCE(tc_conv3x3_c64_kernel<true>, C64_FUSE_SMEM);
   const int num_sms = imw_num_sms();
   const int total = B * ceil_div(H, C64_TH) * (W / C64_TW);
@@ -830,7 +883,8 @@ int tc_conv_general(const void* in_planes, const void* w_planes, const float* bi
   if (int e = make_map_wgt(&tmW, w_planes, NP * ksize * ksize * Cout, Cin, BN)) return e;
   ConvArgs g{H, W, Cin, Cout, B, act, 0, out_fp32, bias, (plane_t*)out, (float*)out};
   g.ksize = ksize; g.stride = stride; g.res_planes = (const plane_t*)res_planes;
-  if (g_conv_halo && ksize == 3 && stride == 1 && W % C64_TW == 0) return launch_conv_halo(in_planes, w_planes, g, st);
+  if (g_conv_halo && ksize == 3 && stride == 1 && W % C64_TW == 0)
+    return (g_conv_pair & 1) ? launch_conv_halo_pair(in_planes, w_planes, g, st) : launch_conv_halo(in_planes, w_planes, g, st);
   return BN == 128 ? launch_conv<128>(tmA, tmW, g, st) : launch_conv<64>(tmA, tmW, g, st);
 }
 

@@ -383,6 +383,8 @@ int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, con
 int imw_debug_set_sp_sub(int n);
 /* 1 (default): 3x3 stride-1 tcgen05 convs with W % 8 == 0 use the halo-copy kernel, 0: the per-tap generic kernel; < 0: query */
 int imw_debug_set_conv_halo(int on);
+/* 1 = Cin = Cout = 64 convs (and the fused first layer) on CTA pairs, tcgen05 cta_group::2 (default); 0 = single-CTA kernels; < 0 = query */
+int imw_debug_set_conv_pair(int mode);
 int imw_debug_conv1ab_fused(const float* image, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,
                             void* out_planes, int batch, int height, int width, int pool, imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,

@@ -338,19 +338,49 @@ def test_tcgen05_conv_unit(dev):
         w = torch.randn(9, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
         b = torch.randn(Cout, device=dev) * 0.1
         ref = ops.debug_conv3x3(x, w, b, relu=True, pool=pool, tensor_cores=False)
-        for halo in (1, 0):   # halo-copy kernel (default for W % 8 == 0) and the per-tap generic kernel
+        # halo kernels (default for W % 8 == 0) and the per-tap generic kernel
+        for halo, pair in ((1, 1), (1, 0), (0, 1)):   # pair = 1: CTA-pair kernels (cta_group::2), 0: their single-CTA predecessors
             _lib.lib().imw_debug_set_conv_halo(halo)
+            _lib.lib().imw_debug_set_conv_pair(pair)
             out = ops.debug_conv3x3(x, w, b, relu=True, pool=pool, tensor_cores=True)
             torch.cuda.synchronize()
             err = float((out - ref).abs().max())
-            print(f"[conv] {B}x{H}x{W} {Cin}->{Cout} pool={pool} halo={halo}: max |tc - fp32| = {err:.2e} (ref max {float(ref.abs().max()):.2f})")
-            assert err < 1e-5, (B, H, W, Cin, Cout, pool, halo, err)
+            print(f"[conv] {B}x{H}x{W} {Cin}->{Cout} pool={pool} halo={halo} pair={pair}: max |tc - fp32| = {err:.2e} (ref max {float(ref.abs().max()):.2f})")
+            assert err < 1e-5, (B, H, W, Cin, Cout, pool, halo, pair, err)
         _lib.lib().imw_debug_set_conv_halo(1)
+        _lib.lib().imw_debug_set_conv_pair(1)
     # against torch (NCHW) once, to pin the CUDA-core conv itself
     x = torch.rand(1, 16, 32, 64, device=dev); w = torch.randn(9, 64, 64, device=dev) * 0.05; b = torch.zeros(64, device=dev)
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.view(3, 3, 64, 64).permute(3, 2, 0, 1).double(), padding=1).relu()
     out = ops.debug_conv3x3(x, w, b, relu=True, pool=False, tensor_cores=True)
     assert float((out.permute(0, 3, 1, 2) - ref.float()).abs().max()) < 1e-5
+
+
+def test_tcgen05_fused_first_layer_unit(dev):
+    """SuperPoint conv1a + conv1b in one kernel (conv1a evaluated by producer warps straight into the tcgen05 operand tile) == torch
+    fp64 conv -> ReLU -> conv -> ReLU -> max-pool, on the CTA-pair kernel (default) and the single-CTA kernel; odd tile counts, partial
+    tiles (H % 16 != 0), several images."""
+    from imcui_b200 import _lib as L, ops
+    torch.manual_seed(3)
+    lib = L.lib()
+    for (B, H, W, pool) in ((1, 16, 16, False), (2, 48, 64, True), (1, 40, 24, True), (3, 16, 8, False), (1, 120, 160, True)):
+        img = torch.rand(B, H, W, device=dev)
+        w1a = torch.randn(9, 64, device=dev) / 3.0; b1a = torch.randn(64, device=dev) * 0.1
+        w1b = torch.randn(9, 64, 64, device=dev) / 24.0; b1b = torch.randn(64, device=dev) * 0.1
+        y = torch.nn.functional.conv2d(img[:, None].double(), w1a.view(3, 3, 1, 64).permute(3, 2, 0, 1).double(), b1a.double(), padding=1).relu()
+        y = torch.nn.functional.conv2d(y.float().double(), w1b.view(3, 3, 64, 64).permute(3, 2, 0, 1).double(), b1b.double(), padding=1).relu()
+        if pool: y = torch.nn.functional.max_pool2d(y, 2)
+        ref = y.permute(0, 2, 3, 1).float()
+        wp = ops.split_f16_planes(w1b.permute(0, 2, 1).contiguous()).to(dev)   # [2][9][Cout][Cin]
+        for pair in (1, 0):
+            lib.imw_debug_set_conv_pair(pair)
+            out = torch.empty(2, *ref.shape, dtype=torch.float16, device=dev)
+            L.check(lib.imw_debug_conv1ab_fused(L.ptr(img), L.ptr(w1a), L.ptr(b1a), L.ptr(wp), L.ptr(b1b), L.ptr(out), B, H, W, int(pool), L.stream_ptr(dev)))
+            torch.cuda.synchronize()
+            err = float((out[0].float() + out[1].float() / 2048.0 - ref).abs().max())
+            print(f"[conv1ab] {B}x{H}x{W} pool={pool} pair={pair}: max err {err:.2e}")
+            assert err < 5e-6, (B, H, W, pool, pair, err)
+        lib.imw_debug_set_conv_pair(1)
 
 
 def test_tcgen05_attention_unit(dev):

@@ -778,7 +778,7 @@ static int launch_conv_c64_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, 
   const int total = g.B * ceil_div(g.H, C64_TH) * (g.W / C64_TW);
   const int pairs = (total + 1) / 2, max_clusters = imw_num_sms() / 2;
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
-  tc_conv3x3_c64_pair_kernel<FUSE><<<dim3((unsigned)(2 * clusters)), FUSE ? P2_FUSE_THREADS : P2_THREADS, P2_SMEM, st>>>(tmA, tmW, g, total,
+  tc_conv3x3_c64_pair_kernel<FUSE><<<dim3((unsigned)(2 * clusters)), FUSE ? P2_FUSE_THREADS : P2_PLAIN_THREADS, P2_SMEM, st>>>(tmA, tmW, g, total,
                                                                                                                         (g_conv_pair == 2) | (g_conv_pair & ~3));
   IMW_CHECK_LAUNCH_T(FUSE ? "tc_conv1ab_fused -> tc_conv3x3_c64_pair_kernel<fused conv1a>" : "tc_conv3x3 -> tc_conv3x3_c64_pair_kernel");
   return IMW_OK;

@@ -27,41 +27,16 @@ constexpr int P2_W_TAP = 12288;
 constexpr int P2_W_BYTES = 9 * P2_W_TAP;
 constexpr int P2_BAR_OFF = P2_A_BYTES + P2_W_BYTES;
 constexpr size_t P2_SMEM = P2_BAR_OFF + 128 + 2 * 240 * sizeof(float) + 64 * sizeof(float) /*bias*/ + 1024;
-constexpr int P2_EPI_WARPS = 8, P2_PROD_WARPS = 8;
+constexpr int P2_EPI_WARPS = 8, P2_PROD_WARPS = 8;   // fused first layer: 8 epilogue + 8 conv1a producer warps
+constexpr int P2_EPI_WARPS_PLAIN = 16;              // plain conv: the epilogue is the only CUDA-core work, 4 warps per TMEM sub-partition
 constexpr int P2_THREADS = 64 + 32 * P2_EPI_WARPS, P2_FUSE_THREADS = P2_THREADS + 32 * P2_PROD_WARPS;
+constexpr int P2_PLAIN_THREADS = 64 + 32 * P2_EPI_WARPS_PLAIN;
 
-__device__ __forceinline__ uint64_t p2_desc(uint32_t smem_addr, uint32_t sbo) {   // K-major SWIZZLE_128B, group stride sbo
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ uint32_t p2_mapa(const void* p, uint32_t rank) {   // shared::cluster address of p in CTA `rank`
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(tc::smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void p2_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void p2_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(tc::smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 22)) { printf("p2_wait_cluster timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
-}
+// (short names for the cta_group::2 primitives of tc_common.cuh)
+__device__ __forceinline__ uint64_t p2_desc(uint32_t smem_addr, uint32_t sbo) { return tc::make_smem_desc_sw128_sbo(smem_addr, sbo); }
+__device__ __forceinline__ uint32_t p2_mapa(const void* p, uint32_t rank) { return tc::mapa(p, rank); }
+__device__ __forceinline__ void p2_arrive_remote(uint32_t cluster_addr) { tc::mbar_arrive_cluster(cluster_addr); }
+__device__ __forceinline__ void p2_wait_cluster(uint64_t* bar, uint32_t parity) { tc::mbar_wait_cluster(bar, parity); }
 __device__ __forceinline__ void p2_tma_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
@@ -69,25 +44,10 @@ __device__ __forceinline__ void p2_tma_4d_pair(void* smem_dst, const CUtensorMap
       "l"(m), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void p2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void p2_commit(uint64_t* bar) {   // both CTAs' barrier at this offset
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void p2_tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_result)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void p2_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
+__device__ __forceinline__ void p2_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { tc::mma_f16_pair(d, a, b, idesc, acc); }
+__device__ __forceinline__ void p2_commit(uint64_t* bar) { tc::mma_commit_pair(bar); }
+__device__ __forceinline__ void p2_tmem_alloc(uint32_t* smem_result, uint32_t ncols) { tc::tmem_alloc_pair(smem_result, ncols); }
+__device__ __forceinline__ void p2_tmem_dealloc(uint32_t taddr, uint32_t ncols) { tc::tmem_dealloc_pair(taddr, ncols); }
 
 // two non-negative values (ReLU outputs) -> fp16 plane pairs: packed converts, no lower clamp (4 instructions per value instead of 7)
 __device__ __forceinline__ void split2_pos(float x0, float x1, __half2& hi, __half2& lo) {
@@ -97,12 +57,38 @@ __device__ __forceinline__ void split2_pos(float x0, float x1, __half2& hi, __ha
   lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
 }
 
+// the same without the upper clamp, for values known to be far below fp16's range (conv1a of a [0, 1] image: |x| < sum |w| + |b|)
+__device__ __forceinline__ void split2_small(float x0, float x1, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hi);
+  lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
+}
+
+// N (16 / 32) columns of a split-precision accumulator: (set0.main + set1.main) + (set0.cross + set1.cross) 2^-11 (tc::tmem_ld_acc32)
+template <int N>
+__device__ __forceinline__ void p2_ld_acc(uint32_t lane_base, int cross_off, int set_stride, float (&v)[N]) {
+#pragma unroll
+  for (int h = 0; h < N / 16; h++) {
+    uint32_t m0[16], m1[16], c0[16], c1[16];
+    tc::tmem_ld16_async(lane_base + 16 * h, m0);
+    tc::tmem_ld16_async(lane_base + set_stride + 16 * h, m1);
+    tc::tmem_ld16_async(lane_base + cross_off + 16 * h, c0);
+    tc::tmem_ld16_async(lane_base + set_stride + cross_off + 16 * h, c1);
+    tc::tmem_wait_ld();
+    tc::tmem_ld_fence(m0); tc::tmem_ld_fence(m1); tc::tmem_ld_fence(c0); tc::tmem_ld_fence(c1);
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      v[16 * h + j] = fmaf(__uint_as_float(c0[j]) + __uint_as_float(c1[j]), PLANE_LO_INV, __uint_as_float(m0[j]) + __uint_as_float(m1[j]));
+  }
+}
+
 // swap_halves: debugging aid (which CTA's rows are the first half of B's N)
 template <bool FUSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? P2_FUSE_THREADS : P2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? P2_FUSE_THREADS : P2_PLAIN_THREADS, 1)
 tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles,
                            int swap_halves) {
   constexpr int BN = 64;
+  constexpr int EPW = FUSE ? P2_EPI_WARPS : P2_EPI_WARPS_PLAIN, CPW = 256 / EPW;   // epilogue warps; output channels per warp (32 / 16)
   extern __shared__ uint8_t cv_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // [buf][plane][180 px][128 B]
@@ -127,7 +113,7 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       tc::mbar_init(a_full + i, FUSE ? 2 * P2_PROD_WARPS : 1);
       tc::mbar_init(a_empty + i, 1);
       tc::mbar_init(tmem_full + i, 1);
-      tc::mbar_init(tmem_empty + i, 2 * P2_EPI_WARPS);
+      tc::mbar_init(tmem_empty + i, 2 * EPW);
     }
     tc::mbar_init(w_full, 1);
     tc::fence_barrier_init();
@@ -209,7 +195,7 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         __syncwarp();
       }
     }
-  } else if (FUSE && warp >= 2 + P2_EPI_WARPS) {
+  } else if (FUSE && warp >= 2 + EPW) {
     // conv1a producers.  Thread = (segment of 6 halo rows, pair of adjacent halo columns, quad of 4 output channels): its 36 weights
     // live in registers and it walks down its two columns with the 3 x 4 image window in registers (four new values per row):
     // 72 FMAs on 8 independent accumulators per row step, no weight loads, no index arithmetic in the loop.  (8 channels per thread
@@ -257,7 +243,7 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           const float2 lo2 = *reinterpret_cast<const float2*>(im + (6 * seg + r) * 12 + hx), hi2 = *reinterpret_cast<const float2*>(im + (6 * seg + r) * 12 + hx + 2);
           win[r + 1][0] = lo2.x; win[r + 1][1] = lo2.y; win[r + 1][2] = hi2.x; win[r + 1][3] = hi2.y;
         }
-#pragma unroll 2
+#pragma unroll
         for (int r = 0; r < 6; r++) {
           const int hy = 6 * seg + r, pidx = hy * P2_HALO_W + hx;
           {
@@ -289,11 +275,11 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           uint2 h2, l2;
           __half2* hp = reinterpret_cast<__half2*>(&h2);
           __half2* lp = reinterpret_cast<__half2*>(&l2);
-          split2_pos(a0[0], a0[1], hp[0], lp[0]); split2_pos(a0[2], a0[3], hp[1], lp[1]);
+          split2_small(a0[0], a0[1], hp[0], lp[0]); split2_small(a0[2], a0[3], hp[1], lp[1]);
           int off = pidx * 128 + (((quad >> 1) ^ (pidx & 7)) * 16);   // SWIZZLE_128B: 16-byte unit c of row r sits at c ^ (r & 7)
           *reinterpret_cast<uint2*>(dst + off) = h2;
           *reinterpret_cast<uint2*>(dst + P2_PLANE + off) = l2;
-          split2_pos(a1[0], a1[1], hp[0], lp[0]); split2_pos(a1[2], a1[3], hp[1], lp[1]);
+          split2_small(a1[0], a1[1], hp[0], lp[0]); split2_small(a1[2], a1[3], hp[1], lp[1]);
           off = (pidx + 1) * 128 + (((quad >> 1) ^ ((pidx + 1) & 7)) * 16);
           *reinterpret_cast<uint2*>(dst + off) = h2;
           *reinterpret_cast<uint2*>(dst + P2_PLANE + off) = l2;
@@ -305,18 +291,18 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       if (t < 240) s_img[((i + 1) & 1) * 240 + t] = nxt;
       asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");   // next patch complete; every thread is done reading this one
     }
-  } else if (warp >= 2 && warp < 2 + P2_EPI_WARPS) {
-    const int q = warp % 4, chalf = (warp - 2) / 4;   // TMEM sub-partition; output channels [32 chalf, +32)
+  } else if (warp >= 2 && warp < 2 + EPW) {
+    // epilogue: EPW / 4 warps per TMEM sub-partition, CPW output channels each
+    const int q = warp % 4, c0 = ((warp - 2) / 4) * CPW;
     const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
     const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
-    const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
     const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
-    // pooled outputs: after the 2x2 exchange lane (b0 = lane & 1, b3 = lane & 8) owns channels [c0 + 16 b0 + 8 b3, +8) of its window
+    // pooled outputs: after the 2x2 exchange lane (b0 = lane & 1, b3 = lane & 8) owns channels [cq, cq + CPW / 4) of its window
     const bool b0 = (lane & 1) != 0, b3 = (lane & 8) != 0;
-    const int cq = chalf * 32 + (b0 ? 16 : 0) + (b3 ? 8 : 0);
-    float bq[8];
+    const int cq = c0 + (b0 ? CPW / 2 : 0) + (b3 ? CPW / 4 : 0);
+    float bq[CPW / 4];
 #pragma unroll
-    for (int e = 0; e < 8; e++) bq[e] = g.bias[cq + e];
+    for (int e = 0; e < CPW / 4; e++) bq[e] = g.bias[cq + e];
     for (int i = 0; i < my_iters; i++) {
       int tile; bool valid;
       tile_of(i, tile, valid);
@@ -329,59 +315,61 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const int oy = g.pool ? py / 2 : py, ox = g.pool ? px / 2 : px;
       const bool in_img = valid && (py < g.H) && (px < g.W);
       const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout;
-      const int c0 = chalf * 32;
-      float v[32];
+      float v[CPW];
       const uint32_t lane_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + c0;
-      tc::tmem_ld_acc32(lane_base, BN, 2 * BN, PLANE_LO_INV, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
+      p2_ld_acc<CPW>(lane_base, BN, 2 * BN, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) p2_arrive_remote(p2_mapa(tmem_empty + acc, 0));   // this warp's only TMEM read of the set: back to the MMA warp
       if (swap_halves & 512) continue;
       if (g.pool) {
-        // 2x2 max-pool = lanes {l, l^1, l^8} (4 image rows x 8 cols per warp) as an exchange-and-halve butterfly: 24 shuffles per
-        // lane instead of 64, and every lane ends up with 8 pooled channels to bias / ReLU / split / store (bias and ReLU commute
-        // with the max: same values bit for bit)
-        float u[16], r[8];
+        // 2x2 max-pool = lanes {l, l^1, l^8} (4 image rows x 8 cols per warp) as an exchange-and-halve butterfly: 3/4 CPW shuffles per
+        // lane instead of 2 CPW, and every lane ends up with CPW / 4 pooled channels to bias / ReLU / split / store (bias and ReLU
+        // commute with the max: same values bit for bit)
+        float u[CPW / 2], r[CPW / 4];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const float keep = b0 ? v[16 + j] : v[j], send = b0 ? v[j] : v[16 + j];
+        for (int j = 0; j < CPW / 2; j++) {
+          const float keep = b0 ? v[CPW / 2 + j] : v[j], send = b0 ? v[j] : v[CPW / 2 + j];
           u[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          const float keep = b3 ? u[8 + e] : u[e], send = b3 ? u[e] : u[8 + e];
+        for (int e = 0; e < CPW / 4; e++) {
+          const float keep = b3 ? u[CPW / 4 + e] : u[e], send = b3 ? u[e] : u[CPW / 4 + e];
           r[e] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < CPW / 4; e++) {
           r[e] += bq[e];
           if (g.relu) r[e] = fmaxf(r[e], 0.f);
         }
         if (in_img) {
           if (g.out_fp32) {
-            float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + cq);
-            o[0] = make_float4(r[0], r[1], r[2], r[3]); o[1] = make_float4(r[4], r[5], r[6], r[7]);
+#pragma unroll
+            for (int e = 0; e < CPW / 4; e += 4) *reinterpret_cast<float4*>(g.out_f32 + opix + cq + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
           } else {
-            uint4 h4, l4;
-            __half2* hp = reinterpret_cast<__half2*>(&h4);
-            __half2* lp = reinterpret_cast<__half2*>(&l4);
+            __align__(16) __half2 hp[CPW / 8], lp[CPW / 8];
             if (g.relu) {
 #pragma unroll
-              for (int e = 0; e < 4; e++) split2_pos(r[2 * e], r[2 * e + 1], hp[e], lp[e]);
+              for (int e = 0; e < CPW / 8; e++) split2_pos(r[2 * e], r[2 * e + 1], hp[e], lp[e]);
             } else {
-              plane_t* hh = reinterpret_cast<plane_t*>(&h4);
-              plane_t* ll = reinterpret_cast<plane_t*>(&l4);
+              plane_t* hh = reinterpret_cast<plane_t*>(hp);
+              plane_t* ll = reinterpret_cast<plane_t*>(lp);
 #pragma unroll
-              for (int e = 0; e < 8; e++) split2(r[e], hh[e], ll[e]);
+              for (int e = 0; e < CPW / 4; e++) split2(r[e], hh[e], ll[e]);
             }
-            *reinterpret_cast<uint4*>(g.out_planes + opix + cq) = h4;
-            *reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + cq) = l4;
+            if (CPW == 32) {
+              *reinterpret_cast<uint4*>(g.out_planes + opix + cq) = *reinterpret_cast<const uint4*>(hp);
+              *reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + cq) = *reinterpret_cast<const uint4*>(lp);
+            } else {
+              *reinterpret_cast<uint2*>(g.out_planes + opix + cq) = *reinterpret_cast<const uint2*>(hp);
+              *reinterpret_cast<uint2*>(g.out_planes + plane_stride + opix + cq) = *reinterpret_cast<const uint2*>(lp);
+            }
           }
         }
         continue;
       }
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
+      for (int j = 0; j < CPW; j++) {
         float x = v[j] + s_bias[c0 + j];
         if (g.relu) x = fmaxf(x, 0.f);
         v[j] = x;
@@ -390,22 +378,22 @@ tc_conv3x3_c64_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         if (g.out_fp32) {
           float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
 #pragma unroll
-          for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < CPW / 4; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-          __align__(16) __half2 p0[16], p1[16];
+          __align__(16) __half2 p0[CPW / 2], p1[CPW / 2];
           if (g.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) split2_pos(v[2 * j], v[2 * j + 1], p0[j], p1[j]);
+            for (int j = 0; j < CPW / 2; j++) split2_pos(v[2 * j], v[2 * j + 1], p0[j], p1[j]);
           } else {
             plane_t* hh = reinterpret_cast<plane_t*>(p0);
             plane_t* ll = reinterpret_cast<plane_t*>(p1);
 #pragma unroll
-            for (int j = 0; j < 32; j++) split2(v[j], hh[j], ll[j]);
+            for (int j = 0; j < CPW; j++) split2(v[j], hh[j], ll[j]);
           }
           uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
           uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int j = 0; j < CPW / 8; j++) {
             o0[j] = reinterpret_cast<const uint4*>(p0)[j];
             o1[j] = reinterpret_cast<const uint4*>(p1)[j];
           }

@@ -162,6 +162,8 @@ def lib():
         L.imw_dual_softmax.restype = C.c_int
         L.imw_dual_softmax.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp, vp,
                                        C.c_size_t, vp]
+        L.imw_debug_set_gemm_ablate.restype = C.c_int
+        L.imw_debug_set_gemm_ablate.argtypes = [C.c_int]
         L.imw_debug_set_conv_pair.restype = C.c_int
         L.imw_debug_set_conv_pair.argtypes = [C.c_int]
         L.imw_debug_conv1ab_fused.restype = C.c_int

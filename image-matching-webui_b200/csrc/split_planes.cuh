@@ -21,4 +21,11 @@ __device__ __forceinline__ void split2(float x, plane_t& hi, plane_t& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn((x - __half2float(hi)) * PLANE_LO_SCALE);
 }
+// two values at once with packed converts (same results as split2 on each)
+__device__ __forceinline__ void split2x2(float x0, float x1, __half2& hi, __half2& lo) {
+  x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+  hi = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hi);
+  lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
+}
 __device__ __forceinline__ float merge2(plane_t hi, plane_t lo) { return fmaf(__half2float(lo), PLANE_LO_INV, __half2float(hi)); }

@@ -795,12 +795,13 @@ static int launch_conv_halo_pair_t(const CUtensorMap& tmA, const CUtensorMap& tm
   const int total = g.B * ceil_div(g.H, C64_TH) * (g.W / C64_TW);
   const int items = ((total + 1) / 2) * (g.Cout / BN), max_clusters = imw_num_sms() / 2;
   const int clusters = items < max_clusters ? items : max_clusters;
-  tc_conv3x3_halo_pair_kernel<BN, RES><<<dim3((unsigned)(2 * clusters)), PH_THREADS, smem, st>>>(tmA, tmW, g, total);
+  tc_conv3x3_halo_pair_kernel<BN, RES><<<dim3((unsigned)(2 * clusters)), ph_threads<RES>(), smem, st>>>(tmA, tmW, g, total);
   IMW_CHECK_LAUNCH_T(BN == 128 ? "tc_conv3x3 -> tc_conv3x3_halo_pair_kernel<128>" : "tc_conv3x3 -> tc_conv3x3_halo_pair_kernel<64>");
   return IMW_OK;
 }
 // 3x3, stride 1, W % 8 == 0 on CTA pairs: dense halo patch (10 x 18 box), each CTA fetches its half of the Cout slice
 static int launch_conv_halo_pair(const void* in_planes, const void* w_planes, const ConvArgs& g, cudaStream_t st) {
+  IMW_REQUIRE(!(g.res_planes && g.pool), "tc_conv (pair halo kernel): a residual input with a fused max-pool is not built");
   CUtensorMap tmA, tmW;
   const int BN = (g.Cout % 128 == 0) ? 128 : 64;
   if (int e = make_map_act(&tmA, in_planes, NP * g.B, g.H, g.W, g.Cin, P2_HALO_W, P2_HALO_H)) return e;

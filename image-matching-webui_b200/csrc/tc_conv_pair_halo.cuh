@@ -9,10 +9,10 @@
 //     a_hi x b_hi -> main      a_hi x b_lo -> cross      a_lo x b_hi -> cross          (N = BN, each CTA supplies BN / 2 rows)
 // (the N-concatenated [b_hi | b_lo] form of the single-CTA kernels would need the two halves of b_hi at different offsets in the two
 // CTAs for the third product).  Roles per CTA: warp 0 weight TMA, warp 1 TMEM alloc (+ all MMAs in the leader CTA), warp 2
-// activation TMA, warps 3..10 epilogue.  All loads complete on the LEADER's full barriers (TMA .cta_group::2); tcgen05.commit
+// activation TMA, warps 3.. epilogue.  All loads complete on the LEADER's full barriers (TMA .cta_group::2); tcgen05.commit
 // multicasts the empty barriers and tmem_full to both CTAs; both CTAs' epilogue warps arrive on the leader's tmem_empty.
-constexpr int PH_EPI_WARPS = 8;
-constexpr int PH_THREADS = (3 + PH_EPI_WARPS) * 32;
+template <bool RES> constexpr int ph_epi_warps() { return RES ? 8 : 16; }   // (the residual variant needs the registers of a 11-warp CTA)
+template <bool RES> constexpr int ph_threads() { return (3 + ph_epi_warps<RES>()) * 32; }
 template <int BN> constexpr int ph_w_stage() { return BN * 128; }                 // [b_hi half | b_lo half] of one (chunk, tap)
 template <int BN> constexpr int ph_w_stages() { return BN == 128 ? 8 : 12; }
 template <int BN> constexpr int ph_bar_off() { return P2_A_BYTES + ph_w_stages<BN>() * ph_w_stage<BN>(); }
@@ -27,9 +27,10 @@ __device__ __forceinline__ void p2_tma_2d_pair(void* smem_dst, const CUtensorMap
 }
 
 template <int BN, bool RES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ph_threads<RES>(), 1)
 tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles) {
   constexpr int STAGES = ph_w_stages<BN>(), W_STAGE = ph_w_stage<BN>(), HALF = BN / 2;
+  constexpr int EPW = ph_epi_warps<RES>(), CPW = 4 * BN / EPW, CH = CPW < 32 ? CPW : 32;   // epilogue warps, columns per warp, chunk
   extern __shared__ uint8_t cv_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // [buf][plane][180 px][128 B]
@@ -54,7 +55,7 @@ tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int i = 0; i < 2; i++) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
     for (int s = 0; s < STAGES; s++) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
     tc::mbar_init(tmem_full, 1);
-    tc::mbar_init(tmem_empty, 2 * PH_EPI_WARPS);
+    tc::mbar_init(tmem_empty, 2 * EPW);
     tc::fence_barrier_init();
   }
   if (warp == 1) p2_tmem_alloc(tmem_slot, 4 * BN);
@@ -153,11 +154,13 @@ tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
     }
   } else {
-    const int q = warp % 4, chalf = (warp - 3) / 4;   // TMEM sub-partition; columns [chalf * BN / 2, +BN / 2) of the slice
+    // epilogue: EPW / 4 warps per TMEM sub-partition, CPW columns of the slice each, in chunks of CH <= 32.  The accumulators are
+    // single-buffered (512 TMEM columns at BN = 128), so this is exposed time: 16 warps without a residual input.
+    const int q = warp % 4, cw0 = ((warp - 3) / 4) * CPW;
     const int m = q * 32 + lane;              // pixel index in the tile: row m/8, col m%8
     const int Ho = g.pool ? g.H / 2 : g.H, Wo = g.pool ? g.W / 2 : g.W;
-    const bool writer = g.pool ? ((lane & 1) == 0 && (lane & 8) == 0) : true;
     const size_t plane_stride = (size_t)g.B * Ho * Wo * g.Cout;
+    const bool b0 = (lane & 1) != 0, b3 = (lane & 8) != 0;   // pooled outputs: lane owns CH / 4 channels of its 2x2 window
     for (int i = 0; i < my_iters; i++) {
       int b, x0, y0, n0; bool valid;
       decode(i, b, x0, y0, n0, valid);
@@ -168,19 +171,60 @@ tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const bool in_img = valid && (py < g.H) && (px < g.W);
       const size_t opix = (((size_t)b * Ho + oy) * Wo + ox) * g.Cout + n0;
 #pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
-        float v[32], t[32];
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-        tc::tmem_ld_acc32(lane_base, BN, 2 * BN, PLANE_LO_INV, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
-        if (c0 + 32 >= (chalf + 1) * (BN / 2)) {  // this warp's last TMEM read of the item: hand the accumulators back to the MMA warp
+      for (int c0 = cw0; c0 < cw0 + CPW; c0 += CH) {
+        float v[CH];
+        p2_ld_acc<CH>(tmem_base + ((uint32_t)(q * 32) << 16) + c0, BN, 2 * BN, v);   // (main0 + main1) + (cross0 + cross1) 2^-11
+        if (c0 + CH >= cw0 + CPW) {  // this warp's last TMEM read of the item: hand the accumulators back to the MMA warp
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) p2_arrive_remote(p2_mapa(tmem_empty, 0));
         }
+        if (!RES && g.pool) {
+          // 2x2 max-pool = lanes {l, l^1, l^8} as an exchange-and-halve butterfly; bias and the (monotone) activation commute with
+          // the max, so they run on the CH / 4 pooled channels this lane ends up with (tc_conv_pair.cuh)
+          float u[CH / 2], r[CH / 4];
+#pragma unroll
+          for (int j = 0; j < CH / 2; j++) {
+            const float keep = b0 ? v[CH / 2 + j] : v[j], send = b0 ? v[j] : v[CH / 2 + j];
+            u[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+          }
+#pragma unroll
+          for (int e = 0; e < CH / 4; e++) {
+            const float keep = b3 ? u[CH / 4 + e] : u[e], send = b3 ? u[e] : u[CH / 4 + e];
+            r[e] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+          }
+          const int cq = c0 + (b0 ? CH / 2 : 0) + (b3 ? CH / 4 : 0);
+#pragma unroll
+          for (int e = 0; e < CH / 4; e++) {
+            float x = r[e] + (g.bias ? g.bias[n0 + cq + e] : 0.f);
+            if (g.relu == 1) x = fmaxf(x, 0.f);
+            else if (g.relu == 2) x = x > 0.f ? x : 0.01f * x;
+            r[e] = x;
+          }
+          if (in_img) {
+            if (g.out_fp32) {
+#pragma unroll
+              for (int e = 0; e < CH / 4; e += 4) *reinterpret_cast<float4*>(g.out_f32 + opix + cq + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+            } else {
+              __align__(16) __half2 hp[CH / 8], lp[CH / 8];
+#pragma unroll
+              for (int e = 0; e < CH / 8; e++) split2x2(r[2 * e], r[2 * e + 1], hp[e], lp[e]);
+              if (CH == 32) {
+                *reinterpret_cast<uint4*>(g.out_planes + opix + cq) = *reinterpret_cast<const uint4*>(hp);
+                *reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + cq) = *reinterpret_cast<const uint4*>(lp);
+              } else {
+                *reinterpret_cast<uint2*>(g.out_planes + opix + cq) = *reinterpret_cast<const uint2*>(hp);
+                *reinterpret_cast<uint2*>(g.out_planes + plane_stride + opix + cq) = *reinterpret_cast<const uint2*>(lp);
+              }
+            }
+          }
+          continue;
+        }
+        float t[RES ? CH : 1];
         if (RES && in_img) {  // residual branch of a BasicBlock (added before the activation)
           const plane_t* r0 = g.res_planes + opix + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < (RES ? CH : 0); j += 8) {
             uint4 a = *reinterpret_cast<const uint4*>(r0 + j), bq = *reinterpret_cast<const uint4*>(r0 + plane_stride + j);
             const plane_t *pa = reinterpret_cast<const plane_t*>(&a), *pb = reinterpret_cast<const plane_t*>(&bq);
 #pragma unroll
@@ -188,33 +232,29 @@ tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           }
         } else if (RES) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) t[j] = 0.f;
+          for (int j = 0; j < (RES ? CH : 0); j++) t[j] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
+        for (int j = 0; j < CH; j++) {
           float x = v[j] + (g.bias ? g.bias[n0 + c0 + j] : 0.f);
-          if (RES) x += t[j];
+          if (RES) x += t[RES ? j : 0];
           if (g.relu == 1) x = fmaxf(x, 0.f);
           else if (g.relu == 2) x = x > 0.f ? x : 0.01f * x;
-          if (g.pool) {  // 2x2 window = lanes {l, l^1, l^8}: 4 image rows x 8 cols per warp
-            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
-          }
           v[j] = x;
         }
-        if (writer && in_img) {
+        if (in_img) {
           if (g.out_fp32) {
             float4* o = reinterpret_cast<float4*>(g.out_f32 + opix + c0);
 #pragma unroll
-            for (int j = 0; j < 8; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CH / 4; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            __align__(16) plane_t p0[32], p1[32];
+            __align__(16) __half2 p0[CH / 2], p1[CH / 2];
 #pragma unroll
-            for (int j = 0; j < 32; j++) split2(v[j], p0[j], p1[j]);
+            for (int j = 0; j < CH / 2; j++) split2x2(v[2 * j], v[2 * j + 1], p0[j], p1[j]);
             uint4* o0 = reinterpret_cast<uint4*>(g.out_planes + opix + c0);
             uint4* o1 = reinterpret_cast<uint4*>(g.out_planes + plane_stride + opix + c0);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < CH / 8; j++) {
               o0[j] = reinterpret_cast<const uint4*>(p0)[j];
               o1[j] = reinterpret_cast<const uint4*>(p1)[j];
             }

@@ -258,6 +258,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tf32_kernel(const __gri
 //   * MMAs are kind::f16 (K = 16 per instruction): A_hi x [W_hi | W_lo] -> [main | cross], A_lo x W_hi -> cross; the epilogue adds
 //     main + cross 2^-11.
 // Same persistent tile walk, roles and functor epilogues as the kernel above.
+// timing ablations of the split-fp16 GEMM (imw_debug_set_gemm_ablate): bit 1 = splitters skip their work, bit 2 = epilogue functors
+// skipped (results are garbage).  Measured on 131072 x 768 x 256: full 0.290 ms, no split 0.250, no epilogue 0.188, neither 0.113 (= 82 %
+// of the tensor peak): the kernel is bound by the CUDA-core work of its splitter and epilogue warps, not by the operand stream.
+// (A weights-stationary CTA-pair form -- cta_group::2, M = 256, half of the weight slice resident per CTA, activations only
+// streamed -- was built and measured in round 2: bit-identical results, 0.407 ms on the same shape: its cross-CTA ready / empty
+// round trips cost more than the halved L2 traffic saves.  Removed.)
+inline int& tc_gemm_ablate() {
+  static int mode = 0;
+  return mode;
+}
 constexpr int TH_BKE = 64, TH_STAGES = 3, TH_SPLIT_WARPS = 4, TH_THREADS = 64 + 32 * TH_SPLIT_WARPS + 256;
 
 // Functors may provide a PAIR form of the epilogue -- two adjacent output columns per lane, sixteen column pairs x two rows per
@@ -279,7 +289,7 @@ constexpr size_t tc_gemm_f16_smem_bytes() {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi,
-                                                                   int m_tiles) {
+                                                                   int m_tiles, int ablate) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   // The fp32 tile lands as two 32-column boxes of 16 KB; the splitters rewrite it IN PLACE as the two fp16 operand tiles
@@ -385,6 +395,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
         uint8_t* row_hi = smem + s * STAGE + r * 128;          // box 0 row r -> A_hi row r
         uint8_t* row_lo = row_hi + AP_BYTES;                   // box 1 row r -> A_lo row r
         uint4 v[16];
+        if (!(ablate & 2)) {
 #pragma unroll
         for (int ch = 0; ch < 8; ch++) {
           v[ch] = *reinterpret_cast<const uint4*>(row_hi + ((ch ^ sw) << 4));        // elements 4 ch .. 4 ch + 3
@@ -395,11 +406,12 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
           const uint4 a = v[2 * cc], b = v[2 * cc + 1];
           const float x[8] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
                               __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
-          __align__(16) plane_t h[8], l[8];
+          __align__(16) __half2 h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 8; e++) split2(x[e], h[e], l[e]);
+          for (int e = 0; e < 4; e++) split2x2(x[2 * e], x[2 * e + 1], h[e], l[e]);
           *reinterpret_cast<uint4*>(row_hi + ((cc ^ sw) << 4)) = *reinterpret_cast<const uint4*>(h);
           *reinterpret_cast<uint4*>(row_lo + ((cc ^ sw) << 4)) = *reinterpret_cast<const uint4*>(l);
+        }
         }
         tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         tc::mbar_arrive(ready + s);
@@ -433,6 +445,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
           tc::fence_before_sync();
           tc::mbar_arrive(tmem_empty + acc);
         }
+        if (ablate & 4) continue;
         if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
         __syncwarp();
 #pragma unroll
@@ -479,7 +492,7 @@ static inline int launch_tc_gemm_f16(const float* A, long long rows_total, int l
   const int num_sms = imw_num_sms();
   const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
   dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-  tc_gemm_f16_kernel<BN, Epi><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles);
+  tc_gemm_f16_kernel<BN, Epi><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles, tc_gemm_ablate());
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

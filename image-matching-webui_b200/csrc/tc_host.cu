@@ -70,3 +70,9 @@ extern "C" int imw_debug_gemm_fp32(const float* A, const float* W, const float* 
   IMW_CHECK_CUDA(launch_gemm(g, 1, EpiBias{out, 0, N, bias, 0}, st));
   return IMW_OK;
 }
+
+// timing ablations of the split-fp16 GEMM (tc_gemm.cuh: tc_gemm_ablate): 0 = off
+extern "C" int imw_debug_set_gemm_ablate(int mode) {
+  if (mode >= 0) tc_gemm_ablate() = mode;
+  return tc_gemm_ablate();
+}

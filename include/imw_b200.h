@@ -385,6 +385,8 @@ int imw_debug_set_sp_sub(int n);
 int imw_debug_set_conv_halo(int on);
 /* 1 = Cin = Cout = 64 convs (and the fused first layer) on CTA pairs, tcgen05 cta_group::2 (default); 0 = single-CTA kernels; < 0 = query */
 int imw_debug_set_conv_pair(int mode);
+/* timing ablations of the split-fp16 GEMM: bit 1 = no operand split, bit 2 = no epilogue (garbage results); 0 = off; < 0 = query */
+int imw_debug_set_gemm_ablate(int mode);
 int imw_debug_conv1ab_fused(const float* image, const float* w1a, const float* b1a, const void* w1b_planes, const float* b1b,
                             void* out_planes, int batch, int height, int width, int pool, imw_stream_t stream);
 int imw_debug_conv3x3(const float* in, const float* w, const float* bias, float* out, int batch, int height, int width,

@@ -298,7 +298,7 @@ def test_tcgen05_gemm_unit(dev):
     """tcgen05/TMA GEMM against the CUDA-core GEMM and torch fp64."""
     from imcui_b200 import ops
     torch.manual_seed(0)
-    for (M, N, K) in ((128, 128, 32), (256, 256, 256), (1024, 768, 256), (512, 512, 512)):
+    for (M, N, K) in ((128, 128, 32), (256, 256, 256), (1024, 768, 256), (512, 512, 512), (4096, 256, 512), (2048, 512, 128)):
         A = torch.randn(M, K, device=dev); Wt = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
         ref = (A.double() @ Wt.double().t() + b.double()).float()
         simt = ops.debug_gemm(A, Wt, b, "fp32")

@@ -53,10 +53,12 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ k
   }
 }
 
-// ---- LayerNorm(512) + exact GELU, in place (lightglue.py:152-157) -------------------------------
+// ---- LayerNorm(512) + exact GELU (lightglue.py:152-157): in place, or -- planes != NULL -- written as the split-fp16 operand
+// planes [2][slots * cap][512] of the next linear (split_planes.cuh; plane_elems apart), so that its GEMM needs no splitter warps
 __global__ void __launch_bounds__(256) ln_gelu_kernel(float* __restrict__ h, const int* __restrict__ counts,
                                                       const int* __restrict__ skip, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, int cap) {
+                                                      const float* __restrict__ beta, int cap, plane_t* __restrict__ planes,
+                                                      long long plane_elems) {
   const int z = blockIdx.y, row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (skip[z >> 1] || row >= counts[z]) return;
   float* p = h + ((long long)z * cap + row) * 512;
@@ -83,7 +85,15 @@ __global__ void __launch_bounds__(256) ln_gelu_kernel(float* __restrict__ h, con
       float y = (v[4 * q + i] - mean) * rstd * gamma[c + i] + beta[c + i];
       o[i] = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
     }
-    *reinterpret_cast<float4*>(p + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (planes) {
+      __align__(8) __half2 hi[2], lo[2];
+      split2x2(o[0], o[1], hi[0], lo[0]); split2x2(o[2], o[3], hi[1], lo[1]);
+      plane_t* pp = planes + ((long long)z * cap + row) * 512 + c;
+      *reinterpret_cast<uint2*>(pp) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(pp + plane_elems) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      *reinterpret_cast<float4*>(p + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -244,7 +254,8 @@ __global__ void __launch_bounds__(1024) prune_kernel(const float* __restrict__ x
                                                      const float* __restrict__ conf, const float* __restrict__ mscore,
                                                      int* __restrict__ counts, const int* __restrict__ done,
                                                      int* __restrict__ prune, int cap, int pruning_th, float width_conf,
-                                                     float conf_thr, int have_conf) {
+                                                     float conf_thr, int have_conf, const plane_t* __restrict__ xp_in,
+                                                     plane_t* __restrict__ xp_out, long long plane_elems) {
   const int z = blockIdx.x, tid = threadIdx.x, lane = tid % 32, wid = tid / 32;
   const int n = counts[z];
   // pairs that already stopped (incl. at this layer: the reference breaks before pruning) are
@@ -279,6 +290,15 @@ __global__ void __launch_bounds__(1024) prune_kernel(const float* __restrict__ x
       float4* dx = reinterpret_cast<float4*>(xm_out + ((long long)z * cap + dst) * 512);
 #pragma unroll 8
       for (int q = 0; q < 64; q++) dx[q] = sx[q];
+      if (xp_in) {   // ... and its operand planes (256 halves = 32 x 16 B per plane)
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+          const uint4* sp = reinterpret_cast<const uint4*>(xp_in + pl * plane_elems + ((long long)z * cap + i) * 512);
+          uint4* dp = reinterpret_cast<uint4*>(xp_out + pl * plane_elems + ((long long)z * cap + dst) * 512);
+#pragma unroll 8
+          for (int q = 0; q < 32; q++) dp[q] = sp[q];
+        }
+      }
       const float4* se = reinterpret_cast<const float4*>(enc_in + ((long long)z * cap + i) * 64);
       float4* de = reinterpret_cast<float4*>(enc_out + ((long long)z * cap + dst) * 64);
 #pragma unroll
@@ -383,7 +403,8 @@ __global__ void init_state_kernel(const int* __restrict__ counts_in, int* __rest
 __global__ void __launch_bounds__(256) init_tokens_kernel(const float* __restrict__ desc, float* __restrict__ xm,
                                                           int* __restrict__ ind, int* __restrict__ matches,
                                                           float* __restrict__ mscores, int* __restrict__ prune,
-                                                          const int* __restrict__ counts, int cap, int prune_init) {
+                                                          const int* __restrict__ counts, int cap, int prune_init,
+                                                          plane_t* __restrict__ xp, long long plane_elems) {
   const int z = blockIdx.y, row = blockIdx.x * 4 + threadIdx.x / 64, t = threadIdx.x % 64;
   if (row >= cap) return;
   if (t == 0) {
@@ -392,9 +413,17 @@ __global__ void __launch_bounds__(256) init_tokens_kernel(const float* __restric
     mscores[(long long)z * cap + row] = 0.f;
     prune[(long long)z * cap + row] = prune_init;
   }
-  if (desc && row < counts[z])
-    reinterpret_cast<float4*>(xm + ((long long)z * cap + row) * 512)[t] =
-        reinterpret_cast<const float4*>(desc + ((long long)z * cap + row) * D)[t];
+  if (desc && row < counts[z]) {
+    const float4 v = reinterpret_cast<const float4*>(desc + ((long long)z * cap + row) * D)[t];
+    reinterpret_cast<float4*>(xm + ((long long)z * cap + row) * 512)[t] = v;
+    if (xp) {   // the same values as operand planes of the first projection
+      __align__(8) __half2 hi[2], lo[2];
+      split2x2(v.x, v.y, hi[0], lo[0]); split2x2(v.z, v.w, hi[1], lo[1]);
+      plane_t* pp = xp + ((long long)z * cap + row) * 512 + 4 * t;
+      *reinterpret_cast<uint2*>(pp) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(pp + plane_elems) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
 }
 
 }  // namespace
@@ -412,6 +441,8 @@ int imw_attention_simt(const float* q, const float* k, const float* v, float* ct
 struct LGBuffers {
   float *xm[2], *enc[2]; int* ind[2];
   float *q, *k, *v, *ctx, *h, *conf, *mscore, *md, *zl, *rmax, *rlse, *best_v;
+  plane_t* hp;     // LayerNorm + GELU output as split-fp16 planes [2][slots * cap][512] (tensor-core path)
+  plane_t* xp[2];  // the token state [x | message] as split-fp16 planes, written next to xm by every producer of xm (tensor-core path)
   int *best_j, *counts, *counts0, *done, *empty, *cnt;
 };
 
@@ -420,7 +451,8 @@ static size_t lg_carve(Workspace& ws, LGBuffers& b, int P, int cap) {
   for (int i = 0; i < 2; i++) { b.xm[i] = ws.take<float>(T * 512); b.enc[i] = ws.take<float>(T * 64); b.ind[i] = ws.take<int>(T); }
   // x2: hi/lo planes for the tcgen05 attention operands (the CUDA-core path uses the first plane only)
   b.q = ws.take<float>(2 * T * D); b.k = ws.take<float>(2 * T * D); b.v = ws.take<float>(2 * T * D);
-  b.ctx = ws.take<float>(T * D); b.h = ws.take<float>(T * 512);
+  b.ctx = ws.take<float>(T * D); b.h = ws.take<float>(T * 512); b.hp = ws.take<plane_t>(2 * T * 512);
+  for (int i = 0; i < 2; i++) b.xp[i] = ws.take<plane_t>(2 * T * 512);
   b.conf = ws.take<float>(T); b.mscore = ws.take<float>(T); b.md = ws.take<float>(T * D); b.zl = ws.take<float>(T);
   b.rmax = ws.take<float>(T); b.rlse = ws.take<float>(T); b.best_v = ws.take<float>(T); b.best_j = ws.take<int>(T);
   b.counts = ws.take<int>(S); b.counts0 = ws.take<int>(S); b.done = ws.take<int>(P); b.empty = ws.take<int>(P); b.cnt = ws.take<int>(P);
@@ -471,8 +503,12 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
   init_state_kernel<<<ceil_div(P, 128), 128, 0, st>>>(counts_in, b.counts, b.counts0, b.done, b.empty, stop, b.cnt, P, L);
   IMW_CHECK_LAUNCH_T("init_state_kernel");
   // prune output: 1 (+1 per surviving pruning step) when pruning is enabled, n_layers otherwise (:617-619)
+  // tensor-core path with host-packed weight planes: every producer of the token state / the MLP hidden layer also writes it as
+  // split-fp16 operand planes, and the linears take those by TMA (no splitter warps; the split is done once, not per N tile)
+  const bool planes_on = conf->use_tensor_cores == 1 && W->has_lo_planes == 2;
+  const long long xp_elems = (long long)S * cap * 512;
   init_tokens_kernel<<<dim3(ceil_div(cap, 4), S), 256, 0, st>>>(W->input_dim == D ? desc : nullptr, b.xm[0], b.ind[0], matches, mscores, prune, b.counts, cap,
-                                                                prune_semantics ? 1 : L);
+                                                                prune_semantics ? 1 : L, planes_on ? b.xp[0] : nullptr, xp_elems);
   IMW_CHECK_LAUNCH_T("init_tokens_kernel");
   posenc_kernel<<<S, 256, 0, st>>>(kpts, b.counts, W->posenc_wr, b.enc[0], cap, pe_dim, scales, oris);
   IMW_CHECK_LAUNCH_T("posenc_kernel");
@@ -486,9 +522,10 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
   IMW_REQUIRE(!use_tc || cap % 128 == 0, "imw_lightglue_forward: use_tensor_cores needs cap %% 128 == 0 (got %d)", cap);
   // Y = X W^T (+ functor epilogue) over all slots: tcgen05 TF32 tiles or the exact-fp32 CUDA-core kernel
   auto linear = [&](const float* A, int lda, const float* Wt, long long w_rows, int N, int K, auto epi, const int* skip,
-                    const int* wsel) -> int {
+                    const int* wsel, const plane_t* a_planes = nullptr) -> int {
     if (use_tc) {
       TcGemmArgs t{};
+      if (a_planes) { t.a_planes = a_planes; t.a_plane_rows = (long long)S * cap; t.a_plane_ld = lda; }
       t.K = K; t.N = N; t.tiles_per_slot = cap / 128; t.counts = b.counts; t.skip = skip; t.skip_shift = 1;
       t.wsel_minus1 = wsel; t.wsel_shift = 1; t.wsel_rows = N;
       if (W->has_lo_planes == 2) { t.w_planes = Wt + (size_t)w_rows * K; t.w_plane_rows = w_rows; }   // [W fp32 ; split-fp16 planes]
@@ -520,31 +557,40 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
     g.Mdyn = b.counts; g.Ndyn = nullptr; g.skip = b.done; g.skip_shift = 1;
     return g;
   };
+  // EpiStore into the token state (+ its planes when the plane path is on): col0 = 0 (x, residual) or D (message)
+  auto store_xm = [&](int col0, const float* bias, int residual) {
+    EpiStore e{b.xm[cur] + col0, 512, sXM, bias, residual};
+    if (planes_on) { e.planes = b.xp[cur] + col0; e.plane_elems = xp_elems; }
+    return e;
+  };
+  auto xplanes = [&]() -> const plane_t* { return planes_on ? b.xp[cur] : nullptr; };
   auto ffn = [&](const imw_lg_block& blk) -> int {
     float* xm = b.xm[cur];
-    if (int e = linear(xm, 512, blk.ffn0_w, 512, 512, 512, EpiStore{b.h, 512, sXM, blk.ffn0_b, 0}, b.done, nullptr)) return e;
-    ln_gelu_kernel<<<rows8, 256, 0, st>>>(b.h, b.counts, b.done, blk.ln_g, blk.ln_b, cap);
+    if (int e = linear(xm, 512, blk.ffn0_w, 512, 512, 512, EpiStore{b.h, 512, sXM, blk.ffn0_b, 0}, b.done, nullptr, xplanes())) return e;
+    // with host-packed weight planes the second linear takes its activations as planes written right here (no splitter warps)
+    const plane_t* hp = planes_on ? b.hp : nullptr;
+    ln_gelu_kernel<<<rows8, 256, 0, st>>>(b.h, b.counts, b.done, blk.ln_g, blk.ln_b, cap, const_cast<plane_t*>(hp), (long long)S * cap * 512);
     IMW_CHECK_LAUNCH_T("ln_gelu_kernel");
-    if (int e = linear(b.h, 512, blk.ffn3_w, D, D, 512, EpiStore{xm, 512, sXM, blk.ffn3_b, 1}, b.done, nullptr)) return e;
+    if (int e = linear(b.h, 512, blk.ffn3_w, D, D, 512, store_xm(0, blk.ffn3_b, 1), b.done, nullptr, hp)) return e;
     return IMW_OK;
   };
 
   if (W->input_dim != D) {  // x = input_proj(desc) (lightglue.py:519-520)
-    if (int e = linear(desc, W->input_dim, W->input_proj_w, D, D, W->input_dim, EpiStore{b.xm[0], 512, sXM, W->input_proj_b, 0}, b.done, nullptr)) return e;
+    if (int e = linear(desc, W->input_dim, W->input_proj_w, D, D, W->input_dim, store_xm(0, W->input_proj_b, 0), b.done, nullptr)) return e;
   }
   for (int i = 0; i < L; i++) {
     const imw_lg_layer& ly = W->layers[i];
     float* xm = b.xm[cur];
     float* enc = b.enc[cur];
     // ---- self attention (lightglue.py:159-172)
-    if (int e = linear(xm, 512, ly.self_blk.qkv_w, 3 * D, 3 * D, D, EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap, plane}, b.done, nullptr)) return e;
+    if (int e = linear(xm, 512, ly.self_blk.qkv_w, 3 * D, 3 * D, D, EpiQKVRotary{b.q, b.k, b.v, ly.self_blk.qkv_b, enc, cap, plane}, b.done, nullptr, xplanes())) return e;
     if (int e = attention(b.q, b.k, b.v, 0.125f, 0)) return e;
-    if (int e = linear(b.ctx, D, ly.self_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.self_blk.out_b, 0}, b.done, nullptr)) return e;
+    if (int e = linear(b.ctx, D, ly.self_blk.out_w, D, D, D, store_xm(D, ly.self_blk.out_b, 0), b.done, nullptr)) return e;
     if (int e = ffn(ly.self_blk)) return e;
     // ---- cross attention (lightglue.py:199-230)
-    if (int e = linear(xm, 512, ly.cross_blk.qkv_w, 2 * D, 2 * D, D, EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f, plane}, b.done, nullptr)) return e;
+    if (int e = linear(xm, 512, ly.cross_blk.qkv_w, 2 * D, 2 * D, D, EpiCrossQKV{b.q, b.v, ly.cross_blk.qkv_b, cap, 0.35355339059327373f, plane}, b.done, nullptr, xplanes())) return e;
     if (int e = attention(b.q, b.q, b.v, 1.0f, 1)) return e;
-    if (int e = linear(b.ctx, D, ly.cross_blk.out_w, D, D, D, EpiStore{xm + D, 512, sXM, ly.cross_blk.out_b, 0}, b.done, nullptr)) return e;
+    if (int e = linear(b.ctx, D, ly.cross_blk.out_w, D, D, D, store_xm(D, ly.cross_blk.out_b, 0), b.done, nullptr)) return e;
     if (int e = ffn(ly.cross_blk)) return e;
     if (i == L - 1) break;
     // ---- early stop / pruning (lightglue.py:549-571)
@@ -560,7 +606,7 @@ extern "C" int imw_lightglue_forward_so(const imw_lg_weights* W, const imw_lg_co
       IMW_CHECK_LAUNCH_T("token_logit_kernel");
       prune_kernel<<<S, 1024, 0, st>>>(b.xm[cur], b.xm[cur ^ 1], b.enc[cur], b.enc[cur ^ 1], b.ind[cur], b.ind[cur ^ 1], b.conf,
                                        b.mscore, b.counts, b.done, prune, cap, conf->pruning_min_kpts, conf->width_confidence, thr,
-                                       do_stop ? 1 : 0);
+                                       do_stop ? 1 : 0, planes_on ? b.xp[cur] : nullptr, planes_on ? b.xp[cur ^ 1] : nullptr, xp_elems);
       IMW_CHECK_LAUNCH_T("prune_kernel");
       cur ^= 1;
     }

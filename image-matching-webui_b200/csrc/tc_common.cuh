@@ -281,3 +281,5 @@ int tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64
                        uint32_t box_rows);
 // 2-D row-major fp16 [rows][cols] tensor (dense rows), box = {box_cols (64 = one 128-byte swizzled row), box_rows}
 int tc_make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
+// the same with a row pitch of ld_elems >= cols elements (a column range of a wider tensor)
+int tc_make_map_2d_f16_ld(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);

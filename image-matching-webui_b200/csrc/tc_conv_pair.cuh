@@ -49,20 +49,9 @@ __device__ __forceinline__ void p2_commit(uint64_t* bar) { tc::mma_commit_pair(b
 __device__ __forceinline__ void p2_tmem_alloc(uint32_t* smem_result, uint32_t ncols) { tc::tmem_alloc_pair(smem_result, ncols); }
 __device__ __forceinline__ void p2_tmem_dealloc(uint32_t taddr, uint32_t ncols) { tc::tmem_dealloc_pair(taddr, ncols); }
 
-// two non-negative values (ReLU outputs) -> fp16 plane pairs: packed converts, no lower clamp (4 instructions per value instead of 7)
-__device__ __forceinline__ void split2_pos(float x0, float x1, __half2& hi, __half2& lo) {
-  x0 = fminf(x0, 65504.f); x1 = fminf(x1, 65504.f);
-  hi = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(hi);
-  lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
-}
-
-// the same without the upper clamp, for values known to be far below fp16's range (conv1a of a [0, 1] image: |x| < sum |w| + |b|)
-__device__ __forceinline__ void split2_small(float x0, float x1, __half2& hi, __half2& lo) {
-  hi = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(hi);
-  lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
-}
+// two values -> fp16 plane pairs (split_planes.cuh: packed saturating converts, 4 instructions per value instead of 7)
+__device__ __forceinline__ void split2_pos(float x0, float x1, __half2& hi, __half2& lo) { split2x2(x0, x1, hi, lo); }
+__device__ __forceinline__ void split2_small(float x0, float x1, __half2& hi, __half2& lo) { split2x2(x0, x1, hi, lo); }
 
 // N (16 / 32) columns of a split-precision accumulator: (set0.main + set1.main) + (set0.cross + set1.cross) 2^-11 (tc::tmem_ld_acc32)
 template <int N>

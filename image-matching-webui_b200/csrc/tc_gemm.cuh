@@ -46,6 +46,9 @@ struct TcGemmArgs {
                          //      0: W_lo is computed in the kernel like A_lo
   const void* w_planes;  // non-null: the weights as split-fp16 planes [2][w_plane_rows][K] (split_planes.cuh, packed by the host):
   long long w_plane_rows;  //         the GEMM runs on kind::f16 (tc_gemm_f16_kernel) -- half the tensor time and 2/3 of the L2 -> SM bytes
+  const void* a_planes = nullptr;   // non-null (with w_planes): the ACTIVATIONS as split-fp16 planes [2][a_plane_rows][a_plane_ld] written by
+  long long a_plane_rows = 0;       //   their producer (e.g. LayerNorm + GELU): both operand tiles land by TMA, no splitter warps -- the kernel is
+  int a_plane_ld = 0;               //   bound by its CUDA-core work (tc_gemm_ablate), and the split is redone for every N tile otherwise
 };
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 448;
@@ -286,7 +289,7 @@ constexpr size_t tc_gemm_f16_smem_bytes() {
          8 * 32 * 33 * sizeof(float);
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, bool APL>
 __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW, TcGemmArgs g, Epi epi,
                                                                    int m_tiles, int ablate) {
@@ -341,8 +344,13 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
           tc::mbar_wait(empty + s, ph ^ 1);
           tc::mbar_expect_tx(full + s, LAND_BYTES + 2 * WP_BYTES);
           uint8_t* st = smem + s * STAGE;
-          tc::tma_load_2d(st, &tmA, full + s, kb * TH_BKE, m_tile * TC_BM);
-          tc::tma_load_2d(st + LAND_BYTES / 2, &tmA, full + s, kb * TH_BKE + 32, m_tile * TC_BM);
+          if (APL) {   // fp16 planes: A_hi and A_lo tiles as they are
+            tc::tma_load_2d(st, &tmA, full + s, kb * TH_BKE, m_tile * TC_BM);
+            tc::tma_load_2d(st + AP_BYTES, &tmA, full + s, kb * TH_BKE, (int)(g.a_plane_rows + (long long)m_tile * TC_BM));
+          } else {
+            tc::tma_load_2d(st, &tmA, full + s, kb * TH_BKE, m_tile * TC_BM);
+            tc::tma_load_2d(st + LAND_BYTES / 2, &tmA, full + s, kb * TH_BKE + 32, m_tile * TC_BM);
+          }
           tc::tma_load_2d(st + W_OFF, &tmW, full + s, kb * TH_BKE, n0);
           tc::tma_load_2d(st + W_OFF + WP_BYTES, &tmW, full + s, kb * TH_BKE, (int)(g.w_plane_rows + n0));
         }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
       const uint32_t d_main = tmem_base + acc * ACC_COLS, d_cross = d_main + BN;
       for (int kb = 0; kb < KB; kb++, c++) {
         const int s = c % TH_STAGES, ph = (c / TH_STAGES) & 1;
-        tc::mbar_wait(ready + s, ph);   // splitters done (they waited for the TMA bytes: W planes have landed too)
+        tc::mbar_wait(APL ? full + s : ready + s, ph);   // splitters done (they waited for the TMA bytes: W planes have landed too)
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * STAGE + A_OFF), b_addr = tc::smem_u32(smem + s * STAGE + W_OFF);
 #pragma unroll
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
     const int r = threadIdx.x - 64;  // 0 .. 127
     const int sw = r & 7;
     int c = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = blockIdx.x; !APL && tile < total; tile += gridDim.x) {
       int m_tile, n0, z, row0, nrows;
       if (!tile_info(tile, m_tile, n0, z, row0, nrows)) continue;
       for (int kb = 0; kb < KB; kb++, c++) {
@@ -485,14 +493,23 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
 template <int BN, class Epi>
 static inline int launch_tc_gemm_f16(const float* A, long long rows_total, int lda, TcGemmArgs g, Epi epi, cudaStream_t st) {
   CUtensorMap tmA, tmW;
-  if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, 32, TC_BM)) return e;
+  if (g.a_planes) {
+    if (int e = tc_make_map_2d_f16_ld(&tmA, g.a_planes, (uint64_t)(2 * g.a_plane_rows), (uint64_t)g.K, (uint64_t)g.a_plane_ld, TH_BKE, TC_BM)) return e;
+  } else {
+    if (int e = tc_make_map_2d_f32(&tmA, A, (uint64_t)rows_total, (uint64_t)g.K, (uint64_t)lda, 32, TC_BM)) return e;
+  }
   if (int e = tc_make_map_2d_f16(&tmW, g.w_planes, (uint64_t)(2 * g.w_plane_rows), (uint64_t)g.K, TH_BKE, BN)) return e;
   constexpr size_t smem = tc_gemm_f16_smem_bytes<BN>();
-  IMW_SMEM_ATTR_ONCE((tc_gemm_f16_kernel<BN, Epi>), smem);
   const int num_sms = imw_num_sms();
   const int m_tiles = (int)(rows_total / TC_BM), total = m_tiles * (g.N / BN);
   dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-  tc_gemm_f16_kernel<BN, Epi><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles, tc_gemm_ablate());
+  if (g.a_planes) {
+    IMW_SMEM_ATTR_ONCE((tc_gemm_f16_kernel<BN, Epi, true>), smem);
+    tc_gemm_f16_kernel<BN, Epi, true><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles, tc_gemm_ablate());
+  } else {
+    IMW_SMEM_ATTR_ONCE((tc_gemm_f16_kernel<BN, Epi, false>), smem);
+    tc_gemm_f16_kernel<BN, Epi, false><<<grid, TH_THREADS, smem, st>>>(tmA, tmW, g, epi, m_tiles, tc_gemm_ablate());
+  }
   IMW_CHECK_LAUNCH();
   return IMW_OK;
 }

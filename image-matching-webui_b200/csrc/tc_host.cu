@@ -36,10 +36,13 @@ int tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64
 
 // 2-D row-major fp16 [rows][cols] tensor (dense rows), box = {box_cols (inner, 64 = one 128-byte swizzled row), box_rows}
 int tc_make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  return tc_make_map_2d_f16_ld(map, base, rows, cols, cols, box_cols, box_rows);
+}
+int tc_make_map_2d_f16_ld(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
   PFN_encodeTiled fn = tc_get_encode_fn();
   if (!fn) { imw_set_error("cuTensorMapEncodeTiled not available"); return IMW_ERR_CUDA; }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {ld_elems * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -57,7 +60,8 @@ extern "C" int imw_debug_gemm_tf32(const float* A, const float* W, const float* 
   TcGemmArgs g{};
   g.K = K; g.N = N; g.tiles_per_slot = M / 128;
   if (split == 4) g.wlo_rows = N;   // W is [2N][K]: the weights followed by their pre-computed lo plane
-  if (split == 5) { g.w_planes = W + (size_t)N * K; g.w_plane_rows = N; }   // W [N][K] fp32 followed by its split-fp16 planes [2][N][K]
+  if (split >= 5) { g.w_planes = W + (size_t)N * K; g.w_plane_rows = N; }   // W [N][K] fp32 followed by its split-fp16 planes [2][N][K]
+  if (split == 6) { g.a_planes = A; g.a_plane_rows = M; g.a_plane_ld = K; }   // A holds its split-fp16 planes [2][M][K] (producer-written operand)
   if (split >= 3) return launch_tc_gemm<128, 3>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
   return launch_tc_gemm<128, 1>(A, M, K, W, N, g, EpiBias{out, 0, N, bias, 0}, st);
 }

@@ -12,10 +12,8 @@ constexpr int D = 256, HEADS = 4, HD = 64, NF = 32;
 // 165-169).  Output buffers [slots][HEADS][cap][HD].
 // two adjacent elements (off even): one 4-byte store per plane
 __device__ __forceinline__ void store_planes2(float* base, long long plane, long long off, float x0, float x1) {
-  x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
-  const __half2 hi = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(hi);
-  const __half2 lo = __floats2half2_rn((x0 - hf.x) * PLANE_LO_SCALE, (x1 - hf.y) * PLANE_LO_SCALE);
+  __half2 hi, lo;
+  split2x2(x0, x1, hi, lo);
   plane_t* p = reinterpret_cast<plane_t*>(base);
   *reinterpret_cast<__half2*>(p + off) = hi;
   *reinterpret_cast<__half2*>(p + plane + off) = lo;
@@ -154,6 +152,8 @@ struct EpiStore {
   float* out; int ldo; long long strideOut; const float* bias; int residual;
   int relu = 0;        // SuperGlue MLP: ReLU after the (BatchNorm-folded) first layer
   float scale = 1.f;   // applied to acc before the bias (SuperGlue score matrix: 1/sqrt(256))
+  plane_t* planes = nullptr;    // optional second output: the same values as split-fp16 planes (same [z][row][col] geometry as `out`,
+  long long plane_elems = 0;    //   lo plane plane_elems elements behind hi): the operand of the next linear, written by its producer
   __device__ void operator()(int z, int row, int col, float4 a, int) const {
     float4* o = reinterpret_cast<float4*>(out + z * strideOut + (long long)row * ldo + col);
     float4 r = make_float4(a.x * scale + (bias ? bias[col] : 0.f), a.y * scale + (bias ? bias[col + 1] : 0.f),
@@ -168,7 +168,9 @@ struct EpiStore {
   __device__ void elem(int z, int row, int col, float a, float2 res) const {
     float r = a * scale + (bias ? bias[col] : 0.f);
     if (relu) r = fmaxf(r, 0.f);
-    out[z * strideOut + (long long)row * ldo + col] = r + res.x;
+    const long long off = z * strideOut + (long long)row * ldo + col;
+    out[off] = r + res.x;
+    if (planes) split2(r + res.x, planes[off], planes[plane_elems + off]);
   }
   // pair form (col, ldo, strideOut even; `out` 8-byte aligned): (residual_0, residual_1, bias_0, bias_1) prefetched
   __device__ float4 pair_prefetch(int z, int row, int col) const {
@@ -180,7 +182,14 @@ struct EpiStore {
   __device__ void pair(int z, int row, int col, float a0, float a1, float4 pre) const {
     float r0 = a0 * scale + pre.z, r1 = a1 * scale + pre.w;
     if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
-    *reinterpret_cast<float2*>(out + z * strideOut + (long long)row * ldo + col) = make_float2(r0 + pre.x, r1 + pre.y);
+    const long long off = z * strideOut + (long long)row * ldo + col;
+    *reinterpret_cast<float2*>(out + off) = make_float2(r0 + pre.x, r1 + pre.y);
+    if (planes) {
+      __half2 hi, lo;
+      split2x2(r0 + pre.x, r1 + pre.y, hi, lo);
+      *reinterpret_cast<__half2*>(planes + off) = hi;
+      *reinterpret_cast<__half2*>(planes + plane_elems + off) = lo;
+    }
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };

@@ -709,14 +709,16 @@ def debug_gemm(A, W, bias, mode="3xtf32"):
     out = torch.empty(M, N, device=A.device)
     if mode == "3xtf32_wlo":
         W = with_tf32_lo_plane(W)
-    if mode == "f16x2":
+    if mode in ("f16x2", "f16x2_ap"):
         W = with_f16_planes(W)
+    if mode == "f16x2_ap":   # the activations arrive as split-fp16 planes too (what a producer kernel writes)
+        A = split_f16_planes(A)
     args = (L.ptr(A.contiguous()), L.ptr(W.contiguous()), L.ptr(bias.contiguous()), L.ptr(out), M, N, K)
     with torch.cuda.device(A.device):
         if mode == "fp32":
             L.check(L.lib().imw_debug_gemm_fp32(*args, L.stream_ptr(A.device)))
         else:
-            L.check(L.lib().imw_debug_gemm_tf32(*args, {"3xtf32": 3, "3xtf32_wlo": 4, "f16x2": 5, "tf32": 1}[mode], L.stream_ptr(A.device)))
+            L.check(L.lib().imw_debug_gemm_tf32(*args, {"3xtf32": 3, "3xtf32_wlo": 4, "f16x2": 5, "f16x2_ap": 6, "tf32": 1}[mode], L.stream_ptr(A.device)))
     return out
 
 

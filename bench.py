@@ -244,7 +244,7 @@ class Config2:
         if tc:
             traffic = None
             try:  # per-launch DRAM bytes of this kernel from the committed ncu --set full capture
-                traffic = json.loads((ROOT / "profiles" / "r2_conv1b_ncu.json").read_text()).get("dram_bytes_per_launch")
+                traffic = json.loads((ROOT / "profiles" / "r2d_conv1b_ncu.json").read_text()).get("dram_bytes_per_launch")
             except Exception:
                 pass
             return roofline_from_sites(prof, ["tc_conv1ab_fused"], (SP_LAYER_GFLOP["conv1a"] + SP_LAYER_GFLOP["conv1b"]) * n_img, "TFLOP/s", "tensor",

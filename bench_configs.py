@@ -379,7 +379,7 @@ class Config1(_Base):
 
     def roofline(self, prof):
         return roofline_from_sites(prof, ["tc_conv1ab_fused"], (bench.SP_LAYER_GFLOP["conv1a"] + bench.SP_LAYER_GFLOP["conv1b"]) * 2, "TFLOP/s", "tensor",
-                                   "tc_conv3x3_c64_kernel<fused conv1a> at batch 2 (one pair): 2 x 1200 tiles over 148 persistent CTAs",
+                                   "tc_conv3x3_c64_pair_kernel<fused conv1a> at batch 2 (one pair): 2 x 2400 tiles over 74 persistent CTA pairs",
                                    note="single-pair latency case: the grid covers the SMs but nothing amortises launch gaps")
 
     def _cpu_pair(self):

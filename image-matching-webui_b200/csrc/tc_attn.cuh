@@ -154,15 +154,18 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     const bool leader = tc::elect_one();
     constexpr uint32_t idesc64 = tc::make_idesc(tc::FMT_F16, 128, 64), idesc128 = tc::make_idesc(tc::FMT_F16, 128, 128);
-    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+    // operand descriptors = one base descriptor per buffer + (byte offset >> 4) in the 14-bit address field: a 64-bit add per operand
+    // instead of a rebuild (the issuing thread's instruction stream sits on the critical path of every key tile)
+    const uint64_t dQ = tc::make_smem_desc_sw128(tc::smem_u32(sQ)), dK = tc::make_smem_desc_sw128(tc::smem_u32(sK)),
+                   dV = tc::make_smem_desc_sw128(tc::smem_u32(sV)), dP = tc::make_smem_desc_sw128(tc::smem_u32(sP));
     auto issue_S = [&](int j) {  // S_j = Q K_j^T : main = hi*hi, cross = (hi*lo + lo*hi) 2^11
       tc::fence_after_sync();
       const uint32_t d_main = tmem_base + TA_S_COL + (j & 1) * 128, d_cross = d_main + 64;
-      const uint32_t kb = aK + (j % TA_NK) * TA_K_BYTES;
+      const uint64_t kb = dK + (uint64_t)(((j % TA_NK) * TA_K_BYTES) >> 4);
 #pragma unroll
       for (int ks = 0; ks < 4; ks++) {
-        uint64_t qh = tc::make_smem_desc_sw128(aQ + ks * 32), ql = tc::make_smem_desc_sw128(aQ + TA_Q_BYTES / 2 + ks * 32);
-        uint64_t kh = tc::make_smem_desc_sw128(kb + ks * 32);   // [K_hi | K_lo]: 128 adjacent rows
+        const uint64_t qh = dQ + (uint64_t)(ks * 2), ql = qh + (uint64_t)((TA_Q_BYTES / 2) >> 4);
+        const uint64_t kh = kb + (uint64_t)(ks * 2);   // [K_hi | K_lo]: 128 adjacent rows
         if (leader) {
           tc::mma_f16(d_main, qh, kh, idesc128, ks ? 1u : 0u);   // Q_hi x [K_hi | K_lo] -> [main | cross]
           tc::mma_f16(d_cross, ql, kh, idesc64, 1u);             // Q_lo x K_hi -> cross
@@ -178,12 +181,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::fence_after_sync();
       const int st = j & 1;
       const uint32_t d_main = tmem_base + TA_O_COL + st * 128, d_cross = d_main + 64;
-      const uint32_t vb = aV + (j % TA_NV) * TA_V_BYTES, pb = aP + st * TA_P_BYTES;
+      const uint64_t vb = dV + (uint64_t)(((j % TA_NV) * TA_V_BYTES) >> 4), pb = dP + (uint64_t)((st * TA_P_BYTES) >> 4);
       const uint32_t first = (j < 2) ? 0u : 1u;   // the stream's first tile overwrites its accumulator
 #pragma unroll
       for (int ks = 0; ks < 4; ks++) {
-        uint64_t ph = tc::make_smem_desc_sw128(pb + ks * 32), pl = tc::make_smem_desc_sw128(pb + TA_P_BYTES / 2 + ks * 32);
-        uint64_t vh = tc::make_smem_desc_sw128(vb + ks * 32);   // [V_hi | V_lo]
+        const uint64_t ph = pb + (uint64_t)(ks * 2), pl = ph + (uint64_t)((TA_P_BYTES / 2) >> 4);
+        const uint64_t vh = vb + (uint64_t)(ks * 2);   // [V_hi | V_lo]
         if (leader) {
           tc::mma_f16(d_main, ph, vh, idesc128, ks ? 1u : first);
           tc::mma_f16(d_cross, pl, vh, idesc64, 1u);

@@ -11,7 +11,7 @@
 // CTAs for the third product).  Roles per CTA: warp 0 weight TMA, warp 1 TMEM alloc (+ all MMAs in the leader CTA), warp 2
 // activation TMA, warps 3.. epilogue.  All loads complete on the LEADER's full barriers (TMA .cta_group::2); tcgen05.commit
 // multicasts the empty barriers and tmem_full to both CTAs; both CTAs' epilogue warps arrive on the leader's tmem_empty.
-template <bool RES> constexpr int ph_epi_warps() { return RES ? 8 : 16; }   // (the residual variant needs the registers of a 11-warp CTA)
+template <bool RES> constexpr int ph_epi_warps() { return 16; }   // 19 warps = 96 registers per thread: the residual variant works in 16-column chunks
 template <bool RES> constexpr int ph_threads() { return (3 + ph_epi_warps<RES>()) * 32; }
 template <int BN> constexpr int ph_w_stage() { return BN * 128; }                 // [b_hi half | b_lo half] of one (chunk, tap)
 template <int BN> constexpr int ph_w_stages() { return BN == 128 ? 8 : 12; }
@@ -30,7 +30,7 @@ template <int BN, bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ph_threads<RES>(), 1)
 tc_conv3x3_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvArgs g, int total_tiles) {
   constexpr int STAGES = ph_w_stages<BN>(), W_STAGE = ph_w_stage<BN>(), HALF = BN / 2;
-  constexpr int EPW = ph_epi_warps<RES>(), CPW = 4 * BN / EPW, CH = CPW < 32 ? CPW : 32;   // epilogue warps, columns per warp, chunk
+  constexpr int EPW = ph_epi_warps<RES>(), CPW = 4 * BN / EPW, CH = RES ? 16 : (CPW < 32 ? CPW : 32);   // epilogue warps, columns per warp, chunk
   extern __shared__ uint8_t cv_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // [buf][plane][180 px][128 B]

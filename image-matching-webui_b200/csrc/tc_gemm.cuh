@@ -283,6 +283,15 @@ struct tc_has_pair : std::false_type {};
 template <class Epi>
 struct tc_has_pair<Epi, std::void_t<decltype(&Epi::pair)>> : std::true_type {};
 
+// ... and a QUAD form -- four adjacent columns per lane, eight quads x four rows per warp instruction:  bool quad_ok()  (run-time
+// alignment check),  float4 quad_col(col)  (per-column constants, once per block),  float4 quad_prefetch(z, row, col)  and
+// quad(z, row, col, a, colconst, pre).  The block goes through a swizzled [32 rows][8 x 16 B] smem tile (conflict-free 16-byte
+// stores by row and loads by quad).
+template <class Epi, class = void>
+struct tc_has_quad : std::false_type {};
+template <class Epi>
+struct tc_has_quad<Epi, std::void_t<decltype(&Epi::quad)>> : std::true_type {};
+
 template <int BN>
 constexpr size_t tc_gemm_f16_smem_bytes() {
   return (size_t)TH_STAGES * (2 * TC_BM * 128 /*fp32 landing = A planes, split in place*/ + 2 * BN * 128 /*W planes*/) + 1024 + 256 +
@@ -455,11 +464,31 @@ __global__ void __launch_bounds__(TH_THREADS, 1) tc_gemm_f16_kernel(const __grid
         }
         if (ablate & 4) continue;
         if (epi.rowwise(z, row_base + lane, row_base + lane < nrows, n0 + c0, v)) continue;
+        const int rmax = min(32, nrows - row_base);  // warp-uniform
+        if constexpr (tc_has_quad<Epi>::value) {
+          if (epi.quad_ok()) {
+            float4* T4 = reinterpret_cast<float4*>(T);   // [32 rows][8 quads], quad q of row r at q ^ (r & 7)
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++) T4[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int cq = lane & 7, ro = lane >> 3, col = n0 + c0 + 4 * cq;
+            const float4 cc = epi.quad_col(col);
+            float4 pre[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pre[k] = (4 * k + ro < rmax) ? epi.quad_prefetch(z, row_base + 4 * k + ro, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int r = 4 * k + ro;
+              if (r < rmax) epi.quad(z, row_base + r, col, T4[r * 8 + (cq ^ (r & 7))], cc, pre[k]);
+            }
+            continue;
+          }
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j++) T[lane * 33 + j] = v[j];
         __syncwarp();
-        const int rmax = min(32, nrows - row_base);  // warp-uniform
         if constexpr (tc_has_pair<Epi>::value) {
           // lane = (row parity, column pair): rows 2k + (lane >> 4), columns 2 (lane & 15), +1.  T reads are conflict-free
           // (row stride 33 words: even rows hit the even banks, odd rows the odd ones)

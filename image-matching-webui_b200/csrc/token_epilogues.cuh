@@ -86,6 +86,41 @@ struct EpiQKVRotary {
     if (plane) store_planes2(dst, plane, off, r0, r1);
     else *reinterpret_cast<float2*>(dst + off) = make_float2(r0, r1);
   }
+  // quad form (col % 4 == 0): two rotary pairs per lane; (cos_0, sin_0, cos_1, sin_1) prefetched, the bias once per block.  Same
+  // operations per element as pair().
+  __device__ bool quad_ok() const {
+    return !(reinterpret_cast<uintptr_t>(q) & 15) && !(reinterpret_cast<uintptr_t>(k) & 15) && !(reinterpret_cast<uintptr_t>(v) & 15) &&
+           !(reinterpret_cast<uintptr_t>(enc) & 7);
+  }
+  __device__ float4 quad_col(int col) const { return make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]); }
+  __device__ float4 quad_prefetch(int z, int row, int col) const {
+    if (col >= 2 * D || !enc) return make_float4(1.f, 0.f, 1.f, 0.f);
+    const float* e = enc + ((long long)z * cap + row) * 64 + (col % HD) / 2;
+    const float2 cs = *reinterpret_cast<const float2*>(e), sn = *reinterpret_cast<const float2*>(e + 32);
+    return make_float4(cs.x, sn.x, cs.y, sn.y);
+  }
+  __device__ void quad(int z, int row, int col, float4 a, float4 b, float4 pre) const {
+    float r0 = a.x + b.x, r1 = a.y + b.y, r2 = a.z + b.z, r3 = a.w + b.w;
+    const int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which < 2) {
+      const float o0 = __fadd_rn(__fmul_rn(r0, pre.x), __fmul_rn(-r1, pre.y));
+      const float o1 = __fadd_rn(__fmul_rn(r1, pre.x), __fmul_rn(r0, pre.y));
+      const float o2 = __fadd_rn(__fmul_rn(r2, pre.z), __fmul_rn(-r3, pre.w));
+      const float o3 = __fadd_rn(__fmul_rn(r3, pre.z), __fmul_rn(r2, pre.w));
+      r0 = o0; r1 = o1; r2 = o2; r3 = o3;
+    }
+    float* dst = (which == 0 ? q : which == 1 ? k : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) {
+      __align__(8) __half2 hi[2], lo[2];
+      split2x2(r0, r1, hi[0], lo[0]); split2x2(r2, r3, hi[1], lo[1]);
+      plane_t* p = reinterpret_cast<plane_t*>(dst);
+      *reinterpret_cast<uint2*>(p + off) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(p + plane + off) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      *reinterpret_cast<float4*>(dst + off) = make_float4(r0, r1, r2, r3);
+    }
+  }
   // tcgen05 attention wants V transposed ([head][d][token], tokens contiguous): taken straight from the
   // thread-per-row TMEM layout (lanes = consecutive tokens -> coalesced), before the epilogue transpose.
   __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
@@ -134,6 +169,26 @@ struct EpiCrossQKV {
     const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
     if (plane) store_planes2(dst, plane, off, r0, r1);
     else *reinterpret_cast<float2*>(dst + off) = make_float2(r0, r1);
+  }
+  // quad form (col % 4 == 0), see EpiQKVRotary
+  __device__ bool quad_ok() const { return !(reinterpret_cast<uintptr_t>(qk) & 15) && !(reinterpret_cast<uintptr_t>(v) & 15); }
+  __device__ float4 quad_col(int col) const { return make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]); }
+  __device__ float4 quad_prefetch(int, int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ void quad(int z, int row, int col, float4 a, float4 b, float4) const {
+    float r0 = a.x + b.x, r1 = a.y + b.y, r2 = a.z + b.z, r3 = a.w + b.w;
+    const int which = col / D, c = col % D, head = c / HD, d = c % HD;
+    if (which == 0) { r0 *= qk_scale; r1 *= qk_scale; r2 *= qk_scale; r3 *= qk_scale; }
+    float* dst = (which == 0 ? qk : v);
+    const long long off = (((long long)z * HEADS + head) * cap + row) * HD + d;
+    if (plane) {
+      __align__(8) __half2 hi[2], lo[2];
+      split2x2(r0, r1, hi[0], lo[0]); split2x2(r2, r3, hi[1], lo[1]);
+      plane_t* p = reinterpret_cast<plane_t*>(dst);
+      *reinterpret_cast<uint2*>(p + off) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(p + plane + off) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      *reinterpret_cast<float4*>(dst + off) = make_float4(r0, r1, r2, r3);
+    }
   }
   __device__ bool rowwise(int z, int row, bool valid, int col0, const float (&a)[32]) const {
     if (!plane || col0 < D) return false;

@@ -147,6 +147,20 @@ struct EpiLinAttnQKV {
     const float2 o = which < 2 ? make_float2(fmap(a0), fmap(a1)) : make_float2(__fdiv_rn(a0, pre.x), __fdiv_rn(a1, pre.x));
     *reinterpret_cast<float2*>(dst) = o;
   }
+  // quad form (col % 4 == 0, dm % 4 == 0; tc_gemm.cuh): one 16-byte store per four columns
+  __device__ bool quad_ok() const {
+    return !(reinterpret_cast<uintptr_t>(q) & 15) && !(reinterpret_cast<uintptr_t>(k) & 15) && !(reinterpret_cast<uintptr_t>(v) & 15) &&
+           !(dm & 3) && !(slot_stride & 3);
+  }
+  __device__ float4 quad_col(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ float4 quad_prefetch(int z, int, int) const { return make_float4(kv_counts ? (float)kv_counts[z] : kv_len, 0.f, 0.f, 0.f); }
+  __device__ void quad(int z, int row, int col, float4 a, float4, float4 pre) const {
+    const int which = col / dm, c = col - which * dm;
+    float* dst = (which == 0 ? q : which == 1 ? k : v) + z * slot_stride + (long long)row * dm + c;
+    const float4 o = which < 2 ? make_float4(fmap(a.x), fmap(a.y), fmap(a.z), fmap(a.w))
+                               : make_float4(__fdiv_rn(a.x, pre.x), __fdiv_rn(a.y, pre.x), __fdiv_rn(a.z, pre.x), __fdiv_rn(a.w, pre.x));
+    *reinterpret_cast<float4*>(dst) = o;
+  }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };
 
@@ -294,6 +308,17 @@ struct EpiPlain {
     float x0 = a0 + pre.x, x1 = a1 + pre.y;
     if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
     *reinterpret_cast<float2*>(out + z * strideOut + (long long)row * ldo + col) = make_float2(x0, x1);
+  }
+  // quad form (col % 4 == 0; rows of `out` 16-byte aligned): the bias is fetched once per block
+  __device__ bool quad_ok() const { return !(reinterpret_cast<uintptr_t>(out) & 15) && !(ldo & 3) && !(strideOut & 3); }
+  __device__ float4 quad_col(int col) const {
+    return bias ? make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ float4 quad_prefetch(int, int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ void quad(int z, int row, int col, float4 a, float4 b, float4) const {
+    float4 x = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+    *reinterpret_cast<float4*>(out + z * strideOut + (long long)row * ldo + col) = x;
   }
   __device__ bool rowwise(int, int, bool, int, const float (&)[32]) const { return false; }
 };

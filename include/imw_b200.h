@@ -360,7 +360,8 @@ int imw_magsac(int n_sets, int cap, const float* pts0, const float* pts1, const 
 
 /* Unit-test hooks: out[M][N] = A[M][K] W[N][K]^T + bias on the tcgen05 path (split = 1: single TF32,
  * split = 3: 3xTF32 fp32-equivalent, split = 4: the same with W [2N][K] = weights + host-computed lo plane, split = 5: the
- * split-fp16 GEMM the linears run on, W [2N][K] = weights + their two fp16 planes) and on the CUDA-core fp32 path. */
+ * split-fp16 GEMM the linears run on, W [2N][K] = weights + their two fp16 planes, split = 6: the same with A handed over as
+ * split-fp16 planes [2][M][K] too, as a producer kernel writes them) and on the CUDA-core fp32 path. */
 int imw_debug_gemm_tf32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K, int split,
                         imw_stream_t stream);
 int imw_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int M, int N, int K,
@@ -383,7 +384,9 @@ int imw_debug_conv3x3_tc_planes(const void* in_planes, const void* w_planes, con
 int imw_debug_set_sp_sub(int n);
 /* 1 (default): 3x3 stride-1 tcgen05 convs with W % 8 == 0 use the halo-copy kernel, 0: the per-tap generic kernel; < 0: query */
 int imw_debug_set_conv_halo(int on);
-/* 1 = Cin = Cout = 64 convs (and the fused first layer) on CTA pairs, tcgen05 cta_group::2 (default); 0 = single-CTA kernels; < 0 = query */
+/* 1 (default) = 3x3 stride-1 convs with W % 8 == 0 (and the fused first layer) on CTA pairs, tcgen05 cta_group::2; 0 = their
+ * single-CTA predecessors; 2 = probe (B halves of the two CTAs swapped: wrong results); 1 + 256 / 512 / 1024 = timing ablations of
+ * the 64-channel pair kernel (no conv1a arithmetic / no epilogue arithmetic / no MMAs: garbage results); < 0 = query */
 int imw_debug_set_conv_pair(int mode);
 /* timing ablations of the split-fp16 GEMM: bit 1 = no operand split, bit 2 = no epilogue (garbage results); 0 = off; < 0 = query */
 int imw_debug_set_gemm_ablate(int mode);

@@ -1,8 +1,8 @@
 // Cin = Cout = 64 3x3 conv on a CTA PAIR (tcgen05 cta_group::2, M = 256): included by tc_conv.cu inside its anonymous namespace.
 //
 // What bounded the single-CTA c64 kernel (ncu, profiles/r2c_*): every 16 x 8 pixel tile re-streamed the nine weight taps
-// (144 KB) and three dx-shifted halo copies (108 KB) from L2 -- 252 KB per 3456 clk of MMA against a chip-wide L2 -> SM
-// throughput of ~28 B/clk per SM -- and, in the fused first layer, the producer warps wrote every conv1a value four times
+// (144 KB) and three dx-shifted halo copies (108 KB) from L2 -- 252 KB per 3456 clk of MMA, and the kernel sustained ~28 B/clk
+// per SM -- and, in the fused first layer, the producer warps wrote every conv1a value four times
 // (staging + three copies) through the same shared-memory data pipe the tensor core reads its operands from (LSU 40 % +
 // tensor 39 % of the wavefront peak).  Here:
 //   * ONE dense halo patch per plane (18 rows x 10 px x 128 B, SWIZZLE_128B as TMA writes it) serves all nine taps: the A
@@ -16,7 +16,7 @@
 //     Per tap and CTA: [0, 8 KB) = this CTA's half of [b_hi | b_lo] (rank 0: b_hi, rank 1: b_lo), [8 KB, 12 KB) = its half of
 //     b_hi for the a_lo x b_hi product (rank 0: rows 0..31, rank 1: rows 32..63).
 // Roles per CTA: warp 0 TMA (weights once; halo patches unless FUSE), warp 1 TMEM alloc (+ all MMAs, leader CTA only),
-// warps 2..9 epilogue, warps 10..15 conv1a producers (FUSE).  Cross-CTA signalling: halo patches complete on the LEADER's
+// warps 2..9 epilogue (2..17 in the plain conv), warps 10..17 conv1a producers (FUSE).  Cross-CTA signalling: halo patches complete on the LEADER's
 // a_full barrier (TMA .cta_group::2 / remote mbarrier.arrive), tcgen05.commit multicasts a_empty and tmem_full to both CTAs, the
 // epilogue warps of both CTAs arrive on the leader's tmem_empty.
 constexpr int P2_HALO_W = 10, P2_HALO_H = 18, P2_HALO_PX = P2_HALO_W * P2_HALO_H;

@@ -2,8 +2,8 @@
 // of tc_conv_pair.cuh, included by tc_conv.cu inside its anonymous namespace.
 //
 // The single-CTA halo kernel moved, per 64-channel chunk and 128-pixel tile, 108 KB of dx-shifted activation copies and 9 x 32 KB
-// of weight planes (BN = 128) through L2 -> SM: 396 KB per 6912 clk of MMA = 57 B/clk per SM against the ~28 B/clk the chip sustains
-// on all SMs at once.  Here one dense halo patch per plane and chunk (46 KB, see tc_conv_pair.cuh) serves the nine taps, and the two
+// of weight planes (BN = 128) through L2 -> SM: 396 KB per 6912 clk of MMA = 57 B/clk per SM at the tensor peak, twice what it
+// sustained.  Here one dense halo patch per plane and chunk (46 KB, see tc_conv_pair.cuh) serves the nine taps, and the two
 // CTAs of a pair each fetch HALF of every weight stage ([b_hi | b_lo] rows of their half of the Cout slice): 46 + 144 = 190 KB per
 // chunk and CTA = 27.5 B/clk.  Three MMAs per k-step, all with the operand halves at the same offsets in both CTAs:
 //     a_hi x b_hi -> main      a_hi x b_lo -> cross      a_lo x b_hi -> cross          (N = BN, each CTA supplies BN / 2 rows)

@@ -198,8 +198,8 @@ class Config2:
         self.stream = PairStream(self.eng)
         self.record = self.eng.new_record()
         self.d_batches = [hb.to(dev) for hb in self.h_batches]       # decoded uint8 frames, resident in HBM
-        self.dtype = "f32" if args.fp32 else ("f32-equivalent: split-fp16 (2 planes, 3 products) tcgen05 convs (SuperPoint), " + ("single-TF32" if args.tf32 else "3xTF32 split") +
-                                              " tcgen05 linears / attention / assignment (LightGlue), f32 detector post-processing")
+        self.dtype = "f32" if args.fp32 else ("f32-equivalent: split-fp16 (2 planes, 3 products) tcgen05 convs (SuperPoint), " + ("single-TF32 linears," if args.tf32 else "split-fp16 linears /") +
+                                              " split-fp16 attention / assignment on tcgen05 (LightGlue), f32 detector post-processing")
 
     def step_device(self, b):
         """decoded frames resident in HBM -> match records resident in HBM (pre-processing, SuperPoint, LightGlue, match gather).

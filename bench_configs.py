@@ -43,7 +43,7 @@ class Config5(_Base):
     default_pairs = 64
     workload_desc = ("dual-softmax matcher (inv_temperature 20, threshold 0.01) on 4096 x 128-d synthetic descriptor pairs with a planted "
                      "50 % partial permutation (BASELINE configs[4]: the matcher side of DISK+NN; the DISK net is not in the reference tree)")
-    dtype = "f32-equivalent: 3xTF32 split tcgen05 similarity tiles, f32 softmax statistics"
+    dtype = "f32-equivalent: split-fp16 (2 planes, 3 products) tcgen05 similarity tiles, f32 softmax statistics"
     N, D = 4096, 128
     cpu_sample_desc = "hloc DualSoftMax restated (oracle/matchers.py): torch CPU fp32 einsum + two softmax passes + host scatter"
 
@@ -89,9 +89,9 @@ class Config5(_Base):
 
     def roofline(self, prof):
         return roofline_from_sites(prof, ["launch_tc_simreduce"], self.gflop_per_pair() * self.P, "TFLOP/s", "tensor",
-                                   "tc_simreduce_kernel<dual-softmax ops> (streaming 128x128 3xTF32 similarity tiles in TMEM, never materialised)",
+                                   "tc_simreduce_kernel<dual-softmax ops> (streaming 128x128 split-fp16 similarity tiles in TMEM, never materialised)",
                                    note="algorithmic = ONE 4096x4096x128 similarity per pair (4.29 GFLOP); every extra sweep over the tiles and the "
-                                        "3xTF32 split (3 MMAs per product at the half-rate tf32 kind) are overheads of the implementation")
+                                        "split-precision products (three fp16 partial products per product) are overheads of the implementation")
 
     def cpu_unit(self):
         from oracle import matchers as om
@@ -128,7 +128,7 @@ class Config3(_Base):
     workload_desc = ("LoFTR (ResNet-FPN 8/2, 4x(self,cross) linear-attention coarse transformer, dual-softmax coarse matching, fine refinement), "
                      "batch=32 synthetic 1024x1024 grayscale pairs per GPU (BASELINE configs[2]); seeded random weights (no LoFTR checkpoint "
                      "offline), coarse threshold lowered so that the fine stage is loaded")
-    dtype = "f32-equivalent: split-fp16 tcgen05 convs (backbone), 3xTF32 tcgen05 linears / coarse similarity, f32 linear attention"
+    dtype = "f32-equivalent: split-fp16 tcgen05 convs (backbone), split-fp16 tcgen05 linears / coarse similarity, f32 linear attention"
     HW = 1024
     THR = 1e-9
     cpu_sample_desc = "SE2LoFTR module restated (oracle/loftr.py), torch CPU fp32, one 1024x1024 pair (materialises the 1.07 GB confidence matrix)"
@@ -207,7 +207,7 @@ class Config4(_Base):
                      "weights + GIM LightGlue weights with an input_proj FITTED (ridge regression, tools/make_golden.py aliked_lg_case) so that "
                      "the trained matcher sees SuperPoint-like descriptors: no aliked checkpoints offline, yet hundreds of geometrically "
                      "correct matches per pair reach MAGSAC; reference LightGlue semantics (depth 0.95 / width 0.99 / threshold 0.2)")
-    dtype = "f32 (ALIKED, CUDA cores), 3xTF32 tcgen05 (LightGlue), f64 (MAGSAC++ solvers)"
+    dtype = "f32 (ALIKED, CUDA cores), split-fp16 tcgen05 = f32-equivalent (LightGlue), f64 (MAGSAC++ solvers)"
     cpu_sample_desc = "ALIKED x2 + LightGlue restated in torch CPU fp32 (oracle/aliked.py, oracle/lightglue.py) + cv2.findFundamentalMat(USAC_MAGSAC)"
     ACONF = {"detection_threshold": 0.1, "max_num_keypoints": 1024, "nms_radius": 2}
     # the reference's defaults (lightglue.py:331-344; hloc passes match_threshold 0.2 as filter_threshold): early stop + CUDA pruning
@@ -320,7 +320,7 @@ class Config1(_Base):
     workload_desc = ("the reference's CPU-runnable case (tests/test_basic.py `test_one`, BASELINE configs[0]): tests/data pair (780x1063 and "
                      "1013x673 RGB JPEGs) -> RGB2GRAY, INTER_AREA force-resize to 640x480 -> SuperPoint (nms 3, thr 0.015, max 1024) -> mutual NN "
                      "-> MAGSAC F + H 3 px / 0.9999 / 10000; ONE pair per step (latency-bound by construction)")
-    dtype = "f32-equivalent: split-fp16 tcgen05 convs, 3xTF32 tcgen05 similarity, f64 MAGSAC++ solvers"
+    dtype = "f32-equivalent: split-fp16 tcgen05 convs and similarity tiles, f64 MAGSAC++ solvers"
     cpu_sample_desc = "cv2 pre-processing + SuperPoint x2 + NearestNeighbor (oracle ports, torch CPU fp32) + cv2 USAC_MAGSAC F and H"
     SP = {"nms_radius": 3, "max_keypoints": 1024, "keypoint_threshold": 0.015, "remove_borders": 4}
     PRE = {"grayscale": True, "resize_max": 1024, "dfactor": 8, "force_resize": True, "width": 640, "height": 480}
